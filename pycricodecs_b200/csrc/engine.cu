@@ -1,0 +1,567 @@
+// C-ABI implementation (include/cricodecs_b200.h): contexts, jobs, host<->HBM
+// movement. The per-sample work is in *_kernels.cu; the per-stream header work
+// is in formats.cpp. There is deliberately no CPU fallback anywhere in this
+// file: without a CUDA device every compute entry point returns -400.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cricodecs_b200.h"
+#include "engine.h"
+
+using namespace cri;
+
+// --------------------------------------------------------------- context
+#define CU_TRY(ctx, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(e_);              \
+            return ERR_CUDA;                                                                \
+        }                                                                                   \
+    } while (0)
+
+extern "C" int cri_version(void) { return 0x000100; }
+
+extern "C" int cri_ctx_create(int device, cri_ctx** out) {
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ERR_CUDA;
+    cri_ctx* c = new (std::nothrow) cri_ctx();
+    if (!c) return ERR_BUFFER;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev[0]) != cudaSuccess || cudaEventCreate(&c->ev[1]) != cudaSuccess ||
+        cudaEventCreate(&c->ev[2]) != cudaSuccess || cudaEventCreate(&c->ev[3]) != cudaSuccess) {
+        delete c;
+        return ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return OK;
+}
+
+extern "C" void cri_ctx_destroy(cri_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* cri_last_error(const cri_ctx* c) { return c ? c->error.c_str() : "no context"; }
+extern "C" uint64_t cri_ctx_launch_count(const cri_ctx* c) { return c ? c->launches : 0; }
+extern "C" float cri_ctx_last_kernel_ms(const cri_ctx* c) { return c ? c->last_ms : 0.f; }
+extern "C" float cri_ctx_last_dominant_ms(const cri_ctx* c) { return c ? c->last_dominant_ms : 0.f; }
+extern "C" void cri_free(void* p) { free(p); }
+
+// ------------------------------------------------------------ host helpers
+extern "C" uint16_t cri_crc16(const uint8_t* p, size_t n) { return crc16(p, n); }
+extern "C" int cri_hca_cipher_table(int type, uint64_t key, uint8_t t[256]) { return cipher_table(type, key, t) ? ERR_HCA_HEADER : OK; }
+extern "C" uint64_t cri_hca_mix_subkey(uint64_t key, uint16_t subkey) { return mix_subkey(key, subkey); }
+extern "C" void cri_adx_coefficients(uint32_t highpass, uint32_t rate, int32_t coef[2]) {
+    int c[2];
+    adx_coefficients(highpass, rate, c);
+    coef[0] = c[0];
+    coef[1] = c[1];
+}
+
+extern "C" const char* cri_strerror(int st) {
+    static const char* adx[] = {  // adx.cpp:11-30
+        "Invalid ADX file header.", "AHX file provided, unsopported.", "Encrypted ADX detected, unsupported.",
+        "Invalid/Unknown encoding mode found.", "Unknown ADX version provided.", "Invalid Bitdepth found on the provided ADX.",
+        "ADX does not contain any channels info.", "Invalid ADX header, loop information size is bigger than the header.",
+        "Inavlid ADX header, Criware copyright string not found.", "Numbers of Channel cannot exceed 255 or go below 0.",
+        "Bitdepth must be between 2 and 15 inclusive.", "Blocksize must be between 3 and 255 inclusive.",
+        "EncodingMode must be either 2, 3, or 4.", "HighpassFrequency must be between 0 and 65535 inclusive.",
+        "Filter is used with EncodingMode == 2 and must be between 0 and 4 inclusive.", "AdxVersion must be either 3, 4 or 5.",
+        "Provided Bitdepth does not fit correctly with the provided BlockSize", "Given WAVE file is not valid for ADX encoding."};
+    static const char* wav[] = {  // pcm.cpp:22-33
+        "Invalid WAVE file header.", "Invalid WAVE file header. Format info is not present.",
+        "Unsupported/Unknown WAVE compression mode.", "Invalid looping sample info data.",
+        "Invalid looping sample info data, Number of loops/loop data is larger than the available size.",
+        "Data tag is not present.", "Header is not valid.", "PCM Bitdepth does not match compression type.",
+        "Filesize exceeds 2GB use python to load in with buffer.", "Filesize is too low to be viable for loading."};
+    if (st == 0) return "ok";
+    if (st <= -1 && st >= -18) return adx[-st - 1];
+    if (st <= -101 && st >= -110) return wav[-st - 101];
+    switch (st) {  // hca.cpp:3252-3268
+        case ERR_HCA_HEADER: return "Header decoding error, the header is not a valid HCA header.";
+        case ERR_HCA_DECODE: return "Decoding error, either an incorrect key or an unknown exception.";
+        case ERR_HCA_CHANNELS: return "Error setting up channel configuration.";
+        case ERR_HCA_ENCODE: return "Unknown Encoding error.";
+        case ERR_UNSUPPORTED: return "Input is valid but not supported by this build of cricodecs_b200.";
+        case ERR_BUFFER: return "Truncated input or output buffer too small.";
+        case ERR_CUDA: return "CUDA failure (no device, or a launch/copy failed); there is no CPU fallback.";
+    }
+    return "unknown status";
+}
+
+// ---------------------------------------------------------------- planning
+// Each planner fills job->status / out_sizes and the kind-specific launch
+// tables on the host. Output layout is the packed concatenation of the exact
+// per-stream output sizes (failed streams get size 0).
+
+static void finish_layout(cri_job* j, const std::vector<uint64_t>& sizes) {
+    j->out_off.assign(j->n + 1, 0);
+    for (uint32_t i = 0; i < j->n; i++) j->out_off[i + 1] = j->out_off[i] + sizes[i];
+    j->out_bytes = j->out_off[j->n];
+}
+
+static void add_patch(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n) {
+    Patch p{dst, (uint32_t)j->patch_bytes.size(), n};
+    j->patch_bytes.insert(j->patch_bytes.end(), bytes, bytes + n);
+    j->patches.push_back(p);
+}
+
+static int adx_decode_size_one(const uint8_t* d, size_t n, AdxInfo* a, uint64_t* size) {
+    const int r = parse_adx(d, n, a);
+    if (r < 0) return r;
+    *size = wav_header_size(a->looping) + (uint64_t)a->samples * a->channels * 2;
+    return OK;
+}
+
+static void plan_adx_decode(cri_job* j) {
+    std::vector<uint64_t> sizes(j->n, 0);
+    std::vector<AdxInfo> infos(j->n);
+    for (uint32_t i = 0; i < j->n; i++)
+        j->status[i] = adx_decode_size_one(j->blob + j->in_off[i], j->in_off[i + 1] - j->in_off[i], &infos[i], &sizes[i]);
+    finish_layout(j, sizes);
+    std::vector<AdxChain> fast, generic;
+    for (uint32_t i = 0; i < j->n; i++) {
+        if (j->status[i] != OK) continue;
+        const AdxInfo& a = infos[i];
+        const uint64_t len = j->in_off[i + 1] - j->in_off[i];
+        const uint64_t data = (uint64_t)a.data_offset + 4;
+        const uint64_t frame_bytes = (uint64_t)a.channels * a.block_size;
+        uint64_t avail = len > data ? (len - data) / frame_bytes : 0;  // never read past the caller's buffer
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(a.blocks, avail);
+        const size_t hdr = wav_header_size(a.looping);
+        uint8_t h[0x70];
+        write_wav_header(h, a.samples, a.channels, (int)a.rate, a.looping, a.loop_start, a.loop_end);
+        add_patch(j, j->out_off[i], h, (uint32_t)hdr);
+        const uint64_t pcm0 = j->out_off[i] + hdr;
+        const bool aligned = (pcm0 & 1) == 0;
+        const bool is_fast = aligned && a.bit_depth == 4 && a.block_size == 18;
+        for (int c = 0; c < a.channels; c++) {
+            AdxChain ch{};
+            ch.eof_off = j->in_off[i] + data;
+            ch.in_off = ch.eof_off + (uint64_t)c * a.block_size;
+            ch.out_off = pcm0 + (uint64_t)c * 2;
+            ch.blocks = blocks;
+            ch.samples = a.samples;
+            ch.in_stride = (uint32_t)frame_bytes;
+            ch.out_stride = (uint32_t)a.channels;
+            ch.coef0 = a.coef[0];
+            ch.coef1 = a.coef[1];
+            ch.hist1 = a.history[c][0];
+            ch.hist2 = a.history[c][1];
+            ch.mode = (uint8_t)a.mode;
+            ch.bit_depth = (uint8_t)a.bit_depth;
+            ch.block_size = (uint8_t)a.block_size;
+            ch.stream = i;
+            (is_fast ? fast : generic).push_back(ch);
+        }
+        j->units += (uint64_t)blocks * a.channels;
+        // samples past the last decoded block stay zero: zero-filled by the tail patch below
+        if ((uint64_t)blocks * a.samples_per_block < a.samples) j->needs_clear = true;
+    }
+    j->n_fast = (uint32_t)fast.size();
+    j->n_generic = (uint32_t)generic.size();
+    j->adx_chains = fast;
+    j->adx_chains.insert(j->adx_chains.end(), generic.begin(), generic.end());
+}
+
+static void plan_adx_encode(cri_job* j) {
+    std::vector<uint64_t> sizes(j->n, 0);
+    std::vector<WavInfo> wavs(j->n);
+    std::vector<AdxEncPlan> plans(j->n);
+    const cri_adx_params& q = j->adx;
+    for (uint32_t i = 0; i < j->n; i++) {
+        const uint8_t* d = j->blob + j->in_off[i];
+        const size_t len = j->in_off[i + 1] - j->in_off[i];
+        int r = parse_wav(d, len, &wavs[i]);
+        if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
+        // A looping WAV (smpl chunk) encodes a loop header unless version 5 + force flag (adx.cpp:421); not built yet.
+        if (wavs[i].looping && !(q.force_not_looping && q.version == 5)) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        r = plan_adx_encode(wavs[i], q.bit_depth, q.block_size, q.encoding, q.highpass, q.filter, q.version, &plans[i]);
+        if (r < 0) { j->status[i] = r; continue; }
+        sizes[i] = plans[i].out_size;
+    }
+    finish_layout(j, sizes);
+    std::vector<AdxChain> fast, generic;
+    std::vector<uint8_t> tmp;
+    for (uint32_t i = 0; i < j->n; i++) {
+        if (j->status[i] != OK) continue;
+        const AdxEncPlan& p = plans[i];
+        const uint8_t* d = j->blob + j->in_off[i];
+        const int16_t* pcm = reinterpret_cast<const int16_t*>(d + wavs[i].data_offset);
+        int16_t firsts[256];
+        for (int c = 0; c < p.channels; c++) memcpy(&firsts[c], d + wavs[i].data_offset + 2 * (size_t)c, 2);
+        (void)pcm;
+        // header + EOF block are host-built patches; block payload comes from the kernel
+        tmp.assign(p.out_size, 0);
+        write_adx_frame(tmp.data(), p, firsts);
+        add_patch(j, j->out_off[i], tmp.data(), (uint32_t)p.header_size);
+        add_patch(j, j->out_off[i] + p.out_size - p.block_size, tmp.data() + p.out_size - p.block_size, (uint32_t)p.block_size);
+        const uint64_t pcm0 = j->in_off[i] + wavs[i].data_offset;
+        const bool is_fast = (pcm0 & 1) == 0 && p.bit_depth == 4 && p.block_size == 18;
+        for (int c = 0; c < p.channels; c++) {
+            AdxChain ch{};
+            ch.in_off = pcm0 + (uint64_t)c * 2;
+            ch.out_off = j->out_off[i] + (uint64_t)p.header_size + (uint64_t)c * p.block_size;
+            ch.blocks = p.frames;
+            ch.samples = p.samples;
+            ch.in_stride = (uint32_t)p.channels;
+            ch.out_stride = (uint32_t)p.channels * (uint32_t)p.block_size;
+            ch.coef0 = p.coef[0];
+            ch.coef1 = p.coef[1];
+            ch.hist1 = ch.hist2 = p.version == 3 ? (int16_t)0 : firsts[c];
+            ch.mode = (uint8_t)p.mode;
+            ch.bit_depth = (uint8_t)p.bit_depth;
+            ch.block_size = (uint8_t)p.block_size;
+            ch.filter = (uint8_t)p.filter;
+            ch.stream = i;
+            (is_fast ? fast : generic).push_back(ch);
+        }
+        j->units += (uint64_t)p.frames * p.channels;
+    }
+    j->n_fast = (uint32_t)fast.size();
+    j->n_generic = (uint32_t)generic.size();
+    j->adx_chains = fast;
+    j->adx_chains.insert(j->adx_chains.end(), generic.begin(), generic.end());
+}
+
+// ------------------------------------------------------------------- jobs
+template <class T>
+static int upload_vec(cri_ctx* c, const std::vector<T>& v, T** d) {
+    *d = nullptr;
+    if (v.empty()) return OK;
+    CU_TRY(c, cudaMalloc((void**)d, v.size() * sizeof(T)));
+    CU_TRY(c, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return OK;
+}
+
+extern "C" int cri_job_create(cri_ctx* c, const cri_job_desc* d, cri_job** out) {
+    *out = nullptr;
+    if (!c || !d || (!d->blob && d->n) || !d->offsets) return ERR_BUFFER;
+    CU_TRY(c, cudaSetDevice(c->device));
+    cri_job* j = new (std::nothrow) cri_job();
+    if (!j) return ERR_BUFFER;
+    j->kind = d->kind;
+    j->n = d->n;
+    j->blob = d->blob;
+    j->in_off.assign(d->offsets, d->offsets + d->n + 1);
+    j->in_bytes = j->in_off[d->n];
+    j->status.assign(d->n, OK);
+    j->adx = d->adx;
+    j->quality = d->quality;
+    j->encrypt = d->encrypt;
+    j->ciph_type = d->ciph_type;
+    if (d->keys) j->keys.assign(d->keys, d->keys + d->n);
+    if (d->subkeys) j->subkeys.assign(d->subkeys, d->subkeys + d->n);
+    int rc = OK;
+    switch (d->kind) {
+        case CRI_JOB_ADX_DECODE: plan_adx_decode(j); break;
+        case CRI_JOB_ADX_ENCODE: plan_adx_encode(j); break;
+        case CRI_JOB_HCA_DECODE: rc = plan_hca_decode(c, j); break;
+        case CRI_JOB_HCA_CRYPT: rc = plan_hca_crypt(c, j); break;
+        case CRI_JOB_HCA_ENCODE: rc = plan_hca_encode(c, j); break;
+        default: rc = ERR_UNSUPPORTED;
+    }
+    if (rc == OK) rc = [&]() -> int {
+        CU_TRY(c, cudaMalloc((void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 16));
+        CU_TRY(c, cudaMalloc((void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16));
+        CU_TRY(c, cudaMalloc((void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1)));
+        CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes + 16, c->stream));
+        int r = upload_vec(c, j->adx_chains, &j->d_adx_chains);
+        if (r == OK) r = upload_vec(c, j->patches, &j->d_patches);
+        if (r == OK) r = upload_vec(c, j->patch_bytes, &j->d_patch_bytes);
+        if (r == OK) r = upload_hca_tables(c, j);
+        if (r != OK) return r;
+        return cri_job_upload(c, j);
+    }();
+    if (rc != OK) {
+        cri_job_destroy(c, j);
+        return rc;
+    }
+    *out = j;
+    return OK;
+}
+
+extern "C" uint64_t cri_job_out_bytes(const cri_job* j) { return j->out_bytes; }
+extern "C" const uint64_t* cri_job_out_offsets(const cri_job* j) { return j->out_off.data(); }
+extern "C" uint64_t cri_job_units(const cri_job* j) { return j->units; }
+
+extern "C" int cri_job_upload(cri_ctx* c, cri_job* j) {
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (j->in_bytes) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return OK;
+}
+
+extern "C" int cri_job_run(cri_ctx* c, cri_job* j) {
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CU_TRY(c, cudaMemsetAsync(j->d_status, 0, sizeof(int32_t) * std::max<uint32_t>(j->n, 1), s));
+    if (j->needs_clear) CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes, s));
+    CU_TRY(c, cudaEventRecord(c->ev[0], s));
+    launch_scatter_patches(j->d_out, j->d_patch_bytes, j->d_patches, (uint32_t)j->patches.size(), s, &c->launches);
+    bool have_dominant = false;
+    switch (j->kind) {
+        case CRI_JOB_ADX_DECODE:
+            CU_TRY(c, cudaEventRecord(c->ev[2], s));
+            launch_adx_decode(j->d_in, j->d_out, j->d_adx_chains, j->n_fast, j->n_generic, s, &c->launches);
+            CU_TRY(c, cudaEventRecord(c->ev[3], s));
+            have_dominant = true;
+            break;
+        case CRI_JOB_ADX_ENCODE:
+            CU_TRY(c, cudaEventRecord(c->ev[2], s));
+            launch_adx_encode(j->d_in, j->d_out, j->d_adx_chains, j->n_fast, j->n_generic, s, &c->launches);
+            CU_TRY(c, cudaEventRecord(c->ev[3], s));
+            have_dominant = true;
+            break;
+        case CRI_JOB_HCA_DECODE:
+        case CRI_JOB_HCA_CRYPT:
+        case CRI_JOB_HCA_ENCODE: {
+            const int r = run_hca(c, j, &have_dominant);
+            if (r != OK) return r;
+            break;
+        }
+    }
+    CU_TRY(c, cudaEventRecord(c->ev[1], s));
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[1]);
+    c->last_dominant_ms = 0.f;
+    if (have_dominant) cudaEventElapsedTime(&c->last_dominant_ms, c->ev[2], c->ev[3]);
+    return OK;
+}
+
+extern "C" int cri_job_download(cri_ctx* c, cri_job* j, uint8_t* out_blob, int32_t* status) {
+    CU_TRY(c, cudaSetDevice(c->device));
+    std::vector<int32_t> dev(j->n, 0);
+    if (j->n) CU_TRY(c, cudaMemcpyAsync(dev.data(), j->d_status, sizeof(int32_t) * j->n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_blob && j->out_bytes)
+        CU_TRY(c, cudaMemcpyAsync(out_blob, j->d_out, j->out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < j->n; i++) {
+        int32_t st = j->status[i] != OK ? j->status[i] : dev[i];
+        if (status) status[i] = st;
+        if (st != OK && out_blob && j->status[i] == OK)  // a stream that failed on the device leaves silence, not garbage
+            memset(out_blob + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i]);
+    }
+    return OK;
+}
+
+extern "C" void cri_job_destroy(cri_ctx* c, cri_job* j) {
+    if (!j) return;
+    if (c) cudaSetDevice(c->device);
+    cudaFree(j->d_in);
+    cudaFree(j->d_out);
+    cudaFree(j->d_status);
+    cudaFree(j->d_adx_chains);
+    cudaFree(j->d_patches);
+    cudaFree(j->d_patch_bytes);
+    free_hca_tables(j);
+    delete j;
+}
+
+// ------------------------------------------------- batch = job in one call
+static int run_batch(cri_ctx* c, cri_job_desc d, uint8_t* out_blob, const uint64_t* out_offsets, int32_t* status) {
+    if (!c) return ERR_CUDA;
+    cri_job* j = nullptr;
+    int rc = cri_job_create(c, &d, &j);
+    if (rc != OK) return rc;
+    rc = cri_job_run(c, j);
+    if (rc == OK) {
+        bool packed = true;
+        if (out_offsets)
+            for (uint32_t i = 0; i <= d.n && packed; i++) packed = out_offsets[i] - out_offsets[0] == j->out_off[i];
+        if (packed) {
+            rc = cri_job_download(c, j, out_blob + (out_offsets ? out_offsets[0] : 0), status);
+        } else {  // caller chose a different layout: gather into a staging blob, then place each stream
+            std::vector<uint8_t> tmp(j->out_bytes);
+            rc = cri_job_download(c, j, tmp.data(), status);
+            if (rc == OK)
+                for (uint32_t i = 0; i < d.n; i++) {
+                    const uint64_t sz = j->out_off[i + 1] - j->out_off[i];
+                    if (out_offsets[i + 1] - out_offsets[i] < sz) { if (status) status[i] = ERR_BUFFER; continue; }
+                    memcpy(out_blob + out_offsets[i], tmp.data() + j->out_off[i], sz);
+                }
+        }
+    }
+    cri_job_destroy(c, j);
+    return rc;
+}
+
+static cri_job_desc make_desc(int kind, const uint8_t* blob, const uint64_t* offsets, uint32_t n) {
+    cri_job_desc d;
+    memset(&d, 0, sizeof d);
+    d.kind = kind;
+    d.blob = blob;
+    d.offsets = offsets;
+    d.n = n;
+    return d;
+}
+
+extern "C" int cri_adx_decode_sizes(const uint8_t* blob, const uint64_t* off, uint32_t n, uint64_t* sizes, int32_t* status) {
+    for (uint32_t i = 0; i < n; i++) {
+        AdxInfo a;
+        sizes[i] = 0;
+        const int r = adx_decode_size_one(blob + off[i], off[i + 1] - off[i], &a, &sizes[i]);
+        if (status) status[i] = r;
+    }
+    return OK;
+}
+
+extern "C" int cri_adx_decode_batch(cri_ctx* c, const uint8_t* blob, const uint64_t* off, uint32_t n, uint8_t* out,
+                                    const uint64_t* out_off, int32_t* status) {
+    return run_batch(c, make_desc(CRI_JOB_ADX_DECODE, blob, off, n), out, out_off, status);
+}
+
+extern "C" int cri_adx_encode_sizes(const uint8_t* blob, const uint64_t* off, uint32_t n, const cri_adx_params* p,
+                                    uint64_t* sizes, int32_t* status) {
+    for (uint32_t i = 0; i < n; i++) {
+        WavInfo w;
+        AdxEncPlan pl;
+        sizes[i] = 0;
+        int r = parse_wav(blob + off[i], off[i + 1] - off[i], &w);
+        if (r < 0) r += ERR_WAV_BASE;
+        else if (w.looping && !(p->force_not_looping && p->version == 5)) r = ERR_UNSUPPORTED;
+        else r = plan_adx_encode(w, p->bit_depth, p->block_size, p->encoding, p->highpass, p->filter, p->version, &pl);
+        if (r == OK) sizes[i] = pl.out_size;
+        if (status) status[i] = r;
+    }
+    return OK;
+}
+
+extern "C" int cri_adx_encode_batch(cri_ctx* c, const uint8_t* blob, const uint64_t* off, uint32_t n, const cri_adx_params* p,
+                                    uint8_t* out, const uint64_t* out_off, int32_t* status) {
+    cri_job_desc d = make_desc(CRI_JOB_ADX_ENCODE, blob, off, n);
+    d.adx = *p;
+    return run_batch(c, d, out, out_off, status);
+}
+
+extern "C" int cri_hca_decode_sizes(const uint8_t* blob, const uint64_t* off, uint32_t n, uint64_t* sizes, int32_t* status) {
+    for (uint32_t i = 0; i < n; i++) {
+        HcaInfo h;
+        sizes[i] = 0;
+        const int r = parse_hca(blob + off[i], off[i + 1] - off[i], &h);
+        if (r == OK) sizes[i] = wav_header_size(h.loop_flag) + (uint64_t)(h.frame_count * 1024u - h.delay - h.padding) * h.channels * 2;
+        if (status) status[i] = r == OK ? OK : ERR_HCA_HEADER;
+    }
+    return OK;
+}
+
+extern "C" int cri_hca_decode_batch(cri_ctx* c, const uint8_t* blob, const uint64_t* off, uint32_t n, const uint64_t* keys,
+                                    const uint16_t* subkeys, uint8_t* out, const uint64_t* out_off, int32_t* status) {
+    cri_job_desc d = make_desc(CRI_JOB_HCA_DECODE, blob, off, n);
+    d.keys = keys;
+    d.subkeys = subkeys;
+    return run_batch(c, d, out, out_off, status);
+}
+
+extern "C" int cri_hca_crypt_batch(cri_ctx* c, const uint8_t* blob, const uint64_t* off, uint32_t n, int encrypt,
+                                   uint32_t ciph_type, const uint64_t* keys, const uint16_t* subkeys, uint8_t* out,
+                                   int32_t* status) {
+    cri_job_desc d = make_desc(CRI_JOB_HCA_CRYPT, blob, off, n);
+    d.keys = keys;
+    d.subkeys = subkeys;
+    d.encrypt = encrypt;
+    d.ciph_type = ciph_type;
+    return run_batch(c, d, out, off, status);
+}
+
+extern "C" int cri_hca_encode_sizes(const uint8_t* blob, const uint64_t* off, uint32_t n, uint32_t quality, uint64_t* sizes,
+                                    int32_t* status) {
+    for (uint32_t i = 0; i < n; i++) {
+        WavInfo w;
+        HcaEncPlan pl;
+        sizes[i] = 0;
+        int r = parse_wav(blob + off[i], off[i + 1] - off[i], &w);
+        if (r < 0) r += ERR_WAV_BASE;
+        else if (w.looping) r = ERR_UNSUPPORTED;
+        else if (plan_hca_encode((unsigned)w.channels, (unsigned)w.rate, w.total_samples / (unsigned)w.channels, quality, &pl) < 0)
+            r = ERR_HCA_CHANNELS;
+        if (r == OK) sizes[i] = (uint64_t)pl.header_size + (uint64_t)pl.frame_count * pl.frame_size;
+        if (status) status[i] = r;
+    }
+    return OK;
+}
+
+extern "C" int cri_hca_encode_batch(cri_ctx* c, const uint8_t* blob, const uint64_t* off, uint32_t n, uint32_t quality,
+                                    uint32_t force_not_looping, uint8_t* out, const uint64_t* out_off, int32_t* status) {
+    cri_job_desc d = make_desc(CRI_JOB_HCA_ENCODE, blob, off, n);
+    d.quality = quality;
+    d.adx.force_not_looping = force_not_looping;
+    return run_batch(c, d, out, out_off, status);
+}
+
+// ------------------------------------------------------ single-stream API
+static int run_single(cri_ctx* c, cri_job_desc d, size_t n, uint8_t** out, size_t* out_n) {
+    *out = nullptr;
+    *out_n = 0;
+    if (!c) return ERR_CUDA;
+    const uint64_t off[2] = {0, n};
+    d.offsets = off;
+    d.n = 1;
+    cri_job* j = nullptr;
+    int rc = cri_job_create(c, &d, &j);
+    if (rc != OK) return rc;
+    int32_t st = OK;
+    if (j->status[0] != OK) {
+        st = j->status[0];
+    } else {
+        rc = cri_job_run(c, j);
+        if (rc == OK) {
+            uint8_t* buf = (uint8_t*)malloc(std::max<uint64_t>(j->out_bytes, 1));
+            rc = buf ? cri_job_download(c, j, buf, &st) : ERR_BUFFER;
+            if (rc == OK && st == OK) {
+                *out = buf;
+                *out_n = j->out_bytes;
+            } else {
+                free(buf);
+            }
+        }
+    }
+    cri_job_destroy(c, j);
+    return rc != OK ? rc : st;
+}
+
+extern "C" int cri_adx_decode(cri_ctx* c, const uint8_t* in, size_t n, uint8_t** out, size_t* out_n) {
+    return run_single(c, make_desc(CRI_JOB_ADX_DECODE, in, nullptr, 1), n, out, out_n);
+}
+extern "C" int cri_adx_encode(cri_ctx* c, const uint8_t* in, size_t n, const cri_adx_params* p, uint8_t** out, size_t* out_n) {
+    cri_job_desc d = make_desc(CRI_JOB_ADX_ENCODE, in, nullptr, 1);
+    d.adx = *p;
+    return run_single(c, d, n, out, out_n);
+}
+extern "C" int cri_hca_decode(cri_ctx* c, const uint8_t* in, size_t n, uint64_t key, uint16_t subkey, uint8_t** out, size_t* out_n) {
+    cri_job_desc d = make_desc(CRI_JOB_HCA_DECODE, in, nullptr, 1);
+    d.keys = &key;
+    d.subkeys = &subkey;
+    return run_single(c, d, n, out, out_n);
+}
+extern "C" int cri_hca_crypt(cri_ctx* c, const uint8_t* in, size_t n, int encrypt, uint32_t ciph_type, uint64_t key,
+                             uint16_t subkey, uint8_t** out, size_t* out_n) {
+    cri_job_desc d = make_desc(CRI_JOB_HCA_CRYPT, in, nullptr, 1);
+    d.keys = &key;
+    d.subkeys = &subkey;
+    d.encrypt = encrypt;
+    d.ciph_type = ciph_type;
+    return run_single(c, d, n, out, out_n);
+}
+extern "C" int cri_hca_encode(cri_ctx* c, const uint8_t* in, size_t n, uint32_t quality, uint32_t force_not_looping,
+                              uint8_t** out, size_t* out_n) {
+    cri_job_desc d = make_desc(CRI_JOB_HCA_ENCODE, in, nullptr, 1);
+    d.quality = quality;
+    d.adx.force_not_looping = force_not_looping;
+    return run_single(c, d, n, out, out_n);
+}

@@ -1,0 +1,41 @@
+// Device-side launch tables and kernel launchers shared by engine.cu and the
+// *_kernels.cu translation units. Names follow the codec domain: an ADX "chain"
+// is one channel of one stream (a strictly serial predictor recurrence), an HCA
+// "unit" is a run of consecutive frames of one stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace cri {
+
+// ------------------------------------------------------------------ ADX
+struct AdxChain {
+    uint64_t in_off;      // decode: first block of this channel; encode: first PCM sample of this channel (bytes into the in blob)
+    uint64_t out_off;     // decode: first PCM sample of this channel; encode: first block of this channel (bytes into the out blob)
+    uint64_t eof_off;     // decode: channel-0 block of frame 0 (EOF marker probe); unused for encode
+    uint32_t blocks;      // blocks to walk
+    uint32_t samples;     // valid samples per channel (decode: clip writes; encode: pad reads with zeros)
+    uint32_t in_stride;   // decode: bytes between this channel's blocks; encode: int16 elements between samples
+    uint32_t out_stride;  // decode: int16 elements between samples; encode: bytes between blocks
+    int32_t coef0, coef1;
+    int16_t hist1, hist2;
+    uint8_t mode, bit_depth, block_size, filter;  // filter: encode mode 2 predictor index
+    uint32_t stream;
+};
+
+void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
+                       cudaStream_t s, uint64_t* launches);
+void launch_adx_encode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
+                       cudaStream_t s, uint64_t* launches);
+
+// Scatter host-built header/trailer bytes into the output blob (one patch per stream piece).
+struct Patch {
+    uint64_t dst_off;
+    uint32_t src_off;
+    uint32_t bytes;
+};
+void launch_scatter_patches(uint8_t* d_out, const uint8_t* d_patch_bytes, const Patch* d_patches, uint32_t n,
+                            cudaStream_t s, uint64_t* launches);
+
+}  // namespace cri
