@@ -108,17 +108,21 @@ extern "C" const char* cri_strerror(int st) {
 // tables on the host. Output layout is the packed concatenation of the exact
 // per-stream output sizes (failed streams get size 0).
 
-static void finish_layout(cri_job* j, const std::vector<uint64_t>& sizes) {
+namespace cri {
+void finish_layout_public(cri_job* j, const std::vector<uint64_t>& sizes) {
     j->out_off.assign(j->n + 1, 0);
     for (uint32_t i = 0; i < j->n; i++) j->out_off[i + 1] = j->out_off[i] + sizes[i];
     j->out_bytes = j->out_off[j->n];
 }
 
-static void add_patch(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n) {
+void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n) {
     Patch p{dst, (uint32_t)j->patch_bytes.size(), n};
     j->patch_bytes.insert(j->patch_bytes.end(), bytes, bytes + n);
     j->patches.push_back(p);
 }
+}  // namespace cri
+static void finish_layout(cri_job* j, const std::vector<uint64_t>& sizes) { finish_layout_public(j, sizes); }
+static void add_patch(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n) { add_patch_public(j, dst, bytes, n); }
 
 static int adx_decode_size_one(const uint8_t* d, size_t n, AdxInfo* a, uint64_t* size) {
     const int r = parse_adx(d, n, a);
@@ -276,7 +280,7 @@ extern "C" int cri_job_create(cri_ctx* c, const cri_job_desc* d, cri_job** out) 
         default: rc = ERR_UNSUPPORTED;
     }
     if (rc == OK) rc = [&]() -> int {
-        CU_TRY(c, cudaMalloc((void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 16));
+        CU_TRY(c, cudaMalloc((void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 64));  // slack: kernels read whole 16-byte rows
         CU_TRY(c, cudaMalloc((void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16));
         CU_TRY(c, cudaMalloc((void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1)));
         CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes + 16, c->stream));

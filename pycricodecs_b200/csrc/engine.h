@@ -55,6 +55,8 @@ struct cri_job {
 };
 
 namespace cri {
+void finish_layout_public(cri_job* j, const std::vector<uint64_t>& sizes);
+void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n);
 int plan_hca_decode(cri_ctx* c, cri_job* j);
 int plan_hca_crypt(cri_ctx* c, cri_job* j);
 int plan_hca_encode(cri_ctx* c, cri_job* j);

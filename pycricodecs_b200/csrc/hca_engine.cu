@@ -1,9 +1,224 @@
+// HCA job planning (host) and kernel sequencing. Header parsing is formats.cpp;
+// the kernels are hca_dec_kernels.cu / hca_crypt_kernels.cu / hca_enc_kernels.cu.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
 #include "engine.h"
+#include "hca_kernels.h"
+
 namespace cri {
-int plan_hca_decode(cri_ctx*, cri_job*) { return ERR_UNSUPPORTED; }
+
+#define CU_TRY(ctx, expr)                                                      \
+    do {                                                                       \
+        cudaError_t e_ = (expr);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(e_); \
+            return ERR_CUDA;                                                   \
+        }                                                                      \
+    } while (0)
+
+static uint32_t env_u32(const char* name, uint32_t fallback) {
+    const char* v = getenv(name);
+    if (!v || !*v) return fallback;
+    const long x = strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t)x : fallback;
+}
+
+// cipher tables are shared between streams that use the same (type, key)
+struct CipherPool {
+    std::map<std::pair<int, uint64_t>, uint32_t> index;
+    std::vector<uint8_t>* bytes;
+    explicit CipherPool(std::vector<uint8_t>* b) : bytes(b) {
+        bytes->resize(256);
+        for (int i = 0; i < 256; i++) (*bytes)[i] = (uint8_t)i;
+    }
+    uint32_t get(int type, uint64_t key, bool invert = false) {
+        if (type == 56 && key == 0) type = 0;
+        if (type == 0) return 0;
+        const auto k = std::make_pair(invert ? -type : type, key);
+        auto it = index.find(k);
+        if (it != index.end()) return it->second;
+        uint8_t t[256], inv[256];
+        cipher_table(type, key, t);
+        if (invert) {
+            for (int i = 0; i < 256; i++) inv[t[i]] = (uint8_t)i;
+            memcpy(t, inv, 256);
+        }
+        const uint32_t id = (uint32_t)(bytes->size() / 256);
+        bytes->insert(bytes->end(), t, t + 256);
+        index[k] = id;
+        return id;
+    }
+};
+
+static void fill_stream(HcaStreamDev* s, const HcaInfo& h) {
+    memset(s, 0, sizeof *s);
+    s->frame_size = h.frame_size;
+    s->frame_count = h.frame_count;
+    s->delay = h.delay;
+    s->channels = (uint8_t)h.channels;
+    s->total_bands = (uint8_t)h.total_bands;
+    s->base_bands = (uint8_t)h.base_bands;
+    s->stereo_bands = (uint8_t)h.stereo_bands;
+    s->bands_per_hfr = (uint8_t)h.bands_per_hfr;
+    s->hfr_groups = (uint8_t)h.hfr_groups;
+    s->min_res = (uint8_t)h.min_res;
+    s->max_res = (uint8_t)h.max_res;
+    bool joint = h.bands_per_hfr != 0;
+    for (unsigned c = 0; c < h.channels; c++) {
+        s->type[c] = h.type[c];
+        s->coded[c] = (uint8_t)h.coded[c];
+        if (h.type[c]) joint = true;
+    }
+    s->joint = joint ? 1 : 0;
+}
+
+int plan_hca_decode(cri_ctx* c, cri_job* j) {
+    (void)c;
+    HcaJob& J = j->hca;
+    std::vector<uint64_t> sizes(j->n, 0);
+    std::vector<HcaInfo> infos(j->n);
+    for (uint32_t i = 0; i < j->n; i++) {
+        const uint8_t* d = j->blob + j->in_off[i];
+        const uint64_t len = j->in_off[i + 1] - j->in_off[i];
+        HcaInfo& h = infos[i];
+        if (parse_hca(d, len, &h) != OK) { j->status[i] = ERR_HCA_HEADER; continue; }
+        if ((uint64_t)h.header_size + (uint64_t)h.frame_count * h.frame_size > len) { j->status[i] = ERR_HCA_HEADER; continue; }
+        // v3.0 streams (delta-coded intensity, derived HFR scales, noise fill with a cross-frame LCG) are a later row
+        if (h.version > 0x0200) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        const uint64_t total = (uint64_t)h.frame_count * 1024;
+        if (total < (uint64_t)h.delay + h.padding) { j->status[i] = ERR_HCA_HEADER; continue; }
+        sizes[i] = wav_header_size(h.loop_flag) + (total - h.delay - h.padding) * h.channels * 2;
+    }
+    finish_layout_public(j, sizes);
+
+    CipherPool pool(&J.cipher_tables);
+    J.ath_tables.assign(128, 0);
+    const uint32_t run = std::max(1u, env_u32("CRI_HCA_RUN", 12));
+    J.max_channels = 1;
+    J.streams.assign(j->n, HcaStreamDev{});   // one entry per input stream: the device status array shares the index
+    for (uint32_t i = 0; i < j->n; i++) {
+        if (j->status[i] != OK) continue;
+        const HcaInfo& h = infos[i];
+        HcaStreamDev s;
+        fill_stream(&s, h);
+        const uint32_t samples = h.frame_count * 1024u - h.delay - h.padding;
+        const size_t hdr = wav_header_size(h.loop_flag);
+        uint8_t hb[0x70];
+        const uint32_t ls = h.loop_start_frame * 1024u + h.loop_start_delay - h.delay;
+        const uint32_t le = h.loop_end_frame * 1024u + (1024u - h.loop_end_padding) - h.delay;
+        write_wav_header(hb, samples, (int)h.channels, (int)h.rate, h.loop_flag, ls, le);
+        add_patch_public(j, j->out_off[i], hb, (uint32_t)hdr);
+        s.in_off = j->in_off[i] + h.header_size;
+        s.out_off = j->out_off[i] + hdr;
+        s.out_samples = samples;
+        const uint64_t key = mix_subkey(j->keys.empty() ? 0 : j->keys[i], j->subkeys.empty() ? 0 : j->subkeys[i]);
+        s.cipher = pool.get((int)h.ciph_type, key);
+        if (h.ath_type == 1) {
+            s.ath = (uint32_t)(J.ath_tables.size() / 128);
+            J.ath_tables.insert(J.ath_tables.end(), h.ath, h.ath + 128);
+        }
+        J.streams[i] = s;
+        J.max_channels = std::max<uint32_t>(J.max_channels, h.channels);
+        // the reference stops decoding once it has produced every output sample (hca.cpp:3401)
+        const uint32_t needed = (uint32_t)std::min<uint64_t>(h.frame_count, ((uint64_t)samples + h.delay + 1023) / 1024);
+        for (uint32_t f = 0; f < needed; f += run) {
+            HcaUnit u{i, f, std::min(run, needed - f)};
+            J.units.push_back(u);
+        }
+        j->units += needed;
+    }
+    while (J.units.size() % 32) J.units.push_back(HcaUnit{0, 0, 0});
+    // transform lanes: the channels of one unit sit next to each other inside one warp
+    uint32_t in_warp = 0;
+    for (uint32_t ui = 0; ui < J.units.size(); ui++) {
+        const HcaUnit& u = J.units[ui];
+        if (!u.count) continue;
+        const uint32_t nch = J.streams[u.stream].channels;
+        if (in_warp + nch > 32) {
+            for (; in_warp < 32; in_warp++) J.lanes.push_back(HcaLane{0xFFFFFFFFu, 0});
+            in_warp = 0;
+        }
+        for (uint32_t ch = 0; ch < nch; ch++) J.lanes.push_back(HcaLane{ui, ch});
+        in_warp = (in_warp + nch) % 32;
+    }
+    const uint32_t gran = hca_imdct_lane_granule();
+    while (J.lanes.size() % gran) J.lanes.push_back(HcaLane{0xFFFFFFFFu, 0});
+    J.max_steps = run + 1;
+    const uint64_t blocks = J.units.size() / 32;
+    J.total_groups = blocks * J.max_steps;
+    const uint64_t slots = J.total_groups * J.max_channels;
+    J.q_bytes = slots * 8 * 16 * 32 * sizeof(uint4);
+    J.g_bytes = slots * 32 * 32 * sizeof(float4);
+    J.i_bytes = slots * 32 * sizeof(uint32_t);
+    return OK;
+}
+
 int plan_hca_crypt(cri_ctx*, cri_job*) { return ERR_UNSUPPORTED; }
 int plan_hca_encode(cri_ctx*, cri_job*) { return ERR_UNSUPPORTED; }
-int upload_hca_tables(cri_ctx*, cri_job*) { return OK; }
-int run_hca(cri_ctx*, cri_job*, bool*) { return ERR_UNSUPPORTED; }
-void free_hca_tables(cri_job*) {}
+
+template <class T>
+static int upload(cri_ctx* c, const std::vector<T>& v, T** d) {
+    *d = nullptr;
+    if (v.empty()) return OK;
+    CU_TRY(c, cudaMalloc((void**)d, v.size() * sizeof(T)));
+    CU_TRY(c, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return OK;
+}
+
+int upload_hca_tables(cri_ctx* c, cri_job* j) {
+    HcaJob& J = j->hca;
+    int r = upload(c, J.streams, &J.d_streams);
+    if (r == OK) r = upload(c, J.units, &J.d_units);
+    if (r == OK) r = upload(c, J.lanes, &J.d_lanes);
+    if (r == OK) r = upload(c, J.cipher_tables, &J.d_cipher);
+    if (r == OK) r = upload(c, J.ath_tables, &J.d_ath);
+    if (r != OK) return r;
+    if (J.q_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_q, J.q_bytes));
+    if (J.g_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_g, J.g_bytes));
+    if (J.i_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_i, J.i_bytes));
+    return OK;
+}
+
+int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
+    HcaJob& J = j->hca;
+    if (j->kind == CRI_JOB_HCA_DECODE) {
+        HcaDecodeArgs a{};
+        a.in = j->d_in;
+        a.out = j->d_out;
+        a.streams = J.d_streams;
+        a.units = J.d_units;
+        a.lanes = J.d_lanes;
+        a.cipher = J.d_cipher;
+        a.ath = J.d_ath;
+        a.quant = reinterpret_cast<uint4*>(J.d_q);
+        a.gain = reinterpret_cast<float4*>(J.d_g);
+        a.inten = reinterpret_cast<uint32_t*>(J.d_i);
+        a.status = j->d_status;
+        a.total_groups = J.total_groups;
+        a.steps = J.max_steps;
+        a.max_channels = J.max_channels;
+        // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
+        launch_hca_decode(a, (uint32_t)J.lanes.size(), c->stream, &c->launches, c->ev[2]);
+        CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        *have_dominant = J.total_groups != 0;
+        return OK;
+    }
+    return ERR_UNSUPPORTED;
+}
+
+void free_hca_tables(cri_job* j) {
+    HcaJob& J = j->hca;
+    cudaFree(J.d_streams);
+    cudaFree(J.d_units);
+    cudaFree(J.d_lanes);
+    cudaFree(J.d_cipher);
+    cudaFree(J.d_ath);
+    cudaFree(J.d_q);
+    cudaFree(J.d_g);
+    cudaFree(J.d_i);
+}
+
 }  // namespace cri

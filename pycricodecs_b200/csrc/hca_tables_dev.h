@@ -1,6 +1,80 @@
-// Device-side launch tables of the HCA kernels.
+// Device-side launch tables of the HCA kernels (decode, crypt, encode).
+//
+// Vocabulary: a "unit" is a run of consecutive frames of one stream that one
+// lane walks (decode: plus one look-back frame, because the IMDCT overlap needs
+// the previous subframe's DCT output; frames are otherwise independent,
+// CriCodecs/hca.cpp:1990-1991). 32 units form a "unit block"; step t of a unit
+// block is the t-th frame of each of its 32 units, and the intermediate arrays
+// are laid out [unit block][step][...][lane] so that the unpack kernel (lane =
+// unit) writes and the transform kernel (lane = unit x channel) reads them as
+// coalesced 512-byte rows.
 #pragma once
 #include <cstdint>
+#include <vector>
+
 namespace cri {
-struct HcaJob {};
+
+constexpr int kHcaMaxChannels = 16;
+
+struct HcaStreamDev {
+    uint64_t in_off;        // byte offset of frame 0 in the input blob
+    uint64_t out_off;       // decode: first PCM sample in the output blob; crypt/encode: frame 0 in the output blob
+    uint32_t frame_size;
+    uint32_t frame_count;
+    uint32_t out_samples;   // decode: samples per channel in the WAV image
+    uint32_t delay;         // decode: samples dropped at the start (encoder delay)
+    uint32_t cipher;        // index into the cipher-table array (0 = identity)
+    uint32_t ath;           // index into the ATH-curve array (0 = all zero)
+    uint8_t channels, total_bands, base_bands, stereo_bands;
+    uint8_t bands_per_hfr, hfr_groups, min_res, max_res;
+    uint8_t type[kHcaMaxChannels];    // 0 discrete, 1 stereo primary, 2 stereo secondary
+    uint8_t coded[kHcaMaxChannels];   // coded band count per channel
+    uint8_t joint;          // 1 if any HFR / intensity reconstruction is needed
+    uint8_t pad[3];
+};
+
+struct HcaUnit {
+    uint32_t stream;
+    uint32_t first;   // first frame of the run
+    uint32_t count;   // frames in the run (0 = idle lane)
+};
+
+struct HcaUnitBlock {
+    uint64_t q_off;    // int16 quantised spectra: [step][channel][subframe][16 chunks][32 lanes][8]   (uint4 units)
+    uint64_t g_off;    // fp32 gains / HFR multipliers: [step][channel][128][32 lanes]
+    uint64_t i_off;    // intensity nibbles: [step][channel][32 lanes] (uint32)
+    uint32_t channels; // max channels of the block's units (strides)
+    uint32_t steps;    // max run length + 1 (step 0 = look-back frame)
+};
+
+// one transform-kernel lane: a (unit, channel) pair
+struct HcaLane {
+    uint32_t unit;     // global unit index (block = unit / 32, lane-in-block = unit % 32); 0xFFFFFFFF = idle
+    uint32_t channel;
+};
+
+struct HcaJob {
+    std::vector<HcaStreamDev> streams;
+    std::vector<HcaUnit> units;            // padded to a multiple of 32
+    std::vector<HcaUnitBlock> blocks;
+    std::vector<HcaLane> lanes;            // padded to a multiple of 32
+    std::vector<uint8_t> cipher_tables;    // 256 bytes each, [0] identity
+    std::vector<uint8_t> ath_tables;       // 128 bytes each, [0] zero
+    uint64_t q_bytes = 0, g_bytes = 0, i_bytes = 0;
+    uint32_t max_channels = 1, max_steps = 0;
+
+    HcaStreamDev* d_streams = nullptr;
+    HcaUnit* d_units = nullptr;
+    HcaUnitBlock* d_blocks = nullptr;
+    HcaLane* d_lanes = nullptr;
+    uint8_t* d_cipher = nullptr;
+    uint8_t* d_ath = nullptr;
+    uint8_t* d_q = nullptr;
+    uint8_t* d_g = nullptr;
+    uint8_t* d_i = nullptr;
+    uint64_t* d_block_step_prefix = nullptr;  // exclusive prefix of steps per unit block (maps a flat group id to (block, step))
+    std::vector<uint64_t> block_step_prefix;
+    uint64_t total_groups = 0;
+};
+
 }  // namespace cri

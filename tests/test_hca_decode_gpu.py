@@ -1,0 +1,61 @@
+"""GPU parity: HCA decode kernels (through the C-ABI) vs the oracle, bit-exact PCM."""
+import numpy as np
+import pytest
+
+from pycricodecs_b200 import HCA, synth
+
+pytestmark = pytest.mark.gpu
+KEY = 0xCF222F1FE0748978
+
+
+def _first_diff(a: bytes, b: bytes):
+    x = np.frombuffer(a, np.uint8); y = np.frombuffer(b, np.uint8)
+    if len(x) != len(y):
+        return f"len {len(x)} vs {len(y)}"
+    d = np.nonzero(x != y)[0]
+    return None if len(d) == 0 else f"{len(d)} bytes differ, first at {d[0]} (frame {(d[0] - 44) // 4096 if d[0] >= 44 else 'hdr'})"
+
+
+@pytest.mark.parametrize("quality", [0, 1, 2, 3])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_decode_matches_oracle(port, ctx, quality, channels):
+    hcas = [port.hca_encode(synth.wav(s, channels), quality)[1] for s in range(3)]
+    got = HCA.decode_batch(hcas, ctx=ctx)
+    for h, g in zip(hcas, got):
+        r, want = port.hca_decode(h)
+        assert r == 0
+        assert _first_diff(g, want) is None
+
+
+def test_short_and_ragged_streams(port, ctx):
+    cases = [(0, 2, 1), (1, 2, 127), (2, 1, 128), (3, 2, 129), (4, 2, 1024), (5, 1, 1024 - 128), (6, 2, 1024 * 13 + 5), (7, 2, 40000)]
+    hcas = [port.hca_encode(synth.wav(s, c, n), 1)[1] for s, c, n in cases]
+    got = HCA.decode_batch(hcas, ctx=ctx)
+    for h, g in zip(hcas, got):
+        assert _first_diff(g, port.hca_decode(h)[1]) is None
+
+
+def test_encrypted_decode(port, ctx):
+    plain = [port.hca_encode(synth.wav(s, 2, 20000), q)[1] for s, q in [(0, 1), (1, 3)]]
+    enc = [port.hca_crypt(p, 1, 56, KEY)[1] for p in plain] + [port.hca_crypt(plain[0], 1, 1, 0)[1], port.hca_crypt(plain[1], 1, 56, KEY, 0x1234)[1]]
+    got = HCA.decode_batch(enc, keys=[KEY, KEY, 0, KEY], subkeys=[0, 0, 0, 0x1234], ctx=ctx)
+    want = [port.hca_decode(plain[0])[1], port.hca_decode(plain[1])[1], port.hca_decode(plain[0])[1], port.hca_decode(plain[1])[1]]
+    for g, w in zip(got, want):
+        assert _first_diff(g, w) is None
+
+
+def test_corrupt_frame_reports_decode_error(port, ctx):
+    h = bytearray(port.hca_encode(synth.wav(0, 2, 8192), 1)[1])
+    h[96 + 682 * 3 + 100] ^= 0x55          # breaks the CRC of frame 3
+    res = HCA.decode_batch([bytes(h), b"junk" * 30], ctx=ctx, raise_errors=False)
+    assert isinstance(res[0], Exception) and res[0].status == -202
+    assert isinstance(res[1], Exception) and res[1].status == -201
+    with pytest.raises(ValueError, match="Decoding error"):
+        HCA(bytes(h)).decode()
+
+
+def test_class_surface(port):
+    h = port.hca_encode(synth.wav(2, 2, 5000), 1)[1]
+    obj = HCA(h)
+    assert obj.info()["FrameCount"] == 6 and obj.filetype == "hca"
+    assert obj.decode() == port.hca_decode(h)[1]

@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Emit the register-resident 128-point DCT-IV / IMDCT / MDCT networks used by
+the HCA kernels as straight-line CUDA (pycricodecs_b200/csrc/hca_dct_gen.inc).
+
+Why generated code: one thread owns one whole 128-point transform in registers.
+Every stage of the network is a set of 64 two-in/two-out butterflies, so each
+butterfly can overwrite its own inputs and the stage's index shuffle becomes a
+compile-time renaming of registers -- no shared memory, no shuffles, no moves;
+the instruction stream is the 4 k fp32 operations of the transform and nothing
+else. That only works if every array index is a literal, hence this generator:
+it tracks the logical->physical register permutation through the stages and
+bakes the twiddle factors in as immediates (IEEE-754 bit patterns).
+
+Arithmetic contract: the network, the operand order and the rounding points
+are those of the reference (decoder: imdct_transform, CriCodecs/hca.cpp:1898-
+1992; encoder: mdct_transform + DCT4, hca.cpp:2481-2553). Every product and
+sum is a separate __fmul_rn / __fadd_rn / __fsub_rn, so nothing is contracted
+into FMA and results are bit-identical to the reference's scalar SSE2 build.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import gen_tables as T  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def f(bits: int) -> str:
+    return f"__uint_as_float(0x{int(bits):08X}u)"
+
+
+def gen_imdct() -> list[str]:
+    sin, cos = T.imdct_trig()
+    sin = sin.reshape(7, 64)
+    cos = cos.reshape(7, 64)
+    win = T.window()
+    out = []
+    phys = list(range(128))  # phys[logical index] = register index
+    out.append("// 128-point DCT-IV of the HCA decoder, in place on registers x[0..127].")
+    out.append("// Input x[i] = spectra[i]; afterwards dct[i] lives in x[kImdctPerm[i]] (see hca_imdct_window).")
+    out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
+    out.append("    float t0, t1, t2, t3;")
+    # sum/difference passes, half = 64 .. 1  (hca.cpp:1907-1935)
+    half = 64
+    while half >= 1:
+        blocks = 64 // half
+        nxt = [None] * 128
+        for j in range(blocks):
+            for k in range(half):
+                a = phys[j * 2 * half + 2 * k]
+                b = phys[j * 2 * half + 2 * k + 1]
+                out.append(f"    t0 = __fadd_rn(x[{a}], x[{b}]); x[{b}] = __fsub_rn(x[{a}], x[{b}]); x[{a}] = t0;")
+                nxt[j * 2 * half + k] = a
+                nxt[j * 2 * half + half + k] = b
+        phys = nxt
+        half //= 2
+    # rotation passes, half = 1 .. 64  (hca.cpp:1937-1972)
+    for stage in range(7):
+        half = 1 << stage
+        blocks = 64 >> stage
+        nxt = [None] * 128
+        for j in range(blocks):
+            for k in range(half):
+                a = phys[j * 2 * half + k]
+                b = phys[j * 2 * half + half + k]
+                s = f(sin[stage, j * half + k])
+                c = f(cos[stage, j * half + k])
+                out.append(f"    t0 = __fmul_rn(x[{a}], {s}); t1 = __fmul_rn(x[{b}], {c}); "
+                           f"t2 = __fmul_rn(x[{a}], {c}); t3 = __fmul_rn(x[{b}], {s}); "
+                           f"x[{a}] = __fsub_rn(t0, t1); x[{b}] = __fadd_rn(t2, t3);")
+                nxt[j * 2 * half + k] = a
+                nxt[j * 2 * half + 2 * half - 1 - k] = b
+        phys = nxt
+    out.append("}")
+    out.append("")
+    # window + overlap (hca.cpp:1983-1992). dprev holds dct[0..63] of the previous subframe of this channel.
+    out.append("// Window + overlap-add. `dprev[i]` = previous subframe's dct[i], i < 64 (imdct_previous is its windowed")
+    out.append("// form: prev[i] = w[127-i]*dct[63-i], prev[64+i] = w[63-i]*dct[i]). Calls emit(i, wave[i]) for i = 0..127")
+    out.append("// in sample order, then replaces dprev by this subframe's dct[0..63].")
+    out.append("template <class Emit>")
+    out.append("__device__ __forceinline__ void hca_imdct_window(const float (&x)[128], float (&dprev)[64], Emit emit) {")
+    for i in range(64):
+        out.append(f"    emit({i}, __fadd_rn(__fmul_rn({f(win[i])}, x[{phys[i + 64]}]), __fmul_rn({f(win[127 - i])}, dprev[{63 - i}])));")
+    for i in range(64):
+        out.append(f"    emit({i + 64}, __fsub_rn(__fmul_rn({f(win[i + 64])}, x[{phys[127 - i]}]), __fmul_rn({f(win[63 - i])}, dprev[{i}])));")
+    for i in range(64):
+        out.append(f"    dprev[{i}] = x[{phys[i]}];")
+    out.append("}")
+    out.append("")
+    out.append("// Only the carry of hca_imdct_window (used for the look-back subframe in front of a run of frames).")
+    out.append("__device__ __forceinline__ void hca_imdct_carry(const float (&x)[128], float (&dprev)[64]) {")
+    for i in range(64):
+        out.append(f"    dprev[{i}] = x[{phys[i]}];")
+    out.append("}")
+    return out
+
+
+def gen_mdct() -> list[str]:
+    sin, cos = T.mdct_trig()
+    sin = sin.reshape(8, 128)
+    cos = cos.reshape(8, 128)
+    win = T.window()
+    shuffle = T.enc_shuffle()
+    out = []
+    out.append("// Forward MDCT of the HCA encoder (hca.cpp:2529-2553 + DCT4 :2481-2527), on registers.")
+    out.append("// cur[i] = this subframe's 128 input samples (as float), prv[i] = the previous 128; t[] is scratch.")
+    out.append("// Calls emit(k, spectra[k]) for k = 0..127.")
+    out.append("template <class Emit>")
+    out.append("__device__ __forceinline__ void hca_mdct_enc(const float (&cur)[128], const float (&prv)[128], float (&t)[128], Emit emit) {")
+    out.append("    float a, b, c0, c1, c2, c3;")
+    # windowing into in[] (kept in t[] with identity placement), hca.cpp:2537-2546
+    # in[i] = W[63-i]*(-cur[64+i]) - (-W[64+i])*cur[63-i];  in[64+i] = W[i]*prv[i] - (-W[127-i])*prv[127-i]
+    for i in range(64):
+        out.append(f"    t[{i}] = __fsub_rn(__fmul_rn({f(win[63 - i])}, -cur[{64 + i}]), __fmul_rn({f(int(win[64 + i]) ^ 0x80000000)}, cur[{63 - i}]));")
+        out.append(f"    t[{64 + i}] = __fsub_rn(__fmul_rn({f(win[i])}, prv[{i}]), __fmul_rn({f(int(win[127 - i]) ^ 0x80000000)}, prv[{127 - i}]));")
+    # pre-rotation: dct[2i] = a*cos + b*sin, dct[2i+1] = a*sin - b*cos with a = in[2i], b = in[127-2i]  (row 7)
+    # both outputs depend on in[2i] and in[127-2i]; outputs go to positions 2i and 2i+1. Pairs (2i, 127-2i) for i<64 cover
+    # all 128 inputs exactly once, so do it in place: out[2i] -> reg of in[2i], out[2i+1] -> reg of in[127-2i].
+    phys = list(range(128))
+    nxt = [None] * 128
+    for i in range(64):
+        ra, rb = phys[2 * i], phys[127 - 2 * i]
+        s = f(sin[7, i]); c = f(cos[7, i])
+        out.append(f"    a = t[{ra}]; b = t[{rb}]; c0 = __fmul_rn(a, {c}); c1 = __fmul_rn(b, {s}); c2 = __fmul_rn(a, {s}); c3 = __fmul_rn(b, {c}); "
+                   f"t[{ra}] = __fadd_rn(c0, c1); t[{rb}] = __fsub_rn(c2, c3);")
+        nxt[2 * i] = ra
+        nxt[2 * i + 1] = rb
+    phys = nxt
+    # six in-place radix-2 stages (hca.cpp:2501-2523); index pattern is already in place in the reference
+    for stage in range(6):
+        blocks = 1 << stage
+        size_bits = 6 - stage
+        half_bits = size_bits - 1
+        size = 1 << size_bits
+        half = 1 << half_bits
+        for blk in range(blocks):
+            for i in range(half):
+                fp = (blk * size + i) * 2
+                bp = fp + size
+                s = f(sin[half_bits, i]); c = f(cos[half_bits, i])
+                f0, f1, b0, b1 = phys[fp], phys[fp + 1], phys[bp], phys[bp + 1]
+                out.append(f"    a = __fsub_rn(t[{f0}], t[{b0}]); b = __fsub_rn(t[{f1}], t[{b1}]); "
+                           f"t[{f0}] = __fadd_rn(t[{f0}], t[{b0}]); t[{f1}] = __fadd_rn(t[{f1}], t[{b1}]); "
+                           f"c0 = __fmul_rn(a, {c}); c1 = __fmul_rn(b, {s}); c2 = __fmul_rn(a, {s}); c3 = __fmul_rn(b, {c}); "
+                           f"t[{b0}] = __fadd_rn(c0, c1); t[{b1}] = __fsub_rn(c2, c3);")
+    for k in range(128):
+        out.append(f"    emit({k}, __fmul_rn(t[{phys[int(shuffle[k])]}], 0.125f));")
+    out.append("}")
+    return out
+
+
+def main():
+    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""]
+    lines += gen_imdct()
+    lines.append("")
+    lines += gen_mdct()
+    path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_gen.inc")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    print("wrote", path, len(lines), "lines")
+
+
+if __name__ == "__main__":
+    main()
