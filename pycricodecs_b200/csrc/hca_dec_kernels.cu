@@ -261,7 +261,7 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     }
 
     // ---- spectra: subframe-major, channel-minor runs of codes (hca.cpp:1540-1571)
-    const uint64_t max_bits_lo = 0x4444433320ull;            // resolutions 0..9: 0,2,3,3,4,4,4,4,5,6 (4 bits each)
+    const uint64_t max_bits_lo = 0x6544443320ull;            // resolutions 0..9: 0,2,3,3,4,4,4,4,5,6 (4 bits each, r0 lowest)
     for (int sub = 0; sub < 8 && !bad; sub++) {
         for (int c = 0; c < nch; c++) {
             const int coded = S.coded[c];
