@@ -9,25 +9,30 @@
 //
 // Two kernels, split where the parallelism changes shape:
 //
-//  hca_unpack_kernel     one LANE per frame. The code lengths are data dependent,
-//      so a frame's 2048 codes are one serial chain; the batch supplies the
-//      parallelism (770 k frames at the headline config). Each lane streams its
-//      frame with 16-byte loads, keeps a 64-bit bit window in registers and writes
-//      quantised coefficients (int16) and per-band gains (fp32) to an intermediate
-//      laid out [step][channel][...][lane], i.e. every warp store is one
-//      contiguous 512-byte row.
+//  hca_unpack_kernel   one LANE per frame. Code lengths are data dependent, so a
+//      frame's 2048 codes are one serial chain and the batch supplies the
+//      parallelism (770 k frames at the headline config). Phase 1 walks the frame
+//      once: CRC16 (table-free byte step), cipher LUT, byte swap, into an aligned
+//      scratch row. Phase 2 parses from a 64-bit register window refilled with
+//      prefetched 32-bit words; the per-code path is branch-free (both code
+//      families are evaluated and selected) because lanes of a warp sit on
+//      different resolutions and would otherwise serialise. Quantised
+//      coefficients go through a 128-byte-per-lane shared tile so that HBM
+//      sees full 128-byte rows.
 //
-//  hca_imdct_kernel      one THREAD per (run of frames, channel), the whole
-//      128-point transform in registers (hca_dct_gen.inc, generated): the stage
-//      shuffles of the network are register renamings, so the instruction stream
-//      is the transform's ~4 k separately rounded fp32 operations (no FMA: the
-//      reference build has none, and PCM parity is bit-exact) plus dequantisation
-//      and PCM conversion. The overlap state (first half of the previous DCT
-//      output) is carried in registers along the run. PCM leaves through a
-//      per-warp shared-memory tile so that global stores are coalesced per stream.
+//  hca_imdct_kernel    one WARP per run of frames of one stream. Coefficient p of
+//      a 128-point block lives in lane p>>2, register p&3 and never moves: the
+//      reference's 7 sum/difference passes pair slots differing in bit 0..6 of
+//      p, its 7 rotation passes pair bit 6..0, the window pairs bit 0 (see
+//      tools/gen_dct.py), so every exchange is a register swap or one
+//      __shfl_xor, every global access is a coalesced 256/512-byte row, and the
+//      overlap state is two registers per lane. All products and sums are
+//      separately rounded (__fmul_rn/__fadd_rn): the reference build has no FMA,
+//      and PCM parity is bit-exact.
 //
 // HBM traffic per stereo frame: frame_size + 4096 B compulsory, plus the
-// intermediate (4 KB int16 + 1 KB gains written and read once).
+// intermediate (4 KB int16 spectra + 1 KB gains + the scratch row, written and
+// read once; the scratch row normally stays in L2).
 #include <cstdint>
 
 #include "cri_tables.h"
@@ -43,97 +48,61 @@ __constant__ uint32_t c_conv[128] = CRI_TBL_SCALE_CONV;
 __constant__ uint32_t c_intensity[16] = CRI_TBL_INTENSITY_RATIO;
 __constant__ uint8_t c_read_bits[128] = CRI_TBL_READ_BITS;
 __constant__ int8_t c_read_vals[128] = CRI_TBL_READ_VALS;
+__constant__ uint8_t c_max_bits[16] = CRI_TBL_MAX_BITS;
 
 #include "hca_dct_gen.inc"
 
 // ------------------------------------------------------------------ unpack
 constexpr int kUnpackThreads = 128;
+constexpr int kStageRow = 9;    // uint4 per lane in the store tile: 8 payload + 1 pad (36-word rows: conflict-free)
 
-struct UnpackTables {           // small per-CTA copies: per-lane indices diverge, shared memory does not serialise
+struct UnpackTables {           // per-CTA copies: per-lane indices diverge, shared memory does not serialise
     uint8_t invert[68];
-    uint8_t code[128];          // (value + 8) | bits << 4 for resolutions 1..7
+    uint8_t code[128];          // resolutions 0..7: (value + 8) | bits << 4
+    uint8_t max_bits[16];
     float scaling[64];
     float range[16];
     float conv[128];
 };
 
 // CRC-16 (poly 0x8005, MSB first) of one more byte without a table: the reference's
-// table entry is (v<<1) ^ (v<<2) ^ (parity(v) ? 0x8003 : 0)  (checked in tests/test_tables.py).
+// table entry is (v<<1) ^ (v<<2) ^ (parity(v) ? 0x8003 : 0)  (tests/test_tables.py).
 __device__ __forceinline__ uint32_t crc16_step(uint32_t crc, uint32_t byte) {
     const uint32_t v = ((crc >> 8) ^ byte) & 0xFF;
     const uint32_t t = (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u);
     return ((crc << 8) ^ t) & 0xFFFF;
 }
 
-struct FrameReader {
-    const uint4* src;           // 16-byte aligned load cursor
-    uint4 cur;
-    int sub;                    // next 32-bit lane of `cur`
-    int byte_pos;               // frame-relative index of the next byte that fetch() returns
-    int frame_size;
-    uint32_t crc;
-    const uint8_t* cipher;      // nullptr = identity
-    uint64_t win;               // bit window, MSB first
-    int have;                   // valid bits in win
-    int pos;                    // frame-relative bit position of win's MSB
+struct BitWindow {              // MSB-first reader over big-endian 32-bit words
+    uint64_t win;
+    const uint32_t* next_ptr;
+    uint32_t next;              // prefetched word
+    int have;                   // valid bits in win (kept above 32)
+    int pos;                    // bits consumed so far
     int nbits;
 
-    __device__ __forceinline__ uint32_t fetch_word() {  // next 4 stream bytes, big endian, CRC'd and deciphered
-        if (sub == 4) { cur = __ldg(src++); sub = 0; }
-        uint32_t w = sub == 0 ? cur.x : sub == 1 ? cur.y : sub == 2 ? cur.z : cur.w;
-        sub++;
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t b = (w >> (8 * k)) & 0xFF;   // memory order = little-endian lanes
-            const int p = byte_pos + k;
-            if (p >= 0 && p < frame_size) crc = crc16_step(crc, b);
-            if (cipher) b = __ldg(cipher + b);
-            out = (out << 8) | b;
-        }
-        byte_pos += 4;
-        return out;
+    __device__ __forceinline__ void init(const uint32_t* words, int frame_bits) {
+        win = ((uint64_t)words[0] << 32) | words[1];
+        next = words[2];
+        next_ptr = words + 3;
+        have = 64; pos = 0; nbits = frame_bits;
     }
-
-    __device__ __forceinline__ void init(const uint8_t* frame, int size, const uint8_t* table) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(frame);
-        src = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-        const int lead = (int)(a & 15);            // bytes of the first 16-byte row that precede the frame
-        sub = 4;
-        byte_pos = -lead;
-        frame_size = size;
-        crc = 0;
-        cipher = table;
-        nbits = size * 8;
-        pos = 0;
-        for (int k = 0; k < (lead >> 2); k++) fetch_word();
-        win = (uint64_t)fetch_word() << 32;
-        have = 32 - 8 * (lead & 3);
-        win <<= 8 * (lead & 3);
-        win |= (uint64_t)fetch_word() << (32 - have);
-        have += 32;
-        if (have <= 32) { win |= (uint64_t)fetch_word() << (32 - have); have += 32; }
-    }
-
-    __device__ __forceinline__ uint32_t peek(int n) const {  // n in 0..31; 0 once the read would cross the frame end
+    // n in 0..16. A read that would cross the end of the frame returns 0 (hca.cpp:232-233).
+    __device__ __forceinline__ uint32_t peek(int n) const {
         const uint32_t v = ((uint32_t)(win >> 32) >> 1) >> (31 - n);
         return pos + n <= nbits ? v : 0u;
     }
-    __device__ __forceinline__ void skip(int n) {            // n in 0..16; keeps more than 32 valid bits in the window
+    __device__ __forceinline__ void skip(int n) {
         win <<= n;
         have -= n;
         pos += n;
-        if (have <= 32) {
-            win |= (uint64_t)fetch_word() << (32 - have);
+        if (have <= 32) {       // predicated, no divergence: shift in the prefetched word, fetch the one after
+            win |= (uint64_t)next << (32 - have);
             have += 32;
+            next = *next_ptr++;
         }
     }
     __device__ __forceinline__ uint32_t read(int n) { const uint32_t v = peek(n); skip(n); return v; }
-
-    __device__ __forceinline__ uint32_t finish_crc() {       // run the CRC to the end of the frame
-        while (byte_pos < frame_size) fetch_word();
-        return crc;
-    }
 };
 
 __global__ void __launch_bounds__(kUnpackThreads)
@@ -146,41 +115,86 @@ hca_unpack_kernel(HcaDecodeArgs a) {
         tb.conv[i] = __uint_as_float(c_conv[i]);
     }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) tb.scaling[i] = __uint_as_float(c_scaling[i]);
-    for (int i = threadIdx.x; i < 16; i += blockDim.x) tb.range[i] = __uint_as_float(c_range[i]);
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        tb.range[i] = __uint_as_float(c_range[i]);
+        tb.max_bits[i] = c_max_bits[i];
+    }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const uint64_t group = (uint64_t)blockIdx.x * (kUnpackThreads / 32) + (threadIdx.x >> 5);
-    if (group >= a.total_groups) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const int T = kUnpackThreads;
+    const uint64_t group = (uint64_t)blockIdx.x * (kUnpackThreads / 32) + warp;
+    if (group >= a.total_groups) return;                    // whole warp
     const uint32_t block = (uint32_t)(group / a.steps), step = (uint32_t)(group % a.steps);
-    const HcaUnit u = a.units[block * 32 + lane];
+    const uint32_t unit = block * 32 + lane;
+    const HcaUnit u = a.units[unit];
     // step 0 is the look-back frame in front of the run (needed only for its last subframe)
-    if (u.count == 0 || (step == 0 && u.first == 0) || (step > u.count)) return;
+    const bool active = u.count != 0 && !(step == 0 && u.first == 0) && step <= u.count;
     const uint32_t frame = u.first + step - 1;
     const HcaStreamDev& S = a.streams[u.stream];
-    const int nch = S.channels;
-    const bool lookback = step == 0;
+    const int nch = active ? S.channels : 0;
+    const uint64_t slot = (uint64_t)unit * a.steps + step;   // frame slot of the intermediate arrays
 
-    // per-thread shared scratch: scalefactors of the channel being parsed + resolutions of every channel
-    const int T = blockDim.x;
-    uint8_t* s_sf = s_dyn;                                   // [128][T] bytes
-    uint32_t* s_res = reinterpret_cast<uint32_t*>(s_dyn + 128 * T);  // [channel][16][T] words of 8 nibbles
-    const int tid = threadIdx.x;
+    // shared scratch: [0,128T) scalefactors of the channel being parsed; then per channel 128 bytes of
+    // (resolution | max_bits << 4) per band; then the store tile.
+    uint8_t* s_sf = s_dyn;
+    uint8_t* s_rb = s_dyn + 128 * T;
+    uint4* s_stage = reinterpret_cast<uint4*>(s_dyn + (size_t)(128 + 128 * a.max_channels) * T) + (size_t)warp * 32 * kStageRow;
 
-    FrameReader br;
-    br.init(a.in + S.in_off + (uint64_t)frame * S.frame_size, (int)S.frame_size,
-            S.cipher ? a.cipher + (size_t)S.cipher * 256 : nullptr);
-    bool bad = br.read(16) != 0xFFFF;                        // sync word (never enciphered: table[0xFF] = 0xFF)
+    bool bad = false;
+    uint32_t* words = a.scratch + slot * a.scratch_words;    // this frame's aligned, deciphered, byte-swapped copy
+    const int frame_size = active ? (int)S.frame_size : 0;
 
-    const uint32_t noise_level = br.read(9), boundary = br.read(7);
-    const uint32_t packed = (noise_level << 8) - boundary;
-    const uint8_t* ath = a.ath + (size_t)S.ath * 128;
-    const uint64_t slot = ((uint64_t)block * a.steps + step) * a.max_channels;
+    // ---- phase 1: CRC over the raw frame, cipher LUT, byte swap -> scratch row
+    if (active) {
+        const uint8_t* src = a.in + S.in_off + (uint64_t)frame * S.frame_size;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+        const int sh = (int)(addr & 3) * 8;
+        const uint8_t* cipher = S.cipher ? a.cipher + (size_t)S.cipher * 256 : nullptr;
+        uint32_t crc = 0;
+        uint32_t lo = __ldg(ap++);
+        const int nwords = (frame_size + 3) >> 2;
+        uint4 pack = make_uint4(0, 0, 0, 0);
+        for (int w = 0; w < nwords; w++) {
+            const uint32_t hi = __ldg(ap++);
+            const uint32_t raw = __funnelshift_r(lo, hi, sh);   // 4 frame bytes in memory order (little-endian lanes)
+            lo = hi;
+            uint32_t be = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t b = (raw >> (8 * k)) & 0xFF;
+                if (4 * w + k < frame_size) crc = crc16_step(crc, b); else b = 0;
+                if (cipher) b = __ldg(cipher + b);
+                be = (be << 8) | b;
+            }
+            if ((w & 3) == 0) pack.x = be; else if ((w & 3) == 1) pack.y = be; else if ((w & 3) == 2) pack.z = be; else pack.w = be;
+            if ((w & 3) == 3 || w == nwords - 1) {
+                if ((w & 3) < 3) pack.w = 0;
+                if ((w & 3) < 2) pack.z = 0;
+                if ((w & 3) < 1) pack.y = 0;
+                reinterpret_cast<uint4*>(words)[w >> 2] = pack;
+            }
+        }
+        // a zero row of slack so the prefetching reader never sees stale data
+        reinterpret_cast<uint4*>(words)[(nwords + 3) >> 2] = make_uint4(0, 0, 0, 0);
+        if (crc != 0) bad = true;                           // a valid frame's CRC over all its bytes is 0 (hca.cpp:1166)
+    }
 
+    // ---- phase 2: frame header
+    BitWindow br;
+    br.init(words, frame_size * 8);
+    uint32_t packed = 0;
+    if (active) {
+        if (br.read(16) != 0xFFFF) bad = true;               // sync word (cipher tables keep 0xFF fixed)
+        const uint32_t noise_level = br.read(9), boundary = br.read(7);
+        packed = (noise_level << 8) - boundary;
+    }
+    const uint8_t* ath = a.ath + (size_t)(active ? S.ath : 0) * 128;
     for (int c = 0; c < nch && !bad; c++) {
         const int coded = S.coded[c];
         const int type = S.type[c];
-        // ---- scalefactors (hca.cpp:1290-1358, v2.0 and older)
+        // scalefactors (hca.cpp:1290-1358, v2.0 and older)
         const uint32_t delta_bits = br.read(3);
         if (delta_bits >= 6) {
             for (int i = 0; i < coded; i++) s_sf[i * T + tid] = (uint8_t)br.read(6);
@@ -203,26 +217,24 @@ hca_unpack_kernel(HcaDecodeArgs a) {
             for (int i = 0; i < 128; i++) s_sf[i * T + tid] = 0;
         }
         if (bad) break;
-        // ---- intensity (secondary) or HFR scales (others), hca.cpp:1361-1441
-        uint32_t inten = 0;
+        // intensity (secondary channel) or HFR scales (others), hca.cpp:1361-1441
         if (type == 2) {
             const uint32_t v0 = br.peek(4);
-            inten = v0;
+            uint32_t inten = v0;
             if (v0 < 15) {
                 br.skip(4);
                 for (int i = 1; i < 8; i++) inten |= br.read(4) << (4 * i);
             }
-            a.inten[(slot + c) * 32 + lane] = inten;
+            a.inten[slot * a.max_channels + c] = inten;
         } else {
             for (int g = 0; g < S.hfr_groups; g++) s_sf[(128 - S.hfr_groups + g) * T + tid] = (uint8_t)br.read(6);
         }
-        // ---- resolution + gain per band (hca.cpp:1444-1507)
-        float4* gdst = a.gain + ((slot + c) * 32) * 32 + lane;   // [32 chunks of 4 bands][32 lanes]
-        for (int i0 = 0; i0 < 128; i0 += 8) {
-            uint32_t resw = 0;
-            float g[8];
+        // resolution + gain per band (hca.cpp:1444-1507)
+        float4* gdst = reinterpret_cast<float4*>(a.gain + (slot * a.max_channels + c) * 128);
+        for (int i0 = 0; i0 < 128; i0 += 4) {
+            float g[4];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < 4; k++) {
                 const int i = i0 + k;
                 uint32_t r = 0;
                 g[k] = 0.f;
@@ -236,202 +248,251 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                     }
                     g[k] = __fmul_rn(tb.scaling[sf], tb.range[r]);
                 }
-                resw |= r << (4 * k);
+                s_rb[(c * 128 + i) * T + tid] = (uint8_t)(r | ((uint32_t)tb.max_bits[r] << 4));
             }
-            s_res[(c * 16 + (i0 >> 3)) * T + tid] = resw;
-            if (i0 < coded) {
-                gdst[(i0 >> 2) * 32] = make_float4(g[0], g[1], g[2], g[3]);
-                gdst[((i0 >> 2) + 1) * 32] = make_float4(g[4], g[5], g[6], g[7]);
-            }
+            gdst[i0 >> 2] = make_float4(g[0], g[1], g[2], g[3]);
         }
-        // ---- HFR multipliers for the bands above the coded ones (hca.cpp:1638-1683, v2.0 rule)
+        // HFR multipliers for the bands above the coded ones (hca.cpp:1638-1683, v2.0 rule)
         if (S.bands_per_hfr && type != 2) {
             const int start = S.base_bands + S.stereo_bands;
             int high = start, low = start - 1;
-            float* gflat = reinterpret_cast<float*>(a.gain + ((slot + c) * 32) * 32);
+            float* gflat = a.gain + (slot * a.max_channels + c) * 128;
             for (int g = 0; g < S.hfr_groups; g++)
                 for (int i = 0; i < S.bands_per_hfr; i++) {
                     if (high >= S.total_bands || low < 0) break;
                     int k = (int)s_sf[(128 - S.hfr_groups + g) * T + tid] - (int)s_sf[low * T + tid] + 63;
                     k &= ~(k >> 31);
-                    gflat[((high >> 2) * 32 + lane) * 4 + (high & 3)] = tb.conv[k];
+                    gflat[high] = tb.conv[k];
                     high++; low--;
                 }
         }
     }
 
-    // ---- spectra: subframe-major, channel-minor runs of codes (hca.cpp:1540-1571)
-    const uint64_t max_bits_lo = 0x6544443320ull;            // resolutions 0..9: 0,2,3,3,4,4,4,4,5,6 (4 bits each, r0 lowest)
-    for (int sub = 0; sub < 8 && !bad; sub++) {
-        for (int c = 0; c < nch; c++) {
-            const int coded = S.coded[c];
-            uint4* qdst = a.quant + (((slot + c) * 8 + sub) * 16) * 32 + lane;
-            const bool keep = !lookback || sub == 7;
-            for (int i0 = 0; i0 < coded; i0 += 8) {
-                const uint32_t resw = s_res[(c * 16 + (i0 >> 3)) * T + tid];
-                int q[8];
+    // ---- spectra: subframe-major, channel-minor runs of codes (hca.cpp:1540-1571). The loops are warp-uniform
+    // (bounded by the widest stream of the warp) because the store tile is flushed cooperatively.
+    int warp_nch = nch;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    q[k] = 0;
-                    if (i0 + k < coded) {
-                        const uint32_t r = (resw >> (4 * k)) & 15;
-                        const int bits = r < 10 ? (int)((max_bits_lo >> (4 * r)) & 15) : (int)r - 3;
-                        const uint32_t code = br.peek(bits);
-                        int used;
-                        if (r > 7) {
+    for (int o = 16; o; o >>= 1) warp_nch = max(warp_nch, __shfl_xor_sync(0xFFFFFFFFu, warp_nch, o));
+    const bool lookback = step == 0;
+    uint4* my_stage = s_stage + lane * kStageRow;
+    for (int sub = 0; sub < 8; sub++) {
+        for (int c = 0; c < warp_nch; c++) {
+            const bool mine = c < nch && !bad;
+            const int coded = mine ? (int)S.coded[c] : 0;
+            for (int halfband = 0; halfband < 2; halfband++) {
+#pragma unroll 1
+                for (int i0 = halfband * 64; i0 < halfband * 64 + 64; i0 += 8) {
+                    uint32_t pk[4] = {0, 0, 0, 0};
+                    if (i0 < coded) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const int i = i0 + k;
+                            const uint32_t rb = i < coded ? s_rb[(c * 128 + i) * T + tid] : 0u;
+                            const uint32_t r = rb & 15;
+                            const int bits = (int)(rb >> 4);
+                            const uint32_t code = br.peek(bits);
+                            // sign-magnitude family (resolution >= 8): LSB is the sign, zero gives one bit back
                             const int mag = (int)(code >> 1);
-                            q[k] = (code & 1) ? -mag : mag;
-                            used = bits - (mag == 0);
-                        } else {
-                            const uint32_t e = tb.code[(r << 4) + code];
-                            q[k] = (int)(e & 15) - 8;
-                            used = (int)(e >> 4);
+                            const int v_hi = (code & 1) ? -mag : mag;
+                            const int used_hi = bits - (mag == 0);
+                            // prefix-codebook family (resolution <= 7)
+                            const uint32_t e = tb.code[((r & 7) << 4) | (code & 15)];
+                            const int v_lo = (int)(e & 15) - 8;
+                            const int used_lo = (int)(e >> 4);
+                            const bool hi = r > 7;
+                            const int v = hi ? v_hi : v_lo;
+                            br.skip(hi ? used_hi : used_lo);
+                            pk[k >> 1] |= ((uint32_t)v & 0xFFFFu) << (16 * (k & 1));
                         }
-                        br.skip(used);
+                    }
+                    my_stage[(i0 >> 3) & 7] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                __syncwarp();
+                // flush: 64 coefficients (128 B) of each lane's frame as one full row; 4 frames per warp store
+                if (!lookback || sub == 7) {
+                    const uint64_t my_row = ((slot * a.max_channels + c) * 8 + sub) * 16 + halfband * 8;  // uint4 index
+                    const bool my_ok = c < nch;
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int j = it * 4 + (lane >> 3);
+                        const uint64_t row = __shfl_sync(0xFFFFFFFFu, my_row, j);
+                        const bool ok = __shfl_sync(0xFFFFFFFFu, (int)my_ok, j);
+                        if (ok) a.quant[row + (lane & 7)] = s_stage[j * kStageRow + (lane & 7)];
                     }
                 }
-                if (keep) {
-                    uint4 v;
-                    v.x = (uint32_t)(q[0] & 0xFFFF) | ((uint32_t)q[1] << 16);
-                    v.y = (uint32_t)(q[2] & 0xFFFF) | ((uint32_t)q[3] << 16);
-                    v.z = (uint32_t)(q[4] & 0xFFFF) | ((uint32_t)q[5] << 16);
-                    v.w = (uint32_t)(q[6] & 0xFFFF) | ((uint32_t)q[7] << 16);
-                    qdst[(i0 >> 3) * 32] = v;
-                }
+                __syncwarp();
             }
         }
     }
-    if (!bad) bad = br.finish_crc() != 0;                    // a valid frame's CRC over all bytes is 0 (hca.cpp:1166)
-    if (bad) a.status[u.stream] = ERR_HCA_DECODE;
+    if (bad && active) a.status[u.stream] = ERR_HCA_DECODE;
 }
 
 // --------------------------------------------------------------- transform
-constexpr int kImdctThreads = 64;
-constexpr int kTileRow = 130;   // int16 per lane: 128 samples + 2 pad -> 65-word rows, conflict-free
+constexpr int kImdctWarps = 4;
 
-__device__ __forceinline__ int pcm16(float f) {              // hca.cpp:339-360; (int) of an out-of-range float is INT_MIN on x86
+__device__ __forceinline__ int pcm16(float f) {   // hca.cpp:339-360; (int) of an out-of-range float is INT_MIN on x86
     const float v = __fmul_rn(f, 32768.0f);
     int s = __float2int_rz(v);
     if (!(fabsf(v) < 2147483648.0f)) s = INT_MIN;
     return max(-32768, min(32767, s));
 }
 
-__global__ void __launch_bounds__(kImdctThreads)
+__device__ __forceinline__ float flip(float v, uint32_t mask) { return __uint_as_float(__float_as_uint(v) ^ mask); }
+
+__global__ void __launch_bounds__(kImdctWarps * 32)
 hca_imdct_kernel(HcaDecodeArgs a) {
-    __shared__ __align__(16) int16_t s_tile[kImdctThreads / 32][32][kTileRow];
+    extern __shared__ __align__(16) uint8_t s_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t li = blockIdx.x * kImdctThreads + threadIdx.x;   // lanes[] is padded to the grid
-    const HcaLane me = a.lanes[li];
-    const bool idle = me.unit == 0xFFFFFFFFu;
-    HcaUnit u{0, 0, 0};
-    if (!idle) u = a.units[me.unit];
+    const uint32_t unit = blockIdx.x * kImdctWarps + warp;
+    if (unit >= a.n_units) return;
+    const HcaUnit u = a.units[unit];
+    if (u.count == 0) return;
     const HcaStreamDev& S = a.streams[u.stream];
-    const int ch = (int)me.channel;
-    const int nch = idle ? 1 : S.channels;
-    const int coded = idle ? 0 : S.coded[ch];
-    const int type = idle ? 0 : S.type[ch];
-    const uint32_t block = idle ? 0 : me.unit >> 5, ulane = idle ? 0 : me.unit & 31;
-    uint32_t steps_here = idle ? 0 : u.count + 1;
-    uint32_t warp_steps = steps_here;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) warp_steps = max(warp_steps, __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o));
-    const bool warp_joint = __any_sync(0xFFFFFFFFu, !idle && S.joint);
+    const int nch = S.channels;
+    const int MC = (int)a.max_channels;
+    // per-warp shared: PCM tile [MC][128] int16, overlap carry [MC][32] float2, HFR scratch [128] float
+    uint8_t* base = s_dyn + (size_t)warp * (MC * 512 + 512);
+    int16_t* tile = reinterpret_cast<int16_t*>(base);
+    float2* carry = reinterpret_cast<float2*>(base + MC * 256);
+    float* xs = reinterpret_cast<float*>(base + MC * 512);
 
-    float x[128];
-    float dprev[64];
+    // per-lane constants of the transform (slot p = 4*lane + r)
+    float rs[7][4], rc[7][4];
 #pragma unroll
-    for (int i = 0; i < 64; i++) dprev[i] = 0.f;
+    for (int st = 0; st < 7; st++) {
+        const uint4 s4 = reinterpret_cast<const uint4*>(kRotS + st * 128)[lane];
+        const uint4 c4 = reinterpret_cast<const uint4*>(kRotC + st * 128)[lane];
+        rs[st][0] = __uint_as_float(s4.x); rs[st][1] = __uint_as_float(s4.y); rs[st][2] = __uint_as_float(s4.z); rs[st][3] = __uint_as_float(s4.w);
+        rc[st][0] = __uint_as_float(c4.x); rc[st][1] = __uint_as_float(c4.y); rc[st][2] = __uint_as_float(c4.z); rc[st][3] = __uint_as_float(c4.w);
+    }
+    const float wa0 = __uint_as_float(kWinA[2 * lane]), wa1 = __uint_as_float(kWinA[2 * lane + 1]);
+    const float wb0 = __uint_as_float(kWinB[2 * lane]), wb1 = __uint_as_float(kWinB[2 * lane + 1]);
+    const int pa0 = kWinPosA[2 * lane], pa1 = kWinPosA[2 * lane + 1], pb0 = kWinPosB[2 * lane], pb1 = kWinPosB[2 * lane + 1];
+    uint32_t sgn[5];   // sum/difference passes across lanes: the slot with the pass bit set holds b of (a+b, a-b)
+#pragma unroll
+    for (int b = 0; b < 5; b++) sgn[b] = (lane >> b) & 1 ? 0x80000000u : 0u;
 
-    for (uint32_t step = 0; step < warp_steps; step++) {
-        const bool live = step < steps_here && !(step == 0 && u.first == 0);
+    for (int c = 0; c < nch; c++) carry[c * 32 + lane] = make_float2(0.f, 0.f);
+    const int total = S.total_bands, basebands = S.base_bands;
+    const int start = S.base_bands + S.stereo_bands;
+    const int room = min(min(total - start, (int)S.hfr_groups * (int)S.bands_per_hfr), start);
+    const bool joint = S.joint;
+
+    const uint32_t first_step = u.first == 0 ? 1u : 0u;
+    for (uint32_t step = first_step; step <= u.count; step++) {
         const uint32_t frame = u.first + step - 1;
-        const uint64_t slot = ((uint64_t)block * a.steps + step) * a.max_channels + ch;
-        uint32_t inten = 0;
-        if (warp_joint && live && type == 2) inten = a.inten[slot * 32 + ulane];
+        const uint64_t slot = (uint64_t)unit * a.steps + step;
         for (int sub = (step == 0 ? 7 : 0); sub < 8; sub++) {
-            if (live) {
-                // ---- dequantise: spectra = gain * q  (hca.cpp:1568)
-                const uint4* qsrc = a.quant + ((slot * 8 + sub) * 16) * 32 + ulane;
-                const float4* gsrc = a.gain + (slot * 32) * 32 + ulane;
+            float xl[4] = {0.f, 0.f, 0.f, 0.f};   // primary channel's spectra for intensity stereo
+            for (int c = 0; c < nch; c++) {
+                const int coded = S.coded[c];
+                const int type = S.type[c];
+                // ---- dequantise: spectra = gain * q  (hca.cpp:1568); bands past the coded count are zero
+                const uint2 q2 = reinterpret_cast<const uint2*>(a.quant + ((slot * MC + c) * 8 + sub) * 16)[lane];
+                const float4 g4 = reinterpret_cast<const float4*>(a.gain + (slot * MC + c) * 128)[lane];
+                float x[4];
+                x[0] = 4 * lane + 0 < coded ? __fmul_rn(g4.x, (float)(int)(short)(q2.x & 0xFFFF)) : 0.f;
+                x[1] = 4 * lane + 1 < coded ? __fmul_rn(g4.y, (float)((int)q2.x >> 16)) : 0.f;
+                x[2] = 4 * lane + 2 < coded ? __fmul_rn(g4.z, (float)(int)(short)(q2.y & 0xFFFF)) : 0.f;
+                x[3] = 4 * lane + 3 < coded ? __fmul_rn(g4.w, (float)((int)q2.y >> 16)) : 0.f;
+                if (joint) {
+                    // ---- HFR: mirrored low bands scaled into the high bands (hca.cpp:1638-1683)
+                    if (S.bands_per_hfr && type != 2) {
+                        __syncwarp();
+                        reinterpret_cast<float4*>(xs)[lane] = make_float4(x[0], x[1], x[2], x[3]);
+                        __syncwarp();
+                        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-                for (int c8 = 0; c8 < 16; c8++) {
-                    if (c8 * 8 < coded) {
-                        const uint4 q = qsrc[c8 * 32];
-                        const float4 g0 = gsrc[(2 * c8) * 32], g1 = gsrc[(2 * c8 + 1) * 32];
-                        const int q0 = (int)(short)(q.x & 0xFFFF), q1 = (int)q.x >> 16, q2 = (int)(short)(q.y & 0xFFFF), q3 = (int)q.y >> 16;
-                        const int q4 = (int)(short)(q.z & 0xFFFF), q5 = (int)q.z >> 16, q6 = (int)(short)(q.w & 0xFFFF), q7 = (int)q.w >> 16;
-                        x[c8 * 8 + 0] = c8 * 8 + 0 < coded ? __fmul_rn(g0.x, (float)q0) : 0.f;
-                        x[c8 * 8 + 1] = c8 * 8 + 1 < coded ? __fmul_rn(g0.y, (float)q1) : 0.f;
-                        x[c8 * 8 + 2] = c8 * 8 + 2 < coded ? __fmul_rn(g0.z, (float)q2) : 0.f;
-                        x[c8 * 8 + 3] = c8 * 8 + 3 < coded ? __fmul_rn(g0.w, (float)q3) : 0.f;
-                        x[c8 * 8 + 4] = c8 * 8 + 4 < coded ? __fmul_rn(g1.x, (float)q4) : 0.f;
-                        x[c8 * 8 + 5] = c8 * 8 + 5 < coded ? __fmul_rn(g1.y, (float)q5) : 0.f;
-                        x[c8 * 8 + 6] = c8 * 8 + 6 < coded ? __fmul_rn(g1.z, (float)q6) : 0.f;
-                        x[c8 * 8 + 7] = c8 * 8 + 7 < coded ? __fmul_rn(g1.w, (float)q7) : 0.f;
-                    } else {
+                        for (int r = 0; r < 4; r++) {
+                            const int p = 4 * lane + r;
+                            if (p >= start && p < start + room) x[r] = __fmul_rn(gg[r], xs[2 * start - 1 - p]);
+                            if (p == start + room - 1) x[r] = 0.f;
+                        }
+                    }
+                    // ---- intensity stereo: the secondary channel is rebuilt from the primary (hca.cpp:1696-1714)
+                    if (type == 1) {
+                        const uint32_t inten = a.inten[slot * MC + c + 1];
+                        const float rl = __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]);
 #pragma unroll
-                        for (int k = 0; k < 8; k++) x[c8 * 8 + k] = 0.f;
+                        for (int r = 0; r < 4; r++) {
+                            xl[r] = x[r];
+                            const int p = 4 * lane + r;
+                            if (p >= basebands && p < total) x[r] = __fmul_rn(x[r], rl);
+                        }
+                    } else if (type == 2) {
+                        const uint32_t inten = a.inten[slot * MC + c];
+                        const float rr = __fsub_rn(2.0f, __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]));
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const int p = 4 * lane + r;
+                            if (p >= basebands && p < total) x[r] = __fmul_rn(xl[r], rr);
+                        }
                     }
                 }
-            }
-            if (warp_joint) {
-                // ---- HFR: copy mirrored low bands upward (hca.cpp:1638-1683)
-                if (live && S.bands_per_hfr && type != 2) {
-                    float tmp[128];
-#pragma unroll
-                    for (int i = 0; i < 128; i++) tmp[i] = x[i];
-                    const int start = S.base_bands + S.stereo_bands;
-                    const int room = min(min((int)S.total_bands - start, (int)S.hfr_groups * (int)S.bands_per_hfr), start);
-                    const float* gflat = reinterpret_cast<const float*>(a.gain + (slot * 32) * 32);
-                    for (int n = 0; n < room; n++) {
-                        const int high = start + n, low = start - 1 - n;
-                        tmp[high] = __fmul_rn(gflat[((high >> 2) * 32 + ulane) * 4 + (high & 3)], tmp[low]);
-                    }
-                    const int last = start + max(room, 0) - 1;
-                    if (last >= 0) tmp[last] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 128; i++) x[i] = tmp[i];
+                // ---- 7 sum/difference passes: slot bit 0, 1 (registers), 2..6 (lanes)
+                {
+                    const float t0 = __fadd_rn(x[0], x[1]), t1 = __fsub_rn(x[0], x[1]), t2 = __fadd_rn(x[2], x[3]), t3 = __fsub_rn(x[2], x[3]);
+                    x[0] = __fadd_rn(t0, t2); x[2] = __fsub_rn(t0, t2); x[1] = __fadd_rn(t1, t3); x[3] = __fsub_rn(t1, t3);
                 }
-                // ---- intensity stereo: the secondary channel is rebuilt from the primary (hca.cpp:1696-1714)
-                const float rl = __uint_as_float(c_intensity[(__shfl_down_sync(0xFFFFFFFFu, inten, 1) >> (4 * sub)) & 15]);
-                const float rr_self = __fsub_rn(2.0f, __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]));
-                const int lo = S.base_bands, hi = S.total_bands;
 #pragma unroll
-                for (int i = 0; i < 128; i++) {
-                    const float left = __shfl_up_sync(0xFFFFFFFFu, x[i], 1);
-                    if (live && i >= lo && i < hi) {
-                        if (type == 2) x[i] = __fmul_rn(left, rr_self);
-                        else if (type == 1) x[i] = __fmul_rn(x[i], rl);
+                for (int b = 0; b < 5; b++) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const float other = __shfl_xor_sync(0xFFFFFFFFu, x[r], 1 << b);
+                        x[r] = __fadd_rn(other, flip(x[r], sgn[b]));
                     }
                 }
+                // ---- 7 rotation passes: slot bit 6..2 (lanes), 1, 0 (registers):  v*S + partner*C
+#pragma unroll
+                for (int st = 0; st < 5; st++) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const float other = __shfl_xor_sync(0xFFFFFFFFu, x[r], 16 >> st);
+                        x[r] = __fadd_rn(__fmul_rn(x[r], rs[st][r]), __fmul_rn(other, rc[st][r]));
+                    }
+                }
+                {
+                    const float y0 = __fadd_rn(__fmul_rn(x[0], rs[5][0]), __fmul_rn(x[2], rc[5][0]));
+                    const float y2 = __fadd_rn(__fmul_rn(x[2], rs[5][2]), __fmul_rn(x[0], rc[5][2]));
+                    const float y1 = __fadd_rn(__fmul_rn(x[1], rs[5][1]), __fmul_rn(x[3], rc[5][1]));
+                    const float y3 = __fadd_rn(__fmul_rn(x[3], rs[5][3]), __fmul_rn(x[1], rc[5][3]));
+                    x[0] = __fadd_rn(__fmul_rn(y0, rs[6][0]), __fmul_rn(y1, rc[6][0]));
+                    x[1] = __fadd_rn(__fmul_rn(y1, rs[6][1]), __fmul_rn(y0, rc[6][1]));
+                    x[2] = __fadd_rn(__fmul_rn(y2, rs[6][2]), __fmul_rn(y3, rc[6][2]));
+                    x[3] = __fadd_rn(__fmul_rn(y3, rs[6][3]), __fmul_rn(y2, rc[6][3]));
+                }
+                // ---- window + overlap (hca.cpp:1983-1992): odd slots hold dct[j>=64], even slots dct[127-j]
+                const float2 prev = carry[c * 32 + lane];
+                carry[c * 32 + lane] = make_float2(x[0], x[2]);
+                if (step != 0) {
+                    int16_t* t = tile + c * 128;
+                    t[pa0] = (int16_t)pcm16(__fadd_rn(__fmul_rn(wa0, x[1]), __fmul_rn(wb0, prev.x)));
+                    t[pb0] = (int16_t)pcm16(__fsub_rn(__fmul_rn(wb0, x[1]), __fmul_rn(wa0, prev.x)));
+                    t[pa1] = (int16_t)pcm16(__fadd_rn(__fmul_rn(wa1, x[3]), __fmul_rn(wb1, prev.y)));
+                    t[pb1] = (int16_t)pcm16(__fsub_rn(__fmul_rn(wb1, x[3]), __fmul_rn(wa1, prev.y)));
+                }
             }
-            if (live) hca_dct4_dec(x);
-            if (step == 0) {                       // look-back subframe: only its DCT output is needed
-                if (live) hca_imdct_carry(x, dprev);
-                continue;
-            }
-            // ---- window + overlap, PCM16 into the warp's tile
-            if (live) hca_imdct_window(x, dprev, [&](int i, float w) { s_tile[warp][lane][i] = (int16_t)pcm16(w); });
+            if (step == 0) continue;
             __syncwarp();
-            // ---- coalesced store: all lanes write consecutive samples of ONE (unit, channel) at a time
-            const long long n0 = (long long)frame * 1024 + sub * 128 - (long long)S.delay;  // stream sample index of tile[0]
-            long long base = 0;
-            int i_lo = 0, i_hi = 0, stride = 0;
-            if (live) {
-                base = (long long)S.out_off + (n0 * nch + ch) * 2;
-                stride = nch * 2;
-                i_lo = (int)max(0ll, -n0);
-                i_hi = (int)min(128ll, (long long)S.out_samples - n0);
-            }
-            for (int j = 0; j < 32; j++) {
-                const long long b = __shfl_sync(0xFFFFFFFFu, base, j);
-                const int st = __shfl_sync(0xFFFFFFFFu, stride, j);
-                const int lo = __shfl_sync(0xFFFFFFFFu, i_lo, j), hi = __shfl_sync(0xFFFFFFFFu, i_hi, j);
-                if (lo >= hi) continue;
+            // ---- interleave the channels and store this subframe's samples (contiguous in the WAV image)
+            const long long n0 = (long long)frame * 1024 + sub * 128 - (long long)S.delay;
+            uint8_t* dst = a.out + S.out_off;
+            if (nch == 2 && ((S.out_off & 3) == 0)) {
 #pragma unroll
                 for (int m = 0; m < 4; m++) {
                     const int i = lane + 32 * m;
-                    if (i >= lo && i < hi) *reinterpret_cast<int16_t*>(a.out + b + (long long)i * st) = s_tile[warp][j][i];
+                    const long long n = n0 + i;
+                    if (n >= 0 && n < (long long)S.out_samples) {
+                        const uint32_t w = (uint32_t)(uint16_t)tile[i] | ((uint32_t)(uint16_t)tile[128 + i] << 16);
+                        *reinterpret_cast<uint32_t*>(dst + n * 4) = w;
+                    }
+                }
+            } else {
+                for (int e = lane; e < 128 * nch; e += 32) {
+                    const int i = e / nch, c = e - i * nch;
+                    const long long n = n0 + i;
+                    if (n >= 0 && n < (long long)S.out_samples)
+                        *reinterpret_cast<int16_t*>(dst + (n * nch + c) * 2) = tile[c * 128 + i];
                 }
             }
             __syncwarp();
@@ -441,19 +502,22 @@ hca_imdct_kernel(HcaDecodeArgs a) {
 
 }  // namespace
 
-void launch_hca_decode(const HcaDecodeArgs& a, uint32_t n_lanes, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
+size_t hca_unpack_smem(uint32_t max_channels) {
+    return (size_t)(128 + 128 * max_channels) * kUnpackThreads + (size_t)(kUnpackThreads / 32) * 32 * kStageRow * sizeof(uint4);
+}
+
+void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
     if (!a.total_groups) return;
-    const size_t per_thread = 128 + 64 * (size_t)a.max_channels;
-    const size_t smem = per_thread * kUnpackThreads;
+    const size_t smem = hca_unpack_smem(a.max_channels);
     cudaFuncSetAttribute(hca_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint64_t groups_per_cta = kUnpackThreads / 32;
     hca_unpack_kernel<<<(unsigned)((a.total_groups + groups_per_cta - 1) / groups_per_cta), kUnpackThreads, smem, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    hca_imdct_kernel<<<n_lanes / kImdctThreads, kImdctThreads, 0, s>>>(a);
+    const size_t smem2 = (size_t)kImdctWarps * (a.max_channels * 512 + 512);
+    cudaFuncSetAttribute(hca_imdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    hca_imdct_kernel<<<(a.n_units + kImdctWarps - 1) / kImdctWarps, kImdctWarps * 32, smem2, s>>>(a);
     ++*launches;
 }
-
-uint32_t hca_imdct_lane_granule() { return kImdctThreads; }
 
 }  // namespace cri

@@ -96,7 +96,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
 
     CipherPool pool(&J.cipher_tables);
     J.ath_tables.assign(128, 0);
-    const uint32_t run = std::max(1u, env_u32("CRI_HCA_RUN", 12));
+    const uint32_t run = std::max(1u, env_u32("CRI_HCA_RUN", 16));
     J.max_channels = 1;
     J.streams.assign(j->n, HcaStreamDev{});   // one entry per input stream: the device status array shares the index
     for (uint32_t i = 0; i < j->n; i++) {
@@ -131,28 +131,16 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         j->units += needed;
     }
     while (J.units.size() % 32) J.units.push_back(HcaUnit{0, 0, 0});
-    // transform lanes: the channels of one unit sit next to each other inside one warp
-    uint32_t in_warp = 0;
-    for (uint32_t ui = 0; ui < J.units.size(); ui++) {
-        const HcaUnit& u = J.units[ui];
-        if (!u.count) continue;
-        const uint32_t nch = J.streams[u.stream].channels;
-        if (in_warp + nch > 32) {
-            for (; in_warp < 32; in_warp++) J.lanes.push_back(HcaLane{0xFFFFFFFFu, 0});
-            in_warp = 0;
-        }
-        for (uint32_t ch = 0; ch < nch; ch++) J.lanes.push_back(HcaLane{ui, ch});
-        in_warp = (in_warp + nch) % 32;
-    }
-    const uint32_t gran = hca_imdct_lane_granule();
-    while (J.lanes.size() % gran) J.lanes.push_back(HcaLane{0xFFFFFFFFu, 0});
     J.max_steps = run + 1;
-    const uint64_t blocks = J.units.size() / 32;
-    J.total_groups = blocks * J.max_steps;
-    const uint64_t slots = J.total_groups * J.max_channels;
-    J.q_bytes = slots * 8 * 16 * 32 * sizeof(uint4);
-    J.g_bytes = slots * 32 * 32 * sizeof(float4);
-    J.i_bytes = slots * 32 * sizeof(uint32_t);
+    J.total_groups = (J.units.size() / 32) * J.max_steps;
+    const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
+    uint32_t max_frame = 8;
+    for (const auto& st : J.streams) max_frame = std::max(max_frame, st.frame_size);
+    J.scratch_words = ((max_frame + 3) / 4 + 3) / 4 * 4 + 8;       // whole 16-byte rows + slack for the prefetching reader
+    J.s_bytes = slots * J.scratch_words * sizeof(uint32_t);
+    J.q_bytes = slots * J.max_channels * 8 * 16 * sizeof(uint4);
+    J.g_bytes = slots * J.max_channels * 128 * sizeof(float);
+    J.i_bytes = slots * J.max_channels * sizeof(uint32_t);
     return OK;
 }
 
@@ -172,13 +160,13 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
     int r = upload(c, J.streams, &J.d_streams);
     if (r == OK) r = upload(c, J.units, &J.d_units);
-    if (r == OK) r = upload(c, J.lanes, &J.d_lanes);
     if (r == OK) r = upload(c, J.cipher_tables, &J.d_cipher);
     if (r == OK) r = upload(c, J.ath_tables, &J.d_ath);
     if (r != OK) return r;
     if (J.q_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_q, J.q_bytes));
     if (J.g_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_g, J.g_bytes));
     if (J.i_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_i, J.i_bytes));
+    if (J.s_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_s, J.s_bytes));
     return OK;
 }
 
@@ -190,18 +178,20 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.out = j->d_out;
         a.streams = J.d_streams;
         a.units = J.d_units;
-        a.lanes = J.d_lanes;
         a.cipher = J.d_cipher;
         a.ath = J.d_ath;
         a.quant = reinterpret_cast<uint4*>(J.d_q);
-        a.gain = reinterpret_cast<float4*>(J.d_g);
+        a.gain = reinterpret_cast<float*>(J.d_g);
+        a.scratch = reinterpret_cast<uint32_t*>(J.d_s);
+        a.scratch_words = J.scratch_words;
+        a.n_units = (uint32_t)J.units.size();
         a.inten = reinterpret_cast<uint32_t*>(J.d_i);
         a.status = j->d_status;
         a.total_groups = J.total_groups;
         a.steps = J.max_steps;
         a.max_channels = J.max_channels;
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
-        launch_hca_decode(a, (uint32_t)J.lanes.size(), c->stream, &c->launches, c->ev[2]);
+        launch_hca_decode(a, c->stream, &c->launches, c->ev[2]);
         CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         *have_dominant = J.total_groups != 0;
         return OK;
@@ -213,7 +203,7 @@ void free_hca_tables(cri_job* j) {
     HcaJob& J = j->hca;
     cudaFree(J.d_streams);
     cudaFree(J.d_units);
-    cudaFree(J.d_lanes);
+    cudaFree(J.d_s);
     cudaFree(J.d_cipher);
     cudaFree(J.d_ath);
     cudaFree(J.d_q);

@@ -9,25 +9,27 @@
 
 namespace cri {
 
+// Intermediate arrays are indexed by frame slot = unit * steps + step (step 0 = look-back frame of the unit).
 struct HcaDecodeArgs {
     const uint8_t* in;
     uint8_t* out;
     const HcaStreamDev* streams;
-    const HcaUnit* units;
-    const HcaLane* lanes;
+    const HcaUnit* units;       // padded to a multiple of 32
     const uint8_t* cipher;      // [n][256]
     const uint8_t* ath;         // [n][128]
-    uint4* quant;               // [group][channel][8][16][32] x 8 int16
-    float4* gain;               // [group][channel][32][32] x 4 fp32
-    uint32_t* inten;            // [group][channel][32]
+    uint32_t* scratch;          // [slot][scratch_words] aligned, deciphered, big-endian frame words
+    uint4* quant;               // [slot][channel][8 subframes][16] x 8 int16 quantised spectra
+    float* gain;                // [slot][channel][128] gain per coded band, HFR multiplier per reconstructed band
+    uint32_t* inten;            // [slot][channel] 8 intensity nibbles
     int32_t* status;
-    uint64_t total_groups;      // unit blocks x steps
-    uint32_t steps;             // frames per unit + 1 (step 0 = look-back frame)
+    uint64_t total_groups;      // unit blocks (32 units) x steps: one unpack warp each
+    uint32_t n_units;
+    uint32_t steps;             // frames per unit + 1
     uint32_t max_channels;
+    uint32_t scratch_words;     // multiple of 4
 };
 
 // `mid` (optional) is recorded between the unpack and the transform kernel.
-void launch_hca_decode(const HcaDecodeArgs& a, uint32_t n_lanes, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
-uint32_t hca_imdct_lane_granule();
+void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
 
 }  // namespace cri

@@ -60,7 +60,9 @@ struct HcaJob {
     std::vector<HcaLane> lanes;            // padded to a multiple of 32
     std::vector<uint8_t> cipher_tables;    // 256 bytes each, [0] identity
     std::vector<uint8_t> ath_tables;       // 128 bytes each, [0] zero
-    uint64_t q_bytes = 0, g_bytes = 0, i_bytes = 0;
+    uint64_t q_bytes = 0, g_bytes = 0, i_bytes = 0, s_bytes = 0;
+    uint32_t scratch_words = 0;
+    uint8_t* d_s = nullptr;
     uint32_t max_channels = 1, max_steps = 0;
 
     HcaStreamDev* d_streams = nullptr;

@@ -152,11 +152,72 @@ def gen_mdct() -> list[str]:
     return out
 
 
+def gen_warp_tables() -> list[str]:
+    """Tables for the warp-cooperative transform (hca_imdct_kernel): coefficient p of a 128-point block lives in
+    lane p>>2, register p&3, and never moves. The seven sum/difference passes then pair slots that differ in bit
+    0,1,..,6 of p, the seven rotation passes pair bit 6,5,..,0, and the window pairs bit 0 -- i.e. every exchange is
+    a register swap or one __shfl_xor. Per slot and rotation pass the update is  v*S + partner*C  with the sign of
+    the reference's subtraction folded into C (x - y == x + (-y) exactly in IEEE arithmetic)."""
+    sin, cos = T.imdct_trig()
+    sin = sin.reshape(7, 64)
+    cos = cos.reshape(7, 64)
+    win = T.window()
+    phys = list(range(128))
+    half = 64
+    bit = 0
+    while half >= 1:
+        nxt = [None] * 128
+        for j in range(64 // half):
+            for k in range(half):
+                a, b = phys[j * 2 * half + 2 * k], phys[j * 2 * half + 2 * k + 1]
+                assert a ^ b == 1 << bit and not a & (1 << bit)
+                nxt[j * 2 * half + k], nxt[j * 2 * half + half + k] = a, b
+        phys = nxt
+        half //= 2
+        bit += 1
+    rs = [[0] * 128 for _ in range(7)]
+    rc = [[0] * 128 for _ in range(7)]
+    for stage in range(7):
+        half = 1 << stage
+        nxt = [None] * 128
+        for j in range(64 >> stage):
+            for k in range(half):
+                a, b = phys[j * 2 * half + k], phys[j * 2 * half + half + k]
+                assert a ^ b == 1 << (6 - stage)
+                s, c = int(sin[stage, j * half + k]), int(cos[stage, j * half + k])
+                rs[stage][a], rc[stage][a] = s, c ^ 0x80000000      # a*sin - b*cos
+                rs[stage][b], rc[stage][b] = s, c                   # b*sin + a*cos
+                nxt[j * 2 * half + k], nxt[j * 2 * half + 2 * half - 1 - k] = a, b
+        phys = nxt
+    final = [0] * 128
+    for logical, p in enumerate(phys):
+        final[p] = logical
+    # window: odd slots hold dct[j], j >= 64, their even neighbour holds dct[127-j] (carried to the next subframe)
+    w1, w2, s1, s2 = [0] * 64, [0] * 64, [0] * 64, [0] * 64
+    for p in range(1, 128, 2):
+        j = final[p]
+        assert j >= 64 and final[p ^ 1] == 127 - j
+        w1[p >> 1], w2[p >> 1] = int(win[j - 64]), int(win[191 - j])
+        s1[p >> 1], s2[p >> 1] = j - 64, 191 - j
+    out = ["// per-slot tables of the warp-cooperative IMDCT (slot p = 4*lane + register)"]
+
+    def emit(name, ctype, vals, fmt):
+        out.append(f"__device__ const {ctype} {name}[{len(vals)}] = {{")
+        for i in range(0, len(vals), 8):
+            out.append("    " + ", ".join(fmt(v) for v in vals[i:i + 8]) + ",")
+        out.append("};")
+    emit("kRotS", "uint32_t", [v for row in rs for v in row], lambda v: f"0x{v:08X}u")
+    emit("kRotC", "uint32_t", [v for row in rc for v in row], lambda v: f"0x{v:08X}u")
+    emit("kWinA", "uint32_t", w1, lambda v: f"0x{v:08X}u")   # weight of sample kWinPosA: w[j-64]
+    emit("kWinB", "uint32_t", w2, lambda v: f"0x{v:08X}u")   # weight of sample kWinPosB: w[191-j]
+    emit("kWinPosA", "uint8_t", s1, str)
+    emit("kWinPosB", "uint8_t", s2, str)
+    return out
+
+
 def main():
     lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""]
-    lines += gen_imdct()
-    lines.append("")
-    lines += gen_mdct()
+    lines += gen_warp_tables()
     path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_gen.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
