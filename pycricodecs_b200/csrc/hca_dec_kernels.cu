@@ -76,7 +76,7 @@ __device__ __forceinline__ uint32_t crc16_step(uint32_t crc, uint32_t byte) {
 struct BitWindow {              // MSB-first reader over big-endian 32-bit words
     uint64_t win;
     const uint32_t* next_ptr;
-    uint32_t next;              // prefetched word
+    uint32_t next, next2;       // two prefetched words: the scratch row comes back from L2, one word ahead is too late
     int have;                   // valid bits in win (kept above 32)
     int pos;                    // bits consumed so far
     int nbits;
@@ -84,7 +84,8 @@ struct BitWindow {              // MSB-first reader over big-endian 32-bit words
     __device__ __forceinline__ void init(const uint32_t* words, int frame_bits) {
         win = ((uint64_t)words[0] << 32) | words[1];
         next = words[2];
-        next_ptr = words + 3;
+        next2 = words[3];
+        next_ptr = words + 4;
         have = 64; pos = 0; nbits = frame_bits;
     }
     // n in 0..16. A read that would cross the end of the frame returns 0 (hca.cpp:232-233).
@@ -99,7 +100,8 @@ struct BitWindow {              // MSB-first reader over big-endian 32-bit words
         if (have <= 32) {       // predicated, no divergence: shift in the prefetched word, fetch the one after
             win |= (uint64_t)next << (32 - have);
             have += 32;
-            next = *next_ptr++;
+            next = next2;
+            next2 = *next_ptr++;
         }
     }
     __device__ __forceinline__ uint32_t read(int n) { const uint32_t v = peek(n); skip(n); return v; }
@@ -145,39 +147,46 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     uint32_t* words = a.scratch + slot * a.scratch_words;    // this frame's aligned, deciphered, byte-swapped copy
     const int frame_size = active ? (int)S.frame_size : 0;
 
-    // ---- phase 1: CRC over the raw frame, cipher LUT, byte swap -> scratch row
+    // ---- phase 1: CRC over the raw frame, cipher LUT, byte swap -> scratch row (16-byte loads, one row ahead)
     if (active) {
         const uint8_t* src = a.in + S.in_off + (uint64_t)frame * S.frame_size;
         const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
-        const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
-        const int sh = (int)(addr & 3) * 8;
+        const uint4* ap = reinterpret_cast<const uint4*>(addr & ~(uintptr_t)15);
+        const int lead = (int)(addr & 15);                  // bytes of the first row that precede the frame
+        const int wsel = lead >> 2, sh = (lead & 3) * 8;
         const uint8_t* cipher = S.cipher ? a.cipher + (size_t)S.cipher * 256 : nullptr;
         uint32_t crc = 0;
-        uint32_t lo = __ldg(ap++);
-        const int nwords = (frame_size + 3) >> 2;
-        uint4 pack = make_uint4(0, 0, 0, 0);
-        for (int w = 0; w < nwords; w++) {
-            const uint32_t hi = __ldg(ap++);
-            const uint32_t raw = __funnelshift_r(lo, hi, sh);   // 4 frame bytes in memory order (little-endian lanes)
-            lo = hi;
-            uint32_t be = 0;
+        const int nrows = (frame_size + 15) >> 4;
+        uint4 cur = __ldg(ap), nxt = __ldg(ap + 1);
+        for (int row = 0; row < nrows; row++) {
+            const uint4 nn = __ldg(ap + row + 2);           // the input blob has 64 bytes of slack behind it
+            // the 5 aligned words that cover this output row, then a byte funnel
+            uint32_t v[5];
+            {
+                const uint32_t t[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t b = (raw >> (8 * k)) & 0xFF;
-                if (4 * w + k < frame_size) crc = crc16_step(crc, b); else b = 0;
-                if (cipher) b = __ldg(cipher + b);
-                be = (be << 8) | b;
+                for (int k = 0; k < 5; k++) v[k] = wsel == 0 ? t[k] : wsel == 1 ? t[k + 1] : wsel == 2 ? t[k + 2] : t[k + 3];
             }
-            if ((w & 3) == 0) pack.x = be; else if ((w & 3) == 1) pack.y = be; else if ((w & 3) == 2) pack.z = be; else pack.w = be;
-            if ((w & 3) == 3 || w == nwords - 1) {
-                if ((w & 3) < 3) pack.w = 0;
-                if ((w & 3) < 2) pack.z = 0;
-                if ((w & 3) < 1) pack.y = 0;
-                reinterpret_cast<uint4*>(words)[w >> 2] = pack;
+            uint32_t o[4];
+#pragma unroll
+            for (int wq = 0; wq < 4; wq++) {
+                const uint32_t raw = __funnelshift_r(v[wq], v[wq + 1], sh);  // 4 frame bytes, memory order
+                uint32_t be = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t bb = (raw >> (8 * k)) & 0xFF;
+                    if (16 * row + 4 * wq + k < frame_size) crc = crc16_step(crc, bb); else bb = 0;
+                    if (cipher) bb = __ldg(cipher + bb);
+                    be = (be << 8) | bb;
+                }
+                o[wq] = be;
             }
+            reinterpret_cast<uint4*>(words)[row] = make_uint4(o[0], o[1], o[2], o[3]);
+            cur = nxt; nxt = nn;
         }
-        // a zero row of slack so the prefetching reader never sees stale data
-        reinterpret_cast<uint4*>(words)[(nwords + 3) >> 2] = make_uint4(0, 0, 0, 0);
+        // zero rows of slack so the prefetching reader never sees stale data
+        reinterpret_cast<uint4*>(words)[nrows] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(words)[nrows + 1] = make_uint4(0, 0, 0, 0);
         if (crc != 0) bad = true;                           // a valid frame's CRC over all its bytes is 0 (hca.cpp:1166)
     }
 
@@ -339,14 +348,28 @@ __device__ __forceinline__ int pcm16(float f) {   // hca.cpp:339-360; (int) of a
 
 __device__ __forceinline__ float flip(float v, uint32_t mask) { return __uint_as_float(__float_as_uint(v) ^ mask); }
 
+struct Spectra4 {              // one lane's share of a 128-point block as it sits in memory
+    uint2 q;                    // 4 x int16 quantised coefficients
+    float4 g;                   // 4 gains (or HFR multipliers above the coded bands)
+};
+
 __global__ void __launch_bounds__(kImdctWarps * 32)
 hca_imdct_kernel(HcaDecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ __align__(16) float s_rot_s[7 * 128];
+    __shared__ __align__(16) float s_rot_c[7 * 128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * kImdctWarps + warp;
-    if (unit >= a.n_units) return;
+    const bool dead = unit >= a.n_units || a.units[unit < a.n_units ? unit : 0].count == 0;
+    // rotation factors per slot (p = 4*lane + r): one shared copy per CTA, read as one LDS.128 per pass and table.
+    // Keeping the 56 per-lane factors in registers instead costs half the occupancy.
+    for (int i = threadIdx.x; i < 7 * 128; i += blockDim.x) {
+        s_rot_s[i] = __uint_as_float(kRotS[i]);
+        s_rot_c[i] = __uint_as_float(kRotC[i]);
+    }
+    __syncthreads();
+    if (dead) return;
     const HcaUnit u = a.units[unit];
-    if (u.count == 0) return;
     const HcaStreamDev& S = a.streams[u.stream];
     const int nch = S.channels;
     const int MC = (int)a.max_channels;
@@ -356,52 +379,61 @@ hca_imdct_kernel(HcaDecodeArgs a) {
     float2* carry = reinterpret_cast<float2*>(base + MC * 256);
     float* xs = reinterpret_cast<float*>(base + MC * 512);
 
-    // per-lane constants of the transform (slot p = 4*lane + r)
-    float rs[7][4], rc[7][4];
-#pragma unroll
-    for (int st = 0; st < 7; st++) {
-        const uint4 s4 = reinterpret_cast<const uint4*>(kRotS + st * 128)[lane];
-        const uint4 c4 = reinterpret_cast<const uint4*>(kRotC + st * 128)[lane];
-        rs[st][0] = __uint_as_float(s4.x); rs[st][1] = __uint_as_float(s4.y); rs[st][2] = __uint_as_float(s4.z); rs[st][3] = __uint_as_float(s4.w);
-        rc[st][0] = __uint_as_float(c4.x); rc[st][1] = __uint_as_float(c4.y); rc[st][2] = __uint_as_float(c4.z); rc[st][3] = __uint_as_float(c4.w);
-    }
     const float wa0 = __uint_as_float(kWinA[2 * lane]), wa1 = __uint_as_float(kWinA[2 * lane + 1]);
     const float wb0 = __uint_as_float(kWinB[2 * lane]), wb1 = __uint_as_float(kWinB[2 * lane + 1]);
     const int pa0 = kWinPosA[2 * lane], pa1 = kWinPosA[2 * lane + 1], pb0 = kWinPosB[2 * lane], pb1 = kWinPosB[2 * lane + 1];
     uint32_t sgn[5];   // sum/difference passes across lanes: the slot with the pass bit set holds b of (a+b, a-b)
 #pragma unroll
     for (int b = 0; b < 5; b++) sgn[b] = (lane >> b) & 1 ? 0x80000000u : 0u;
+    const float4* rot_s = reinterpret_cast<const float4*>(s_rot_s) + lane;   // [pass * 32]
+    const float4* rot_c = reinterpret_cast<const float4*>(s_rot_c) + lane;
 
     for (int c = 0; c < nch; c++) carry[c * 32 + lane] = make_float2(0.f, 0.f);
     const int total = S.total_bands, basebands = S.base_bands;
     const int start = S.base_bands + S.stereo_bands;
     const int room = min(min(total - start, (int)S.hfr_groups * (int)S.bands_per_hfr), start);
     const bool joint = S.joint;
+    const uint64_t slot0 = (uint64_t)unit * a.steps;
+
+    auto fetch = [&](uint32_t step, int sub, int c) {
+        Spectra4 r;
+        const uint64_t sc = (slot0 + step) * MC + c;
+        r.q = reinterpret_cast<const uint2*>(a.quant + (sc * 8 + sub) * 16)[lane];
+        r.g = reinterpret_cast<const float4*>(a.gain + sc * 128)[lane];
+        return r;
+    };
 
     const uint32_t first_step = u.first == 0 ? 1u : 0u;
+    Spectra4 nxt = fetch(first_step, first_step == 0 ? 7 : 0, 0);
     for (uint32_t step = first_step; step <= u.count; step++) {
         const uint32_t frame = u.first + step - 1;
-        const uint64_t slot = (uint64_t)unit * a.steps + step;
+        const uint64_t slot = slot0 + step;
         for (int sub = (step == 0 ? 7 : 0); sub < 8; sub++) {
             float xl[4] = {0.f, 0.f, 0.f, 0.f};   // primary channel's spectra for intensity stereo
             for (int c = 0; c < nch; c++) {
                 const int coded = S.coded[c];
                 const int type = S.type[c];
+                const Spectra4 cur = nxt;
+                {   // software prefetch: the next block's row is requested before this block's arithmetic starts
+                    int nc = c + 1, ns = sub;
+                    uint32_t nstep = step;
+                    if (nc == nch) { nc = 0; ns++; }
+                    if (ns == 8) { ns = 0; nstep++; }
+                    if (nstep <= u.count) nxt = fetch(nstep, ns, nc);
+                }
                 // ---- dequantise: spectra = gain * q  (hca.cpp:1568); bands past the coded count are zero
-                const uint2 q2 = reinterpret_cast<const uint2*>(a.quant + ((slot * MC + c) * 8 + sub) * 16)[lane];
-                const float4 g4 = reinterpret_cast<const float4*>(a.gain + (slot * MC + c) * 128)[lane];
                 float x[4];
-                x[0] = 4 * lane + 0 < coded ? __fmul_rn(g4.x, (float)(int)(short)(q2.x & 0xFFFF)) : 0.f;
-                x[1] = 4 * lane + 1 < coded ? __fmul_rn(g4.y, (float)((int)q2.x >> 16)) : 0.f;
-                x[2] = 4 * lane + 2 < coded ? __fmul_rn(g4.z, (float)(int)(short)(q2.y & 0xFFFF)) : 0.f;
-                x[3] = 4 * lane + 3 < coded ? __fmul_rn(g4.w, (float)((int)q2.y >> 16)) : 0.f;
+                x[0] = 4 * lane + 0 < coded ? __fmul_rn(cur.g.x, (float)(int)(short)(cur.q.x & 0xFFFF)) : 0.f;
+                x[1] = 4 * lane + 1 < coded ? __fmul_rn(cur.g.y, (float)((int)cur.q.x >> 16)) : 0.f;
+                x[2] = 4 * lane + 2 < coded ? __fmul_rn(cur.g.z, (float)(int)(short)(cur.q.y & 0xFFFF)) : 0.f;
+                x[3] = 4 * lane + 3 < coded ? __fmul_rn(cur.g.w, (float)((int)cur.q.y >> 16)) : 0.f;
                 if (joint) {
                     // ---- HFR: mirrored low bands scaled into the high bands (hca.cpp:1638-1683)
                     if (S.bands_per_hfr && type != 2) {
                         __syncwarp();
                         reinterpret_cast<float4*>(xs)[lane] = make_float4(x[0], x[1], x[2], x[3]);
                         __syncwarp();
-                        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+                        const float gg[4] = {cur.g.x, cur.g.y, cur.g.z, cur.g.w};
 #pragma unroll
                         for (int r = 0; r < 4; r++) {
                             const int p = 4 * lane + r;
@@ -445,21 +477,24 @@ hca_imdct_kernel(HcaDecodeArgs a) {
                 // ---- 7 rotation passes: slot bit 6..2 (lanes), 1, 0 (registers):  v*S + partner*C
 #pragma unroll
                 for (int st = 0; st < 5; st++) {
+                    const float4 s4 = rot_s[st * 32], c4 = rot_c[st * 32];
+                    const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         const float other = __shfl_xor_sync(0xFFFFFFFFu, x[r], 16 >> st);
-                        x[r] = __fadd_rn(__fmul_rn(x[r], rs[st][r]), __fmul_rn(other, rc[st][r]));
+                        x[r] = __fadd_rn(__fmul_rn(x[r], ss[r]), __fmul_rn(other, cc[r]));
                     }
                 }
                 {
-                    const float y0 = __fadd_rn(__fmul_rn(x[0], rs[5][0]), __fmul_rn(x[2], rc[5][0]));
-                    const float y2 = __fadd_rn(__fmul_rn(x[2], rs[5][2]), __fmul_rn(x[0], rc[5][2]));
-                    const float y1 = __fadd_rn(__fmul_rn(x[1], rs[5][1]), __fmul_rn(x[3], rc[5][1]));
-                    const float y3 = __fadd_rn(__fmul_rn(x[3], rs[5][3]), __fmul_rn(x[1], rc[5][3]));
-                    x[0] = __fadd_rn(__fmul_rn(y0, rs[6][0]), __fmul_rn(y1, rc[6][0]));
-                    x[1] = __fadd_rn(__fmul_rn(y1, rs[6][1]), __fmul_rn(y0, rc[6][1]));
-                    x[2] = __fadd_rn(__fmul_rn(y2, rs[6][2]), __fmul_rn(y3, rc[6][2]));
-                    x[3] = __fadd_rn(__fmul_rn(y3, rs[6][3]), __fmul_rn(y2, rc[6][3]));
+                    const float4 s5 = rot_s[5 * 32], c5 = rot_c[5 * 32], s6 = rot_s[6 * 32], c6 = rot_c[6 * 32];
+                    const float y0 = __fadd_rn(__fmul_rn(x[0], s5.x), __fmul_rn(x[2], c5.x));
+                    const float y2 = __fadd_rn(__fmul_rn(x[2], s5.z), __fmul_rn(x[0], c5.z));
+                    const float y1 = __fadd_rn(__fmul_rn(x[1], s5.y), __fmul_rn(x[3], c5.y));
+                    const float y3 = __fadd_rn(__fmul_rn(x[3], s5.w), __fmul_rn(x[1], c5.w));
+                    x[0] = __fadd_rn(__fmul_rn(y0, s6.x), __fmul_rn(y1, c6.x));
+                    x[1] = __fadd_rn(__fmul_rn(y1, s6.y), __fmul_rn(y0, c6.y));
+                    x[2] = __fadd_rn(__fmul_rn(y2, s6.z), __fmul_rn(y3, c6.z));
+                    x[3] = __fadd_rn(__fmul_rn(y3, s6.w), __fmul_rn(y2, c6.w));
                 }
                 // ---- window + overlap (hca.cpp:1983-1992): odd slots hold dct[j>=64], even slots dct[127-j]
                 const float2 prev = carry[c * 32 + lane];

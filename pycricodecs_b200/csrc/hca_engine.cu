@@ -136,7 +136,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
     uint32_t max_frame = 8;
     for (const auto& st : J.streams) max_frame = std::max(max_frame, st.frame_size);
-    J.scratch_words = ((max_frame + 3) / 4 + 3) / 4 * 4 + 8;       // whole 16-byte rows + slack for the prefetching reader
+    J.scratch_words = ((max_frame + 15) / 16 + 4) * 4;             // whole 16-byte rows + zeroed slack rows for the prefetching reader
     J.s_bytes = slots * J.scratch_words * sizeof(uint32_t);
     J.q_bytes = slots * J.max_channels * 8 * 16 * sizeof(uint4);
     J.g_bytes = slots * J.max_channels * 128 * sizeof(float);
@@ -144,7 +144,56 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     return OK;
 }
 
-int plan_hca_crypt(cri_ctx*, cri_job*) { return ERR_UNSUPPORTED; }
+// HcaCrypt (hca.cpp:3271-3337): output has the input's size and layout; frames come from the kernel, the
+// rewritten header (and any bytes outside header + frames) from host-built patches.
+int plan_hca_crypt(cri_ctx* c, cri_job* j) {
+    (void)c;
+    HcaJob& J = j->hca;
+    std::vector<uint64_t> sizes(j->n, 0);
+    CipherPool pool(&J.cipher_tables);
+    J.streams.assign(j->n, HcaStreamDev{});
+    J.frame_prefix.assign(j->n + 1, 0);
+    std::vector<uint8_t> hdr;
+    for (uint32_t i = 0; i < j->n; i++) {
+        const uint8_t* d = j->blob + j->in_off[i];
+        const uint64_t len = j->in_off[i + 1] - j->in_off[i];
+        sizes[i] = len;
+        HcaInfo h;
+        uint64_t frames = 0;
+        if (parse_hca(d, len, &h) != OK || (uint64_t)h.header_size + (uint64_t)h.frame_count * h.frame_size > len) {
+            j->status[i] = ERR_HCA_HEADER;
+        } else {
+            const unsigned type = j->encrypt ? j->ciph_type : h.ciph_type;   // hca.cpp:3307
+            if (type != 0 && type != 1 && type != 56) {
+                j->status[i] = ERR_HCA_HEADER;
+            } else {
+                const uint64_t key = mix_subkey(j->keys.empty() ? 0 : j->keys[i], j->subkeys.empty() ? 0 : j->subkeys[i]);
+                HcaStreamDev s{};
+                s.frame_size = h.frame_size;
+                s.frame_count = h.frame_count;
+                s.in_off = j->in_off[i] + h.header_size;
+                s.cipher = pool.get((int)type, key, j->encrypt != 0);
+                J.streams[i] = s;
+                frames = h.frame_count;
+                j->units += frames;
+            }
+        }
+        J.frame_prefix[i + 1] = J.frame_prefix[i] + frames;
+    }
+    finish_layout_public(j, sizes);   // out_off == in_off
+    for (uint32_t i = 0; i < j->n; i++) {
+        if (j->status[i] != OK) continue;
+        const uint8_t* d = j->blob + j->in_off[i];
+        const uint64_t len = j->in_off[i + 1] - j->in_off[i];
+        const unsigned hs = (unsigned)be16(d + 6);
+        hdr.assign(d, d + hs);
+        crypt_header(hdr.data(), hs, j->encrypt ? j->ciph_type : 0);
+        add_patch_public(j, j->out_off[i], hdr.data(), hs);
+        const uint64_t body_end = (uint64_t)hs + (uint64_t)J.streams[i].frame_count * J.streams[i].frame_size;
+        if (body_end < len) add_patch_public(j, j->out_off[i] + body_end, d + body_end, (uint32_t)(len - body_end));
+    }
+    return OK;
+}
 int plan_hca_encode(cri_ctx*, cri_job*) { return ERR_UNSUPPORTED; }
 
 template <class T>
@@ -162,6 +211,7 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     if (r == OK) r = upload(c, J.units, &J.d_units);
     if (r == OK) r = upload(c, J.cipher_tables, &J.d_cipher);
     if (r == OK) r = upload(c, J.ath_tables, &J.d_ath);
+    if (r == OK) r = upload(c, J.frame_prefix, &J.d_frame_prefix);
     if (r != OK) return r;
     if (J.q_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_q, J.q_bytes));
     if (J.g_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_g, J.g_bytes));
@@ -196,6 +246,22 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         *have_dominant = J.total_groups != 0;
         return OK;
     }
+    if (j->kind == CRI_JOB_HCA_CRYPT) {
+        HcaCryptArgs a{};
+        a.in = j->d_in;
+        a.out = j->d_out;
+        a.streams = J.d_streams;
+        a.frame_prefix = J.d_frame_prefix;
+        a.tables = J.d_cipher;
+        a.n_frames = J.frame_prefix.empty() ? 0 : J.frame_prefix.back();
+        a.n_streams = j->n;
+        a.n_tables = (uint32_t)(J.cipher_tables.size() / 256);
+        CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+        launch_hca_crypt(a, c->stream, &c->launches);
+        CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        *have_dominant = a.n_frames != 0;
+        return OK;
+    }
     return ERR_UNSUPPORTED;
 }
 
@@ -204,6 +270,7 @@ void free_hca_tables(cri_job* j) {
     cudaFree(J.d_streams);
     cudaFree(J.d_units);
     cudaFree(J.d_s);
+    cudaFree(J.d_frame_prefix);
     cudaFree(J.d_cipher);
     cudaFree(J.d_ath);
     cudaFree(J.d_q);

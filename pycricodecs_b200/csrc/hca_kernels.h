@@ -32,4 +32,16 @@ struct HcaDecodeArgs {
 // `mid` (optional) is recorded between the unpack and the transform kernel.
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
 
+struct HcaCryptArgs {
+    const uint8_t* in;
+    uint8_t* out;                  // same byte offsets as `in`
+    const HcaStreamDev* streams;   // in_off = frame 0, cipher = table index
+    const uint64_t* frame_prefix;  // [n_streams + 1] exclusive prefix of frame counts
+    const uint8_t* tables;         // [n_tables][256] (already inverted when encrypting)
+    uint64_t n_frames;
+    uint32_t n_streams;
+    uint32_t n_tables;
+};
+void launch_hca_crypt(const HcaCryptArgs& a, cudaStream_t s, uint64_t* launches);
+
 }  // namespace cri

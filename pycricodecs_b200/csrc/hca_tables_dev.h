@@ -62,6 +62,8 @@ struct HcaJob {
     std::vector<uint8_t> ath_tables;       // 128 bytes each, [0] zero
     uint64_t q_bytes = 0, g_bytes = 0, i_bytes = 0, s_bytes = 0;
     uint32_t scratch_words = 0;
+    std::vector<uint64_t> frame_prefix;    // crypt: exclusive prefix of frame counts per stream
+    uint64_t* d_frame_prefix = nullptr;
     uint8_t* d_s = nullptr;
     uint32_t max_channels = 1, max_steps = 0;
 
