@@ -1,0 +1,55 @@
+"""CPU: generated constant tables are pinned by digest and equal the reference's literal arrays."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import gen_tables as G  # noqa: E402
+
+PINNED = {
+    "CRC16": "756cf0d79c4503b3", "DEC_SCALING": "80eaaab769802ab8", "DEC_RANGE": "594acbd539f7b4dd", "SCALE_CONV": "ce3889e5db50fcd8",
+    "INTENSITY_RATIO": "6f53503da52ecfb0", "IMDCT_SIN": "bf110e682f8cec86", "IMDCT_COS": "72d09011bd727778", "WINDOW": "fd4b9f1973aa0a78",
+    "INVERT": "596fe25e69de6eab", "MAX_BITS": "bccecd5122d1510e", "READ_BITS": "2e1cc91f0d50f0d4", "READ_VALS": "2cc4f662b2917a8c",
+    "ENC_RES_CURVE": "ae26f4723b8c0df3", "ENC_Q_BITS": "4dea801cd96da815", "ENC_Q_CODE": "7c9c807b445fc2a3", "ENC_INV_STEP": "cd2e4715a8858fa3",
+    "ENC_DEAD_ZONE": "46be60ec7b43774b", "ENC_RATIO_BOUNDS": "7b0403a9464abe57", "ENC_Q_SCALING": "40bb54ebaca01923",
+    "MDCT_SIN": "f6e0ce2a262954bb", "MDCT_COS": "5cd990a6f62da25a", "ENC_SHUFFLE": "143d219b1e658c0b", "ADX_STATIC_COEF": "f0a57863809129eb",
+    "ATH_BASE": "103a013614c0f314",
+}
+
+
+def test_table_digests_are_pinned():
+    got = {name: G.digest(arr) for name, _, arr in G.all_tables()}
+    assert got == PINNED
+
+
+def test_generated_headers_are_current():
+    text = G.render()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel in ("pycricodecs_b200/csrc/cri_tables.h", "oracle/cri_tables.h"):
+        assert open(os.path.join(root, rel)).read() == text, f"{rel} is stale: run tools/gen_tables.py"
+
+
+def test_crc_byte_step_identity():
+    """The kernels' table-free CRC step: table[v] == (v<<1) ^ (v<<2) ^ (parity(v) ? 0x8003 : 0)."""
+    t = G.crc16_table()
+    for v in range(256):
+        assert int(t[v]) == ((v << 1) ^ (v << 2) ^ (0x8003 if bin(v).count("1") & 1 else 0)) & 0xFFFF
+
+
+def test_tables_equal_reference_arrays(ref):
+    T = {n: np.asarray(a).ravel() for n, _, a in G.all_tables()}
+    same = [("CRC16", "crc", np.uint16), ("DEC_SCALING", "dec_scaling", np.uint32), ("DEC_RANGE", "dec_range", np.uint32),
+            ("SCALE_CONV", "scale_conv", np.uint32), ("INTENSITY_RATIO", "intensity_ratio", np.uint32), ("IMDCT_SIN", "imdct_sin", np.uint32),
+            ("IMDCT_COS", "imdct_cos", np.uint32), ("WINDOW", "window", np.uint32), ("INVERT", "invert", np.uint8), ("MAX_BITS", "max_bit", np.uint8),
+            ("READ_BITS", "read_bit", np.uint8), ("ENC_INV_STEP", "enc_inv_step", np.uint32), ("ENC_DEAD_ZONE", "enc_dead_zone", np.uint32),
+            ("ENC_RATIO_BOUNDS", "enc_ratio_bounds", np.uint32), ("ENC_Q_SCALING", "enc_q_scaling", np.uint32), ("MDCT_SIN", "mdct_sin", np.uint32),
+            ("MDCT_COS", "mdct_cos", np.uint32), ("ENC_SHUFFLE", "enc_shuffle", np.uint8), ("ADX_STATIC_COEF", "adx_static", np.int16),
+            ("ATH_BASE", "ath_base", np.uint8)]
+    for mine, theirs, dt in same:
+        assert np.array_equal(T[mine].astype(dt), ref.table(theirs, dt)), mine
+    assert np.array_equal(T["READ_VALS"].astype(np.float32), ref.table("read_val", np.float32))
+    assert np.array_equal(T["ENC_RES_CURVE"].astype(np.int32), ref.table("enc_res_curve", np.int32))
+    assert np.array_equal(T["ENC_Q_BITS"].astype(np.int32), ref.table("enc_q_bits", np.int32))
+    assert np.array_equal(T["ENC_Q_CODE"].astype(np.int8), ref.table("enc_q_value", np.int8))
