@@ -1,0 +1,597 @@
+// HCA v2.0 encode kernel for sm_100a: one WARP per frame.
+//
+// Reference: EncodeFrame (CriCodecs/hca.cpp:2965-2988, a VGAudio port): PCM ->
+// float, windowed MDCT per subframe (:2529-2553, DCT4 :2481-2527), intensity
+// stereo (:2561-2609), scalefactors (:2611-2637), scaled spectra (:2639-2654),
+// HFR group scales (:2656-2706), header length (:2708-2750), noise-level and
+// evaluation-boundary binary searches over the frame's bit budget
+// (CalculateUsedBits :2763-2790, searches :2792-2866), quantisation (:2868-2892),
+// bit packing + CRC16 (:2894-2963).
+//
+// Frames are independent: the only state that crosses a frame boundary is the
+// previous 128 raw input samples (:2552), which this kernel re-reads. So the
+// batch is a flat list of frames, one warp each. Inside the warp:
+//   * the MDCT keeps the 64 complex points of the reference's DCT4 two per lane
+//     (tools/gen_dct.py): one in-lane pass + five __shfl_xor passes, every
+//     product and sum rounded separately (no FMA: bit parity with the reference);
+//   * everything per band (scalefactors, scaled spectra, bit costs, quantised
+//     codes) is owned by lane = band mod 32, so shared-memory rows are read
+//     conflict-free and integer bit counts are warp reductions;
+//   * the few fp32 running sums whose rounding depends on order (stereo energies,
+//     HFR group averages) are accumulated by one lane per subframe / group in the
+//     reference's order; the fp64 corners (sqrt(2), 1.0/avg) are evaluated in fp64;
+//   * the bitstream is assembled with warp prefix sums of code lengths and
+//     shared-memory atomicOr, 32 bands per step in band order.
+#include <cstdint>
+
+#include "cri_tables.h"
+#include "hca_kernels.h"
+
+namespace cri {
+namespace {
+
+__constant__ uint32_t e_scaling[64] = CRI_TBL_DEC_SCALING;
+__constant__ uint32_t e_qscaling[64] = CRI_TBL_ENC_Q_SCALING;
+__constant__ uint8_t e_curve[59] = CRI_TBL_ENC_RES_CURVE;
+__constant__ uint8_t e_qbits[128] = CRI_TBL_ENC_Q_BITS;
+__constant__ uint8_t e_qcode[128] = CRI_TBL_ENC_Q_CODE;
+__constant__ uint32_t e_inv_step[16] = CRI_TBL_ENC_INV_STEP;
+__constant__ uint32_t e_dead_zone[16] = CRI_TBL_ENC_DEAD_ZONE;
+__constant__ uint32_t e_ratio_bounds[14] = CRI_TBL_ENC_RATIO_BOUNDS;
+__constant__ uint8_t e_max_bits[16] = CRI_TBL_MAX_BITS;
+
+#include "hca_dct_gen.inc"
+
+constexpr int kEncWarps = 4;
+constexpr int kSpecRow = 128;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct EncTables {              // per-CTA shared copies (per-lane indices diverge)
+    float scaling[64];
+    float qscaling[64];
+    float inv_step[16];
+    float dead_zone[16];
+    uint8_t curve[60];
+    uint8_t qbits[128];
+    uint8_t qcode[128];
+    uint8_t max_bits[16];
+};
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFull, x, o);
+        if (lane >= o) x += y;
+    }
+    *total = __shfl_sync(kFull, x, 31);
+    return x - v;
+}
+
+__device__ __forceinline__ int find_scalefactor(const float* table, float v) {   // hca.cpp:2611-2623
+    unsigned lo = 0, hi = 63;
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (table[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return (int)lo;
+}
+
+__device__ __forceinline__ int enc_resolution(const EncTables& tb, int sf, int noise) {   // hca.cpp:2752-2761
+    if (sf == 0) return 0;
+    int pos = noise - 5 * sf / 2 + 2;
+    pos = min(max(pos, 0), 58);
+    return tb.curve[pos];
+}
+
+// Per-warp shared-memory view of one frame being encoded.
+struct FrameSmem {
+    float* spec;        // [nch][8][128] spectra, later scaled spectra
+    int16_t* pcm;       // [nch][1152] previous 128 + current 1024 samples
+    uint8_t* sf;        // [nch][128]
+    uint8_t* res;       // [nch][128]
+    uint32_t* bits;     // packed frame, MSB-first 32-bit words
+    float* hfr_avg;     // [nch][8]
+    int* hfr_scale;     // [nch][8]
+    uint8_t* inten;     // [nch][8]
+    int* header_bits;   // [nch]
+    int* delta_bits;    // [nch]
+};
+
+// Append `len` (<= 32) bits per lane, lanes in order, at bit cursor *cursor of the frame buffer.
+__device__ __forceinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_t code, int len, int* cursor, int limit_bits) {
+    int total;
+    const int at = *cursor + warp_excl_scan(len, lane, &total);
+    *cursor += total;
+    if (len > 0 && at + len <= limit_bits) {     // the reference's writer silently drops what does not fit (IO.cpp:131-134)
+        const int w = at >> 5, bo = at & 31;
+        code &= len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+        if (bo + len <= 32) {
+            atomicOr(&fs.bits[w], code << (32 - bo - len));
+        } else {
+            const int spill = bo + len - 32;
+            atomicOr(&fs.bits[w], code >> spill);
+            atomicOr(&fs.bits[w + 1], code << (32 - spill));
+        }
+    }
+}
+
+// Total frame bits for (noise level, evaluation boundary): CalculateUsedBits, hca.cpp:2763-2790.
+__device__ __forceinline__ int used_bits(const EncTables& tb, const FrameSmem& fs, const HcaStreamDev& S, int lane, int noise_level,
+                                         int boundary) {
+    int len = 0;
+    const int nch = S.channels;
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+        for (int b = lane; b < coded; b += 32) {
+            const int noise = b < boundary ? noise_level - 1 : noise_level;
+            const int r = enc_resolution(tb, fs.sf[c * 128 + b], noise);
+            if (r >= 8) {
+                const int bits = tb.max_bits[r] - 1;
+                const float dz = tb.dead_zone[r];
+#pragma unroll
+                for (int j = 0; j < 8; j++) len += bits + (fabsf(sp[j * kSpecRow + b]) >= dz ? 1 : 0);
+            } else {
+                const float inv = tb.inv_step[r];
+                const float up = __fadd_rn(inv, 1.0f);
+                const int down = r - 7;                                  // (int)(inv + 0.5 - 8)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int q = __float2int_rz(__fadd_rn(__fmul_rn(sp[j * kSpecRow + b], inv), up)) - down;
+                    len += tb.qbits[r * 16 + q];
+                }
+            }
+        }
+    }
+    len = warp_sum(len);
+    int hdr = 48;
+    for (int c = 0; c < nch; c++) hdr += fs.header_bits[c];
+    return len + hdr;
+}
+
+// CalculateOptimalDeltaLength + CalculateFrameHeaderLength, hca.cpp:2708-2750 (warp-collective).
+__device__ __forceinline__ void header_lengths(const FrameSmem& fs, const HcaStreamDev& S, int lane) {
+    const int nch = S.channels;
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        const uint8_t* sf = fs.sf + c * 128;
+        int any = 0, cost[5] = {0, 0, 0, 0, 0};
+        for (int b = lane; b < coded; b += 32) {
+            any |= sf[b] != 0;
+            if (b >= 1) {
+                const int delta = abs((int)sf[b] - (int)sf[b - 1]);
+#pragma unroll
+                for (int db = 1; db < 6; db++) cost[db - 1] += delta > ((1 << (db - 1)) - 1) ? db + 6 : db;
+            }
+        }
+        any = __any_sync(kFull, any);
+        int best_bits = 6, best_len = 3 + 6 * coded;
+#pragma unroll
+        for (int db = 1; db < 6; db++) {
+            const int len = 3 + 6 + warp_sum(cost[db - 1]);
+            if (len < best_len) { best_len = len; best_bits = db; }
+        }
+        if (!any) { best_len = 3; best_bits = 0; }
+        if (S.type[c] == 2) best_len += 32;
+        else if (S.hfr_groups > 0) best_len += 6 * S.hfr_groups;
+        if (lane == 0) { fs.header_bits[c] = best_len; fs.delta_bits[c] = best_bits; }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kEncWarps * 32)
+hca_encode_kernel(HcaEncodeArgs a) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ EncTables tb;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        tb.scaling[i] = __uint_as_float(e_scaling[i]);
+        tb.qscaling[i] = __uint_as_float(e_qscaling[i]);
+    }
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        tb.inv_step[i] = __uint_as_float(e_inv_step[i]);
+        tb.dead_zone[i] = __uint_as_float(e_dead_zone[i]);
+        tb.max_bits[i] = e_max_bits[i];
+    }
+    for (int i = threadIdx.x; i < 59; i += blockDim.x) tb.curve[i] = e_curve[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) { tb.qbits[i] = e_qbits[i]; tb.qcode[i] = e_qcode[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t f = (uint64_t)blockIdx.x * kEncWarps + warp;
+    if (f >= a.n_frames) return;
+    uint32_t lo = 0, hi = a.n_streams;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.frame_prefix[mid] <= f) lo = mid; else hi = mid;
+    }
+    const uint32_t stream = lo;
+    const HcaStreamDev& S = a.streams[stream];
+    const uint32_t frame = (uint32_t)(f - a.frame_prefix[stream]);
+    const int nch = S.channels;
+    const int MC = (int)a.max_channels;
+
+    // carve the warp's shared memory
+    FrameSmem fs;
+    {
+        uint8_t* p = s_dyn + (size_t)warp * a.smem_per_warp;
+        fs.spec = reinterpret_cast<float*>(p); p += (size_t)MC * 8 * kSpecRow * 4;
+        fs.bits = reinterpret_cast<uint32_t*>(p); p += (size_t)a.frame_words * 4;
+        fs.hfr_avg = reinterpret_cast<float*>(p); p += (size_t)MC * 8 * 4;
+        fs.hfr_scale = reinterpret_cast<int*>(p); p += (size_t)MC * 8 * 4;
+        fs.header_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
+        fs.delta_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
+        fs.pcm = reinterpret_cast<int16_t*>(p); p += (size_t)MC * 1152 * 2;
+        fs.sf = p; p += (size_t)MC * 128;
+        fs.res = p; p += (size_t)MC * 128;
+        fs.inten = p;
+    }
+    const int frame_size = (int)S.frame_size;
+    for (uint32_t i = lane; i < a.frame_words; i += 32) fs.bits[i] = 0;
+
+    // ---- PCM: previous 128 + this frame's 1024 samples per channel; silence outside the stream (hca.cpp:3035-3053)
+    {
+        const long long n0 = (long long)frame * 1024 - 128;
+        const uint8_t* src = a.in + S.in_off;
+        for (int e = lane; e < 1152 * nch; e += 32) {
+            const int i = e / nch, c = e - i * nch;
+            const long long n = n0 + i;
+            int16_t v = 0;
+            if (n >= 0 && n < (long long)S.out_samples) {
+                const uint8_t* q = src + ((size_t)n * nch + c) * 2;
+                v = (int16_t)(q[0] | (q[1] << 8));
+            }
+            fs.pcm[c * 1152 + i] = v;
+        }
+    }
+    __syncwarp();
+
+    // ---- MDCT: 8 subframes x channels (hca.cpp:2470-2559)
+    {
+        const float w0 = __uint_as_float(kMdctWin[4 * lane]), w1 = __uint_as_float(kMdctWin[4 * lane + 1]);
+        const float w2 = __uint_as_float(kMdctWin[4 * lane + 2]), w3 = __uint_as_float(kMdctWin[4 * lane + 3]);
+        const float pc0 = __uint_as_float(kMdctPreCos[lane]), ps0 = __uint_as_float(kMdctPreSin[lane]);
+        const float pc1 = __uint_as_float(kMdctPreCos[lane + 32]), ps1 = __uint_as_float(kMdctPreSin[lane + 32]);
+        float tc[6], ts[6];
+#pragma unroll
+        for (int s = 0; s < 6; s++) { tc[s] = __uint_as_float(kMdctCos[s * 32 + lane]); ts[s] = __uint_as_float(kMdctSin[s * 32 + lane]); }
+        const int d0 = kMdctDest[4 * lane], d1 = kMdctDest[4 * lane + 1], d2 = kMdctDest[4 * lane + 2], d3 = kMdctDest[4 * lane + 3];
+        const float k = 1.0f / 32768.0f;
+        for (int c = 0; c < nch; c++) {
+            for (int sub = 0; sub < 8; sub++) {
+                const int16_t* cur = fs.pcm + c * 1152 + 128 + sub * 128;
+                const int16_t* prv = cur - 128;
+                const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
+                const float c0 = __fmul_rn((float)cur[i0], k), c1 = __fmul_rn((float)cur[i1], k);
+                const float c2 = __fmul_rn((float)cur[i2], k), c3 = __fmul_rn((float)cur[i3], k);
+                const float p0 = __fmul_rn((float)prv[i0], k), p1 = __fmul_rn((float)prv[i1], k);
+                const float p2 = __fmul_rn((float)prv[i2], k), p3 = __fmul_rn((float)prv[i3], k);
+                // windowing (hca.cpp:2537-2546): in[i] = W[63-i]*(-cur[64+i]) - (-W[64+i])*cur[63-i],
+                //                               in[64+i] = W[i]*prv[i] - (-W[127-i])*prv[127-i]
+                const float in_a = __fsub_rn(__fmul_rn(w1, -c2), __fmul_rn(-w2, c1));   // in[2l]
+                const float in_b = __fsub_rn(__fmul_rn(w1, p1), __fmul_rn(-w2, p2));    // in[127-2l]
+                const float in_c = __fsub_rn(__fmul_rn(w0, p0), __fmul_rn(-w3, p3));    // in[64+2l]
+                const float in_d = __fsub_rn(__fmul_rn(w0, -c3), __fmul_rn(-w3, c0));   // in[63-2l]
+                // pre-rotation (hca.cpp:2490-2498): z[k] from in[2k], in[127-2k]
+                float re0 = __fadd_rn(__fmul_rn(in_a, pc0), __fmul_rn(in_b, ps0));
+                float im0 = __fsub_rn(__fmul_rn(in_a, ps0), __fmul_rn(in_b, pc0));
+                float re1 = __fadd_rn(__fmul_rn(in_c, pc1), __fmul_rn(in_d, ps1));
+                float im1 = __fsub_rn(__fmul_rn(in_c, ps1), __fmul_rn(in_d, pc1));
+                // pass 0: z[l] with z[l+32], in lane
+                {
+                    const float ar = __fsub_rn(re0, re1), ai = __fsub_rn(im0, im1);
+                    re0 = __fadd_rn(re0, re1); im0 = __fadd_rn(im0, im1);
+                    re1 = __fadd_rn(__fmul_rn(ar, tc[0]), __fmul_rn(ai, ts[0]));
+                    im1 = __fsub_rn(__fmul_rn(ar, ts[0]), __fmul_rn(ai, tc[0]));
+                }
+                // passes 1..5: partner lane = lane ^ (32 >> s); the lane with that bit set holds the "back" element
+#pragma unroll
+                for (int s = 1; s < 6; s++) {
+                    const int d = 32 >> s;
+                    const bool back = lane & d;
+                    const float o_re0 = __shfl_xor_sync(kFull, re0, d), o_im0 = __shfl_xor_sync(kFull, im0, d);
+                    const float o_re1 = __shfl_xor_sync(kFull, re1, d), o_im1 = __shfl_xor_sync(kFull, im1, d);
+                    // front: mine + other; back: other - mine
+                    const float a_re0 = back ? __fsub_rn(o_re0, re0) : __fadd_rn(re0, o_re0);
+                    const float a_im0 = back ? __fsub_rn(o_im0, im0) : __fadd_rn(im0, o_im0);
+                    const float a_re1 = back ? __fsub_rn(o_re1, re1) : __fadd_rn(re1, o_re1);
+                    const float a_im1 = back ? __fsub_rn(o_im1, im1) : __fadd_rn(im1, o_im1);
+                    const float r_re0 = __fadd_rn(__fmul_rn(a_re0, tc[s]), __fmul_rn(a_im0, ts[s]));
+                    const float r_im0 = __fsub_rn(__fmul_rn(a_re0, ts[s]), __fmul_rn(a_im0, tc[s]));
+                    const float r_re1 = __fadd_rn(__fmul_rn(a_re1, tc[s]), __fmul_rn(a_im1, ts[s]));
+                    const float r_im1 = __fsub_rn(__fmul_rn(a_re1, ts[s]), __fmul_rn(a_im1, tc[s]));
+                    re0 = back ? r_re0 : a_re0; im0 = back ? r_im0 : a_im0;
+                    re1 = back ? r_re1 : a_re1; im1 = back ? r_im1 : a_im1;
+                }
+                float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
+                sp[d0] = __fmul_rn(re0, 0.125f); sp[d1] = __fmul_rn(im0, 0.125f);
+                sp[d2] = __fmul_rn(re1, 0.125f); sp[d3] = __fmul_rn(im1, 0.125f);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- intensity stereo (hca.cpp:2561-2609): one lane per subframe accumulates the energies in band order
+    if (S.stereo_bands > 0) {
+        for (int c = 0; c + 1 < nch; c++) {
+            if (S.type[c] != 1) continue;
+            float ratio = 1.0f;
+            if (lane < 8) {
+                const float* l = fs.spec + ((size_t)c * 8 + lane) * kSpecRow;
+                const float* r = fs.spec + ((size_t)(c + 1) * 8 + lane) * kSpecRow;
+                float el = 0.f, er = 0.f, et = 0.f;
+                for (int b = S.base_bands; b < S.total_bands; b++) {
+                    el = __fadd_rn(el, fabsf(l[b]));
+                    er = __fadd_rn(er, fabsf(r[b]));
+                    et = __fadd_rn(et, fabsf(__fadd_rn(l[b], r[b])));
+                }
+                et = __fmul_rn(et, 2.0f);
+                const float elr = __fadd_rn(er, el);
+                const float stored = __fdiv_rn(__fmul_rn(2.0f, el), elr);
+                ratio = __fdiv_rn(elr, et);
+                const double half_sqrt2 = 1.4142135623730951 / 2;
+                if ((double)ratio < 0.5) ratio = 0.5f;
+                else if ((double)ratio > half_sqrt2) ratio = (float)half_sqrt2;
+                int q = 1;
+                if (er > 0.f || el > 0.f) {
+                    while (q < 13 && __uint_as_float(e_ratio_bounds[q]) >= stored) q++;
+                } else {
+                    q = 0;
+                    ratio = 1.0f;
+                }
+                fs.inten[(c + 1) * 8 + lane] = (uint8_t)q;
+            }
+            for (int sub = 0; sub < 8; sub++) {
+                const float rt = __shfl_sync(kFull, ratio, sub);
+                float* l = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
+                float* r = fs.spec + ((size_t)(c + 1) * 8 + sub) * kSpecRow;
+                for (int b = S.base_bands + lane; b < S.total_bands; b += 32) {
+                    l[b] = __fmul_rn(__fadd_rn(l[b], r[b]), rt);
+                    r[b] = 0.f;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- scalefactors (hca.cpp:2625-2637)
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+        for (int b = lane; b < 128; b += 32) {
+            int sfv = 0;
+            if (b < coded) {
+                float mx = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const float v = fabsf(sp[j * kSpecRow + b]); mx = mx < v ? v : mx; }
+                sfv = find_scalefactor(tb.scaling, mx);
+            }
+            fs.sf[c * 128 + b] = (uint8_t)sfv;
+        }
+    }
+    __syncwarp();
+
+    // ---- HFR group averages on the raw spectra (hca.cpp:2656-2674), one lane per group, reference order
+    const int hfr_start = S.stereo_bands + S.base_bands;
+    const int hfr_band_count = S.total_bands - S.base_bands - S.stereo_bands;
+    if (S.hfr_groups > 0) {
+        for (int c = 0; c < nch; c++) {
+            if (S.type[c] == 2) continue;
+            if (lane < S.hfr_groups) {
+                const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+                float sum = 0.f;
+                int count = 0;
+                int band = hfr_start + lane * S.bands_per_hfr;
+                for (int i = 0; i < S.bands_per_hfr && band < 128; band++, i++) {
+                    for (int j = 0; j < 8; j++) sum = __fadd_rn(sum, fabsf(sp[j * kSpecRow + band]));
+                    count += 8;
+                }
+                fs.hfr_avg[c * 8 + lane] = __fdiv_rn(sum, (float)count);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- scaled spectra, in place (hca.cpp:2639-2654)
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+        for (int b = lane; b < coded; b += 32) {
+            const int sfv = fs.sf[c * 128 + b];
+            const float ks = tb.qscaling[sfv];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float v = __fmul_rn(sp[j * kSpecRow + b], ks);
+                v = v > 0.9999999f ? 0.9999999f : v < -0.9999999f ? -0.9999999f : v;
+                sp[j * kSpecRow + b] = sfv == 0 ? 0.f : v;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- HFR scales (hca.cpp:2676-2706)
+    if (S.hfr_groups > 0) {
+        const int lim = min(hfr_band_count, (int)S.total_bands - hfr_band_count);
+        for (int c = 0; c < nch; c++) {
+            if (S.type[c] == 2) continue;
+            if (lane < S.hfr_groups) {
+                const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+                float sum = 0.f;
+                int count = 0;
+                int band = lane * S.bands_per_hfr;            // each earlier group consumed bands_per_hfr mirrored bands ...
+                if (band > lim) band = lim;                   // ... unless it ran into the limit
+                for (int i = 0; i < S.bands_per_hfr && band < lim; band++, i++) {
+                    for (int j = 0; j < 8; j++) sum = __fadd_rn(sum, fabsf(sp[j * kSpecRow + (hfr_start - band - 1)]));
+                    count += 8;
+                }
+                const float avg = __fdiv_rn(sum, (float)count);
+                float g = fs.hfr_avg[c * 8 + lane];
+                if (avg > 0.0f) {
+                    double m = 1.0 / (double)avg;
+                    const double s2 = 1.4142135623730951;
+                    if (s2 < m) m = s2;
+                    g = (float)((double)g * m);
+                }
+                fs.hfr_scale[c * 8 + lane] = find_scalefactor(tb.scaling, g);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- bit allocation (hca.cpp:2809-2866)
+    header_lengths(fs, S, lane);
+    const int avail = frame_size * 8;
+    int noise_level, boundary = 0;
+    bool failed = false;
+    {
+        int highest = (int)S.base_bands + (int)S.stereo_bands - 1;
+        for (;;) {
+            int lo_l = 0, hi_l = 255, mid_value = 0;          // BinarySearchLevel
+            while (lo_l != hi_l) {
+                const int mid = (lo_l + hi_l) / 2;
+                mid_value = used_bits(tb, fs, S, lane, mid, 0);
+                if (mid_value > avail) lo_l = mid + 1; else hi_l = mid;
+            }
+            noise_level = (lo_l == 255 && mid_value > avail) ? -1 : lo_l;
+            if (noise_level >= 0) break;
+            highest -= 2;
+            if (highest < 0) { failed = true; break; }
+            if (lane == 0)
+                for (int c = 0; c < nch; c++) { fs.sf[c * 128 + highest + 1] = 0; fs.sf[c * 128 + highest + 2] = 0; }
+            __syncwarp();
+            header_lengths(fs, S, lane);
+        }
+    }
+    if (!failed && noise_level != 0) {                        // BinarySearchBoundary
+        int lo_b = 0, hi_b = 127;
+        while (abs(hi_b - lo_b) > 1) {
+            const int mid = (lo_b + hi_b) / 2;
+            const int v = used_bits(tb, fs, S, lane, noise_level, mid);
+            if (avail < v) hi_b = mid - 1; else lo_b = mid;
+        }
+        if (lo_b == hi_b) boundary = lo_b < 127 ? lo_b : -1;
+        else boundary = used_bits(tb, fs, S, lane, noise_level, hi_b) > avail ? lo_b : hi_b;
+        if (boundary < 0) failed = true;
+    }
+    if (failed) {                                             // EncodeFrame gives up: HcaErrorCode, hca.cpp:2976-2984
+        if (lane == 0) a.status[stream] = ERR_HCA_ENCODE;
+        return;
+    }
+
+    // ---- final resolutions (hca.cpp:2868-2876)
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        for (int b = lane; b < 128; b += 32)
+            fs.res[c * 128 + b] = b < coded ? (uint8_t)enc_resolution(tb, fs.sf[c * 128 + b], b < boundary ? noise_level - 1 : noise_level) : 0;
+    }
+    __syncwarp();
+
+    // ---- pack (hca.cpp:2894-2963): sync word, noise level, boundary, per-channel headers, spectra, CRC
+    const int limit_bits = (frame_size - 2) * 8 + 16;         // writer buffer = frame_size - 2 bytes after the sync word
+    int cursor = 0;
+    emit_bits(fs, lane, lane == 0 ? 0xFFFFu : lane == 1 ? (uint32_t)noise_level : (uint32_t)boundary,
+              lane == 0 ? 16 : lane == 1 ? 9 : lane == 2 ? 7 : 0, &cursor, limit_bits);
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        const int db = fs.delta_bits[c];
+        const uint8_t* sf = fs.sf + c * 128;
+        emit_bits(fs, lane, (uint32_t)db, lane == 0 ? 3 : 0, &cursor, limit_bits);
+        if (db == 6) {
+            for (int b0 = 0; b0 < coded; b0 += 32) {
+                const int b = b0 + lane;
+                emit_bits(fs, lane, b < coded ? sf[b] : 0u, b < coded ? 6 : 0, &cursor, limit_bits);
+            }
+        } else if (db != 0) {
+            const int maxd = (1 << (db - 1)) - 1, esc = (1 << db) - 1;
+            for (int b0 = 0; b0 < coded; b0 += 32) {
+                const int b = b0 + lane;
+                uint32_t code = 0;
+                int len = 0;
+                if (b == 0) { code = sf[0]; len = 6; }
+                else if (b < coded) {
+                    const int delta = (int)sf[b] - (int)sf[b - 1];
+                    if (abs(delta) > maxd) { code = ((uint32_t)esc << 6) | sf[b]; len = db + 6; }
+                    else { code = (uint32_t)(maxd + delta); len = db; }
+                }
+                emit_bits(fs, lane, code, len, &cursor, limit_bits);
+            }
+        }
+        if (S.type[c] == 2) emit_bits(fs, lane, lane < 8 ? fs.inten[c * 8 + lane] : 0u, lane < 8 ? 4 : 0, &cursor, limit_bits);
+        else if (S.hfr_groups > 0)
+            emit_bits(fs, lane, lane < S.hfr_groups ? (uint32_t)fs.hfr_scale[c * 8 + lane] : 0u, lane < S.hfr_groups ? 6 : 0, &cursor, limit_bits);
+    }
+    for (int sub = 0; sub < 8; sub++) {
+        for (int c = 0; c < nch; c++) {
+            const int coded = S.coded[c];
+            const float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
+            for (int b0 = 0; b0 < coded; b0 += 32) {
+                const int b = b0 + lane;
+                uint32_t code = 0;
+                int len = 0;
+                if (b < coded) {
+                    const int r = fs.res[c * 128 + b];
+                    if (r != 0) {                              // QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936
+                        const float inv = tb.inv_step[r];
+                        const int down = r < 8 ? r + 1 : (1 << (tb.max_bits[r] - 1));   // (int)(inv + 0.5)
+                        const int q = __float2int_rz(__fadd_rn(__fmul_rn(sp[b], inv), __fadd_rn(inv, 1.0f))) - down;
+                        if (r < 8) {
+                            len = tb.qbits[r * 16 + q + 8];
+                            code = tb.qcode[r * 16 + q + 8];
+                        } else {
+                            const int mb = tb.max_bits[r] - 1;
+                            const uint32_t mag = (uint32_t)abs(q) & ((1u << mb) - 1u);
+                            if (q != 0) { code = (mag << 1) | (q > 0 ? 0u : 1u); len = mb + 1; }
+                            else { code = mag; len = mb; }
+                        }
+                    }
+                }
+                emit_bits(fs, lane, code, len, &cursor, limit_bits);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- CRC16 over the first frame_size - 2 bytes (lane 0, serial), then the frame goes out byte by byte
+    uint8_t* dst = a.out + S.out_off + (uint64_t)frame * frame_size;
+    uint32_t crc = 0;
+    if (lane == 0) {
+        for (int i = 0; i < frame_size - 2; i++) {
+            const uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
+            const uint32_t v = ((crc >> 8) ^ byte) & 0xFF;
+            crc = ((crc << 8) ^ (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u)) & 0xFFFF;
+        }
+    }
+    crc = __shfl_sync(kFull, crc, 0);
+    for (int i = lane; i < frame_size; i += 32) {
+        uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
+        if (i == frame_size - 2) byte = crc >> 8;
+        if (i == frame_size - 1) byte = crc & 0xFF;
+        dst[i] = (uint8_t)byte;
+    }
+}
+
+}  // namespace
+
+size_t hca_encode_smem_per_warp(uint32_t max_channels, uint32_t frame_words) {
+    size_t n = (size_t)max_channels * 8 * kSpecRow * 4 + (size_t)frame_words * 4 + (size_t)max_channels * 8 * 4 * 2 +
+               (size_t)max_channels * 4 * 2 + (size_t)max_channels * 1152 * 2 + (size_t)max_channels * 128 * 2 + (size_t)max_channels * 8;
+    return (n + 15) / 16 * 16;
+}
+
+int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
+    if (!a.n_frames) return 0;
+    a.smem_per_warp = (uint32_t)hca_encode_smem_per_warp(a.max_channels, a.frame_words);
+    const size_t smem = (size_t)a.smem_per_warp * kEncWarps;
+    if (smem > 200 * 1024) return -1;
+    cudaFuncSetAttribute(hca_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    hca_encode_kernel<<<(unsigned)((a.n_frames + kEncWarps - 1) / kEncWarps), kEncWarps * 32, smem, s>>>(a);
+    ++*launches;
+    return 0;
+}
+
+}  // namespace cri

@@ -194,7 +194,63 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
     }
     return OK;
 }
-int plan_hca_encode(cri_ctx*, cri_job*) { return ERR_UNSUPPORTED; }
+// HcaEncode (hca.cpp:3459-3489): plan per stream on the host (hca.cpp:2206-2462), frames on the device.
+int plan_hca_encode(cri_ctx* c, cri_job* j) {
+    (void)c;
+    HcaJob& J = j->hca;
+    std::vector<uint64_t> sizes(j->n, 0);
+    std::vector<WavInfo> wavs(j->n);
+    std::vector<HcaEncPlan> plans(j->n);
+    for (uint32_t i = 0; i < j->n; i++) {
+        const uint8_t* d = j->blob + j->in_off[i];
+        const uint64_t len = j->in_off[i + 1] - j->in_off[i];
+        const int r = parse_wav(d, len, &wavs[i]);
+        if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
+        // loop points (smpl chunk -> loop chunk, pre/post audio, hca.cpp:2292-2321, 3000-3053) are a later row
+        if (wavs[i].looping && !j->adx.force_not_looping) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        if (plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels,
+                            j->quality, &plans[i]) < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; continue; }
+        sizes[i] = (uint64_t)plans[i].header_size + (uint64_t)plans[i].frame_count * plans[i].frame_size;
+    }
+    finish_layout_public(j, sizes);
+    J.streams.assign(j->n, HcaStreamDev{});
+    J.frame_prefix.assign(j->n + 1, 0);
+    J.max_channels = 1;
+    uint32_t max_frame = 8;
+    std::vector<uint8_t> hdr;
+    for (uint32_t i = 0; i < j->n; i++) {
+        uint64_t frames = 0;
+        if (j->status[i] == OK) {
+            const HcaEncPlan& p = plans[i];
+            HcaStreamDev s{};
+            s.in_off = j->in_off[i] + wavs[i].data_offset;
+            s.out_off = j->out_off[i] + p.header_size;
+            s.frame_size = p.frame_size;
+            s.frame_count = p.frame_count;
+            s.out_samples = p.samples;
+            s.channels = (uint8_t)p.channels;
+            s.total_bands = (uint8_t)p.total_bands;
+            s.base_bands = (uint8_t)p.base_bands;
+            s.stereo_bands = (uint8_t)p.stereo_bands;
+            s.bands_per_hfr = (uint8_t)p.bands_per_hfr;
+            s.hfr_groups = (uint8_t)p.hfr_groups;
+            s.min_res = 1;
+            s.max_res = 15;
+            for (unsigned ch = 0; ch < p.channels; ch++) { s.type[ch] = p.type[ch]; s.coded[ch] = (uint8_t)p.coded[ch]; }
+            J.streams[i] = s;
+            J.max_channels = std::max<uint32_t>(J.max_channels, p.channels);
+            max_frame = std::max(max_frame, p.frame_size);
+            hdr.assign(p.header_size, 0);
+            write_hca_header(hdr.data(), p);
+            add_patch_public(j, j->out_off[i], hdr.data(), p.header_size);
+            frames = p.frame_count;
+            j->units += frames;
+        }
+        J.frame_prefix[i + 1] = J.frame_prefix[i] + frames;
+    }
+    J.enc_frame_words = (max_frame + 3) / 4 + 2;
+    return OK;
+}
 
 template <class T>
 static int upload(cri_ctx* c, const std::vector<T>& v, T** d) {
@@ -258,6 +314,26 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_tables = (uint32_t)(J.cipher_tables.size() / 256);
         CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
         launch_hca_crypt(a, c->stream, &c->launches);
+        CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        *have_dominant = a.n_frames != 0;
+        return OK;
+    }
+    if (j->kind == CRI_JOB_HCA_ENCODE) {
+        HcaEncodeArgs a{};
+        a.in = j->d_in;
+        a.out = j->d_out;
+        a.streams = J.d_streams;
+        a.frame_prefix = J.d_frame_prefix;
+        a.status = j->d_status;
+        a.n_frames = J.frame_prefix.empty() ? 0 : J.frame_prefix.back();
+        a.n_streams = j->n;
+        a.max_channels = J.max_channels;
+        a.frame_words = J.enc_frame_words;
+        CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+        if (launch_hca_encode(a, c->stream, &c->launches) != 0) {
+            c->error = "HCA encode: frame size / channel count exceeds the kernel's shared-memory budget";
+            return ERR_CUDA;
+        }
         CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         *have_dominant = a.n_frames != 0;
         return OK;

@@ -44,4 +44,18 @@ struct HcaCryptArgs {
 };
 void launch_hca_crypt(const HcaCryptArgs& a, cudaStream_t s, uint64_t* launches);
 
+struct HcaEncodeArgs {
+    const uint8_t* in;             // WAV images
+    uint8_t* out;                  // HCA images (headers are host-built patches)
+    const HcaStreamDev* streams;   // in_off = first PCM sample, out_off = frame 0, out_samples = samples per channel
+    const uint64_t* frame_prefix;  // [n_streams + 1]
+    int32_t* status;
+    uint64_t n_frames;
+    uint32_t n_streams;
+    uint32_t max_channels;
+    uint32_t frame_words;          // 32-bit words of the shared frame buffer (>= frame_size / 4 + 2)
+    uint32_t smem_per_warp;        // filled in by the launcher
+};
+int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches);   // -1: frame too large for shared memory
+
 }  // namespace cri

@@ -215,9 +215,44 @@ def gen_warp_tables() -> list[str]:
     return out
 
 
+def gen_mdct_warp_tables() -> list[str]:
+    """Tables for the warp-cooperative forward MDCT (hca_encode_kernel). The reference's DCT4 (hca.cpp:2481-2527) is a
+    pre-rotation into 64 complex values z[k] = (t[2k], t[2k+1]) followed by a 64-point radix-2 decimation-in-frequency
+    network (pair distance 32,16,..,1) and a bit-reversal gather. Lane l keeps z[l] and z[l+32]: the first pass is
+    in-lane, the other five are one __shfl_xor each; both of a lane's values share the pass's rotation factor."""
+    sin, cos = T.mdct_trig()
+    sin = sin.reshape(8, 128)
+    cos = cos.reshape(8, 128)
+    win = T.window()
+    shuffle = [int(v) for v in T.enc_shuffle()]
+    inv = [0] * 128
+    for i, t in enumerate(shuffle):
+        inv[t] = i
+    out = ["// per-lane tables of the warp-cooperative forward MDCT (lane l holds z[l] and z[l+32])"]
+
+    def emit(name, ctype, vals, fmt):
+        out.append(f"__device__ const {ctype} {name}[{len(vals)}] = {{")
+        for i in range(0, len(vals), 8):
+            out.append("    " + ", ".join(fmt(v) for v in vals[i:i + 8]) + ",")
+        out.append("};")
+    hx = lambda v: f"0x{int(v):08X}u"
+    emit("kMdctPreCos", "uint32_t", [cos[7, k] for k in range(64)], hx)
+    emit("kMdctPreSin", "uint32_t", [sin[7, k] for k in range(64)], hx)
+    # pass s (0..5): pair distance d = 32 >> s, factor row 5 - s, index k mod d (same for k = l and k = l + 32)
+    emit("kMdctCos", "uint32_t", [cos[5 - s, l % (32 >> s)] for s in range(6) for l in range(32)], hx)
+    emit("kMdctSin", "uint32_t", [sin[5 - s, l % (32 >> s)] for s in range(6) for l in range(32)], hx)
+    # window factors a lane needs: W[2l], W[63-2l], W[64+2l], W[127-2l]
+    emit("kMdctWin", "uint32_t", [win[i] for l in range(32) for i in (2 * l, 63 - 2 * l, 64 + 2 * l, 127 - 2 * l)], hx)
+    # where the lane's four results t[2l], t[2l+1], t[2l+64], t[2l+65] go in the spectrum
+    emit("kMdctDest", "uint8_t", [inv[i] for l in range(32) for i in (2 * l, 2 * l + 1, 2 * l + 64, 2 * l + 65)], str)
+    return out
+
+
 def main():
     lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""]
     lines += gen_warp_tables()
+    lines.append("")
+    lines += gen_mdct_warp_tables()
     path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_gen.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
