@@ -203,7 +203,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t f = (uint64_t)blockIdx.x * kEncWarps + warp;
+    const uint64_t f = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (f >= a.n_frames) return;
     uint32_t lo = 0, hi = a.n_streams;
     while (hi - lo > 1) {
@@ -586,10 +586,13 @@ size_t hca_encode_smem_per_warp(uint32_t max_channels, uint32_t frame_words) {
 int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
     if (!a.n_frames) return 0;
     a.smem_per_warp = (uint32_t)hca_encode_smem_per_warp(a.max_channels, a.frame_words);
-    const size_t smem = (size_t)a.smem_per_warp * kEncWarps;
+    // wide streams (up to 8 channels x 6.6 KB) get fewer warps per CTA so the CTA still fits in shared memory
+    int warps = kEncWarps;
+    while (warps > 1 && (size_t)a.smem_per_warp * warps > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)a.smem_per_warp * warps;
     if (smem > 200 * 1024) return -1;
     cudaFuncSetAttribute(hca_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    hca_encode_kernel<<<(unsigned)((a.n_frames + kEncWarps - 1) / kEncWarps), kEncWarps * 32, smem, s>>>(a);
+    hca_encode_kernel<<<(unsigned)((a.n_frames + warps - 1) / warps), warps * 32, smem, s>>>(a);
     ++*launches;
     return 0;
 }
