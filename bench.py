@@ -1,17 +1,18 @@
 #!/usr/bin/env python3
-"""Benchmark of the ADX / HCA hot path (contract: see the task statement / DESIGN.md §Measurement).
+"""Benchmark of the ADX / HCA hot path (contract: task statement; layout of the numbers: DESIGN.md §Measurement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A "step" is one pass of the hot path over one batch of synthetic 48 kHz stereo
-streams (2 s each). Default workload = BASELINE.json configs[1]: 8192 x stereo
-HCA v2.0 (keyless, quality High) decode on one GPU. `value` is frames/s with the
-batch resident in HBM (kernels only, CUDA events on the engine's stream);
-`e2e` is the same metric through the C-ABI batch call with pinned HOST buffers
-(header parsing, planning, H2D, kernels, D2H all inside the timed region).
+A "step" is one pass of the hot path over one batch of synthetic 48 kHz stereo streams (2 s each, all
+distinct). Default workload = BASELINE.json configs[1]: 8192 x stereo HCA v2.0 (keyless, quality High)
+decode on one GPU. `value` is frames/s with the batch resident in HBM (kernels only, CUDA events on the
+engine's stream); `e2e` is the same metric through the C-ABI batch call with pinned HOST buffers (header
+parsing, planning, H2D, kernels, D2H all inside the timed region).
 
-Weak scaling: with --gpus N every rank decodes its own 8192 streams (streams are
-independent; there is no data-path collective), time = max over ranks.
+Inputs are synthesised by the product itself: PCM from pycricodecs_b200.synth (torch on the GPU), HCA / ADX
+streams by this repo's own GPU encoders (bit-exact with the reference, tests/test_hca_encode_gpu.py), untimed.
+Weak scaling: with --gpus N every rank works on its own 8192 streams (streams are independent; there is no
+data-path collective), time = max over ranks.
 """
 from __future__ import annotations
 
@@ -31,12 +32,20 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 KEY = 0xCF222F1FE0748978
+METRIC = "audio frames/sec (48kHz stereo) HCA-decode + ADX-encode at 1/2/4/8 B200 vs CPU ref"
 WORKLOADS = {
-    # name: (kind, unit, description, algorithmic bytes per unit of the whole path)
     "hca_decode": "8192 x 48kHz stereo HCA v2.0 decode (keyless, High), 2 s streams",
     "hca_decrypt_decode": "encrypted HCA (type 56, key 0xCF222F1FE0748978) decrypt+decode, 8192 streams per GPU",
+    "hca_decrypt": "encrypted HCA (type 56, key 0xCF222F1FE0748978) decrypt only (HcaCrypt), 8192 streams per GPU",
+    "hca_encode": "48kHz stereo WAV -> HCA v2.0 encode (High), 2 s streams",
     "adx_encode": "8192 x 48kHz stereo ADX encode bitdepth=4 blocksize=18",
     "adx_decode": "8192 x 48kHz stereo ADX decode bitdepth=4 blocksize=18",
+}
+# dominant kernel of each workload and its ALGORITHMIC bytes per unit
+DOMINANT = {
+    "hca_decode": ("hca_imdct_kernel", 9216), "hca_decrypt_decode": ("hca_imdct_kernel", 9216),
+    "hca_decrypt": ("hca_crypt_kernel", None), "hca_encode": ("hca_encode_kernel", None),
+    "adx_encode": ("adx_encode_fast_kernel", 82), "adx_decode": ("adx_decode_fast_kernel", 82),
 }
 
 
@@ -44,49 +53,56 @@ def rank_info():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def is_hca(w):
+    return w.startswith("hca")
+
+
 # ----------------------------------------------------------------- inputs
-def _encode_unique(args):
-    """Worker: synthesise stream `sid` and encode it with the CPU checker (input synthesis only)."""
-    sid, what = args
-    import oracle
+def make_wav_blob(streams, rank, device):
+    """(pinned uint8 tensor, offsets): `streams` distinct synthetic stereo WAV images for this rank."""
+    import torch
     from pycricodecs_b200 import synth
-    port = oracle.port()
-    w = synth.wav(sid, 2)
-    if what == "wav":
-        return w
-    if what == "adx":
-        return port.adx_encode(w)[1]
-    h = port.hca_encode(w, 1)[1]
-    if what == "hca_enc":
-        h = port.hca_crypt(h, 1, 56, KEY)[1]
-    return h
+    n, ch = synth.DEFAULT_SAMPLES, 2
+    hdr = np.frombuffer(synth.wav_header(ch, n), np.uint8)
+    size = len(hdr) + n * ch * 2
+    blob = torch.empty(streams * size, dtype=torch.uint8, pin_memory=True)
+    view = blob.numpy().reshape(streams, size)
+    view[:, : len(hdr)] = hdr
+    chunk = 128
+    for s0 in range(0, streams, chunk):
+        ids = range(rank * streams + s0, rank * streams + min(s0 + chunk, streams))
+        pcm = synth.pcm_batch_torch(ids, ch, n, device=device).cpu().numpy()
+        view[s0:s0 + len(pcm), len(hdr):] = pcm.reshape(len(pcm), -1).view(np.uint8)
+    offsets = (np.arange(streams + 1, dtype=np.uint64) * np.uint64(size))
+    return blob, offsets
 
 
-def make_inputs(workload: str, streams: int, unique: int, rank: int):
-    """Returns (list of unique stream bytes, tiling factor). Stream ids are offset per rank."""
-    what = {"hca_decode": "hca", "hca_decrypt_decode": "hca_enc", "adx_encode": "wav", "adx_decode": "adx"}[workload]
-    unique = min(unique, streams)
-    ids = [(rank * streams + i, what) for i in range(unique)]
-    if what == "wav":
-        uniq = [_encode_unique(a) for a in ids]
-    else:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool:
-            uniq = pool.map(_encode_unique, ids, chunksize=4)
-    return uniq, (streams + unique - 1) // unique
-
-
-def tile(uniq, streams):
+def run_job_to_pinned(ctx, kind, blob_np, offsets, **kw):
+    """Run one engine job and return (pinned uint8 tensor with the output blob, out_offsets)."""
+    import torch
     from pycricodecs_b200 import engine
-    blob_u, off_u = engine.pack(uniq)
-    reps = (streams + len(uniq) - 1) // len(uniq)
-    sizes = np.diff(off_u)
-    sizes_all = np.tile(sizes, reps)[:streams]
-    offsets = np.zeros(streams + 1, dtype=np.uint64)
-    offsets[1:] = np.cumsum(sizes_all, dtype=np.uint64)
-    blob = np.tile(blob_u, reps)[: int(offsets[-1])] if streams % len(uniq) == 0 else np.concatenate(
-        [blob_u] * (streams // len(uniq)) + [blob_u[: int(off_u[streams % len(uniq)])]])
-    return np.ascontiguousarray(blob), offsets
+    with engine.Job(ctx, kind, blob_np, offsets, **kw) as job:
+        job.run()
+        out = torch.empty(max(job.out_bytes, 1), dtype=torch.uint8, pin_memory=True)
+        _, status = job.download(out.numpy())
+        assert int((status != 0).sum()) == 0, "input synthesis failed"
+        return out, job.out_offsets.copy()
+
+
+def make_inputs(workload, streams, rank, ctx, device):
+    from pycricodecs_b200 import _lib, engine
+    wav, woff = make_wav_blob(streams, rank, device)
+    if workload in ("adx_encode", "hca_encode"):
+        return wav, woff, wav, woff
+    if workload == "adx_decode":
+        out, off = run_job_to_pinned(ctx, _lib.JOB_ADX_ENCODE, wav.numpy(), woff, adx=engine.adx_params())
+        return out, off, wav, woff
+    hca, hoff = run_job_to_pinned(ctx, _lib.JOB_HCA_ENCODE, wav.numpy(), woff, quality=1, adx=engine.adx_params())
+    if workload == "hca_decode":
+        return hca, hoff, wav, woff
+    keys = np.full(streams, KEY, np.uint64)
+    enc, eoff = run_job_to_pinned(ctx, _lib.JOB_HCA_CRYPT, hca.numpy()[: int(hoff[-1])], hoff, keys=keys, encrypt=1, ciph_type=56)
+    return enc, eoff, wav, woff
 
 
 # ------------------------------------------------------------ clock sampler
@@ -102,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -114,7 +130,7 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc:
             self.proc.terminate()
-        sm, smax, reasons = [], 0.0, set()
+        sm, power, smax, reasons = [], [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, line in self.rows:
             p = [x.strip() for x in line.split(",")]
@@ -124,16 +140,16 @@ class ClockSampler:
                 smax = max(smax, float(p[2]))
                 if t0 <= t <= t1:
                     sm.append(float(p[1]))
+                    power.append(float(p[3]))
                     for nm, v in zip(names, p[5:9]):
                         if v.lower().startswith("active"):
                             reasons.add(nm)
             except ValueError:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-# ------------------------------------------------------------------ ours
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -141,44 +157,46 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ------------------------------------------------------------------ ours
 def run_ours(a):
     rank, local_rank, world = rank_info()
     import torch
     from pycricodecs_b200 import _lib, engine
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=device)
     ctx = engine.Context(local_rank)
-    kind = {"hca_decode": _lib.JOB_HCA_DECODE, "hca_decrypt_decode": _lib.JOB_HCA_DECODE, "adx_encode": _lib.JOB_ADX_ENCODE,
-            "adx_decode": _lib.JOB_ADX_DECODE}[a.workload]
-    uniq, reps = make_inputs(a.workload, a.streams, a.unique, rank)
-    blob, offsets = tile(uniq, a.streams)
-    keys = np.full(a.streams, KEY, np.uint64) if a.workload == "hca_decrypt_decode" else None
+    kind = {"hca_decode": _lib.JOB_HCA_DECODE, "hca_decrypt_decode": _lib.JOB_HCA_DECODE, "hca_decrypt": _lib.JOB_HCA_CRYPT,
+            "hca_encode": _lib.JOB_HCA_ENCODE, "adx_encode": _lib.JOB_ADX_ENCODE, "adx_decode": _lib.JOB_ADX_DECODE}[a.workload]
+    pin_in, offsets, wav, woff = make_inputs(a.workload, a.streams, rank, ctx, device)
+    in_bytes = int(offsets[-1])
+    keyed = a.workload in ("hca_decrypt_decode", "hca_decrypt")
+    keys = np.full(a.streams, KEY, np.uint64) if keyed else None
     kw = dict(keys=keys)
-    if kind == _lib.JOB_ADX_ENCODE:
+    if kind in (_lib.JOB_ADX_ENCODE, _lib.JOB_HCA_ENCODE):
         kw["adx"] = engine.adx_params()
-
-    # pinned host buffers for the end-to-end leg
-    pin_in = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
-    pin_in.numpy()[:] = blob
-    job = engine.Job(ctx, kind, pin_in.numpy(), offsets, **kw)
-    units = job.units
-    out_bytes = job.out_bytes
-    pin_out = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    if kind == _lib.JOB_HCA_ENCODE:
+        kw["quality"] = 1
+    if kind == _lib.JOB_HCA_CRYPT:
+        kw.update(encrypt=0, ciph_type=0)
+    blob_np = pin_in.numpy()[:in_bytes]
+    job = engine.Job(ctx, kind, blob_np, offsets, **kw)
+    units, out_bytes = job.units, job.out_bytes
+    pin_out = torch.empty(max(out_bytes, 1), dtype=torch.uint8, pin_memory=True)
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
-    launches0 = ctx.launches
     for _ in range(a.warmup):
         job.run()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.25)
     barrier()
     launches1 = ctx.launches
     t0 = time.perf_counter()
@@ -190,33 +208,50 @@ def run_ours(a):
     barrier()
     t1 = time.perf_counter()
     launches = ctx.launches - launches1
+    if t1 - t0 < 0.6:                       # keep the GPU busy long enough for nvidia-smi to see the clocks under load
+        t_hold = time.perf_counter()
+        while time.perf_counter() - t_hold < 0.6:
+            job.run()
+        t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1)
     out_check, status = job.download(pin_out.numpy())
     assert int((status != 0).sum()) == 0, "engine reported per-stream errors"
-    # spot parity inside the bench: first unique stream against the CPU checker (not timed, not the product path)
+    oo = job.out_offsets.copy()
+    job.close()
+
+    # spot parity inside the bench: stream 0 against the CPU checker (not timed, not on the product path)
     import oracle
     port = oracle.port()
-    oo = job.out_offsets
     got0 = bytes(out_check[int(oo[0]):int(oo[1])])
+    in0 = bytes(blob_np[int(offsets[0]):int(offsets[1])])
     if a.workload == "adx_encode":
-        want0 = port.adx_encode(uniq[0])[1]
+        want0 = port.adx_encode(in0)[1]
     elif a.workload == "adx_decode":
-        want0 = port.adx_decode(uniq[0])[1]
+        want0 = port.adx_decode(in0)[1]
+    elif a.workload == "hca_encode":
+        want0 = port.hca_encode(in0, 1)[1]
+    elif a.workload == "hca_decrypt":
+        want0 = port.hca_crypt(in0, 0, 0, KEY)[1]
     else:
-        want0 = port.hca_decode(uniq[0], KEY if keys is not None else 0)[1]
+        want0 = port.hca_decode(in0, KEY if keyed else 0)[1]
     parity = got0 == want0
-    job.close()
 
     # ---- end to end through the C-ABI batch call, host buffers in, host buffers out
     L = _lib.lib()
     status_arr = np.zeros(a.streams, np.int32)
     out_off = np.ascontiguousarray(oo, dtype=np.uint64)
     adxp = engine.adx_params()
+    kp = keys.ctypes.data if keys is not None else None
 
     def e2e_call():
         if kind == _lib.JOB_HCA_DECODE:
-            rc = L.cri_hca_decode_batch(ctx.handle, pin_in.data_ptr(), offsets.ctypes.data, a.streams,
-                                        keys.ctypes.data if keys is not None else None, None, pin_out.data_ptr(),
+            rc = L.cri_hca_decode_batch(ctx.handle, pin_in.data_ptr(), offsets.ctypes.data, a.streams, kp, None, pin_out.data_ptr(),
+                                        out_off.ctypes.data, status_arr.ctypes.data)
+        elif kind == _lib.JOB_HCA_CRYPT:
+            rc = L.cri_hca_crypt_batch(ctx.handle, pin_in.data_ptr(), offsets.ctypes.data, a.streams, 0, 0, kp, None, pin_out.data_ptr(),
+                                       status_arr.ctypes.data)
+        elif kind == _lib.JOB_HCA_ENCODE:
+            rc = L.cri_hca_encode_batch(ctx.handle, pin_in.data_ptr(), offsets.ctypes.data, a.streams, 1, 0, pin_out.data_ptr(),
                                         out_off.ctypes.data, status_arr.ctypes.data)
         elif kind == _lib.JOB_ADX_ENCODE:
             rc = L.cri_adx_encode_batch(ctx.handle, pin_in.data_ptr(), offsets.ctypes.data, a.streams, ctypes.byref(adxp),
@@ -238,6 +273,7 @@ def run_ours(a):
     ms = dev_ms / a.steps
     wall_ms = (t1 - t0) * 1e3 / a.steps
     dom = dom_ms / a.steps
+    total_units = float(units)
     if dist is not None:
         t = torch.tensor([ms, wall_ms, e2e_s, dom], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -245,66 +281,63 @@ def run_ours(a):
         u = torch.tensor([units], device="cuda", dtype=torch.float64)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
         total_units = float(u.item())
-    else:
-        total_units = float(units)
 
     if rank == 0:
         peak, peak_src = peaks()
-        is_hca = a.workload.startswith("hca")
-        frame_bytes = int(np.diff(offsets)[0] - 96) // 94 if is_hca else 18
-        # algorithmic (compulsory) bytes per unit: compressed bytes + PCM16 bytes, once each
-        path_bytes = (frame_bytes + 4096) if is_hca else 82
-        # dominant kernel: HCA = IMDCT transform kernel (reads int16 spectra 4096 B + gains 1024 B, writes PCM 4096 B
-        # per stereo frame); ADX = the single encode/decode kernel (18 B + 64 B per block)
-        dom_bytes = 9216 if is_hca else 82
+        hca = is_hca(a.workload)
+        unit = "HCA frames/s (1024 samples x 2 ch)" if hca else "ADX blocks/s (32 samples x 1 ch)"
         per_rank_units = total_units / world
+        # algorithmic (compulsory) bytes per unit of the whole path = bytes in + bytes out, once each
+        path_bytes = (in_bytes + out_bytes) / per_rank_units
+        dom_name, dom_bytes = DOMINANT[a.workload]
+        if dom_bytes is None:
+            dom_bytes = path_bytes            # single-kernel workloads: the kernel IS the path
         achieved = per_rank_units * dom_bytes / (dom * 1e-3) / 1e9 if dom > 0 else None
         line = {
-            "metric": "audio frames/sec (48kHz stereo) HCA-decode + ADX-encode at 1/2/4/8 B200 vs CPU ref",
-            "value": total_units / (ms * 1e-3),
-            "unit": "HCA frames/s (1024 samples x 2 ch)" if is_hca else "ADX blocks/s (32 samples x 1 ch)",
+            "metric": METRIC, "value": total_units / (ms * 1e-3), "unit": unit,
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "wall_ms_per_step": wall_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (no FMA, bit-exact) + int16/u8 bitstream" if is_hca else "int32",
+            "dtype": "f32 (no FMA, bit-exact) + int16/u8 bitstream" if hca else "int32",
             "data": "synthetic",
             "config": {"workload": WORKLOADS[a.workload], "name": a.workload, "streams_per_gpu": a.streams,
-                       "unique_streams_per_gpu": len(uniq), "tiling": f"{len(uniq)} unique synthetic streams tiled x{reps}",
-                       "stream_seconds": 2.0, "sample_rate": 48000, "channels": 2,
-                       "input_synthesis": "pycricodecs_b200.synth PCM; HCA/ADX inputs encoded once, untimed, by the CPU checker",
-                       "l2": "inputs and outputs exceed the 126 MB L2 (no flush needed)",
-                       "in_bytes_per_gpu": int(offsets[-1]), "out_bytes_per_gpu": int(out_bytes)},
+                       "unique_streams_per_gpu": a.streams, "stream_seconds": 2.0, "sample_rate": 48000, "channels": 2,
+                       "input_synthesis": "pycricodecs_b200.synth PCM; compressed inputs made once, untimed, by this repo's own GPU encoders",
+                       "l2": "inputs and outputs exceed the 126 MB L2 (no flush needed)" if in_bytes + out_bytes > 3e8 else "working set near L2 size",
+                       "in_bytes_per_gpu": in_bytes, "out_bytes_per_gpu": int(out_bytes)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": None,
-                         "kernel": "hca_imdct_kernel" if is_hca else f"adx_{a.workload.split('_')[1]}_fast_kernel",
-                         "kernel_ms": dom, "algorithmic_bytes_per_unit": dom_bytes, "peak_source": peak_src,
+                         "kernel": dom_name, "kernel_ms": dom, "algorithmic_bytes_per_unit": dom_bytes, "peak_source": peak_src,
                          "whole_path": {"algorithmic_bytes_per_unit": path_bytes,
                                         "achieved_gbs": per_rank_units * path_bytes / (ms * 1e-3) / 1e9,
                                         "frac": per_rank_units * path_bytes / (ms * 1e-3) / 1e9 / peak}},
-            "e2e": {"value": total_units / e2e_s, "unit": "HCA frames/s" if is_hca else "ADX blocks/s",
-                    "h2d_bytes_per_step": int(offsets[-1]), "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
-                    "api": "cri_*_batch (C-ABI), pinned host buffers, parse+plan+H2D+kernels+D2H"},
+            "e2e": {"value": total_units / e2e_s, "unit": unit, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(out_bytes),
+                    "ms_per_step": e2e_s * 1e3, "api": "cri_*_batch (C-ABI), pinned host buffers, parse+plan+H2D+kernels+D2H"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity_spot_check": bool(parity),
         }
-        if not a.no_cpu and world >= 1:
-            line["cpu_baseline"] = cpu_baseline(a.workload, uniq, keys is not None, a.cpu_seconds)
+        if not a.no_cpu:
+            sample = [bytes(blob_np[int(offsets[i]):int(offsets[i + 1])]) for i in range(min(64, a.streams))]
+            line["cpu_baseline"] = cpu_baseline(a.workload, sample, keyed, a.cpu_seconds)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------- CPU baselines
-def _cpu_one(fn_name, data, key):
+def _cpu_one(workload, data, key):
     import oracle
     impl = oracle.ref() if oracle.have_ref() else oracle.port()
-    if fn_name == "hca_decode":
-        r = impl.hca_decode(data, key)
-    elif fn_name == "adx_encode":
-        r = impl.adx_encode(data)
+    if workload in ("hca_decode", "hca_decrypt_decode"):
+        impl.hca_decode(data, key)
+    elif workload == "hca_decrypt":
+        impl.hca_crypt(data, 0, 0, key)
+    elif workload == "hca_encode":
+        impl.hca_encode(data, 1)
+    elif workload == "adx_encode":
+        impl.adx_encode(data)
     else:
-        r = impl.adx_decode(data)
-    return 1
+        impl.adx_decode(data)
 
 
 def cpu_kind():
@@ -313,49 +346,72 @@ def cpu_kind():
 
 
 def units_of(workload, data):
-    if workload.startswith("hca"):
-        return int.from_bytes(data[16:20], "big")          # frames
+    if workload == "hca_encode":
+        return ((len(data) - 44) // 4 + 128 + 1023) // 1024   # frames = ceil((samples + delay) / 1024)
+    if is_hca(workload):
+        return int.from_bytes(data[16:20], "big")             # frame count from the fmt chunk
     if workload == "adx_encode":
-        return (len(data) - 44) // 2 // 32                  # blocks over all channels
+        return (len(data) - 44) // 2 // 32                    # blocks over all channels
     return int.from_bytes(data[12:16], "big") * data[7] // 32
 
 
-def cpu_baseline(workload, uniq, keyed, seconds):
-    """Single-thread CPU baseline on a bounded sample (rank 0 only)."""
-    fn = "hca_decode" if workload.startswith("hca") else workload
+def cpu_baseline(workload, sample, keyed, seconds):
+    """Single-thread CPU baseline on a bounded sample of the same workload (rank 0 only)."""
     key = KEY if keyed else 0
+    _cpu_one(workload, sample[0], key)
     t0 = time.perf_counter()
     n = units = 0
     while time.perf_counter() - t0 < seconds:
-        d = uniq[n % len(uniq)]
-        _cpu_one(fn, d, key)
+        d = sample[n % len(sample)]
+        _cpu_one(workload, d, key)
         units += units_of(workload, d)
         n += 1
     dt = time.perf_counter() - t0
-    is_hca = workload.startswith("hca")
-    return {"value": units / dt, "unit": "HCA frames/s" if is_hca else "ADX blocks/s", "cores": 1, "kind": cpu_kind(),
-            "sample": f"{n} streams of 2 s decoded/encoded back to back on one host thread in {dt:.1f} s"}
+    return {"value": units / dt, "unit": "HCA frames/s" if is_hca(workload) else "ADX blocks/s", "cores": 1, "kind": cpu_kind(),
+            "sample": f"{n} of the workload's 2 s streams processed back to back on one host thread in {dt:.1f} s"}
+
+
+_REF_DATA = None
 
 
 def _ref_worker(args):
-    fn, data, key, reps = args
-    for _ in range(reps):
-        _cpu_one(fn, data, key)
-    return reps
+    workload, idx, key = args
+    _cpu_one(workload, _REF_DATA[idx], key)
+    return 1
+
+
+def reference_inputs(workload, count):
+    """Inputs for the CPU arm, made by the CPU implementation itself (no GPU needed)."""
+    import oracle
+    from pycricodecs_b200 import synth
+    impl = oracle.ref() if oracle.have_ref() else oracle.port()
+    out = []
+    for sid in range(count):
+        w = synth.wav(sid, 2)
+        if workload in ("adx_encode", "hca_encode"):
+            out.append(w)
+        elif workload == "adx_decode":
+            out.append(impl.adx_encode(w)[1])
+        else:
+            h = impl.hca_encode(w, 1)[1]
+            if workload in ("hca_decrypt_decode", "hca_decrypt"):
+                h = bytes(impl.hca_crypt(h, 1, 56, KEY)) if cpu_kind() == "reference" else impl.hca_crypt(h, 1, 56, KEY)[1]
+            out.append(h)
+    return out
 
 
 def run_reference(a):
+    global _REF_DATA
     rank, _, world = rank_info()
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    uniq, _ = make_inputs(a.workload, a.streams, min(a.unique, 64), 0)
-    fn = "hca_decode" if a.workload.startswith("hca") else a.workload
-    key = KEY if a.workload == "hca_decrypt_decode" else 0
-    per_step = cores * 24                                       # streams per step: a bounded sample of the workload
-    tasks = [(fn, uniq[i % len(uniq)], key, 1) for i in range(per_step)]
-    units_step = sum(units_of(a.workload, t[1]) for t in tasks)
+    _REF_DATA = reference_inputs(a.workload, 32)
+    key = KEY if a.workload in ("hca_decrypt_decode", "hca_decrypt") else 0
+    per_step = cores * 24                                      # streams per step: a bounded sample of the workload
+    tasks = [(a.workload, i % len(_REF_DATA), key) for i in range(per_step)]
+    units_step = sum(units_of(a.workload, _REF_DATA[t[1]]) for t in tasks)
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(max(1, a.warmup)):
             pool.map(_ref_worker, tasks, chunksize=4)
@@ -363,16 +419,16 @@ def run_reference(a):
         for _ in range(a.steps):
             pool.map(_ref_worker, tasks, chunksize=4)
         dt = (time.perf_counter() - t0) / a.steps
-    is_hca = a.workload.startswith("hca")
-    unit = "HCA frames/s (1024 samples x 2 ch)" if is_hca else "ADX blocks/s (32 samples x 1 ch)"
+    hca = is_hca(a.workload)
+    unit = "HCA frames/s (1024 samples x 2 ch)" if hca else "ADX blocks/s (32 samples x 1 ch)"
     v = units_step / dt
     print(json.dumps({
-        "impl": "reference", "metric": "audio frames/sec (48kHz stereo) HCA-decode + ADX-encode at 1/2/4/8 B200 vs CPU ref",
-        "value": v, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 scalar SSE2 (no FMA)" if is_hca else "int32",
-        "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 scalar SSE2 (no FMA)" if hca else "int32", "data": "synthetic",
         "config": {"workload": WORKLOADS[a.workload], "name": a.workload, "streams_per_step": per_step,
-                   "note": "the reference's own CPU implementation (oracle/_ref = unmodified CriCodecs C++), one process per host core"},
+                   "note": "the reference's own CPU implementation (oracle/_ref = unmodified CriCodecs C++ where built, else the C port), "
+                           "one process per host core"},
         "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": cpu_kind(),
                          "sample": f"{per_step} streams of 2 s per step over a {cores}-process pool"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -387,15 +443,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hca_decode", choices=list(WORKLOADS))
     ap.add_argument("--streams", type=int, default=8192)
-    ap.add_argument("--unique", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
-    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference(a)
     else:
+        a.warmup = max(a.warmup, 3)
         run_ours(a)
 
 

@@ -83,3 +83,32 @@ def wav_header(channels: int, n: int, rate: int = SAMPLE_RATE) -> bytes:
 
 def wav(sid: int, channels: int = 2, n: int = DEFAULT_SAMPLES, rate: int = SAMPLE_RATE) -> bytes:
     return wav_header(channels, n, rate) + pcm(sid, channels, n).tobytes()
+
+
+def pcm_batch_torch(sids, channels: int = 2, n: int = DEFAULT_SAMPLES, device="cpu"):
+    """int16 tensor [len(sids), n, channels]: the same corpus as `pcm`, vectorised over streams with torch
+    (used by bench.py to synthesise thousands of streams on the GPU; plumbing, not part of the codec path)."""
+    import torch
+    a_pow, cs = _lcg_tables(n)
+    A = torch.from_numpy(a_pow.astype(np.int64)).to(device)          # [n]
+    CS = torch.from_numpy(cs.astype(np.int64)).to(device)
+    sid = torch.as_tensor(list(sids), dtype=torch.int64, device=device).view(-1, 1, 1)   # [S,1,1]
+    ch = torch.arange(channels, dtype=torch.int64, device=device).view(1, 1, -1)         # [1,1,C]
+    m32 = 0xFFFFFFFF
+    st0 = (0x9E3779B9 ^ ((sid * 2654435761) & m32) ^ ((ch * 0x85EBCA6B) & m32)) & m32     # [S,1,C]
+    a = A.view(1, -1, 1)
+    lo = (a & 0xFFFF) * st0                                          # < 2^48
+    hi = (((a >> 16) * st0) & 0xFFFF) << 16
+    st = (lo + hi + CS.view(1, -1, 1)) & m32                         # [S,n,C]
+    noise = (((st >> 16) & 0xFFFF) - 32768) >> 4
+    period = 97 + 13 * ((sid + 3 * ch) % 31)
+    amp = 6000 + 500 * ((sid + ch) % 8)
+    idx = torch.arange(n, dtype=torch.int64, device=device).view(1, -1, 1)
+    ph = idx % period
+    h = period // 2
+    up = torch.div(amp * (2 * ph - h), h, rounding_mode="floor")
+    down = torch.div(amp * (2 * (period - ph) - (period - h)), period - h, rounding_mode="floor")
+    tri = torch.where(ph < h, up, down)
+    env = torch.clamp((idx * 4096) // 2400, max=4096)
+    x = (env * (tri + noise)) >> 12
+    return torch.clamp(x, -32768, 32767).to(torch.int16)
