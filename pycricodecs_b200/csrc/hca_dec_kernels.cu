@@ -1,38 +1,20 @@
-// HCA decode kernels for sm_100a: bitstream unpack and IMDCT transform.
+// HCA decode, first kernel: frame check + bitstream unpack (clHCA_DecodeBlock_unpack, CriCodecs/hca.cpp:1149-1205).
 //
-// Reference pipeline per frame (CriCodecs/hca.cpp): sync + CRC16 + cipher LUT,
-// frame header, per-channel scalefactors / intensity / HFR scales, resolution
-// and gain per band, 8 x channels runs of variable-length codes
-// (clHCA_DecodeBlock_unpack, :1149-1205), then per subframe HFR reconstruction,
-// intensity stereo and a 128-point DCT-IV with window + overlap-add
-// (clHCA_DecodeBlock_transform, :1207-1233), then float -> PCM16 (:339-360).
+// Reference pipeline per frame: sync word, CRC16 over the whole frame (:1166), cipher LUT (:1169), noise level
+// + evaluation boundary, per channel scalefactors (:1290-1358), intensity / HFR scales (:1361-1441), resolution
+// and gain per band (:1444-1507), then 8 x channels runs of variable-length codes (:1540-1571).
 //
-// Two kernels, split where the parallelism changes shape:
-//
-//  hca_unpack_kernel   one LANE per frame. Code lengths are data dependent, so a
-//      frame's 2048 codes are one serial chain and the batch supplies the
-//      parallelism (770 k frames at the headline config). Phase 1 walks the frame
-//      once: CRC16 (table-free byte step), cipher LUT, byte swap, into an aligned
-//      scratch row. Phase 2 parses from a 64-bit register window refilled with
-//      prefetched 32-bit words; the per-code path is branch-free (both code
-//      families are evaluated and selected) because lanes of a warp sit on
-//      different resolutions and would otherwise serialise. Quantised
-//      coefficients go through a 128-byte-per-lane shared tile so that HBM
-//      sees full 128-byte rows.
-//
-//  hca_imdct_kernel    one WARP per run of frames of one stream. Coefficient p of
-//      a 128-point block lives in lane p>>2, register p&3 and never moves: the
-//      reference's 7 sum/difference passes pair slots differing in bit 0..6 of
-//      p, its 7 rotation passes pair bit 6..0, the window pairs bit 0 (see
-//      tools/gen_dct.py), so every exchange is a register swap or one
-//      __shfl_xor, every global access is a coalesced 256/512-byte row, and the
-//      overlap state is two registers per lane. All products and sums are
-//      separately rounded (__fmul_rn/__fadd_rn): the reference build has no FMA,
-//      and PCM parity is bit-exact.
-//
-// HBM traffic per stereo frame: frame_size + 4096 B compulsory, plus the
-// intermediate (4 KB int16 spectra + 1 KB gains + the scratch row, written and
-// read once; the scratch row normally stays in L2).
+// One LANE per frame. Code lengths are data dependent, so a frame's 2048 codes are one serial chain and the
+// batch supplies the parallelism (770 k frames at the headline config).
+//   Phase 1 walks the frame once with 16-byte loads: CRC16 (table-free byte step), cipher LUT, byte swap, into
+//   an aligned scratch row in HBM/L2.
+//   Phase 2 parses from a 128-bit register window that is topped up 64 bits at a time, one 8-byte load in flight
+//   ahead of use (the row comes back from L2/HBM, not L1), and checked once per 4 codes. The per-code path is
+//   branch-free: lanes of a warp sit on different resolutions, so both code families are evaluated and
+//   selected; the end-of-frame rule of the reference's reader (a read that would cross the end yields 0,
+//   hca.cpp:232-233) is decided once per 128-code run, with an exact per-code path for runs that could cross.
+//   Quantised coefficients leave through a 128-byte-per-lane shared tile so that HBM sees full 128-byte rows.
+// The second kernel (hca_imdct_kernels.cu) turns spectra into PCM.
 #include <cstdint>
 
 #include "cri_tables.h"
@@ -45,16 +27,12 @@ __constant__ uint8_t c_invert[66] = CRI_TBL_INVERT;
 __constant__ uint32_t c_scaling[64] = CRI_TBL_DEC_SCALING;
 __constant__ uint32_t c_range[16] = CRI_TBL_DEC_RANGE;
 __constant__ uint32_t c_conv[128] = CRI_TBL_SCALE_CONV;
-__constant__ uint32_t c_intensity[16] = CRI_TBL_INTENSITY_RATIO;
 __constant__ uint8_t c_read_bits[128] = CRI_TBL_READ_BITS;
 __constant__ int8_t c_read_vals[128] = CRI_TBL_READ_VALS;
 __constant__ uint8_t c_max_bits[16] = CRI_TBL_MAX_BITS;
 
-#include "hca_dct_gen.inc"
-
-// ------------------------------------------------------------------ unpack
 constexpr int kUnpackThreads = 128;
-constexpr int kStageRow = 9;    // uint4 per lane in the store tile: 8 payload + 1 pad (36-word rows: conflict-free)
+constexpr unsigned kFull = 0xFFFFFFFFu;
 
 struct UnpackTables {           // per-CTA copies: per-lane indices diverge, shared memory does not serialise
     uint8_t invert[68];
@@ -73,38 +51,48 @@ __device__ __forceinline__ uint32_t crc16_step(uint32_t crc, uint32_t byte) {
     return ((crc << 8) ^ t) & 0xFFFF;
 }
 
-struct BitWindow {              // MSB-first reader over big-endian 32-bit words
-    uint64_t win;
-    const uint32_t* next_ptr;
-    uint32_t next, next2;       // two prefetched words: the scratch row comes back from L2, one word ahead is too late
-    int have;                   // valid bits in win (kept above 32)
-    int pos;                    // bits consumed so far
-    int nbits;
+// MSB-first reader over big-endian 32-bit words: 128 bits in registers (w3 holds the next bits), 64 more
+// prefetched. top_up() must run at least once per 48 consumed bits.
+struct BitWindow {
+    uint32_t w3, w2, w1, w0;
+    uint2 ahead;                // next 64 bits, already loaded
+    const uint2* next_ptr;      // what to load after `ahead`
+    int have;                   // valid bits in the window
+    int loaded;                 // bits taken from the row so far (window + consumed): position = loaded - have
 
-    __device__ __forceinline__ void init(const uint32_t* words, int frame_bits) {
-        win = ((uint64_t)words[0] << 32) | words[1];
-        next = words[2];
-        next2 = words[3];
-        next_ptr = words + 4;
-        have = 64; pos = 0; nbits = frame_bits;
+    __device__ __forceinline__ void init(const uint32_t* row) {
+        const uint4 a = *reinterpret_cast<const uint4*>(row);
+        w3 = a.x; w2 = a.y; w1 = a.z; w0 = a.w;
+        next_ptr = reinterpret_cast<const uint2*>(row + 4);
+        ahead = *next_ptr++;
+        have = 128; loaded = 128;
     }
-    // n in 0..16. A read that would cross the end of the frame returns 0 (hca.cpp:232-233).
-    __device__ __forceinline__ uint32_t peek(int n) const {
-        const uint32_t v = ((uint32_t)(win >> 32) >> 1) >> (31 - n);
-        return pos + n <= nbits ? v : 0u;
-    }
-    __device__ __forceinline__ void skip(int n) {
-        win <<= n;
+    __device__ __forceinline__ int position() const { return loaded - have; }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (w3 >> 1) >> (31 - n); }   // n in 0..31
+    __device__ __forceinline__ void skip(int n) {                                            // n in 0..31
+        w3 = __funnelshift_l(w2, w3, n);
+        w2 = __funnelshift_l(w1, w2, n);
+        w1 = __funnelshift_l(w0, w1, n);
+        w0 <<= n;
         have -= n;
-        pos += n;
-        if (have <= 32) {       // predicated, no divergence: shift in the prefetched word, fetch the one after
-            win |= (uint64_t)next << (32 - have);
-            have += 32;
-            next = next2;
-            next2 = *next_ptr++;
+    }
+    __device__ __forceinline__ void top_up() {
+        if (have <= 64) {       // w1:w0 hold no valid bits; append `ahead` behind the `have` valid bits of w3:w2
+            const uint64_t n64 = ((uint64_t)ahead.x << 32) | ahead.y;
+            const uint64_t hi = (((uint64_t)w3 << 32) | w2) | ((n64 >> 1) >> (have - 1));
+            const uint64_t lo = n64 << (64 - have);
+            w3 = (uint32_t)(hi >> 32); w2 = (uint32_t)hi; w1 = (uint32_t)(lo >> 32); w0 = (uint32_t)lo;
+            have += 64; loaded += 64;
+            ahead = *next_ptr++;
         }
     }
-    __device__ __forceinline__ uint32_t read(int n) { const uint32_t v = peek(n); skip(n); return v; }
+    // generic read for the frame header (rare, not on the per-coefficient path)
+    __device__ __forceinline__ uint32_t read(int n, int nbits) {
+        const uint32_t v = position() + n <= nbits ? peek(n) : 0u;
+        skip(n);
+        top_up();
+        return v;
+    }
 };
 
 __global__ void __launch_bounds__(kUnpackThreads)
@@ -123,8 +111,7 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
-    const int T = kUnpackThreads;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t group = (uint64_t)blockIdx.x * (kUnpackThreads / 32) + warp;
     if (group >= a.total_groups) return;                    // whole warp
     const uint32_t block = (uint32_t)(group / a.steps), step = (uint32_t)(group % a.steps);
@@ -137,15 +124,18 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     const int nch = active ? S.channels : 0;
     const uint64_t slot = (uint64_t)unit * a.steps + step;   // frame slot of the intermediate arrays
 
-    // shared scratch: [0,128T) scalefactors of the channel being parsed; then per channel 128 bytes of
-    // (resolution | max_bits << 4) per band; then the store tile.
-    uint8_t* s_sf = s_dyn;
-    uint8_t* s_rb = s_dyn + 128 * T;
-    uint4* s_stage = reinterpret_cast<uint4*>(s_dyn + (size_t)(128 + 128 * a.max_channels) * T) + (size_t)warp * 32 * kStageRow;
+    // per-warp shared scratch: 4 KB that first holds the scalefactors of the channel being parsed ([band][lane]
+    // bytes) and later the store tile ([lane][8 x 16 B], XOR-swizzled); then per channel 4 KB of
+    // (resolution | max_bits << 4) per band ([band][lane] bytes)
+    uint8_t* wbase = s_dyn + (size_t)warp * (4096 + 4096 * a.max_channels);
+    uint8_t* s_sf = wbase + lane;                            // + band * 32
+    uint8_t* s_rb = wbase + 4096 + lane;                     // + (channel * 128 + band) * 32
+    uint4* s_stage = reinterpret_cast<uint4*>(wbase);
 
     bool bad = false;
     uint32_t* words = a.scratch + slot * a.scratch_words;    // this frame's aligned, deciphered, byte-swapped copy
     const int frame_size = active ? (int)S.frame_size : 0;
+    const int nbits = frame_size * 8;
 
     // ---- phase 1: CRC over the raw frame, cipher LUT, byte swap -> scratch row (16-byte loads, one row ahead)
     if (active) {
@@ -160,8 +150,7 @@ hca_unpack_kernel(HcaDecodeArgs a) {
         uint4 cur = __ldg(ap), nxt = __ldg(ap + 1);
         for (int row = 0; row < nrows; row++) {
             const uint4 nn = __ldg(ap + row + 2);           // the input blob has 64 bytes of slack behind it
-            // the 5 aligned words that cover this output row, then a byte funnel
-            uint32_t v[5];
+            uint32_t v[5];                                  // the 5 aligned words that cover this output row
             {
                 const uint32_t t[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
 #pragma unroll
@@ -192,54 +181,57 @@ hca_unpack_kernel(HcaDecodeArgs a) {
 
     // ---- phase 2: frame header
     BitWindow br;
-    br.init(words, frame_size * 8);
+    br.init(words);
     uint32_t packed = 0;
     if (active) {
-        if (br.read(16) != 0xFFFF) bad = true;               // sync word (cipher tables keep 0xFF fixed)
-        const uint32_t noise_level = br.read(9), boundary = br.read(7);
+        if (br.read(16, nbits) != 0xFFFF) bad = true;        // sync word (cipher tables keep 0xFF fixed)
+        const uint32_t noise_level = br.read(9, nbits), boundary = br.read(7, nbits);
         packed = (noise_level << 8) - boundary;
     }
     const uint8_t* ath = a.ath + (size_t)(active ? S.ath : 0) * 128;
+    int run_bits[kHcaMaxChannels];                           // worst-case bits of one 128-code run per channel
     for (int c = 0; c < nch && !bad; c++) {
         const int coded = S.coded[c];
         const int type = S.type[c];
         // scalefactors (hca.cpp:1290-1358, v2.0 and older)
-        const uint32_t delta_bits = br.read(3);
+        const uint32_t delta_bits = br.read(3, nbits);
         if (delta_bits >= 6) {
-            for (int i = 0; i < coded; i++) s_sf[i * T + tid] = (uint8_t)br.read(6);
+            for (int i = 0; i < coded; i++) s_sf[i * 32] = (uint8_t)br.read(6, nbits);
         } else if (delta_bits > 0) {
             const uint32_t escape = (1u << delta_bits) - 1;
-            uint32_t v = br.read(6);
-            s_sf[tid] = (uint8_t)v;
+            uint32_t v = br.read(6, nbits);
+            s_sf[0] = (uint8_t)v;
             for (int i = 1; i < coded; i++) {
-                const uint32_t d = br.read((int)delta_bits);
+                const uint32_t d = br.read((int)delta_bits, nbits);
                 if (d == escape) {
-                    v = br.read(6);
+                    v = br.read(6, nbits);
                 } else {
                     const int test = (int)v + ((int)d - (int)(escape >> 1));
                     if (test < 0 || test >= 64) { bad = true; break; }
                     v = (v - (escape >> 1) + d) & 0x3F;
                 }
-                s_sf[i * T + tid] = (uint8_t)v;
+                s_sf[i * 32] = (uint8_t)v;
             }
         } else {
-            for (int i = 0; i < 128; i++) s_sf[i * T + tid] = 0;
+            for (int i = 0; i < 128; i++) s_sf[i * 32] = 0;
         }
         if (bad) break;
         // intensity (secondary channel) or HFR scales (others), hca.cpp:1361-1441
         if (type == 2) {
-            const uint32_t v0 = br.peek(4);
+            const uint32_t v0 = br.position() + 4 <= nbits ? br.peek(4) : 0u;
             uint32_t inten = v0;
             if (v0 < 15) {
                 br.skip(4);
-                for (int i = 1; i < 8; i++) inten |= br.read(4) << (4 * i);
+                br.top_up();
+                for (int i = 1; i < 8; i++) inten |= br.read(4, nbits) << (4 * i);
             }
             a.inten[slot * a.max_channels + c] = inten;
         } else {
-            for (int g = 0; g < S.hfr_groups; g++) s_sf[(128 - S.hfr_groups + g) * T + tid] = (uint8_t)br.read(6);
+            for (int g = 0; g < S.hfr_groups; g++) s_sf[(128 - S.hfr_groups + g) * 32] = (uint8_t)br.read(6, nbits);
         }
         // resolution + gain per band (hca.cpp:1444-1507)
         float4* gdst = reinterpret_cast<float4*>(a.gain + (slot * a.max_channels + c) * 128);
+        int sum_bits = 0;
         for (int i0 = 0; i0 < 128; i0 += 4) {
             float g[4];
 #pragma unroll
@@ -248,7 +240,7 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                 uint32_t r = 0;
                 g[k] = 0.f;
                 if (i < coded) {
-                    const uint32_t sf = s_sf[i * T + tid];
+                    const uint32_t sf = s_sf[i * 32];
                     if (sf > 0) {
                         const int level = (int)ath[i] + (int)((packed + (uint32_t)i) >> 8);
                         const int cp = level + 1 - (int)((5 * sf) >> 1);
@@ -257,10 +249,13 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                     }
                     g[k] = __fmul_rn(tb.scaling[sf], tb.range[r]);
                 }
-                s_rb[(c * 128 + i) * T + tid] = (uint8_t)(r | ((uint32_t)tb.max_bits[r] << 4));
+                const uint32_t mb = i < coded ? tb.max_bits[r] : 0u;
+                sum_bits += (int)mb;
+                s_rb[(c * 128 + i) * 32] = (uint8_t)(r | (mb << 4));     // bands past `coded`: r = 0, 0 bits
             }
             gdst[i0 >> 2] = make_float4(g[0], g[1], g[2], g[3]);
         }
+        run_bits[c] = sum_bits;
         // HFR multipliers for the bands above the coded ones (hca.cpp:1638-1683, v2.0 rule)
         if (S.bands_per_hfr && type != 2) {
             const int start = S.base_bands + S.stereo_bands;
@@ -269,7 +264,7 @@ hca_unpack_kernel(HcaDecodeArgs a) {
             for (int g = 0; g < S.hfr_groups; g++)
                 for (int i = 0; i < S.bands_per_hfr; i++) {
                     if (high >= S.total_bands || low < 0) break;
-                    int k = (int)s_sf[(128 - S.hfr_groups + g) * T + tid] - (int)s_sf[low * T + tid] + 63;
+                    int k = (int)s_sf[(128 - S.hfr_groups + g) * 32] - (int)s_sf[low * 32] + 63;
                     k &= ~(k >> 31);
                     gflat[high] = tb.conv[k];
                     high++; low--;
@@ -281,13 +276,17 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     // (bounded by the widest stream of the warp) because the store tile is flushed cooperatively.
     int warp_nch = nch;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) warp_nch = max(warp_nch, __shfl_xor_sync(0xFFFFFFFFu, warp_nch, o));
+    for (int o = 16; o; o >>= 1) warp_nch = max(warp_nch, __shfl_xor_sync(kFull, warp_nch, o));
+    __syncwarp();                                            // the scalefactor bytes are dead: their 4 KB become the store tile
     const bool lookback = step == 0;
-    uint4* my_stage = s_stage + lane * kStageRow;
+    const int sw = lane & 7;                                 // swizzle of this lane's tile row
     for (int sub = 0; sub < 8; sub++) {
         for (int c = 0; c < warp_nch; c++) {
             const bool mine = c < nch && !bad;
             const int coded = mine ? (int)S.coded[c] : 0;
+            // can this run cross the end of the frame? (only corrupt / wrongly keyed frames do)
+            const bool careful = mine && br.position() + run_bits[c < nch ? c : 0] > nbits;
+            const uint8_t* rbp = s_rb + (size_t)c * 128 * 32;
             for (int halfband = 0; halfband < 2; halfband++) {
 #pragma unroll 1
                 for (int i0 = halfband * 64; i0 < halfband * 64 + 64; i0 += 8) {
@@ -295,11 +294,11 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                     if (i0 < coded) {
 #pragma unroll
                         for (int k = 0; k < 8; k++) {
-                            const int i = i0 + k;
-                            const uint32_t rb = i < coded ? s_rb[(c * 128 + i) * T + tid] : 0u;
+                            const uint32_t rb = rbp[(i0 + k) * 32];
                             const uint32_t r = rb & 15;
                             const int bits = (int)(rb >> 4);
-                            const uint32_t code = br.peek(bits);
+                            uint32_t code = br.peek(bits);
+                            if (careful && br.position() + bits > nbits) code = 0;
                             // sign-magnitude family (resolution >= 8): LSB is the sign, zero gives one bit back
                             const int mag = (int)(code >> 1);
                             const int v_hi = (code & 1) ? -mag : mag;
@@ -311,10 +310,11 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                             const bool hi = r > 7;
                             const int v = hi ? v_hi : v_lo;
                             br.skip(hi ? used_hi : used_lo);
+                            if ((k & 3) == 3) br.top_up();
                             pk[k >> 1] |= ((uint32_t)v & 0xFFFFu) << (16 * (k & 1));
                         }
                     }
-                    my_stage[(i0 >> 3) & 7] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    s_stage[lane * 8 + (((i0 >> 3) & 7) ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 __syncwarp();
                 // flush: 64 coefficients (128 B) of each lane's frame as one full row; 4 frames per warp store
@@ -324,9 +324,9 @@ hca_unpack_kernel(HcaDecodeArgs a) {
 #pragma unroll
                     for (int it = 0; it < 8; it++) {
                         const int j = it * 4 + (lane >> 3);
-                        const uint64_t row = __shfl_sync(0xFFFFFFFFu, my_row, j);
-                        const bool ok = __shfl_sync(0xFFFFFFFFu, (int)my_ok, j);
-                        if (ok) a.quant[row + (lane & 7)] = s_stage[j * kStageRow + (lane & 7)];
+                        const uint64_t row = __shfl_sync(kFull, my_row, j);
+                        const bool ok = __shfl_sync(kFull, (int)my_ok, j);
+                        if (ok) a.quant[row + (lane & 7)] = s_stage[j * 8 + ((lane & 7) ^ (j & 7))];
                     }
                 }
                 __syncwarp();
@@ -336,210 +336,9 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     if (bad && active) a.status[u.stream] = ERR_HCA_DECODE;
 }
 
-// --------------------------------------------------------------- transform
-constexpr int kImdctWarps = 4;
-
-__device__ __forceinline__ int pcm16(float f) {   // hca.cpp:339-360; (int) of an out-of-range float is INT_MIN on x86
-    const float v = __fmul_rn(f, 32768.0f);
-    int s = __float2int_rz(v);
-    if (!(fabsf(v) < 2147483648.0f)) s = INT_MIN;
-    return max(-32768, min(32767, s));
-}
-
-__device__ __forceinline__ float flip(float v, uint32_t mask) { return __uint_as_float(__float_as_uint(v) ^ mask); }
-
-struct Spectra4 {              // one lane's share of a 128-point block as it sits in memory
-    uint2 q;                    // 4 x int16 quantised coefficients
-    float4 g;                   // 4 gains (or HFR multipliers above the coded bands)
-};
-
-__global__ void __launch_bounds__(kImdctWarps * 32)
-hca_imdct_kernel(HcaDecodeArgs a) {
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    __shared__ __align__(16) float s_rot_s[7 * 128];
-    __shared__ __align__(16) float s_rot_c[7 * 128];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t unit = blockIdx.x * kImdctWarps + warp;
-    const bool dead = unit >= a.n_units || a.units[unit < a.n_units ? unit : 0].count == 0;
-    // rotation factors per slot (p = 4*lane + r): one shared copy per CTA, read as one LDS.128 per pass and table.
-    // Keeping the 56 per-lane factors in registers instead costs half the occupancy.
-    for (int i = threadIdx.x; i < 7 * 128; i += blockDim.x) {
-        s_rot_s[i] = __uint_as_float(kRotS[i]);
-        s_rot_c[i] = __uint_as_float(kRotC[i]);
-    }
-    __syncthreads();
-    if (dead) return;
-    const HcaUnit u = a.units[unit];
-    const HcaStreamDev& S = a.streams[u.stream];
-    const int nch = S.channels;
-    const int MC = (int)a.max_channels;
-    // per-warp shared: PCM tile [MC][128] int16, overlap carry [MC][32] float2, HFR scratch [128] float
-    uint8_t* base = s_dyn + (size_t)warp * (MC * 512 + 512);
-    int16_t* tile = reinterpret_cast<int16_t*>(base);
-    float2* carry = reinterpret_cast<float2*>(base + MC * 256);
-    float* xs = reinterpret_cast<float*>(base + MC * 512);
-
-    const float wa0 = __uint_as_float(kWinA[2 * lane]), wa1 = __uint_as_float(kWinA[2 * lane + 1]);
-    const float wb0 = __uint_as_float(kWinB[2 * lane]), wb1 = __uint_as_float(kWinB[2 * lane + 1]);
-    const int pa0 = kWinPosA[2 * lane], pa1 = kWinPosA[2 * lane + 1], pb0 = kWinPosB[2 * lane], pb1 = kWinPosB[2 * lane + 1];
-    uint32_t sgn[5];   // sum/difference passes across lanes: the slot with the pass bit set holds b of (a+b, a-b)
-#pragma unroll
-    for (int b = 0; b < 5; b++) sgn[b] = (lane >> b) & 1 ? 0x80000000u : 0u;
-    const float4* rot_s = reinterpret_cast<const float4*>(s_rot_s) + lane;   // [pass * 32]
-    const float4* rot_c = reinterpret_cast<const float4*>(s_rot_c) + lane;
-
-    for (int c = 0; c < nch; c++) carry[c * 32 + lane] = make_float2(0.f, 0.f);
-    const int total = S.total_bands, basebands = S.base_bands;
-    const int start = S.base_bands + S.stereo_bands;
-    const int room = min(min(total - start, (int)S.hfr_groups * (int)S.bands_per_hfr), start);
-    const bool joint = S.joint;
-    const uint64_t slot0 = (uint64_t)unit * a.steps;
-
-    auto fetch = [&](uint32_t step, int sub, int c) {
-        Spectra4 r;
-        const uint64_t sc = (slot0 + step) * MC + c;
-        r.q = reinterpret_cast<const uint2*>(a.quant + (sc * 8 + sub) * 16)[lane];
-        r.g = reinterpret_cast<const float4*>(a.gain + sc * 128)[lane];
-        return r;
-    };
-
-    const uint32_t first_step = u.first == 0 ? 1u : 0u;
-    Spectra4 nxt = fetch(first_step, first_step == 0 ? 7 : 0, 0);
-    for (uint32_t step = first_step; step <= u.count; step++) {
-        const uint32_t frame = u.first + step - 1;
-        const uint64_t slot = slot0 + step;
-        for (int sub = (step == 0 ? 7 : 0); sub < 8; sub++) {
-            float xl[4] = {0.f, 0.f, 0.f, 0.f};   // primary channel's spectra for intensity stereo
-            for (int c = 0; c < nch; c++) {
-                const int coded = S.coded[c];
-                const int type = S.type[c];
-                const Spectra4 cur = nxt;
-                {   // software prefetch: the next block's row is requested before this block's arithmetic starts
-                    int nc = c + 1, ns = sub;
-                    uint32_t nstep = step;
-                    if (nc == nch) { nc = 0; ns++; }
-                    if (ns == 8) { ns = 0; nstep++; }
-                    if (nstep <= u.count) nxt = fetch(nstep, ns, nc);
-                }
-                // ---- dequantise: spectra = gain * q  (hca.cpp:1568); bands past the coded count are zero
-                float x[4];
-                x[0] = 4 * lane + 0 < coded ? __fmul_rn(cur.g.x, (float)(int)(short)(cur.q.x & 0xFFFF)) : 0.f;
-                x[1] = 4 * lane + 1 < coded ? __fmul_rn(cur.g.y, (float)((int)cur.q.x >> 16)) : 0.f;
-                x[2] = 4 * lane + 2 < coded ? __fmul_rn(cur.g.z, (float)(int)(short)(cur.q.y & 0xFFFF)) : 0.f;
-                x[3] = 4 * lane + 3 < coded ? __fmul_rn(cur.g.w, (float)((int)cur.q.y >> 16)) : 0.f;
-                if (joint) {
-                    // ---- HFR: mirrored low bands scaled into the high bands (hca.cpp:1638-1683)
-                    if (S.bands_per_hfr && type != 2) {
-                        __syncwarp();
-                        reinterpret_cast<float4*>(xs)[lane] = make_float4(x[0], x[1], x[2], x[3]);
-                        __syncwarp();
-                        const float gg[4] = {cur.g.x, cur.g.y, cur.g.z, cur.g.w};
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            const int p = 4 * lane + r;
-                            if (p >= start && p < start + room) x[r] = __fmul_rn(gg[r], xs[2 * start - 1 - p]);
-                            if (p == start + room - 1) x[r] = 0.f;
-                        }
-                    }
-                    // ---- intensity stereo: the secondary channel is rebuilt from the primary (hca.cpp:1696-1714)
-                    if (type == 1) {
-                        const uint32_t inten = a.inten[slot * MC + c + 1];
-                        const float rl = __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]);
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            xl[r] = x[r];
-                            const int p = 4 * lane + r;
-                            if (p >= basebands && p < total) x[r] = __fmul_rn(x[r], rl);
-                        }
-                    } else if (type == 2) {
-                        const uint32_t inten = a.inten[slot * MC + c];
-                        const float rr = __fsub_rn(2.0f, __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]));
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            const int p = 4 * lane + r;
-                            if (p >= basebands && p < total) x[r] = __fmul_rn(xl[r], rr);
-                        }
-                    }
-                }
-                // ---- 7 sum/difference passes: slot bit 0, 1 (registers), 2..6 (lanes)
-                {
-                    const float t0 = __fadd_rn(x[0], x[1]), t1 = __fsub_rn(x[0], x[1]), t2 = __fadd_rn(x[2], x[3]), t3 = __fsub_rn(x[2], x[3]);
-                    x[0] = __fadd_rn(t0, t2); x[2] = __fsub_rn(t0, t2); x[1] = __fadd_rn(t1, t3); x[3] = __fsub_rn(t1, t3);
-                }
-#pragma unroll
-                for (int b = 0; b < 5; b++) {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float other = __shfl_xor_sync(0xFFFFFFFFu, x[r], 1 << b);
-                        x[r] = __fadd_rn(other, flip(x[r], sgn[b]));
-                    }
-                }
-                // ---- 7 rotation passes: slot bit 6..2 (lanes), 1, 0 (registers):  v*S + partner*C
-#pragma unroll
-                for (int st = 0; st < 5; st++) {
-                    const float4 s4 = rot_s[st * 32], c4 = rot_c[st * 32];
-                    const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float other = __shfl_xor_sync(0xFFFFFFFFu, x[r], 16 >> st);
-                        x[r] = __fadd_rn(__fmul_rn(x[r], ss[r]), __fmul_rn(other, cc[r]));
-                    }
-                }
-                {
-                    const float4 s5 = rot_s[5 * 32], c5 = rot_c[5 * 32], s6 = rot_s[6 * 32], c6 = rot_c[6 * 32];
-                    const float y0 = __fadd_rn(__fmul_rn(x[0], s5.x), __fmul_rn(x[2], c5.x));
-                    const float y2 = __fadd_rn(__fmul_rn(x[2], s5.z), __fmul_rn(x[0], c5.z));
-                    const float y1 = __fadd_rn(__fmul_rn(x[1], s5.y), __fmul_rn(x[3], c5.y));
-                    const float y3 = __fadd_rn(__fmul_rn(x[3], s5.w), __fmul_rn(x[1], c5.w));
-                    x[0] = __fadd_rn(__fmul_rn(y0, s6.x), __fmul_rn(y1, c6.x));
-                    x[1] = __fadd_rn(__fmul_rn(y1, s6.y), __fmul_rn(y0, c6.y));
-                    x[2] = __fadd_rn(__fmul_rn(y2, s6.z), __fmul_rn(y3, c6.z));
-                    x[3] = __fadd_rn(__fmul_rn(y3, s6.w), __fmul_rn(y2, c6.w));
-                }
-                // ---- window + overlap (hca.cpp:1983-1992): odd slots hold dct[j>=64], even slots dct[127-j]
-                const float2 prev = carry[c * 32 + lane];
-                carry[c * 32 + lane] = make_float2(x[0], x[2]);
-                if (step != 0) {
-                    int16_t* t = tile + c * 128;
-                    t[pa0] = (int16_t)pcm16(__fadd_rn(__fmul_rn(wa0, x[1]), __fmul_rn(wb0, prev.x)));
-                    t[pb0] = (int16_t)pcm16(__fsub_rn(__fmul_rn(wb0, x[1]), __fmul_rn(wa0, prev.x)));
-                    t[pa1] = (int16_t)pcm16(__fadd_rn(__fmul_rn(wa1, x[3]), __fmul_rn(wb1, prev.y)));
-                    t[pb1] = (int16_t)pcm16(__fsub_rn(__fmul_rn(wb1, x[3]), __fmul_rn(wa1, prev.y)));
-                }
-            }
-            if (step == 0) continue;
-            __syncwarp();
-            // ---- interleave the channels and store this subframe's samples (contiguous in the WAV image)
-            const long long n0 = (long long)frame * 1024 + sub * 128 - (long long)S.delay;
-            uint8_t* dst = a.out + S.out_off;
-            if (nch == 2 && ((S.out_off & 3) == 0)) {
-#pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const int i = lane + 32 * m;
-                    const long long n = n0 + i;
-                    if (n >= 0 && n < (long long)S.out_samples) {
-                        const uint32_t w = (uint32_t)(uint16_t)tile[i] | ((uint32_t)(uint16_t)tile[128 + i] << 16);
-                        *reinterpret_cast<uint32_t*>(dst + n * 4) = w;
-                    }
-                }
-            } else {
-                for (int e = lane; e < 128 * nch; e += 32) {
-                    const int i = e / nch, c = e - i * nch;
-                    const long long n = n0 + i;
-                    if (n >= 0 && n < (long long)S.out_samples)
-                        *reinterpret_cast<int16_t*>(dst + (n * nch + c) * 2) = tile[c * 128 + i];
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 }  // namespace
 
-size_t hca_unpack_smem(uint32_t max_channels) {
-    return (size_t)(128 + 128 * max_channels) * kUnpackThreads + (size_t)(kUnpackThreads / 32) * 32 * kStageRow * sizeof(uint4);
-}
+size_t hca_unpack_smem(uint32_t max_channels) { return (size_t)(kUnpackThreads / 32) * (4096 + 4096 * (size_t)max_channels); }
 
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
     if (!a.total_groups) return;
@@ -549,10 +348,7 @@ void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launche
     hca_unpack_kernel<<<(unsigned)((a.total_groups + groups_per_cta - 1) / groups_per_cta), kUnpackThreads, smem, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    const size_t smem2 = (size_t)kImdctWarps * (a.max_channels * 512 + 512);
-    cudaFuncSetAttribute(hca_imdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    hca_imdct_kernel<<<(a.n_units + kImdctWarps - 1) / kImdctWarps, kImdctWarps * 32, smem2, s>>>(a);
-    ++*launches;
+    launch_hca_imdct(a, s, launches);
 }
 
 }  // namespace cri

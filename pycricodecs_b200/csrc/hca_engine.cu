@@ -131,6 +131,15 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         j->units += needed;
     }
     while (J.units.size() % 32) J.units.push_back(HcaUnit{0, 0, 0});
+    // fast transform path: every decodable stream is mono (1) or stereo (2) with all 128 bands coded and no joint tools
+    J.uniform = J.max_channels <= 2 ? J.max_channels : 0;
+    for (uint32_t i = 0; i < j->n && J.uniform; i++) {
+        if (j->status[i] != OK) continue;
+        const HcaStreamDev& st = J.streams[i];
+        bool ok = st.channels == J.uniform && !st.joint;
+        for (unsigned ch = 0; ch < st.channels; ch++) ok = ok && st.coded[ch] == 128;
+        if (!ok) J.uniform = 0;
+    }
     J.max_steps = run + 1;
     J.total_groups = (J.units.size() / 32) * J.max_steps;
     const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
@@ -291,6 +300,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.scratch = reinterpret_cast<uint32_t*>(J.d_s);
         a.scratch_words = J.scratch_words;
         a.n_units = (uint32_t)J.units.size();
+        a.uniform = J.uniform;
         a.inten = reinterpret_cast<uint32_t*>(J.d_i);
         a.status = j->d_status;
         a.total_groups = J.total_groups;

@@ -27,10 +27,12 @@ struct HcaDecodeArgs {
     uint32_t steps;             // frames per unit + 1
     uint32_t max_channels;
     uint32_t scratch_words;     // multiple of 4
+    uint32_t uniform;           // 0 mixed batch; 1 every stream is mono, 2 stereo: all bands coded, no HFR / intensity
 };
 
 // `mid` (optional) is recorded between the unpack and the transform kernel.
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
+void launch_hca_imdct(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // second half of launch_hca_decode
 
 struct HcaCryptArgs {
     const uint8_t* in;

@@ -65,6 +65,7 @@ struct HcaJob {
     std::vector<uint64_t> frame_prefix;    // crypt: exclusive prefix of frame counts per stream
     uint64_t* d_frame_prefix = nullptr;
     uint32_t enc_frame_words = 0;
+    uint32_t uniform = 0;                  // decode: see HcaDecodeArgs::uniform
     uint8_t* d_s = nullptr;
     uint32_t max_channels = 1, max_steps = 0;
 
