@@ -16,6 +16,7 @@
 //   Quantised coefficients leave through a 128-byte-per-lane shared tile so that HBM sees full 128-byte rows.
 // The second kernel (hca_imdct_kernels.cu) turns spectra into PCM.
 #include <cstdint>
+#include <type_traits>
 
 #include "cri_tables.h"
 #include "hca_kernels.h"
@@ -55,8 +56,8 @@ __device__ __forceinline__ uint32_t crc16_step(uint32_t crc, uint32_t byte) {
 // prefetched. top_up() must run at least once per 48 consumed bits.
 struct BitWindow {
     uint32_t w3, w2, w1, w0;
-    uint2 ahead;                // next 64 bits, already loaded
-    const uint2* next_ptr;      // what to load after `ahead`
+    uint2 ahead, ahead2;        // next 2 x 64 bits, already requested (the row comes back from L2 / HBM)
+    const uint2* next_ptr;      // what to load after `ahead2`
     int have;                   // valid bits in the window
     int loaded;                 // bits taken from the row so far (window + consumed): position = loaded - have
 
@@ -65,10 +66,11 @@ struct BitWindow {
         w3 = a.x; w2 = a.y; w1 = a.z; w0 = a.w;
         next_ptr = reinterpret_cast<const uint2*>(row + 4);
         ahead = *next_ptr++;
+        ahead2 = *next_ptr++;
         have = 128; loaded = 128;
     }
     __device__ __forceinline__ int position() const { return loaded - have; }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (w3 >> 1) >> (31 - n); }   // n in 0..31
+    __device__ __forceinline__ uint32_t peek(int n) const { return __funnelshift_l(w3, 0u, n); }   // top n bits, n in 0..31
     __device__ __forceinline__ void skip(int n) {                                            // n in 0..31
         w3 = __funnelshift_l(w2, w3, n);
         w2 = __funnelshift_l(w1, w2, n);
@@ -83,7 +85,8 @@ struct BitWindow {
             const uint64_t lo = n64 << (64 - have);
             w3 = (uint32_t)(hi >> 32); w2 = (uint32_t)hi; w1 = (uint32_t)(lo >> 32); w0 = (uint32_t)lo;
             have += 64; loaded += 64;
-            ahead = *next_ptr++;
+            ahead = ahead2;
+            ahead2 = *next_ptr++;
         }
     }
     // generic read for the frame header (rare, not on the per-coefficient path)
@@ -287,35 +290,39 @@ hca_unpack_kernel(HcaDecodeArgs a) {
             // can this run cross the end of the frame? (only corrupt / wrongly keyed frames do)
             const bool careful = mine && br.position() + run_bits[c < nch ? c : 0] > nbits;
             const uint8_t* rbp = s_rb + (size_t)c * 128 * 32;
+            const bool any_careful = __any_sync(kFull, careful);
             for (int halfband = 0; halfband < 2; halfband++) {
+                auto decode_half = [&](auto careful_tag) {
+                    constexpr bool kCareful = decltype(careful_tag)::value;
 #pragma unroll 1
-                for (int i0 = halfband * 64; i0 < halfband * 64 + 64; i0 += 8) {
-                    uint32_t pk[4] = {0, 0, 0, 0};
-                    if (i0 < coded) {
+                    for (int i0 = halfband * 64; i0 < halfband * 64 + 64; i0 += 8) {
+                        uint32_t pk[4] = {0, 0, 0, 0};
+                        if (i0 < coded) {
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const uint32_t rb = rbp[(i0 + k) * 32];
-                            const uint32_t r = rb & 15;
-                            const int bits = (int)(rb >> 4);
-                            uint32_t code = br.peek(bits);
-                            if (careful && br.position() + bits > nbits) code = 0;
-                            // sign-magnitude family (resolution >= 8): LSB is the sign, zero gives one bit back
-                            const int mag = (int)(code >> 1);
-                            const int v_hi = (code & 1) ? -mag : mag;
-                            const int used_hi = bits - (mag == 0);
-                            // prefix-codebook family (resolution <= 7)
-                            const uint32_t e = tb.code[((r & 7) << 4) | (code & 15)];
-                            const int v_lo = (int)(e & 15) - 8;
-                            const int used_lo = (int)(e >> 4);
-                            const bool hi = r > 7;
-                            const int v = hi ? v_hi : v_lo;
-                            br.skip(hi ? used_hi : used_lo);
-                            if ((k & 3) == 3) br.top_up();
-                            pk[k >> 1] |= ((uint32_t)v & 0xFFFFu) << (16 * (k & 1));
+                            for (int k = 0; k < 8; k++) {
+                                const uint32_t rb = rbp[(i0 + k) * 32];
+                                const int bits = (int)(rb >> 4);
+                                uint32_t code = br.peek(bits);
+                                if (kCareful && br.position() + bits > nbits) code = 0;
+                                // sign-magnitude family (resolution >= 8): LSB is the sign, zero gives one bit back
+                                const int mag = (int)(code >> 1);
+                                const int v_hi = (code & 1) ? -mag : mag;
+                                const int used_hi = code < 2 ? bits - 1 : bits;
+                                // prefix-codebook family (resolution <= 7): one table byte = (value + 8) | bits << 4
+                                const uint32_t e = tb.code[((rb & 7) << 4) | (code & 15)];
+                                const int v_lo = (int)(e & 15) - 8;
+                                const int used_lo = (int)(e >> 4);
+                                const bool hi = rb & 8;
+                                const int v = hi ? v_hi : v_lo;
+                                br.skip(hi ? used_hi : used_lo);
+                                if ((k & 3) == 3) br.top_up();
+                                pk[k >> 1] |= ((uint32_t)v & 0xFFFFu) << (16 * (k & 1));
+                            }
                         }
+                        s_stage[lane * 8 + (((i0 >> 3) & 7) ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
-                    s_stage[lane * 8 + (((i0 >> 3) & 7) ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
+                };
+                if (any_careful) decode_half(std::true_type{}); else decode_half(std::false_type{});
                 __syncwarp();
                 // flush: 64 coefficients (128 B) of each lane's frame as one full row; 4 frames per warp store
                 if (!lookback || sub == 7) {
