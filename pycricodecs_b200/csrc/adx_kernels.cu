@@ -1,25 +1,22 @@
 // ADX (CRI ADPCM) decode / encode kernels for sm_100a.
 //
-// What is computed (reference: CriCodecs/adx.cpp): per channel a 2-tap
-// fixed-point predictor  s = q*scale + (c0*h1 >> 12) + (c1*h2 >> 12), clamped to
-// int16, q a signed n-bit code (ChannelFrame::Decode, adx.cpp:189-214); the
-// encoder searches a per-block scale from the residual range against RAW history
-// and then quantises against the SIMULATED decoder history (ChannelFrame::Encode,
-// adx.cpp:215-273). The clamp and the two floor shifts make the recurrence
-// non-associative, so one channel of one stream ("chain") is strictly serial and
-// the parallelism is chains: one lane per chain, 32 chains per warp.
+// What is computed (reference: CriCodecs/adx.cpp): per channel a 2-tap fixed-point predictor
+//   s = q*scale + (c0*h1 >> 12) + (c1*h2 >> 12), clamped to int16, q a signed n-bit code
+// (ChannelFrame::Decode, adx.cpp:189-214); the encoder picks a per-block scale from the residual range against
+// RAW history and then quantises against the SIMULATED decoder history (ChannelFrame::Encode, adx.cpp:215-273).
+// The clamp and the floor shifts make the recurrence non-associative, so one channel of one stream (a "chain") is
+// strictly serial and the parallelism is chains: one lane per chain, 32 chains (32/channels streams) per warp.
 //
-// Memory plan (fast path: 4-bit codes, 18-byte blocks -- the configuration
-// every CRI tool emits): a warp walks its 32 chains in tiles of kTile blocks.
-// Global traffic is staged through shared memory so that HBM sees coalesced
-// runs: tile-in is loaded cooperatively (all lanes read consecutive bytes /
-// samples of ONE chain at a time), each lane then runs its own recurrence out of
-// shared memory, and tile-out is stored cooperatively the same way. The serial
-// recurrence is latency-bound (~20 dependent cycles per sample), HBM traffic is
-// 82 B per block (18 B code + 64 B PCM).
+// Fast path (4-bit codes, 18-byte blocks, 1/2/4/8/16/32 channels -- what every CRI tool emits): the warp walks its
+// streams in tiles of kTile blocks. A stream's tile is CONTIGUOUS in both blobs (blocks of all channels are
+// interleaved per frame, PCM is interleaved per sample), so the warp copies the aligned 32-bit words that cover
+// each stream's tile with cp.async into a double-buffered shared stage (next tile in flight while this one is
+// decoded; no alignment requirement on the stream itself), every lane runs its own recurrence out of shared
+// memory, and results leave as coalesced stores per stream. The recurrence is latency bound (~20 dependent
+// cycles per decoded sample, ~70 per encoded sample); HBM traffic is the compulsory 82 B per block.
 //
-// Any other bit depth / block size / more than 32 samples per block takes the
-// generic kernel: same arithmetic, one thread per chain straight on global memory.
+// Anything else (other bit depths / block sizes / channel counts, odd PCM alignment) takes the generic kernels:
+// same arithmetic, one thread per chain straight on global memory.
 #include <cstdint>
 
 #include "kernels.h"
@@ -27,14 +24,22 @@
 namespace cri {
 namespace {
 
-constexpr int kTile = 8;               // blocks per tile
-constexpr int kSpb = 32;               // samples per block on the fast path
-constexpr int kBlk = 18;               // bytes per block on the fast path
-constexpr int kCodeRow = kTile * kBlk + 4;   // 148 B = 37 words: odd word stride, no bank conflicts
-constexpr int kPcmRow = kTile * kSpb + 2;    // 258 int16 = 129 words
-constexpr int kWarps = 2;               // 2 warps x 21 KB staging stays under the 48 KB static limit
+constexpr int kTile = 8;                 // blocks per chain per tile
+constexpr int kSpb = 32;                 // samples per block on the fast path
+constexpr int kBlk = 18;                 // bytes per block on the fast path
+constexpr int kWarps = 1;                // warps per CTA (one warp = 26 / 38 KB of static shared memory)
+constexpr int kPcmRow = kTile * kSpb + 2;            // int16 per chain in the PCM tile: odd word stride
+constexpr int kCodeWords = (kTile * 32 * kBlk + 3) / 4 + 1;     // covering words of 32 chains x kTile blocks
+constexpr int kPcmWords = (kTile * 32 * kSpb * 2 + 3) / 4 + 1;  // covering words of 32 chains x kTile x 32 samples
+constexpr unsigned kFull = 0xFFFFFFFFu;
 
 __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1) {
     if (mode == 3) return raw + 1;
@@ -46,52 +51,73 @@ __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1)
     return (raw & 0x1FFF) + 1;
 }
 
+// Copy, for every stream of the warp, the aligned words covering bytes [base + lo, base + hi) of the input blob into
+// the stream's row of `stage` (row stride `row_words`). base / byte ranges come from the stream's channel-0 lane.
+__device__ __forceinline__ void stage_rows(uint32_t* stage, int row_words, const uint8_t* blob, uint64_t my_base, int64_t my_lo,
+                                           int64_t my_hi, int nstreams, int nch, int lane) {
+    for (int s = 0; s < nstreams; s++) {
+        const uint64_t base = __shfl_sync(kFull, my_base, s * nch);
+        const long long lo = __shfl_sync(kFull, (long long)my_lo, s * nch);
+        const long long hi = __shfl_sync(kFull, (long long)my_hi, s * nch);
+        if (hi <= lo) continue;
+        const uint64_t first = (base + (uint64_t)lo) & ~(uint64_t)3;
+        const int words = (int)(((base + (uint64_t)hi + 3) & ~(uint64_t)3) - first) >> 2;
+        for (int w = lane; w < words; w += 32) cp_async4(stage + s * row_words + w, blob + first + 4ull * w);
+    }
+}
+
 // ------------------------------------------------------------ decode, fast
 __global__ void __launch_bounds__(kWarps * 32)
 adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) uint8_t s_code[kWarps][32][kCodeRow];
-    __shared__ __align__(16) int16_t s_pcm[kWarps][32][kPcmRow];
+    __shared__ __align__(16) uint32_t s_code[kWarps][2][kCodeWords + 32];
+    __shared__ __align__(16) int16_t s_pcm[kWarps][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t first = (blockIdx.x * kWarps + warp) * 32u;
     if (first >= n_chains) return;
-    const uint32_t mine = first + lane;
-    const bool active = mine < n_chains;
-    AdxChain ch = chains[active ? mine : first];
-    if (!active) ch.blocks = 0;
+    const AdxChain ch = chains[first + lane];               // the list is padded to whole warps (idle: blocks == 0)
+    const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
+    const int nstreams = 32 / nch;
+    const int frame_bytes = nch * kBlk;
+    const int row_words = (kTile * frame_bytes + 3) / 4 + 1;
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(0xFFFFFFFFu, warp_blocks, o));
-    const uint32_t in_warp = min(32u, n_chains - first);
+    for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(kFull, warp_blocks, o));
+    const int slot = lane / nch;                            // this lane's stream within the warp
+    const int out_row = kTile * kSpb * nch + 2;             // int16 per stream in the PCM tile (odd word stride)
+    int16_t* my_pcm = &s_pcm[warp][slot * out_row + ch.channel];
 
     int h1 = ch.hist1, h2 = ch.hist2, c0 = ch.coef0, c1 = ch.coef1;
-    bool ended = false;  // EOF block seen (adx.cpp:405-406): the rest of the stream stays silent
+    bool ended = false;   // EOF block seen (adx.cpp:405-406): the rest of the stream stays silent
+    const uint64_t stream_base = ch.eof_off;                // channel-0 block of frame 0
 
-    for (uint32_t b0 = 0; b0 < warp_blocks; b0 += kTile) {
-        // ---- stage in: chain j's next kTile blocks, all lanes on one chain at a time
-        for (uint32_t j = 0; j < in_warp; j++) {
-            const AdxChain& cj = chains[first + j];
-            const uint32_t nb = cj.blocks > b0 ? min((uint32_t)kTile, cj.blocks - b0) : 0u;
-            for (uint32_t idx = lane; idx < nb * kBlk; idx += 32) {
-                const uint32_t t = idx / kBlk, k = idx - t * kBlk;
-                s_code[warp][j][idx] = in[cj.in_off + (uint64_t)(b0 + t) * cj.in_stride + k];
-            }
-        }
-        __syncwarp();
-        // ---- each lane decodes its own blocks out of shared memory
+    auto request = [&](uint32_t b0, int buf) {
         const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+        const int64_t lo = (int64_t)b0 * frame_bytes;
+        stage_rows(&s_code[warp][buf][0], row_words, in, stream_base, lo, lo + (int64_t)nb * frame_bytes, nstreams, nch, lane);
+    };
+    int buf = 0;
+    request(0, 0);
+    cp_commit();
+    for (uint32_t b0 = 0; b0 < warp_blocks; b0 += kTile) {
+        request(b0 + kTile, buf ^ 1);
+        cp_commit();
+        cp_wait_all_but_one();
+        __syncwarp();
+        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+        // byte 0 of this lane's first block inside its stream's row
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[warp][buf][slot * row_words]) +
+                             (int)((stream_base + (uint64_t)b0 * frame_bytes) & 3);
         for (uint32_t t = 0; t < nb; t++) {
-            int16_t* dst = &s_pcm[warp][lane][t * kSpb];
-            if (!ended) {
-                const uint64_t probe = ch.eof_off + (uint64_t)(b0 + t) * ch.in_stride;
-                ended = in[probe] == 0x80 && in[probe + 1] == 0x01;
-            }
+            int16_t* dst = my_pcm + t * kSpb * nch;           // sample i of this block -> dst[i * nch]
+            const uint8_t* frame = row + t * frame_bytes;
+            if (!ended) ended = frame[0] == 0x80 && frame[1] == 0x01;       // channel 0's scale word of this frame
             if (ended) {
 #pragma unroll
-                for (int i = 0; i < kSpb; i++) dst[i] = 0;
+                for (int i = 0; i < kSpb; i++) dst[i * nch] = 0;
                 continue;
             }
-            const uint8_t* src = &s_code[warp][lane][t * kBlk];
+            const uint8_t* src = frame + ch.channel * kBlk;
             const int scale = decode_scale((src[0] << 8) | src[1], ch.mode, c0, c1);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
@@ -100,26 +126,37 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 int s = q_hi * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
                 s = clamp16(s);
                 h2 = h1; h1 = s;
-                dst[2 * k] = (int16_t)s;
+                dst[(2 * k) * nch] = (int16_t)s;
                 s = q_lo * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
                 s = clamp16(s);
                 h2 = h1; h1 = s;
-                dst[2 * k + 1] = (int16_t)s;
+                dst[(2 * k + 1) * nch] = (int16_t)s;
             }
         }
         __syncwarp();
-        // ---- stage out: chain j's samples, lanes on consecutive samples (stride = channels)
-        for (uint32_t j = 0; j < in_warp; j++) {
-            const AdxChain& cj = chains[first + j];
-            const uint32_t nbj = cj.blocks > b0 ? min((uint32_t)kTile, cj.blocks - b0) : 0u;
-            const uint32_t base = b0 * kSpb;
-            for (uint32_t idx = lane; idx < nbj * kSpb; idx += 32) {
-                if (base + idx < cj.samples)
-                    *reinterpret_cast<int16_t*>(out + cj.out_off + (uint64_t)(base + idx) * cj.out_stride * 2) =
-                        s_pcm[warp][j][idx];
+        // store: each stream's tile is one contiguous run of interleaved samples
+        {
+            const uint64_t my_out = ch.out_off;              // channel c: first sample of the stream + 2c
+            const uint32_t my_samples = ch.samples;
+            for (int s = 0; s < nstreams; s++) {
+                const uint64_t obase = __shfl_sync(kFull, my_out, s * nch);
+                const uint32_t total = __shfl_sync(kFull, my_samples, s * nch);
+                const uint32_t nbs = __shfl_sync(kFull, nb, s * nch);
+                const uint32_t s0 = b0 * kSpb;
+                const uint32_t count = s0 < total ? min(nbs * kSpb, total - s0) : 0u;   // samples per channel to store
+                uint8_t* dst = out + obase + (size_t)s0 * nch * 2;
+                const int16_t* srow = &s_pcm[warp][s * out_row];
+                const uint32_t halfs = count * nch;
+                if (((reinterpret_cast<uintptr_t>(dst) | (halfs * 2)) & 3) == 0) {
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(srow);
+                    for (uint32_t e = lane; e < halfs / 2; e += 32) reinterpret_cast<uint32_t*>(dst)[e] = w[e];
+                } else {
+                    for (uint32_t e = lane; e < halfs; e += 32) reinterpret_cast<int16_t*>(dst)[e] = srow[e];
+                }
             }
         }
         __syncwarp();
+        buf ^= 1;
     }
 }
 
@@ -190,59 +227,78 @@ __device__ __forceinline__ ScaleChoice choose_scale(int mn, int mx, int limit, i
     return r;
 }
 
-// Exact C-style truncating division of v (|v| < 2^20) by d (1..8192) after the
-// reference's round-half-away bias; only quotients in [-9, 8] need to be exact
-// because the result is clamped to n-bit range right after (adx.cpp:258-260).
-__device__ __forceinline__ int div_trunc(int v, int d) { return v / d; }
+// Exact C-style truncating division by a block-invariant divisor d (1..8192) for |v| < 2^19:
+// q = (|v| * ceil(2^32 / d)) >> 32 is exact while |v| * d < 2^32 (round-up magic number, error < d / 2^32 per unit).
+__device__ __forceinline__ uint32_t div_magic(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }   // ceil(2^32 / d) for d >= 2
+__device__ __forceinline__ int div_trunc(int v, uint32_t magic, int d) {
+    if (d == 1) return v;
+    const int q = (int)__umulhi((uint32_t)abs(v), magic);
+    return v < 0 ? -q : q;
+}
 
 // ------------------------------------------------------------ encode, fast
 __global__ void __launch_bounds__(kWarps * 32)
 adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) int16_t s_pcm[kWarps][32][kPcmRow];
-    __shared__ __align__(16) uint8_t s_code[kWarps][32][kCodeRow];
+    __shared__ __align__(16) uint32_t s_pcm[kWarps][2][kPcmWords + 32];
+    __shared__ __align__(16) uint8_t s_code[kWarps][32 * kTile * kBlk + 128];   // per stream: blocks in file order
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t first = (blockIdx.x * kWarps + warp) * 32u;
     if (first >= n_chains) return;
-    const uint32_t mine = first + lane;
-    const bool active = mine < n_chains;
-    AdxChain ch = chains[active ? mine : first];
-    if (!active) ch.blocks = 0;
+    const AdxChain ch = chains[first + lane];
+    const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
+    const int nstreams = 32 / nch;
+    const int frame_bytes = nch * kSpb * 2;                  // PCM bytes of one block of every channel
+    const int row_words = (kTile * frame_bytes + 3) / 4 + 1;
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(0xFFFFFFFFu, warp_blocks, o));
-    const uint32_t in_warp = min(32u, n_chains - first);
+    for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(kFull, warp_blocks, o));
+    const int slot = lane / nch;
 
     int h1 = ch.hist1, h2 = ch.hist2;
     const int c0 = ch.coef0, c1 = ch.coef1;
     const int limit = 7;
+    const int code_row = kTile * nch * kBlk + 4;             // bytes per stream in the block tile (odd word stride)
+    const uint64_t stream_base = ch.in_off - 2ull * ch.channel;   // first PCM sample of the stream
 
+    auto request = [&](uint32_t b0, int buf) {
+        // valid PCM of this stream in the tile: samples [b0*32, min((b0+nb)*32, samples))
+        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+        const uint32_t s0 = b0 * kSpb;
+        const uint32_t s1 = min((b0 + nb) * kSpb, ch.samples);
+        const int64_t lo = (int64_t)s0 * nch * 2;
+        const int64_t hi = s1 > s0 ? (int64_t)s1 * nch * 2 : lo;
+        stage_rows(&s_pcm[warp][buf][0], row_words, in, stream_base, lo, hi, nstreams, nch, lane);
+    };
+    int buf = 0;
+    request(0, 0);
+    cp_commit();
     for (uint32_t b0 = 0; b0 < warp_blocks; b0 += kTile) {
-        for (uint32_t j = 0; j < in_warp; j++) {  // stage in: lanes on consecutive samples of chain j
-            const AdxChain& cj = chains[first + j];
-            const uint32_t nb = cj.blocks > b0 ? min((uint32_t)kTile, cj.blocks - b0) : 0u;
-            const uint32_t base = b0 * kSpb;
-            for (uint32_t idx = lane; idx < nb * kSpb; idx += 32) {
-                int16_t v = 0;
-                if (base + idx < cj.samples)
-                    v = *reinterpret_cast<const int16_t*>(in + cj.in_off + (uint64_t)(base + idx) * cj.in_stride * 2);
-                s_pcm[warp][j][idx] = v;
-            }
-        }
+        request(b0 + kTile, buf ^ 1);
+        cp_commit();
+        cp_wait_all_but_one();
         __syncwarp();
         const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_pcm[warp][buf][slot * row_words]) +
+                             (int)((stream_base + (uint64_t)b0 * frame_bytes) & 3);
         for (uint32_t t = 0; t < nb; t++) {
-            const int16_t* smp = &s_pcm[warp][lane][t * kSpb];
-            uint8_t* dst = &s_code[warp][lane][t * kBlk];
+            uint8_t* dst = &s_code[warp][slot * code_row + (t * nch + ch.channel) * kBlk];
+            // this block's samples; past the end of the stream the reference pads with silence (adx.cpp:450-460)
+            int smp[kSpb];
+            const uint32_t sbase = (b0 + t) * kSpb;
+#pragma unroll
+            for (int i = 0; i < kSpb; i++) {
+                const int16_t* q = reinterpret_cast<const int16_t*>(row) + (size_t)(t * kSpb + i) * nch + ch.channel;
+                smp[i] = sbase + i < ch.samples ? (int)*q : 0;
+            }
             // pass 1: residual range against RAW history (adx.cpp:221-230)
             const int o1 = h1, o2 = h2;
             int mn = 0, mx = 0;
 #pragma unroll
             for (int i = 0; i < kSpb; i++) {
-                const int s = smp[i];
-                const int r = (s * 4096 - c0 * h1 - c1 * h2) >> 12;
+                const int r = (smp[i] * 4096 - c0 * h1 - c1 * h2) >> 12;
                 mn = min(mn, r); mx = max(mx, r);
-                h2 = h1; h1 = s;
+                h2 = h1; h1 = smp[i];
             }
             if (mn == 0 && mx == 0) {  // silent residual: all-zero block, history stays raw (adx.cpp:231-234)
 #pragma unroll
@@ -254,17 +310,17 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
             dst[1] = (uint8_t)sc.word;
             const int scale = sc.scale ? sc.scale : 1;  // adx.cpp:256-257
             const int half = scale >> 1;
+            const uint32_t magic = div_magic(scale);
             h1 = o1; h2 = o2;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 int byte = 0;
 #pragma unroll
                 for (int n = 0; n < 2; n++) {
-                    const int s = smp[2 * k + n];
                     const int pred = c0 * h1 + c1 * h2;
-                    int d = (s * 4096 - pred) >> 12;
+                    int d = (smp[2 * k + n] * 4096 - pred) >> 12;
                     d = d > 0 ? d + half : d - half;
-                    d = div_trunc(d, scale);
+                    d = div_trunc(d, magic, scale);
                     d = min(max(d, -8), 7);
                     const int sim = clamp16((d * 4096 * scale + pred) >> 12);
                     h2 = h1; h1 = sim;
@@ -274,15 +330,25 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
             }
         }
         __syncwarp();
-        for (uint32_t j = 0; j < in_warp; j++) {  // stage out: lanes on consecutive bytes of chain j's blocks
-            const AdxChain& cj = chains[first + j];
-            const uint32_t nbj = cj.blocks > b0 ? min((uint32_t)kTile, cj.blocks - b0) : 0u;
-            for (uint32_t idx = lane; idx < nbj * kBlk; idx += 32) {
-                const uint32_t t = idx / kBlk, k = idx - t * kBlk;
-                out[cj.out_off + (uint64_t)(b0 + t) * cj.out_stride + k] = s_code[warp][j][idx];
+        // store: each stream's tile of blocks is contiguous in the ADX image
+        {
+            const uint64_t my_out = ch.out_off - (uint64_t)ch.channel * kBlk;   // channel-0 block of frame 0
+            for (int s = 0; s < nstreams; s++) {
+                const uint64_t obase = __shfl_sync(kFull, my_out, s * nch);
+                const uint32_t nbs = __shfl_sync(kFull, nb, s * nch);
+                uint8_t* dst = out + obase + (uint64_t)b0 * nch * kBlk;
+                const uint32_t bytes = nbs * nch * kBlk;                 // even
+                const uint8_t* srow = &s_code[warp][s * code_row];
+                if ((reinterpret_cast<uintptr_t>(dst) & 1) == 0) {
+                    for (uint32_t e = lane; e < bytes / 2; e += 32)
+                        reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(srow)[e];
+                } else {
+                    for (uint32_t e = lane; e < bytes; e += 32) dst[e] = srow[e];
+                }
             }
         }
         __syncwarp();
+        buf ^= 1;
     }
 }
 

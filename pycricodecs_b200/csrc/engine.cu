@@ -124,6 +124,29 @@ void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n
 static void finish_layout(cri_job* j, const std::vector<uint64_t>& sizes) { finish_layout_public(j, sizes); }
 static void add_patch(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n) { add_patch_public(j, dst, bytes, n); }
 
+// Fast-path chain lists: a warp's 32 chains belong to 32/nch whole streams of one channel count (1,2,4,..,32); each
+// channel-count bucket is padded with idle chains to whole warps. Other channel counts go to the generic list.
+struct AdxLists {
+    std::vector<AdxChain> bucket[6], generic;
+    static int bucket_of(int nch) { for (int b = 0; b < 6; b++) if (nch == (1 << b)) return b; return -1; }
+    void add(const std::vector<AdxChain>& stream_chains, bool fast_ok) {
+        const int b = fast_ok ? bucket_of((int)stream_chains.size()) : -1;
+        auto& dst = b >= 0 ? bucket[b] : generic;
+        dst.insert(dst.end(), stream_chains.begin(), stream_chains.end());
+    }
+    void finish(cri_job* j) {
+        j->adx_chains.clear();
+        for (int b = 0; b < 6; b++) {
+            auto& v = bucket[b];
+            while (v.size() % 32) { AdxChain idle{}; idle.channels = (uint8_t)(1 << b); v.push_back(idle); }
+            j->adx_chains.insert(j->adx_chains.end(), v.begin(), v.end());
+        }
+        j->n_fast = (uint32_t)j->adx_chains.size();
+        j->n_generic = (uint32_t)generic.size();
+        j->adx_chains.insert(j->adx_chains.end(), generic.begin(), generic.end());
+    }
+};
+
 static int adx_decode_size_one(const uint8_t* d, size_t n, AdxInfo* a, uint64_t* size) {
     const int r = parse_adx(d, n, a);
     if (r < 0) return r;
@@ -137,10 +160,12 @@ static void plan_adx_decode(cri_job* j) {
     for (uint32_t i = 0; i < j->n; i++)
         j->status[i] = adx_decode_size_one(j->blob + j->in_off[i], j->in_off[i + 1] - j->in_off[i], &infos[i], &sizes[i]);
     finish_layout(j, sizes);
-    std::vector<AdxChain> fast, generic;
+    AdxLists lists;
+    std::vector<AdxChain> one;
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
         const AdxInfo& a = infos[i];
+        one.clear();
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         const uint64_t data = (uint64_t)a.data_offset + 4;
         const uint64_t frame_bytes = (uint64_t)a.channels * a.block_size;
@@ -169,17 +194,17 @@ static void plan_adx_decode(cri_job* j) {
             ch.mode = (uint8_t)a.mode;
             ch.bit_depth = (uint8_t)a.bit_depth;
             ch.block_size = (uint8_t)a.block_size;
+            ch.channels = (uint8_t)a.channels;
+            ch.channel = (uint8_t)c;
             ch.stream = i;
-            (is_fast ? fast : generic).push_back(ch);
+            one.push_back(ch);
         }
+        lists.add(one, is_fast);
         j->units += (uint64_t)blocks * a.channels;
         // samples past the last decoded block stay zero: zero-filled by the tail patch below
         if ((uint64_t)blocks * a.samples_per_block < a.samples) j->needs_clear = true;
     }
-    j->n_fast = (uint32_t)fast.size();
-    j->n_generic = (uint32_t)generic.size();
-    j->adx_chains = fast;
-    j->adx_chains.insert(j->adx_chains.end(), generic.begin(), generic.end());
+    lists.finish(j);
 }
 
 static void plan_adx_encode(cri_job* j) {
@@ -199,11 +224,13 @@ static void plan_adx_encode(cri_job* j) {
         sizes[i] = plans[i].out_size;
     }
     finish_layout(j, sizes);
-    std::vector<AdxChain> fast, generic;
+    AdxLists lists;
+    std::vector<AdxChain> one;
     std::vector<uint8_t> tmp;
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
         const AdxEncPlan& p = plans[i];
+        one.clear();
         const uint8_t* d = j->blob + j->in_off[i];
         const int16_t* pcm = reinterpret_cast<const int16_t*>(d + wavs[i].data_offset);
         int16_t firsts[256];
@@ -231,15 +258,15 @@ static void plan_adx_encode(cri_job* j) {
             ch.bit_depth = (uint8_t)p.bit_depth;
             ch.block_size = (uint8_t)p.block_size;
             ch.filter = (uint8_t)p.filter;
+            ch.channels = (uint8_t)p.channels;
+            ch.channel = (uint8_t)c;
             ch.stream = i;
-            (is_fast ? fast : generic).push_back(ch);
+            one.push_back(ch);
         }
+        lists.add(one, is_fast);
         j->units += (uint64_t)p.frames * p.channels;
     }
-    j->n_fast = (uint32_t)fast.size();
-    j->n_generic = (uint32_t)generic.size();
-    j->adx_chains = fast;
-    j->adx_chains.insert(j->adx_chains.end(), generic.begin(), generic.end());
+    lists.finish(j);
 }
 
 // ------------------------------------------------------------------- jobs

@@ -21,6 +21,8 @@ struct AdxChain {
     int32_t coef0, coef1;
     int16_t hist1, hist2;
     uint8_t mode, bit_depth, block_size, filter;  // filter: encode mode 2 predictor index
+    uint8_t channels, channel;                    // of the stream / this chain's index; fast lists: uniform per warp
+    uint8_t pad[2];
     uint32_t stream;
 };
 
