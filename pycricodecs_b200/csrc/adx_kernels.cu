@@ -27,7 +27,6 @@ namespace {
 constexpr int kTile = 8;                 // blocks per chain per tile
 constexpr int kSpb = 32;                 // samples per block on the fast path
 constexpr int kBlk = 18;                 // bytes per block on the fast path
-constexpr int kWarps = 1;                // warps per CTA (one warp = 26 / 38 KB of static shared memory)
 constexpr int kPcmRow = kTile * kSpb + 2;            // int16 per chain in the PCM tile: odd word stride
 constexpr int kCodeWords = (kTile * 32 * kBlk + 3) / 4 + 1;     // covering words of 32 chains x kTile blocks
 constexpr int kPcmWords = (kTile * 32 * kSpb * 2 + 3) / 4 + 1;  // covering words of 32 chains x kTile x 32 samples
@@ -39,7 +38,7 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1) {
     if (mode == 3) return raw + 1;
@@ -51,113 +50,126 @@ __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1)
     return (raw & 0x1FFF) + 1;
 }
 
-// Copy, for every stream of the warp, the aligned words covering bytes [base + lo, base + hi) of the input blob into
-// the stream's row of `stage` (row stride `row_words`). base / byte ranges come from the stream's channel-0 lane.
-__device__ __forceinline__ void stage_rows(uint32_t* stage, int row_words, const uint8_t* blob, uint64_t my_base, int64_t my_lo,
-                                           int64_t my_hi, int nstreams, int nch, int lane) {
+// Warp specialisation: a CTA is two warps working on the same 32 chains. Warp 0 ("worker") runs the 32 serial
+// recurrences out of shared memory; warp 1 ("mover") keeps the next input tile arriving (cp.async) and drains the
+// previous output tile to HBM, so the recurrence never waits for memory. One __syncthreads per tile hands the
+// double-buffered tiles over.
+struct StreamInfo {
+    uint64_t in_base;    // first byte of the stream's payload in the input blob (decode: frame 0, encode: sample 0)
+    uint64_t out_base;   // first byte of the stream's payload in the output blob
+    uint32_t blocks;     // blocks per channel to walk
+    uint32_t samples;    // valid samples per channel
+};
+
+// mover: request the aligned words that cover bytes [in_base + lo, in_base + hi) of every stream into its stage row
+__device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, const uint8_t* blob, const StreamInfo* info,
+                                              int nstreams, uint32_t b0, int unit_bytes, bool clip_samples, int nch, int lane) {
     for (int s = 0; s < nstreams; s++) {
-        const uint64_t base = __shfl_sync(kFull, my_base, s * nch);
-        const long long lo = __shfl_sync(kFull, (long long)my_lo, s * nch);
-        const long long hi = __shfl_sync(kFull, (long long)my_hi, s * nch);
+        const StreamInfo si = info[s];
+        const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
+        uint64_t lo = (uint64_t)b0 * unit_bytes, hi = lo + (uint64_t)nb * unit_bytes;
+        if (clip_samples) hi = min(hi, (uint64_t)si.samples * nch * 2);   // encode: PCM ends with the stream, the rest is padding
         if (hi <= lo) continue;
-        const uint64_t first = (base + (uint64_t)lo) & ~(uint64_t)3;
-        const int words = (int)(((base + (uint64_t)hi + 3) & ~(uint64_t)3) - first) >> 2;
+        const uint64_t first = (si.in_base + lo) & ~(uint64_t)3;
+        const int words = (int)(((si.in_base + hi + 3) & ~(uint64_t)3) - first) >> 2;
         for (int w = lane; w < words; w += 32) cp_async4(stage + s * row_words + w, blob + first + 4ull * w);
     }
 }
 
 // ------------------------------------------------------------ decode, fast
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(64)
 adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) uint32_t s_code[kWarps][2][kCodeWords + 32];
-    __shared__ __align__(16) int16_t s_pcm[kWarps][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t first = (blockIdx.x * kWarps + warp) * 32u;
+    __shared__ __align__(16) uint32_t s_code[2][kCodeWords + 32];
+    __shared__ __align__(16) int16_t s_pcm[2][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
+    __shared__ StreamInfo s_info[32];
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t first = blockIdx.x * 32u;
     if (first >= n_chains) return;
     const AdxChain ch = chains[first + lane];               // the list is padded to whole warps (idle: blocks == 0)
     const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
     const int nstreams = 32 / nch;
     const int frame_bytes = nch * kBlk;
     const int row_words = (kTile * frame_bytes + 3) / 4 + 1;
+    const int out_row = kTile * kSpb * nch + 2;             // int16 per stream in the PCM tile (odd word stride)
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
     for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(kFull, warp_blocks, o));
-    const int slot = lane / nch;                            // this lane's stream within the warp
-    const int out_row = kTile * kSpb * nch + 2;             // int16 per stream in the PCM tile (odd word stride)
-    int16_t* my_pcm = &s_pcm[warp][slot * out_row + ch.channel];
+    const int slot = lane / nch;                            // this lane's stream within the CTA
+    if (role == 0 && ch.channel == 0) s_info[slot] = StreamInfo{ch.eof_off, ch.out_off, ch.blocks, ch.samples};
+    __syncthreads();
+    const uint32_t ntiles = (warp_blocks + kTile - 1) / kTile;
+
+    auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is one contiguous run in the WAV
+        const uint32_t b0 = t * kTile, s0 = b0 * kSpb;
+        for (int s = 0; s < nstreams; s++) {
+            const StreamInfo si = s_info[s];
+            const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
+            const uint32_t count = s0 < si.samples ? min(nb * kSpb, si.samples - s0) : 0u;
+            uint8_t* dst = out + si.out_base + (size_t)s0 * nch * 2;
+            const int16_t* srow = &s_pcm[t & 1][s * out_row];
+            const uint32_t halfs = count * nch;
+            if (((reinterpret_cast<uintptr_t>(dst) | (halfs * 2)) & 3) == 0) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(srow);
+                for (uint32_t e = lane; e < halfs / 2; e += 32) reinterpret_cast<uint32_t*>(dst)[e] = w[e];
+            } else {
+                for (uint32_t e = lane; e < halfs; e += 32) reinterpret_cast<int16_t*>(dst)[e] = srow[e];
+            }
+        }
+    };
+
+    if (role == 1) {
+        mover_request(&s_code[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, false, nch, lane);
+        cp_commit();
+        cp_wait_all();
+    }
+    __syncthreads();
 
     int h1 = ch.hist1, h2 = ch.hist2, c0 = ch.coef0, c1 = ch.coef1;
     bool ended = false;   // EOF block seen (adx.cpp:405-406): the rest of the stream stays silent
-    const uint64_t stream_base = ch.eof_off;                // channel-0 block of frame 0
-
-    auto request = [&](uint32_t b0, int buf) {
-        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
-        const int64_t lo = (int64_t)b0 * frame_bytes;
-        stage_rows(&s_code[warp][buf][0], row_words, in, stream_base, lo, lo + (int64_t)nb * frame_bytes, nstreams, nch, lane);
-    };
-    int buf = 0;
-    request(0, 0);
-    cp_commit();
-    for (uint32_t b0 = 0; b0 < warp_blocks; b0 += kTile) {
-        request(b0 + kTile, buf ^ 1);
-        cp_commit();
-        cp_wait_all_but_one();
-        __syncwarp();
-        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
-        // byte 0 of this lane's first block inside its stream's row
-        const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[warp][buf][slot * row_words]) +
-                             (int)((stream_base + (uint64_t)b0 * frame_bytes) & 3);
-        for (uint32_t t = 0; t < nb; t++) {
-            int16_t* dst = my_pcm + t * kSpb * nch;           // sample i of this block -> dst[i * nch]
-            const uint8_t* frame = row + t * frame_bytes;
-            if (!ended) ended = frame[0] == 0x80 && frame[1] == 0x01;       // channel 0's scale word of this frame
-            if (ended) {
+    for (uint32_t t = 0; t < ntiles; t++) {
+        const int buf = t & 1;
+        const uint32_t b0 = t * kTile;
+        if (role == 1) {
+            if (t + 1 < ntiles) mover_request(&s_code[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, false, nch, lane);
+            cp_commit();
+            if (t >= 1) store_tile(t - 1);
+            cp_wait_all();
+        } else {
+            const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+            // byte 0 of this lane's first frame inside its stream's row
+            const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[buf][slot * row_words]) +
+                                 (int)((ch.eof_off + (uint64_t)b0 * frame_bytes) & 3);
+            int16_t* my_pcm = &s_pcm[buf][slot * out_row + ch.channel];
+            for (uint32_t tb = 0; tb < nb; tb++) {
+                int16_t* dst = my_pcm + tb * kSpb * nch;      // sample i of this block -> dst[i * nch]
+                const uint8_t* frame = row + tb * frame_bytes;
+                if (!ended) ended = frame[0] == 0x80 && frame[1] == 0x01;       // channel 0's scale word of this frame
+                if (ended) {
 #pragma unroll
-                for (int i = 0; i < kSpb; i++) dst[i * nch] = 0;
-                continue;
-            }
-            const uint8_t* src = frame + ch.channel * kBlk;
-            const int scale = decode_scale((src[0] << 8) | src[1], ch.mode, c0, c1);
+                    for (int i = 0; i < kSpb; i++) dst[i * nch] = 0;
+                    continue;
+                }
+                const uint8_t* src = frame + ch.channel * kBlk;
+                const int scale = decode_scale((src[0] << 8) | src[1], ch.mode, c0, c1);
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const int byte = src[2 + k];
-                const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
-                int s = q_hi * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
-                s = clamp16(s);
-                h2 = h1; h1 = s;
-                dst[(2 * k) * nch] = (int16_t)s;
-                s = q_lo * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
-                s = clamp16(s);
-                h2 = h1; h1 = s;
-                dst[(2 * k + 1) * nch] = (int16_t)s;
-            }
-        }
-        __syncwarp();
-        // store: each stream's tile is one contiguous run of interleaved samples
-        {
-            const uint64_t my_out = ch.out_off;              // channel c: first sample of the stream + 2c
-            const uint32_t my_samples = ch.samples;
-            for (int s = 0; s < nstreams; s++) {
-                const uint64_t obase = __shfl_sync(kFull, my_out, s * nch);
-                const uint32_t total = __shfl_sync(kFull, my_samples, s * nch);
-                const uint32_t nbs = __shfl_sync(kFull, nb, s * nch);
-                const uint32_t s0 = b0 * kSpb;
-                const uint32_t count = s0 < total ? min(nbs * kSpb, total - s0) : 0u;   // samples per channel to store
-                uint8_t* dst = out + obase + (size_t)s0 * nch * 2;
-                const int16_t* srow = &s_pcm[warp][s * out_row];
-                const uint32_t halfs = count * nch;
-                if (((reinterpret_cast<uintptr_t>(dst) | (halfs * 2)) & 3) == 0) {
-                    const uint32_t* w = reinterpret_cast<const uint32_t*>(srow);
-                    for (uint32_t e = lane; e < halfs / 2; e += 32) reinterpret_cast<uint32_t*>(dst)[e] = w[e];
-                } else {
-                    for (uint32_t e = lane; e < halfs; e += 32) reinterpret_cast<int16_t*>(dst)[e] = srow[e];
+                for (int k = 0; k < 16; k++) {
+                    const int byte = src[2 + k];
+                    const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
+                    int s = q_hi * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
+                    s = clamp16(s);
+                    h2 = h1; h1 = s;
+                    dst[(2 * k) * nch] = (int16_t)s;
+                    s = q_lo * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
+                    s = clamp16(s);
+                    h2 = h1; h1 = s;
+                    dst[(2 * k + 1) * nch] = (int16_t)s;
                 }
             }
         }
-        __syncwarp();
-        buf ^= 1;
+        __syncthreads();
     }
+    if (role == 1 && ntiles) store_tile(ntiles - 1);
 }
 
 // --------------------------------------------------------- decode, generic
@@ -237,119 +249,121 @@ __device__ __forceinline__ int div_trunc(int v, uint32_t magic, int d) {
 }
 
 // ------------------------------------------------------------ encode, fast
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(64)
 adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) uint32_t s_pcm[kWarps][2][kPcmWords + 32];
-    __shared__ __align__(16) uint8_t s_code[kWarps][32 * kTile * kBlk + 128];   // per stream: blocks in file order
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t first = (blockIdx.x * kWarps + warp) * 32u;
+    __shared__ __align__(16) uint32_t s_pcm[2][kPcmWords + 32];
+    __shared__ __align__(16) uint8_t s_code[2][32 * kTile * kBlk + 128];   // per stream: blocks in file order
+    __shared__ StreamInfo s_info[32];
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t first = blockIdx.x * 32u;
     if (first >= n_chains) return;
     const AdxChain ch = chains[first + lane];
     const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
     const int nstreams = 32 / nch;
     const int frame_bytes = nch * kSpb * 2;                  // PCM bytes of one block of every channel
     const int row_words = (kTile * frame_bytes + 3) / 4 + 1;
+    const int code_row = kTile * nch * kBlk + 4;             // bytes per stream in the block tile (odd word stride)
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
     for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(kFull, warp_blocks, o));
     const int slot = lane / nch;
+    const uint64_t stream_base = ch.in_off - 2ull * ch.channel;   // first PCM sample of the stream
+    if (role == 0 && ch.channel == 0) s_info[slot] = StreamInfo{stream_base, ch.out_off, ch.blocks, ch.samples};
+    __syncthreads();
+    const uint32_t ntiles = (warp_blocks + kTile - 1) / kTile;
+
+    auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is contiguous in the ADX image
+        const uint32_t b0 = t * kTile;
+        for (int s = 0; s < nstreams; s++) {
+            const StreamInfo si = s_info[s];
+            const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
+            uint8_t* dst = out + si.out_base + (uint64_t)b0 * nch * kBlk;
+            const uint32_t bytes = nb * nch * kBlk;                 // even
+            const uint8_t* srow = &s_code[t & 1][s * code_row];
+            if ((reinterpret_cast<uintptr_t>(dst) & 1) == 0) {
+                for (uint32_t e = lane; e < bytes / 2; e += 32)
+                    reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(srow)[e];
+            } else {
+                for (uint32_t e = lane; e < bytes; e += 32) dst[e] = srow[e];
+            }
+        }
+    };
+
+    if (role == 1) {
+        mover_request(&s_pcm[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, true, nch, lane);
+        cp_commit();
+        cp_wait_all();
+    }
+    __syncthreads();
 
     int h1 = ch.hist1, h2 = ch.hist2;
     const int c0 = ch.coef0, c1 = ch.coef1;
     const int limit = 7;
-    const int code_row = kTile * nch * kBlk + 4;             // bytes per stream in the block tile (odd word stride)
-    const uint64_t stream_base = ch.in_off - 2ull * ch.channel;   // first PCM sample of the stream
-
-    auto request = [&](uint32_t b0, int buf) {
-        // valid PCM of this stream in the tile: samples [b0*32, min((b0+nb)*32, samples))
-        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
-        const uint32_t s0 = b0 * kSpb;
-        const uint32_t s1 = min((b0 + nb) * kSpb, ch.samples);
-        const int64_t lo = (int64_t)s0 * nch * 2;
-        const int64_t hi = s1 > s0 ? (int64_t)s1 * nch * 2 : lo;
-        stage_rows(&s_pcm[warp][buf][0], row_words, in, stream_base, lo, hi, nstreams, nch, lane);
-    };
-    int buf = 0;
-    request(0, 0);
-    cp_commit();
-    for (uint32_t b0 = 0; b0 < warp_blocks; b0 += kTile) {
-        request(b0 + kTile, buf ^ 1);
-        cp_commit();
-        cp_wait_all_but_one();
-        __syncwarp();
-        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
-        const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_pcm[warp][buf][slot * row_words]) +
-                             (int)((stream_base + (uint64_t)b0 * frame_bytes) & 3);
-        for (uint32_t t = 0; t < nb; t++) {
-            uint8_t* dst = &s_code[warp][slot * code_row + (t * nch + ch.channel) * kBlk];
-            // this block's samples; past the end of the stream the reference pads with silence (adx.cpp:450-460)
-            int smp[kSpb];
-            const uint32_t sbase = (b0 + t) * kSpb;
+    for (uint32_t t = 0; t < ntiles; t++) {
+        const int buf = t & 1;
+        const uint32_t b0 = t * kTile;
+        if (role == 1) {
+            if (t + 1 < ntiles) mover_request(&s_pcm[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, true, nch, lane);
+            cp_commit();
+            if (t >= 1) store_tile(t - 1);
+            cp_wait_all();
+        } else {
+            const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+            const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_pcm[buf][slot * row_words]) +
+                                 (int)((stream_base + (uint64_t)b0 * frame_bytes) & 3);
+            for (uint32_t tb = 0; tb < nb; tb++) {
+                uint8_t* dst = &s_code[buf][slot * code_row + (tb * nch + ch.channel) * kBlk];
+                // this block's samples; past the end of the stream the reference pads with silence (adx.cpp:450-460)
+                int smp[kSpb];
+                const uint32_t sbase = (b0 + tb) * kSpb;
 #pragma unroll
-            for (int i = 0; i < kSpb; i++) {
-                const int16_t* q = reinterpret_cast<const int16_t*>(row) + (size_t)(t * kSpb + i) * nch + ch.channel;
-                smp[i] = sbase + i < ch.samples ? (int)*q : 0;
-            }
-            // pass 1: residual range against RAW history (adx.cpp:221-230)
-            const int o1 = h1, o2 = h2;
-            int mn = 0, mx = 0;
-#pragma unroll
-            for (int i = 0; i < kSpb; i++) {
-                const int r = (smp[i] * 4096 - c0 * h1 - c1 * h2) >> 12;
-                mn = min(mn, r); mx = max(mx, r);
-                h2 = h1; h1 = smp[i];
-            }
-            if (mn == 0 && mx == 0) {  // silent residual: all-zero block, history stays raw (adx.cpp:231-234)
-#pragma unroll
-                for (int k = 0; k < kBlk; k++) dst[k] = 0;
-                continue;
-            }
-            const ScaleChoice sc = choose_scale(mn, mx, limit, ch.mode, ch.filter);
-            dst[0] = (uint8_t)(sc.word >> 8);
-            dst[1] = (uint8_t)sc.word;
-            const int scale = sc.scale ? sc.scale : 1;  // adx.cpp:256-257
-            const int half = scale >> 1;
-            const uint32_t magic = div_magic(scale);
-            h1 = o1; h2 = o2;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int byte = 0;
-#pragma unroll
-                for (int n = 0; n < 2; n++) {
-                    const int pred = c0 * h1 + c1 * h2;
-                    int d = (smp[2 * k + n] * 4096 - pred) >> 12;
-                    d = d > 0 ? d + half : d - half;
-                    d = div_trunc(d, magic, scale);
-                    d = min(max(d, -8), 7);
-                    const int sim = clamp16((d * 4096 * scale + pred) >> 12);
-                    h2 = h1; h1 = sim;
-                    byte = (byte << 4) | (d & 0xF);
+                for (int i = 0; i < kSpb; i++) {
+                    const int16_t* q = reinterpret_cast<const int16_t*>(row) + (size_t)(tb * kSpb + i) * nch + ch.channel;
+                    smp[i] = sbase + i < ch.samples ? (int)*q : 0;
                 }
-                dst[2 + k] = (uint8_t)byte;
-            }
-        }
-        __syncwarp();
-        // store: each stream's tile of blocks is contiguous in the ADX image
-        {
-            const uint64_t my_out = ch.out_off - (uint64_t)ch.channel * kBlk;   // channel-0 block of frame 0
-            for (int s = 0; s < nstreams; s++) {
-                const uint64_t obase = __shfl_sync(kFull, my_out, s * nch);
-                const uint32_t nbs = __shfl_sync(kFull, nb, s * nch);
-                uint8_t* dst = out + obase + (uint64_t)b0 * nch * kBlk;
-                const uint32_t bytes = nbs * nch * kBlk;                 // even
-                const uint8_t* srow = &s_code[warp][s * code_row];
-                if ((reinterpret_cast<uintptr_t>(dst) & 1) == 0) {
-                    for (uint32_t e = lane; e < bytes / 2; e += 32)
-                        reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(srow)[e];
-                } else {
-                    for (uint32_t e = lane; e < bytes; e += 32) dst[e] = srow[e];
+                // pass 1: residual range against RAW history (adx.cpp:221-230)
+                const int o1 = h1, o2 = h2;
+                int mn = 0, mx = 0;
+#pragma unroll
+                for (int i = 0; i < kSpb; i++) {
+                    const int r = (smp[i] * 4096 - c0 * h1 - c1 * h2) >> 12;
+                    mn = min(mn, r); mx = max(mx, r);
+                    h2 = h1; h1 = smp[i];
+                }
+                if (mn == 0 && mx == 0) {  // silent residual: all-zero block, history stays raw (adx.cpp:231-234)
+#pragma unroll
+                    for (int k = 0; k < kBlk; k++) dst[k] = 0;
+                    continue;
+                }
+                const ScaleChoice sc = choose_scale(mn, mx, limit, ch.mode, ch.filter);
+                dst[0] = (uint8_t)(sc.word >> 8);
+                dst[1] = (uint8_t)sc.word;
+                const int scale = sc.scale ? sc.scale : 1;  // adx.cpp:256-257
+                const int half = scale >> 1;
+                const uint32_t magic = div_magic(scale);
+                h1 = o1; h2 = o2;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    int byte = 0;
+#pragma unroll
+                    for (int n = 0; n < 2; n++) {
+                        const int pred = c0 * h1 + c1 * h2;
+                        int d = (smp[2 * k + n] * 4096 - pred) >> 12;
+                        d = d > 0 ? d + half : d - half;
+                        d = div_trunc(d, magic, scale);
+                        d = min(max(d, -8), 7);
+                        const int sim = clamp16((d * 4096 * scale + pred) >> 12);
+                        h2 = h1; h1 = sim;
+                        byte = (byte << 4) | (d & 0xF);
+                    }
+                    dst[2 + k] = (uint8_t)byte;
                 }
             }
         }
-        __syncwarp();
-        buf ^= 1;
+        __syncthreads();
     }
+    if (role == 1 && ntiles) store_tile(ntiles - 1);
 }
 
 // --------------------------------------------------------- encode, generic
@@ -415,8 +429,7 @@ __global__ void scatter_patches_kernel(uint8_t* __restrict__ out, const uint8_t*
 void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
-        const uint32_t per_cta = kWarps * 32;
-        adx_decode_fast_kernel<<<(n_fast + per_cta - 1) / per_cta, per_cta, 0, s>>>(d_in, d_out, d_chains, n_fast);
+        adx_decode_fast_kernel<<<(n_fast + 31) / 32, 64, 0, s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
@@ -428,8 +441,7 @@ void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_ch
 void launch_adx_encode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
-        const uint32_t per_cta = kWarps * 32;
-        adx_encode_fast_kernel<<<(n_fast + per_cta - 1) / per_cta, per_cta, 0, s>>>(d_in, d_out, d_chains, n_fast);
+        adx_encode_fast_kernel<<<(n_fast + 31) / 32, 64, 0, s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
