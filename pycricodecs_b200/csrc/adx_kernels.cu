@@ -31,6 +31,7 @@ constexpr int kPcmRow = kTile * kSpb + 2;            // int16 per chain in the P
 constexpr int kCodeWords = (kTile * 32 * kBlk + 3) / 4 + 1;     // covering words of 32 chains x kTile blocks
 constexpr int kPcmWords = (kTile * 32 * kSpb * 2 + 3) / 4 + 1;  // covering words of 32 chains x kTile x 32 samples
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kMovers = 3;               // mover warps per CTA (warp 0 is the worker)
 
 __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
 
@@ -63,8 +64,9 @@ struct StreamInfo {
 
 // mover: request the aligned words that cover bytes [in_base + lo, in_base + hi) of every stream into its stage row
 __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, const uint8_t* blob, const StreamInfo* info,
-                                              int nstreams, uint32_t b0, int unit_bytes, bool clip_samples, int nch, int lane) {
-    for (int s = 0; s < nstreams; s++) {
+                                              int nstreams, uint32_t b0, int unit_bytes, bool clip_samples, int nch, int lane,
+                                              int mover) {
+    for (int s = mover; s < nstreams; s += kMovers) {
         const StreamInfo si = info[s];
         const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
         uint64_t lo = (uint64_t)b0 * unit_bytes, hi = lo + (uint64_t)nb * unit_bytes;
@@ -77,7 +79,7 @@ __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, co
 }
 
 // ------------------------------------------------------------ decode, fast
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32 * (1 + kMovers))
 adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
     __shared__ __align__(16) uint32_t s_code[2][kCodeWords + 32];
@@ -102,7 +104,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
 
     auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is one contiguous run in the WAV
         const uint32_t b0 = t * kTile, s0 = b0 * kSpb;
-        for (int s = 0; s < nstreams; s++) {
+        for (int s = role - 1; s < nstreams; s += kMovers) {
             const StreamInfo si = s_info[s];
             const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
             const uint32_t count = s0 < si.samples ? min(nb * kSpb, si.samples - s0) : 0u;
@@ -118,8 +120,8 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         }
     };
 
-    if (role == 1) {
-        mover_request(&s_code[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, false, nch, lane);
+    if (role >= 1) {
+        mover_request(&s_code[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, false, nch, lane, role - 1);
         cp_commit();
         cp_wait_all();
     }
@@ -130,8 +132,8 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     for (uint32_t t = 0; t < ntiles; t++) {
         const int buf = t & 1;
         const uint32_t b0 = t * kTile;
-        if (role == 1) {
-            if (t + 1 < ntiles) mover_request(&s_code[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, false, nch, lane);
+        if (role >= 1) {
+            if (t + 1 < ntiles) mover_request(&s_code[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, false, nch, lane, role - 1);
             cp_commit();
             if (t >= 1) store_tile(t - 1);
             cp_wait_all();
@@ -151,16 +153,21 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                     continue;
                 }
                 const uint8_t* src = frame + ch.channel * kBlk;
-                const int scale = decode_scale((src[0] << 8) | src[1], ch.mode, c0, c1);
+                // the whole block goes to registers first: one shared-memory latency per block instead of one per byte
+                // (the compiler cannot hoist these loads over the PCM stores below by itself)
+                int blk[kBlk];
+#pragma unroll
+                for (int k = 0; k < kBlk; k++) blk[k] = src[k];
+                const int scale = decode_scale((blk[0] << 8) | blk[1], ch.mode, c0, c1);
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
-                    const int byte = src[2 + k];
+                    const int byte = blk[2 + k];
                     const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
-                    int s = q_hi * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
+                    int s = (q_hi * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);   // same sum, h1 term last (critical path)
                     s = clamp16(s);
                     h2 = h1; h1 = s;
                     dst[(2 * k) * nch] = (int16_t)s;
-                    s = q_lo * scale + ((c0 * h1) >> 12) + ((c1 * h2) >> 12);
+                    s = (q_lo * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);
                     s = clamp16(s);
                     h2 = h1; h1 = s;
                     dst[(2 * k + 1) * nch] = (int16_t)s;
@@ -169,7 +176,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         }
         __syncthreads();
     }
-    if (role == 1 && ntiles) store_tile(ntiles - 1);
+    if (role >= 1 && ntiles) store_tile(ntiles - 1);
 }
 
 // --------------------------------------------------------- decode, generic
@@ -249,7 +256,7 @@ __device__ __forceinline__ int div_trunc(int v, uint32_t magic, int d) {
 }
 
 // ------------------------------------------------------------ encode, fast
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32 * (1 + kMovers))
 adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
     __shared__ __align__(16) uint32_t s_pcm[2][kPcmWords + 32];
@@ -275,7 +282,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
 
     auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is contiguous in the ADX image
         const uint32_t b0 = t * kTile;
-        for (int s = 0; s < nstreams; s++) {
+        for (int s = role - 1; s < nstreams; s += kMovers) {
             const StreamInfo si = s_info[s];
             const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
             uint8_t* dst = out + si.out_base + (uint64_t)b0 * nch * kBlk;
@@ -290,8 +297,8 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         }
     };
 
-    if (role == 1) {
-        mover_request(&s_pcm[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, true, nch, lane);
+    if (role >= 1) {
+        mover_request(&s_pcm[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, true, nch, lane, role - 1);
         cp_commit();
         cp_wait_all();
     }
@@ -303,8 +310,8 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     for (uint32_t t = 0; t < ntiles; t++) {
         const int buf = t & 1;
         const uint32_t b0 = t * kTile;
-        if (role == 1) {
-            if (t + 1 < ntiles) mover_request(&s_pcm[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, true, nch, lane);
+        if (role >= 1) {
+            if (t + 1 < ntiles) mover_request(&s_pcm[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, true, nch, lane, role - 1);
             cp_commit();
             if (t >= 1) store_tile(t - 1);
             cp_wait_all();
@@ -363,7 +370,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         }
         __syncthreads();
     }
-    if (role == 1 && ntiles) store_tile(ntiles - 1);
+    if (role >= 1 && ntiles) store_tile(ntiles - 1);
 }
 
 // --------------------------------------------------------- encode, generic
@@ -429,7 +436,7 @@ __global__ void scatter_patches_kernel(uint8_t* __restrict__ out, const uint8_t*
 void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
-        adx_decode_fast_kernel<<<(n_fast + 31) / 32, 64, 0, s>>>(d_in, d_out, d_chains, n_fast);
+        adx_decode_fast_kernel<<<(n_fast + 31) / 32, 32 * (1 + kMovers), 0, s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
@@ -441,7 +448,7 @@ void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_ch
 void launch_adx_encode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
-        adx_encode_fast_kernel<<<(n_fast + 31) / 32, 64, 0, s>>>(d_in, d_out, d_chains, n_fast);
+        adx_encode_fast_kernel<<<(n_fast + 31) / 32, 32 * (1 + kMovers), 0, s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
