@@ -226,7 +226,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         fs.hfr_scale = reinterpret_cast<int*>(p); p += (size_t)MC * 8 * 4;
         fs.header_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
         fs.delta_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
-        fs.pcm = reinterpret_cast<int16_t*>(p); p += (size_t)MC * 1152 * 2;
+        fs.pcm = reinterpret_cast<int16_t*>(p); p += (size_t)MC * 1152 * 2 + 16;
         fs.sf = p; p += (size_t)MC * 128;
         fs.res = p; p += (size_t)MC * 128;
         fs.inten = p;
@@ -234,20 +234,43 @@ hca_encode_kernel(HcaEncodeArgs a) {
     const int frame_size = (int)S.frame_size;
     for (uint32_t i = lane; i < a.frame_words; i += 32) fs.bits[i] = 0;
 
-    // ---- PCM: previous 128 + this frame's 1024 samples per channel; silence outside the stream (hca.cpp:3035-3053)
+    // ---- PCM: previous 128 + this frame's 1024 sample frames, interleaved as in the WAV; silence outside the stream
+    // (hca.cpp:3035-3053). The aligned 32-bit words covering the run are copied as they are (coalesced); `pcm` then
+    // points at the first sample inside them.
+    const int16_t* pcm;
     {
-        const long long n0 = (long long)frame * 1024 - 128;
-        const uint8_t* src = a.in + S.in_off;
-        for (int e = lane; e < 1152 * nch; e += 32) {
-            const int i = e / nch, c = e - i * nch;
-            const long long n = n0 + i;
-            int16_t v = 0;
-            if (n >= 0 && n < (long long)S.out_samples) {
-                const uint8_t* q = src + ((size_t)n * nch + c) * 2;
-                v = (int16_t)(q[0] | (q[1] << 8));
-            }
-            fs.pcm[c * 1152 + i] = v;
+        const long long n0 = (long long)frame * 1024 - 128;            // first sample frame wanted
+        const long long lo = n0 < 0 ? 0 : n0;
+        const long long hi = min((long long)S.out_samples, n0 + 1152);  // exclusive
+        uint32_t* stage = reinterpret_cast<uint32_t*>(fs.pcm);
+        const int total_words = (1152 * nch * 2) / 4 + 2;
+        for (int w = lane; w < total_words; w += 32) stage[w] = 0;      // silence for everything not covered below
+        __syncwarp();
+        const uint64_t first_byte = S.in_off + (uint64_t)lo * nch * 2;   // of the first real sample in the blob
+        const uint64_t abase = first_byte & ~(uint64_t)3;
+        // sample frame n0 sits at byte `lead` of the stage; real data starts (lo - n0) sample frames later
+        const int lead = (int)(first_byte & 3);
+        const int skip_bytes = (int)(lo - n0) * nch * 2;                 // multiple of 4 only if nch*2*(lo-n0) is
+        // keep 4-byte copies possible: shift the whole stage so that real data keeps its blob alignment
+        const int data_at = skip_bytes + lead;                           // byte offset of the first real sample in the stage
+        const int word0 = data_at >> 2;                                  // stage word that receives blob word `abase`
+        if (hi > lo && (skip_bytes & 3) == 0) {
+            const int nwords = (int)((((first_byte + (uint64_t)(hi - lo) * nch * 2) + 3) & ~(uint64_t)3) - abase) >> 2;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.in + abase);
+            for (int w = lane; w < nwords; w += 32) stage[word0 + w] = __ldg(src + w);
+            __syncwarp();
+            // the covering words may carry up to 3 foreign bytes in front of / behind the run: blank them
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+            const int end_at = data_at + (int)(hi - lo) * nch * 2;
+            if (lane < 4 && (word0 * 4 + lane) < data_at) sb[word0 * 4 + lane] = 0;
+            if (lane < 4 && end_at + lane < (word0 + nwords) * 4) sb[end_at + lane] = 0;
+        } else if (hi > lo) {                                            // odd geometry (3, 5, 7 channels at a stream start)
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+            const uint8_t* src = a.in + first_byte;
+            const int nbytes = (int)(hi - lo) * nch * 2;
+            for (int k = lane; k < nbytes; k += 32) sb[data_at + k] = src[k];
         }
+        pcm = reinterpret_cast<const int16_t*>(reinterpret_cast<const uint8_t*>(stage) + lead);
     }
     __syncwarp();
 
@@ -264,9 +287,9 @@ hca_encode_kernel(HcaEncodeArgs a) {
         const float k = 1.0f / 32768.0f;
         for (int c = 0; c < nch; c++) {
             for (int sub = 0; sub < 8; sub++) {
-                const int16_t* cur = fs.pcm + c * 1152 + 128 + sub * 128;
-                const int16_t* prv = cur - 128;
-                const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
+                const int16_t* cur = pcm + (size_t)(128 + sub * 128) * nch + c;   // sample i of the subframe: cur[i * nch]
+                const int16_t* prv = cur - 128 * nch;
+                const int i0 = 2 * lane * nch, i1 = (63 - 2 * lane) * nch, i2 = (64 + 2 * lane) * nch, i3 = (127 - 2 * lane) * nch;
                 const float c0 = __fmul_rn((float)cur[i0], k), c1 = __fmul_rn((float)cur[i1], k);
                 const float c2 = __fmul_rn((float)cur[i2], k), c3 = __fmul_rn((float)cur[i3], k);
                 const float p0 = __fmul_rn((float)prv[i0], k), p1 = __fmul_rn((float)prv[i1], k);
@@ -529,26 +552,33 @@ hca_encode_kernel(HcaEncodeArgs a) {
         for (int c = 0; c < nch; c++) {
             const int coded = S.coded[c];
             const float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
-            for (int b0 = 0; b0 < coded; b0 += 32) {
-                const int b = b0 + lane;
+            // two consecutive bands per lane and step: 64 bands per warp prefix sum (a code is at most 12 bits)
+            for (int b0 = 0; b0 < coded; b0 += 64) {
                 uint32_t code = 0;
                 int len = 0;
-                if (b < coded) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int b = b0 + 2 * lane + h;
+                    if (b >= coded) continue;
                     const int r = fs.res[c * 128 + b];
-                    if (r != 0) {                              // QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936
-                        const float inv = tb.inv_step[r];
-                        const int down = r < 8 ? r + 1 : (1 << (tb.max_bits[r] - 1));   // (int)(inv + 0.5)
-                        const int q = __float2int_rz(__fadd_rn(__fmul_rn(sp[b], inv), __fadd_rn(inv, 1.0f))) - down;
-                        if (r < 8) {
-                            len = tb.qbits[r * 16 + q + 8];
-                            code = tb.qcode[r * 16 + q + 8];
-                        } else {
-                            const int mb = tb.max_bits[r] - 1;
-                            const uint32_t mag = (uint32_t)abs(q) & ((1u << mb) - 1u);
-                            if (q != 0) { code = (mag << 1) | (q > 0 ? 0u : 1u); len = mb + 1; }
-                            else { code = mag; len = mb; }
-                        }
+                    if (r == 0) continue;
+                    // QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936
+                    const float inv = tb.inv_step[r];
+                    const int down = r < 8 ? r + 1 : (1 << (tb.max_bits[r] - 1));   // (int)(inv + 0.5)
+                    const int q = __float2int_rz(__fadd_rn(__fmul_rn(sp[b], inv), __fadd_rn(inv, 1.0f))) - down;
+                    uint32_t cd;
+                    int ln;
+                    if (r < 8) {
+                        ln = tb.qbits[r * 16 + q + 8];
+                        cd = tb.qcode[r * 16 + q + 8];
+                    } else {
+                        const int mb = tb.max_bits[r] - 1;
+                        const uint32_t mag = (uint32_t)abs(q) & ((1u << mb) - 1u);
+                        if (q != 0) { cd = (mag << 1) | (q > 0 ? 0u : 1u); ln = mb + 1; }
+                        else { cd = mag; ln = mb; }
                     }
+                    code = (code << ln) | (cd & ((1u << ln) - 1u));
+                    len += ln;
                 }
                 emit_bits(fs, lane, code, len, &cursor, limit_bits);
             }
@@ -556,17 +586,31 @@ hca_encode_kernel(HcaEncodeArgs a) {
     }
     __syncwarp();
 
-    // ---- CRC16 over the first frame_size - 2 bytes (lane 0, serial), then the frame goes out byte by byte
+    // ---- CRC16 over the first frame_size - 2 bytes. The CRC (init 0, no final xor) is linear: every lane takes a
+    // contiguous chunk, multiplies its partial CRC by x^(8 * bytes behind the chunk) mod P (host-made per-stream
+    // constants) and the 32 products are XORed together.
     uint8_t* dst = a.out + S.out_off + (uint64_t)frame * frame_size;
     uint32_t crc = 0;
-    if (lane == 0) {
-        for (int i = 0; i < frame_size - 2; i++) {
+    {
+        const int body = frame_size - 2, chunk = (body + 31) >> 5;
+        const int b0 = min(lane * chunk, body), b1 = min(b0 + chunk, body);
+        uint32_t part = 0;
+        for (int i = b0; i < b1; i++) {
             const uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
-            const uint32_t v = ((crc >> 8) ^ byte) & 0xFF;
-            crc = ((crc << 8) ^ (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u)) & 0xFFFF;
+            const uint32_t v = ((part >> 8) ^ byte) & 0xFF;
+            part = ((part << 8) ^ (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u)) & 0xFFFF;
         }
+        const uint32_t mul = a.crc_mul[(size_t)stream * 32 + lane];
+        uint32_t prod = 0;                                   // carry-less part * mul mod x^16 + x^15 + x^2 + 1
+#pragma unroll
+        for (int bit = 15; bit >= 0; bit--) {
+            prod = ((prod << 1) ^ ((prod & 0x8000u) ? 0x18005u : 0u)) & 0xFFFFu;
+            if ((part >> bit) & 1u) prod ^= mul;
+        }
+        crc = prod;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(kFull, crc, o);
     }
-    crc = __shfl_sync(kFull, crc, 0);
     for (int i = lane; i < frame_size; i += 32) {
         uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
         if (i == frame_size - 2) byte = crc >> 8;
@@ -579,7 +623,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
 
 size_t hca_encode_smem_per_warp(uint32_t max_channels, uint32_t frame_words) {
     size_t n = (size_t)max_channels * 8 * kSpecRow * 4 + (size_t)frame_words * 4 + (size_t)max_channels * 8 * 4 * 2 +
-               (size_t)max_channels * 4 * 2 + (size_t)max_channels * 1152 * 2 + (size_t)max_channels * 128 * 2 + (size_t)max_channels * 8;
+               (size_t)max_channels * 4 * 2 + (size_t)max_channels * 1152 * 2 + 16 + (size_t)max_channels * 128 * 2 + (size_t)max_channels * 8;
     return (n + 15) / 16 * 16;
 }
 

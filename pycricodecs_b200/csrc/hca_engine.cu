@@ -19,6 +19,15 @@ namespace cri {
         }                                                                      \
     } while (0)
 
+// one table step of the CRC register with byte b appended (formats.cpp keeps the table)
+static uint16_t crc16_append(uint16_t crc, uint8_t b) {
+    const unsigned v = ((crc >> 8) ^ b) & 0xFF;
+    unsigned t = (v << 1) ^ (v << 2);
+    unsigned par = v; par ^= par >> 4; par ^= par >> 2; par ^= par >> 1;
+    if (par & 1) t ^= 0x8003;
+    return (uint16_t)(((crc << 8) ^ t) & 0xFFFF);
+}
+
 static uint32_t env_u32(const char* name, uint32_t fallback) {
     const char* v = getenv(name);
     if (!v || !*v) return fallback;
@@ -217,6 +226,7 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
         if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
         // loop points (smpl chunk -> loop chunk, pre/post audio, hca.cpp:2292-2321, 3000-3053) are a later row
         if (wavs[i].looping && !j->adx.force_not_looping) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        if ((j->in_off[i] + wavs[i].data_offset) & 1) { j->status[i] = ERR_UNSUPPORTED; continue; }   // PCM must be 2-byte aligned in the blob
         if (plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels,
                             j->quality, &plans[i]) < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; continue; }
         sizes[i] = (uint64_t)plans[i].header_size + (uint64_t)plans[i].frame_count * plans[i].frame_size;
@@ -224,6 +234,7 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
     finish_layout_public(j, sizes);
     J.streams.assign(j->n, HcaStreamDev{});
     J.frame_prefix.assign(j->n + 1, 0);
+    J.crc_mul.assign((size_t)j->n * 32, 0);
     J.max_channels = 1;
     uint32_t max_frame = 8;
     std::vector<uint8_t> hdr;
@@ -254,6 +265,16 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
             add_patch_public(j, j->out_off[i], hdr.data(), p.header_size);
             frames = p.frame_count;
             j->units += frames;
+            // CRC chunk multipliers: lane l covers bytes [l*chunk, (l+1)*chunk) of the frame body; appending k bytes
+            // multiplies a CRC by x^(8k), i.e. k table steps on the value 1 (the CRC register is x^16-scaled already)
+            const int body = (int)p.frame_size - 2, chunk = (body + 31) / 32;
+            for (int l = 0; l < 32; l++) {
+                const int end = std::min(std::min(l * chunk, body) + chunk, body);
+                uint16_t v = 1;
+                const uint8_t zero = 0;
+                for (int k = 0; k < body - end; k++) v = crc16_append(v, zero);
+                J.crc_mul[(size_t)i * 32 + l] = v;
+            }
         }
         J.frame_prefix[i + 1] = J.frame_prefix[i] + frames;
     }
@@ -277,6 +298,7 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     if (r == OK) r = upload(c, J.cipher_tables, &J.d_cipher);
     if (r == OK) r = upload(c, J.ath_tables, &J.d_ath);
     if (r == OK) r = upload(c, J.frame_prefix, &J.d_frame_prefix);
+    if (r == OK) r = upload(c, J.crc_mul, &J.d_crc_mul);
     if (r != OK) return r;
     if (J.q_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_q, J.q_bytes));
     if (J.g_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_g, J.g_bytes));
@@ -334,6 +356,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.out = j->d_out;
         a.streams = J.d_streams;
         a.frame_prefix = J.d_frame_prefix;
+        a.crc_mul = J.d_crc_mul;
         a.status = j->d_status;
         a.n_frames = J.frame_prefix.empty() ? 0 : J.frame_prefix.back();
         a.n_streams = j->n;
@@ -357,6 +380,7 @@ void free_hca_tables(cri_job* j) {
     cudaFree(J.d_units);
     cudaFree(J.d_s);
     cudaFree(J.d_frame_prefix);
+    cudaFree(J.d_crc_mul);
     cudaFree(J.d_cipher);
     cudaFree(J.d_ath);
     cudaFree(J.d_q);

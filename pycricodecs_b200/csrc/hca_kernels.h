@@ -51,6 +51,7 @@ struct HcaEncodeArgs {
     uint8_t* out;                  // HCA images (headers are host-built patches)
     const HcaStreamDev* streams;   // in_off = first PCM sample, out_off = frame 0, out_samples = samples per channel
     const uint64_t* frame_prefix;  // [n_streams + 1]
+    const uint16_t* crc_mul;       // [n_streams][32]: x^(8 * bytes behind lane l's CRC chunk) mod P (hca_engine.cu)
     int32_t* status;
     uint64_t n_frames;
     uint32_t n_streams;

@@ -65,6 +65,8 @@ struct HcaJob {
     std::vector<uint64_t> frame_prefix;    // crypt: exclusive prefix of frame counts per stream
     uint64_t* d_frame_prefix = nullptr;
     uint32_t enc_frame_words = 0;
+    std::vector<uint16_t> crc_mul;         // encode: [stream][32] CRC chunk multipliers
+    uint16_t* d_crc_mul = nullptr;
     uint32_t uniform = 0;                  // decode: see HcaDecodeArgs::uniform
     uint8_t* d_s = nullptr;
     uint32_t max_channels = 1, max_steps = 0;
