@@ -59,6 +59,14 @@ CRI_API uint64_t cri_ctx_launch_count(const cri_ctx* ctx);
  * last *_run / *_batch call, and of the dominant kernel alone. */
 CRI_API float cri_ctx_last_kernel_ms(const cri_ctx* ctx);
 CRI_API float cri_ctx_last_dominant_ms(const cri_ctx* ctx);
+/* A context keeps the HBM blocks of finished calls for the next call (sizes
+ * repeat from batch to batch); cri_ctx_trim returns the idle ones to the driver. */
+CRI_API void cri_ctx_trim(cri_ctx* ctx);
+/* Page-locked host buffers. The *_batch calls accept any host pointer; with
+ * buffers from cri_host_alloc the copies run at PCIe speed and overlap the
+ * kernels (a batch is pipelined in chunks of whole streams). */
+CRI_API void* cri_host_alloc(size_t bytes);
+CRI_API void cri_host_free(void* p);
 
 /* -- ADX decode: replaces CriCodecs.AdxDecode (adx.cpp:546-558), i.e.
  *    ADX::Decode + ChannelFrame::Decode (adx.cpp:380-415, 189-214) ---------- */

@@ -38,6 +38,9 @@ JOB_ADX_DECODE, JOB_ADX_ENCODE, JOB_HCA_DECODE, JOB_HCA_CRYPT, JOB_HCA_ENCODE = 
 SIGNATURES = {
     "cri_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),
     "cri_ctx_destroy": (None, [c_vp]),
+    "cri_ctx_trim": (None, [c_vp]),
+    "cri_host_alloc": (c_vp, [ctypes.c_size_t]),
+    "cri_host_free": (None, [c_vp]),
     "cri_last_error": (ctypes.c_char_p, [c_vp]),
     "cri_version": (ctypes.c_int, []),
     "cri_ctx_launch_count": (ctypes.c_uint64, [c_vp]),

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,13 +37,15 @@ extern "C" int cri_ctx_create(int device, cri_ctx** out) {
     cri_ctx* c = new (std::nothrow) cri_ctx();
     if (!c) return ERR_BUFFER;
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&c->ev[0]) != cudaSuccess || cudaEventCreate(&c->ev[1]) != cudaSuccess ||
-        cudaEventCreate(&c->ev[2]) != cudaSuccess || cudaEventCreate(&c->ev[3]) != cudaSuccess) {
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& s : c->pipe) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
         delete c;
         return ERR_CUDA;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    const char* t = getenv("CRI_TRACE");
+    c->trace = t && *t && *t != '0';
     *out = c;
     return OK;
 }
@@ -50,10 +53,82 @@ extern "C" int cri_ctx_create(int device, cri_ctx** out) {
 extern "C" void cri_ctx_destroy(cri_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (auto& e : c->ev) cudaEventDestroy(e);
+    pool_trim(c);
+    for (auto& kv : c->pool.live) cudaFree(kv.first);   // blocks of jobs the caller never destroyed
+    for (auto& s : c->pipe) cudaStreamDestroy(s);
+    for (auto& p : c->pin_status) cudaFreeHost(p);
     cudaStreamDestroy(c->stream);
     delete c;
 }
+
+extern "C" void cri_ctx_trim(cri_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    pool_trim(c);
+}
+
+// Pinned host buffers for callers that want the batch calls to run at PCIe speed
+// (pageable memory works too, through the driver's staging copies).
+extern "C" void* cri_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+extern "C" void cri_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------ HBM block cache
+namespace cri {
+static size_t pool_round(size_t bytes) {
+    const size_t g = bytes >= (size_t(1) << 20) ? (size_t(2) << 20) : 512;   // 2 MiB granules for large blocks
+    return (std::max<size_t>(bytes, 1) + g - 1) / g * g;
+}
+
+int pool_alloc(cri_ctx* c, void** p, size_t bytes) {
+    *p = nullptr;
+    const size_t want = pool_round(bytes);
+    DevPool& P = c->pool;
+    auto it = P.idle.lower_bound(want);
+    if (it != P.idle.end() && it->first <= want + want / 4) {      // close enough in size: reuse
+        *p = it->second;
+        P.live[*p] = it->first;
+        P.idle_bytes -= it->first;
+        P.idle.erase(it);
+        return OK;
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {                                        // give the cache back to the driver and retry once
+        cudaGetLastError();
+        pool_trim(c);
+        e = cudaMalloc(p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c->error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        *p = nullptr;
+        return ERR_CUDA;
+    }
+    P.live[*p] = want;
+    return OK;
+}
+
+void pool_free(cri_ctx* c, void* p) {
+    if (!p) return;
+    if (!c) { cudaFree(p); return; }
+    DevPool& P = c->pool;
+    auto it = P.live.find(p);
+    if (it == P.live.end()) { cudaFree(p); return; }
+    P.idle.emplace(it->second, p);
+    P.idle_bytes += it->second;
+    P.live.erase(it);
+}
+
+void pool_trim(cri_ctx* c) {
+    for (auto& kv : c->pool.idle) cudaFree(kv.second);
+    c->pool.idle.clear();
+    c->pool.idle_bytes = 0;
+}
+}  // namespace cri
 
 extern "C" const char* cri_last_error(const cri_ctx* c) { return c ? c->error.c_str() : "no context"; }
 extern "C" uint64_t cri_ctx_launch_count(const cri_ctx* c) { return c ? c->launches : 0; }
@@ -271,20 +346,27 @@ static void plan_adx_encode(cri_job* j) {
 
 // ------------------------------------------------------------------- jobs
 template <class T>
-static int upload_vec(cri_ctx* c, const std::vector<T>& v, T** d) {
+static int upload_vec(cri_ctx* c, cudaStream_t s, const std::vector<T>& v, T** d) {
     *d = nullptr;
     if (v.empty()) return OK;
-    CU_TRY(c, cudaMalloc((void**)d, v.size() * sizeof(T)));
-    CU_TRY(c, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    const int r = pool_alloc(c, (void**)d, v.size() * sizeof(T));
+    if (r != OK) return r;
+    CU_TRY(c, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
     return OK;
 }
 
-extern "C" int cri_job_create(cri_ctx* c, const cri_job_desc* d, cri_job** out) {
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Plan on the host, take HBM from the context's cache, and enqueue every upload on `stream`. Nothing here waits for the GPU.
+static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream, cri_job** out) {
     *out = nullptr;
     if (!c || !d || (!d->blob && d->n) || !d->offsets) return ERR_BUFFER;
     CU_TRY(c, cudaSetDevice(c->device));
     cri_job* j = new (std::nothrow) cri_job();
     if (!j) return ERR_BUFFER;
+    j->stream = stream;
     j->kind = d->kind;
     j->n = d->n;
     j->blob = d->blob;
@@ -307,22 +389,34 @@ extern "C" int cri_job_create(cri_ctx* c, const cri_job_desc* d, cri_job** out) 
         default: rc = ERR_UNSUPPORTED;
     }
     if (rc == OK) rc = [&]() -> int {
-        CU_TRY(c, cudaMalloc((void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 64));  // slack: kernels read whole 16-byte rows
-        CU_TRY(c, cudaMalloc((void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16));
-        CU_TRY(c, cudaMalloc((void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1)));
-        CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes + 16, c->stream));
-        int r = upload_vec(c, j->adx_chains, &j->d_adx_chains);
-        if (r == OK) r = upload_vec(c, j->patches, &j->d_patches);
-        if (r == OK) r = upload_vec(c, j->patch_bytes, &j->d_patch_bytes);
+        for (auto& e : j->ev) CU_TRY(c, cudaEventCreate(&e));
+        int r = pool_alloc(c, (void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 64);  // slack: kernels read whole 16-byte rows
+        if (r == OK) r = pool_alloc(c, (void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16);
+        if (r == OK) r = pool_alloc(c, (void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1));
+        if (r != OK) return r;
+        CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes + 16, stream));
+        r = upload_vec(c, stream, j->adx_chains, &j->d_adx_chains);
+        if (r == OK) r = upload_vec(c, stream, j->patches, &j->d_patches);
+        if (r == OK) r = upload_vec(c, stream, j->patch_bytes, &j->d_patch_bytes);
         if (r == OK) r = upload_hca_tables(c, j);
         if (r != OK) return r;
-        return cri_job_upload(c, j);
+        if (j->in_bytes) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, stream));
+        return OK;
     }();
     if (rc != OK) {
+        cudaStreamSynchronize(stream);
         cri_job_destroy(c, j);
         return rc;
     }
     *out = j;
+    return OK;
+}
+
+extern "C" int cri_job_create(cri_ctx* c, const cri_job_desc* d, cri_job** out) {
+    if (!c) return ERR_CUDA;
+    const int rc = job_create_on(c, d, c->stream, out);
+    if (rc != OK) return rc;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     return OK;
 }
 
@@ -332,103 +426,210 @@ extern "C" uint64_t cri_job_units(const cri_job* j) { return j->units; }
 
 extern "C" int cri_job_upload(cri_ctx* c, cri_job* j) {
     CU_TRY(c, cudaSetDevice(c->device));
-    if (j->in_bytes) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (j->in_bytes) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, j->stream));
+    CU_TRY(c, cudaStreamSynchronize(j->stream));
+    return OK;
+}
+
+// Enqueue the kernels of one pass over the job's resident input. No host wait.
+static int job_enqueue_run(cri_ctx* c, cri_job* j) {
+    cudaStream_t s = j->stream;
+    CU_TRY(c, cudaMemsetAsync(j->d_status, 0, sizeof(int32_t) * std::max<uint32_t>(j->n, 1), s));
+    if (j->needs_clear) CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes, s));
+    CU_TRY(c, cudaEventRecord(j->ev[0], s));
+    launch_scatter_patches(j->d_out, j->d_patch_bytes, j->d_patches, (uint32_t)j->patches.size(), s, &c->launches);
+    j->have_dominant = false;
+    switch (j->kind) {
+        case CRI_JOB_ADX_DECODE:
+            CU_TRY(c, cudaEventRecord(j->ev[2], s));
+            launch_adx_decode(j->d_in, j->d_out, j->d_adx_chains, j->n_fast, j->n_generic, s, &c->launches);
+            CU_TRY(c, cudaEventRecord(j->ev[3], s));
+            j->have_dominant = true;
+            break;
+        case CRI_JOB_ADX_ENCODE:
+            CU_TRY(c, cudaEventRecord(j->ev[2], s));
+            launch_adx_encode(j->d_in, j->d_out, j->d_adx_chains, j->n_fast, j->n_generic, s, &c->launches);
+            CU_TRY(c, cudaEventRecord(j->ev[3], s));
+            j->have_dominant = true;
+            break;
+        case CRI_JOB_HCA_DECODE:
+        case CRI_JOB_HCA_CRYPT:
+        case CRI_JOB_HCA_ENCODE: {
+            const int r = run_hca(c, j, &j->have_dominant);
+            if (r != OK) return r;
+            break;
+        }
+    }
+    CU_TRY(c, cudaEventRecord(j->ev[1], s));
+    CU_TRY(c, cudaGetLastError());
+    return OK;
+}
+
+// Wait for the job's stream and fold its device time into the context's counters.
+static int job_wait_run(cri_ctx* c, cri_job* j, bool accumulate) {
+    CU_TRY(c, cudaStreamSynchronize(j->stream));
+    float ms = 0.f, dom = 0.f;
+    cudaEventElapsedTime(&ms, j->ev[0], j->ev[1]);
+    if (j->have_dominant) cudaEventElapsedTime(&dom, j->ev[2], j->ev[3]);
+    c->last_ms = accumulate ? c->last_ms + ms : ms;
+    c->last_dominant_ms = accumulate ? c->last_dominant_ms + dom : dom;
     return OK;
 }
 
 extern "C" int cri_job_run(cri_ctx* c, cri_job* j) {
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    CU_TRY(c, cudaMemsetAsync(j->d_status, 0, sizeof(int32_t) * std::max<uint32_t>(j->n, 1), s));
-    if (j->needs_clear) CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes, s));
-    CU_TRY(c, cudaEventRecord(c->ev[0], s));
-    launch_scatter_patches(j->d_out, j->d_patch_bytes, j->d_patches, (uint32_t)j->patches.size(), s, &c->launches);
-    bool have_dominant = false;
-    switch (j->kind) {
-        case CRI_JOB_ADX_DECODE:
-            CU_TRY(c, cudaEventRecord(c->ev[2], s));
-            launch_adx_decode(j->d_in, j->d_out, j->d_adx_chains, j->n_fast, j->n_generic, s, &c->launches);
-            CU_TRY(c, cudaEventRecord(c->ev[3], s));
-            have_dominant = true;
-            break;
-        case CRI_JOB_ADX_ENCODE:
-            CU_TRY(c, cudaEventRecord(c->ev[2], s));
-            launch_adx_encode(j->d_in, j->d_out, j->d_adx_chains, j->n_fast, j->n_generic, s, &c->launches);
-            CU_TRY(c, cudaEventRecord(c->ev[3], s));
-            have_dominant = true;
-            break;
-        case CRI_JOB_HCA_DECODE:
-        case CRI_JOB_HCA_CRYPT:
-        case CRI_JOB_HCA_ENCODE: {
-            const int r = run_hca(c, j, &have_dominant);
-            if (r != OK) return r;
-            break;
-        }
+    const int r = job_enqueue_run(c, j);
+    if (r != OK) return r;
+    return job_wait_run(c, j, false);
+}
+
+static int job_enqueue_download(cri_ctx* c, cri_job* j, uint8_t* out_blob, int32_t* status, int32_t* landing) {
+    if (!landing) {
+        j->dev_status.assign(j->n, 0);
+        landing = j->dev_status.data();
     }
-    CU_TRY(c, cudaEventRecord(c->ev[1], s));
-    CU_TRY(c, cudaGetLastError());
-    CU_TRY(c, cudaStreamSynchronize(s));
-    cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[1]);
-    c->last_dominant_ms = 0.f;
-    if (have_dominant) cudaEventElapsedTime(&c->last_dominant_ms, c->ev[2], c->ev[3]);
+    j->h_status = landing;
+    j->dl_out = out_blob;
+    j->dl_status = status;
+    if (j->n) CU_TRY(c, cudaMemcpyAsync(landing, j->d_status, sizeof(int32_t) * j->n, cudaMemcpyDeviceToHost, j->stream));
+    if (out_blob && j->out_bytes) CU_TRY(c, cudaMemcpyAsync(out_blob, j->d_out, j->out_bytes, cudaMemcpyDeviceToHost, j->stream));
+    return OK;
+}
+
+static int job_wait_download(cri_ctx* c, cri_job* j) {
+    CU_TRY(c, cudaStreamSynchronize(j->stream));
+    for (uint32_t i = 0; i < j->n; i++) {
+        const int32_t st = j->status[i] != OK ? j->status[i] : j->h_status[i];
+        if (j->dl_status) j->dl_status[i] = st;
+        if (st != OK && j->dl_out && j->status[i] == OK)  // a stream that failed on the device leaves silence, not garbage
+            memset(j->dl_out + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i]);
+    }
     return OK;
 }
 
 extern "C" int cri_job_download(cri_ctx* c, cri_job* j, uint8_t* out_blob, int32_t* status) {
     CU_TRY(c, cudaSetDevice(c->device));
-    std::vector<int32_t> dev(j->n, 0);
-    if (j->n) CU_TRY(c, cudaMemcpyAsync(dev.data(), j->d_status, sizeof(int32_t) * j->n, cudaMemcpyDeviceToHost, c->stream));
-    if (out_blob && j->out_bytes)
-        CU_TRY(c, cudaMemcpyAsync(out_blob, j->d_out, j->out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    for (uint32_t i = 0; i < j->n; i++) {
-        int32_t st = j->status[i] != OK ? j->status[i] : dev[i];
-        if (status) status[i] = st;
-        if (st != OK && out_blob && j->status[i] == OK)  // a stream that failed on the device leaves silence, not garbage
-            memset(out_blob + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i]);
-    }
-    return OK;
+    const int r = job_enqueue_download(c, j, out_blob, status, nullptr);
+    if (r != OK) return r;
+    return job_wait_download(c, j);
 }
 
 extern "C" void cri_job_destroy(cri_ctx* c, cri_job* j) {
     if (!j) return;
     if (c) cudaSetDevice(c->device);
-    cudaFree(j->d_in);
-    cudaFree(j->d_out);
-    cudaFree(j->d_status);
-    cudaFree(j->d_adx_chains);
-    cudaFree(j->d_patches);
-    cudaFree(j->d_patch_bytes);
-    free_hca_tables(j);
+    for (auto& e : j->ev)
+        if (e) cudaEventDestroy(e);
+    for (void* p : {(void*)j->d_in, (void*)j->d_out, (void*)j->d_status, (void*)j->d_adx_chains, (void*)j->d_patches,
+                    (void*)j->d_patch_bytes})
+        pool_free(c, p);
+    free_hca_tables(c, j);
     delete j;
 }
 
 // ------------------------------------------------- batch = job in one call
+// The batch is cut into chunks of whole streams; each chunk is a job of its own
+// on one of kPipeDepth streams, so the upload of chunk k+1, the kernels of
+// chunk k and the download of chunk k-1 overlap (two copy engines + SMs), and
+// the host plans the next chunk while the GPU works. Chunks are independent:
+// no codec on this path carries state from one stream to another.
+struct ChunkRun {
+    cri_job* job = nullptr;
+    uint32_t s0 = 0, s1 = 0;
+    bool packed = true;
+};
+
+static int chunk_finish(cri_ctx* c, ChunkRun& r, uint8_t* out_blob, const uint64_t* out_offsets, int32_t* status) {
+    if (!r.job) return OK;
+    cri_job* j = r.job;
+    int rc = job_wait_run(c, j, true);
+    if (rc == OK) rc = job_wait_download(c, j);
+    if (rc == OK && !r.packed)       // caller chose a different layout: place each stream from the staging blob
+        for (uint32_t i = 0; i < j->n; i++) {
+            const uint64_t sz = j->out_off[i + 1] - j->out_off[i];
+            const uint64_t* oo = out_offsets + r.s0;
+            if (oo[i + 1] - oo[i] < sz) { if (status) status[r.s0 + i] = ERR_BUFFER; continue; }
+            memcpy(out_blob + oo[i], j->staging.data() + j->out_off[i], sz);
+        }
+    cri_job_destroy(c, j);
+    r.job = nullptr;
+    return rc;
+}
+
 static int run_batch(cri_ctx* c, cri_job_desc d, uint8_t* out_blob, const uint64_t* out_offsets, int32_t* status) {
     if (!c) return ERR_CUDA;
-    cri_job* j = nullptr;
-    int rc = cri_job_create(c, &d, &j);
-    if (rc != OK) return rc;
-    rc = cri_job_run(c, j);
-    if (rc == OK) {
-        bool packed = true;
+    if (!d.offsets || (!d.blob && d.n)) return ERR_BUFFER;
+    const double t_begin = now_ms();
+    // chunk count from the larger of the two directions (the copies are what the pipeline hides)
+    const uint64_t in_total = d.n ? d.offsets[d.n] - d.offsets[0] : 0;
+    const uint64_t out_total = (out_offsets && d.n) ? out_offsets[d.n] - out_offsets[0] : 0;
+    // ~16 chunks keeps pipeline fill + drain near 1/8 of the copy time; 8 MiB floor so launches stay amortised
+    const uint64_t larger = std::max(in_total, out_total);
+    uint64_t target = std::min<uint64_t>(std::max<uint64_t>(larger / 16, uint64_t(8) << 20), uint64_t(256) << 20);
+    if (const char* e = getenv("CRI_CHUNK_MB")) target = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 20;
+    uint32_t n_chunks = (uint32_t)std::min<uint64_t>((larger + target - 1) / target, 64);
+    n_chunks = std::max<uint32_t>(1, std::min<uint32_t>(n_chunks, d.n));
+    if (!out_offsets) n_chunks = 1;                                  // no caller layout to place later chunks by
+    c->last_ms = c->last_dominant_ms = 0.f;
+
+    ChunkRun slots[kPipeDepth];
+    std::vector<uint64_t> local;
+    int rc = OK;
+    double plan_ms = 0;
+    for (uint32_t k = 0; k < n_chunks && rc == OK; k++) {
+        ChunkRun& r = slots[k % kPipeDepth];
+        rc = chunk_finish(c, r, out_blob, out_offsets, status);
+        if (rc != OK) break;
+        r.s0 = (uint32_t)((uint64_t)d.n * k / n_chunks);
+        r.s1 = (uint32_t)((uint64_t)d.n * (k + 1) / n_chunks);
+        const uint32_t m = r.s1 - r.s0;
+        local.resize(m + 1);
+        for (uint32_t i = 0; i <= m; i++) local[i] = d.offsets[r.s0 + i] - d.offsets[r.s0];
+        cri_job_desc sub = d;
+        sub.blob = d.blob ? d.blob + d.offsets[r.s0] : nullptr;
+        sub.offsets = local.data();
+        sub.n = m;
+        if (d.keys) sub.keys = d.keys + r.s0;
+        if (d.subkeys) sub.subkeys = d.subkeys + r.s0;
+        const double t0 = now_ms();
+        rc = job_create_on(c, &sub, c->pipe[k % kPipeDepth], &r.job);
+        plan_ms += now_ms() - t0;
+        if (rc != OK) break;
+        cri_job* j = r.job;
+        rc = job_enqueue_run(c, j);
+        if (rc != OK) break;
+        r.packed = true;
         if (out_offsets)
-            for (uint32_t i = 0; i <= d.n && packed; i++) packed = out_offsets[i] - out_offsets[0] == j->out_off[i];
-        if (packed) {
-            rc = cri_job_download(c, j, out_blob + (out_offsets ? out_offsets[0] : 0), status);
-        } else {  // caller chose a different layout: gather into a staging blob, then place each stream
-            std::vector<uint8_t> tmp(j->out_bytes);
-            rc = cri_job_download(c, j, tmp.data(), status);
-            if (rc == OK)
-                for (uint32_t i = 0; i < d.n; i++) {
-                    const uint64_t sz = j->out_off[i + 1] - j->out_off[i];
-                    if (out_offsets[i + 1] - out_offsets[i] < sz) { if (status) status[i] = ERR_BUFFER; continue; }
-                    memcpy(out_blob + out_offsets[i], tmp.data() + j->out_off[i], sz);
-                }
+            for (uint32_t i = 0; i <= m && r.packed; i++) r.packed = out_offsets[r.s0 + i] - out_offsets[r.s0] == j->out_off[i];
+        uint8_t* dst;
+        if (r.packed) {
+            dst = out_blob ? out_blob + (out_offsets ? out_offsets[r.s0] : 0) : nullptr;
+        } else {
+            j->staging.resize(j->out_bytes);
+            dst = j->staging.data();
+        }
+        const int slot = k % kPipeDepth;
+        if (c->pin_status_cap[slot] < m) {
+            cudaFreeHost(c->pin_status[slot]);
+            c->pin_status[slot] = nullptr;
+            c->pin_status_cap[slot] = 0;
+            if (cudaHostAlloc((void**)&c->pin_status[slot], sizeof(int32_t) * m * 2, cudaHostAllocDefault) == cudaSuccess)
+                c->pin_status_cap[slot] = (size_t)m * 2;
+            else
+                cudaGetLastError();      // fall back to the job's pageable landing buffer (correct, just not overlapped)
+        }
+        rc = job_enqueue_download(c, j, dst, status ? status + r.s0 : nullptr, c->pin_status_cap[slot] >= m ? c->pin_status[slot] : nullptr);
+    }
+    for (auto& r : slots) {
+        if (rc == OK) rc = chunk_finish(c, r, out_blob, out_offsets, status);
+        else if (r.job) {
+            cudaStreamSynchronize(r.job->stream);
+            cri_job_destroy(c, r.job);
+            r.job = nullptr;
         }
     }
-    cri_job_destroy(c, j);
+    if (c->trace)
+        fprintf(stderr, "[cri] batch kind=%d n=%u chunks=%u in=%.1f MB out=%.1f MB host-plan=%.2f ms kernels=%.2f ms total=%.2f ms\n",
+                d.kind, d.n, n_chunks, in_total / 1e6, out_total / 1e6, plan_ms, c->last_ms, now_ms() - t_begin);
     return rc;
 }
 

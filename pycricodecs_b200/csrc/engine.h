@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cricodecs_b200.h"
@@ -11,11 +13,26 @@
 #include "hca_tables_dev.h"
 #include "kernels.h"
 
+// Size-bucketed cache of HBM blocks owned by a context: a batch call needs a
+// handful of large buffers whose sizes repeat from call to call, and
+// cudaMalloc/cudaFree of gigabyte blocks costs more than the kernels.
+struct DevPool {
+    std::multimap<size_t, void*> idle;          // size -> block
+    std::unordered_map<void*, size_t> live;     // block -> size
+    size_t idle_bytes = 0;
+};
+
+constexpr int kPipeDepth = 3;                   // chunks of one batch call in flight (copy in / kernels / copy out)
+
 struct cri_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {};       // [0],[1] whole run; [2],[3] dominant kernel
+    cudaStream_t stream = nullptr;              // jobs created through cri_job_create
+    cudaStream_t pipe[kPipeDepth] = {};         // chunk streams of the one-call batch entry points
+    int32_t* pin_status[kPipeDepth] = {};       // page-locked landing buffers of the chunks' status words (a copy to
+    size_t pin_status_cap[kPipeDepth] = {};     //  pageable memory would block the host until the chunk's kernels end)
+    DevPool pool;
+    bool trace = false;                         // CRI_TRACE=1: phase times of every batch call on stderr
     uint64_t launches = 0;
     float last_ms = 0.f, last_dominant_ms = 0.f;
     std::string error;
@@ -36,6 +53,15 @@ struct cri_job {
     uint32_t ciph_type = 0;
     bool needs_clear = false;                 // some output bytes are not produced by kernels / patches
 
+    cudaStream_t stream = nullptr;            // every copy and launch of this job is ordered on it
+    cudaEvent_t ev[4] = {};                   // [0],[1] whole run; [2],[3] dominant kernel
+    bool have_dominant = false;
+    std::vector<int32_t> dev_status;          // landing buffer of d_status (jobs of the create/run/download API)
+    int32_t* h_status = nullptr;              // where d_status lands: dev_status.data() or a page-locked chunk buffer
+    std::vector<uint8_t> staging;             // download target when the caller's layout is not the packed one
+    uint8_t* dl_out = nullptr;                // where the pending download lands
+    int32_t* dl_status = nullptr;
+
     uint8_t* d_in = nullptr;
     uint8_t* d_out = nullptr;
     int32_t* d_status = nullptr;
@@ -55,6 +81,9 @@ struct cri_job {
 };
 
 namespace cri {
+int pool_alloc(cri_ctx* c, void** p, size_t bytes);
+void pool_free(cri_ctx* c, void* p);
+void pool_trim(cri_ctx* c);
 void finish_layout_public(cri_job* j, const std::vector<uint64_t>& sizes);
 void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n);
 int plan_hca_decode(cri_ctx* c, cri_job* j);
@@ -62,5 +91,5 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j);
 int plan_hca_encode(cri_ctx* c, cri_job* j);
 int upload_hca_tables(cri_ctx* c, cri_job* j);
 int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant);
-void free_hca_tables(cri_job* j);
+void free_hca_tables(cri_ctx* c, cri_job* j);
 }  // namespace cri

@@ -238,6 +238,7 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
     J.max_channels = 1;
     uint32_t max_frame = 8;
     std::vector<uint8_t> hdr;
+    std::unordered_map<uint32_t, std::vector<uint16_t>> crc_mul_by_size;
     for (uint32_t i = 0; i < j->n; i++) {
         uint64_t frames = 0;
         if (j->status[i] == OK) {
@@ -267,14 +268,20 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
             j->units += frames;
             // CRC chunk multipliers: lane l covers bytes [l*chunk, (l+1)*chunk) of the frame body; appending k bytes
             // multiplies a CRC by x^(8k), i.e. k table steps on the value 1 (the CRC register is x^16-scaled already)
-            const int body = (int)p.frame_size - 2, chunk = (body + 31) / 32;
-            for (int l = 0; l < 32; l++) {
-                const int end = std::min(std::min(l * chunk, body) + chunk, body);
+            auto& mul = crc_mul_by_size[p.frame_size];
+            if (mul.empty()) {
+                mul.resize(32);
+                const int body = (int)p.frame_size - 2, chunk = (body + 31) / 32;
                 uint16_t v = 1;
+                int done = 0;
                 const uint8_t zero = 0;
-                for (int k = 0; k < body - end; k++) v = crc16_append(v, zero);
-                J.crc_mul[(size_t)i * 32 + l] = v;
+                for (int l = 31; l >= 0; l--) {      // bytes after lane l's chunk grow as l falls: one running product
+                    const int end = std::min(std::min(l * chunk, body) + chunk, body);
+                    for (; done < body - end; done++) v = crc16_append(v, zero);
+                    mul[l] = v;
+                }
             }
+            std::copy(mul.begin(), mul.end(), J.crc_mul.begin() + (size_t)i * 32);
         }
         J.frame_prefix[i + 1] = J.frame_prefix[i] + frames;
     }
@@ -283,28 +290,29 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
 }
 
 template <class T>
-static int upload(cri_ctx* c, const std::vector<T>& v, T** d) {
+static int upload(cri_ctx* c, cudaStream_t s, const std::vector<T>& v, T** d) {
     *d = nullptr;
     if (v.empty()) return OK;
-    CU_TRY(c, cudaMalloc((void**)d, v.size() * sizeof(T)));
-    CU_TRY(c, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    const int r = pool_alloc(c, (void**)d, v.size() * sizeof(T));
+    if (r != OK) return r;
+    CU_TRY(c, cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
     return OK;
 }
 
 int upload_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
-    int r = upload(c, J.streams, &J.d_streams);
-    if (r == OK) r = upload(c, J.units, &J.d_units);
-    if (r == OK) r = upload(c, J.cipher_tables, &J.d_cipher);
-    if (r == OK) r = upload(c, J.ath_tables, &J.d_ath);
-    if (r == OK) r = upload(c, J.frame_prefix, &J.d_frame_prefix);
-    if (r == OK) r = upload(c, J.crc_mul, &J.d_crc_mul);
-    if (r != OK) return r;
-    if (J.q_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_q, J.q_bytes));
-    if (J.g_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_g, J.g_bytes));
-    if (J.i_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_i, J.i_bytes));
-    if (J.s_bytes) CU_TRY(c, cudaMalloc((void**)&J.d_s, J.s_bytes));
-    return OK;
+    cudaStream_t s = j->stream;
+    int r = upload(c, s, J.streams, &J.d_streams);
+    if (r == OK) r = upload(c, s, J.units, &J.d_units);
+    if (r == OK) r = upload(c, s, J.cipher_tables, &J.d_cipher);
+    if (r == OK) r = upload(c, s, J.ath_tables, &J.d_ath);
+    if (r == OK) r = upload(c, s, J.frame_prefix, &J.d_frame_prefix);
+    if (r == OK) r = upload(c, s, J.crc_mul, &J.d_crc_mul);
+    if (r == OK && J.q_bytes) r = pool_alloc(c, (void**)&J.d_q, J.q_bytes);
+    if (r == OK && J.g_bytes) r = pool_alloc(c, (void**)&J.d_g, J.g_bytes);
+    if (r == OK && J.i_bytes) r = pool_alloc(c, (void**)&J.d_i, J.i_bytes);
+    if (r == OK && J.s_bytes) r = pool_alloc(c, (void**)&J.d_s, J.s_bytes);
+    return r;
 }
 
 int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
@@ -329,8 +337,8 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.steps = J.max_steps;
         a.max_channels = J.max_channels;
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
-        launch_hca_decode(a, c->stream, &c->launches, c->ev[2]);
-        CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);
+        CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));
         *have_dominant = J.total_groups != 0;
         return OK;
     }
@@ -344,9 +352,9 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_frames = J.frame_prefix.empty() ? 0 : J.frame_prefix.back();
         a.n_streams = j->n;
         a.n_tables = (uint32_t)(J.cipher_tables.size() / 256);
-        CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-        launch_hca_crypt(a, c->stream, &c->launches);
-        CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        CU_TRY(c, cudaEventRecord(j->ev[2], j->stream));
+        launch_hca_crypt(a, j->stream, &c->launches);
+        CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));
         *have_dominant = a.n_frames != 0;
         return OK;
     }
@@ -362,30 +370,23 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_streams = j->n;
         a.max_channels = J.max_channels;
         a.frame_words = J.enc_frame_words;
-        CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-        if (launch_hca_encode(a, c->stream, &c->launches) != 0) {
+        CU_TRY(c, cudaEventRecord(j->ev[2], j->stream));
+        if (launch_hca_encode(a, j->stream, &c->launches) != 0) {
             c->error = "HCA encode: frame size / channel count exceeds the kernel's shared-memory budget";
             return ERR_CUDA;
         }
-        CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));
         *have_dominant = a.n_frames != 0;
         return OK;
     }
     return ERR_UNSUPPORTED;
 }
 
-void free_hca_tables(cri_job* j) {
+void free_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
-    cudaFree(J.d_streams);
-    cudaFree(J.d_units);
-    cudaFree(J.d_s);
-    cudaFree(J.d_frame_prefix);
-    cudaFree(J.d_crc_mul);
-    cudaFree(J.d_cipher);
-    cudaFree(J.d_ath);
-    cudaFree(J.d_q);
-    cudaFree(J.d_g);
-    cudaFree(J.d_i);
+    for (void* p : {(void*)J.d_streams, (void*)J.d_units, (void*)J.d_s, (void*)J.d_frame_prefix, (void*)J.d_crc_mul,
+                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i})
+        pool_free(c, p);
 }
 
 }  // namespace cri

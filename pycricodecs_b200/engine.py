@@ -166,13 +166,67 @@ class Job:
         self.close()
 
 
-def _run_streams(kind: int, streams: Sequence[bytes], ctx: Optional[Context], raise_errors: bool, **kw):
+def batch_blob(kind: int, blob: np.ndarray, offsets: np.ndarray, ctx: Optional[Context] = None, out: Optional[np.ndarray] = None,
+               *, keys=None, subkeys=None, adx: Optional[AdxParams] = None, quality: int = 1, encrypt: int = 0,
+               ciph_type: int = 0):
+    """One call of the C-ABI batch entry point for `kind`: host blob in, host blob out.
+
+    Returns (out, out_offsets, status). Output sizes come from the matching `cri_*_sizes` call (exact, header-only);
+    the library pipelines the batch in chunks of whole streams (H2D / kernels / D2H overlapped).
+    """
     ctx = ctx or default_context()
+    L = ctx._lib
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    sizes = np.zeros(max(n, 1), dtype=np.uint64)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    bp, op = blob.ctypes.data, offsets.ctypes.data
+    keys = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+    subkeys = None if subkeys is None else np.ascontiguousarray(subkeys, dtype=np.uint16)
+    kp = None if keys is None else keys.ctypes.data
+    sp = None if subkeys is None else subkeys.ctypes.data
+    adx = adx if adx is not None else adx_params()
+    if kind == _lib.JOB_ADX_DECODE:
+        L.cri_adx_decode_sizes(bp, op, n, sizes.ctypes.data, status.ctypes.data)
+    elif kind == _lib.JOB_ADX_ENCODE:
+        L.cri_adx_encode_sizes(bp, op, n, ctypes.byref(adx), sizes.ctypes.data, status.ctypes.data)
+    elif kind == _lib.JOB_HCA_DECODE:
+        L.cri_hca_decode_sizes(bp, op, n, sizes.ctypes.data, status.ctypes.data)
+    elif kind == _lib.JOB_HCA_ENCODE:
+        L.cri_hca_encode_sizes(bp, op, n, int(quality), sizes.ctypes.data, status.ctypes.data)
+    elif kind == _lib.JOB_HCA_CRYPT:
+        sizes[:n] = offsets[1:] - offsets[:-1]
+    else:
+        raise ValueError(f"unknown job kind {kind}")
+    out_offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(sizes[:n], out=out_offsets[1:])
+    if kind == _lib.JOB_HCA_CRYPT:
+        out_offsets = offsets
+    total = int(out_offsets[-1])
+    if out is None:
+        out = np.empty(max(total, 1), dtype=np.uint8)
+    elif out.size < total:
+        raise ValueError("output buffer too small")
+    oo = out_offsets.ctypes.data
+    if kind == _lib.JOB_ADX_DECODE:
+        rc = L.cri_adx_decode_batch(ctx.handle, bp, op, n, out.ctypes.data, oo, status.ctypes.data)
+    elif kind == _lib.JOB_ADX_ENCODE:
+        rc = L.cri_adx_encode_batch(ctx.handle, bp, op, n, ctypes.byref(adx), out.ctypes.data, oo, status.ctypes.data)
+    elif kind == _lib.JOB_HCA_DECODE:
+        rc = L.cri_hca_decode_batch(ctx.handle, bp, op, n, kp, sp, out.ctypes.data, oo, status.ctypes.data)
+    elif kind == _lib.JOB_HCA_ENCODE:
+        rc = L.cri_hca_encode_batch(ctx.handle, bp, op, n, int(quality), int(adx.force_not_looping), out.ctypes.data, oo,
+                                    status.ctypes.data)
+    else:
+        rc = L.cri_hca_crypt_batch(ctx.handle, bp, op, n, int(encrypt), int(ciph_type), kp, sp, out.ctypes.data, status.ctypes.data)
+    ctx.check(rc)
+    return out, out_offsets, status[:n]
+
+
+def _run_streams(kind: int, streams: Sequence[bytes], ctx: Optional[Context], raise_errors: bool, **kw):
     blob, offsets = pack(streams)
-    with Job(ctx, kind, blob, offsets, **kw) as job:
-        job.run()
-        out, status = job.download()
-        offs = job.out_offsets
+    out, offs, status = batch_blob(kind, blob, offsets, ctx, **kw)
     results: List[object] = []
     for i in range(len(streams)):
         if status[i] != 0:
