@@ -150,6 +150,18 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def traffic_of(kernel, streams):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if int(t.get("streams_per_launch", 0)) == int(streams) and kernel in t:
+            return int(t[kernel]["bytes"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -305,7 +317,7 @@ def run_ours(a):
                        "l2": "inputs and outputs exceed the 126 MB L2 (no flush needed)" if in_bytes + out_bytes > 3e8 else "working set near L2 size",
                        "in_bytes_per_gpu": in_bytes, "out_bytes_per_gpu": int(out_bytes)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": None,
+                         "frac": achieved / peak if achieved else None, "traffic": traffic_of(dom_name, a.streams),
                          "kernel": dom_name, "kernel_ms": dom, "algorithmic_bytes_per_unit": dom_bytes, "peak_source": peak_src,
                          "whole_path": {"algorithmic_bytes_per_unit": path_bytes,
                                         "achieved_gbs": per_rank_units * path_bytes / (ms * 1e-3) / 1e9,
