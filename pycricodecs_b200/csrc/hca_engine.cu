@@ -108,6 +108,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     const uint32_t run = std::max(1u, env_u32("CRI_HCA_RUN", 16));
     J.max_channels = 1;
     J.streams.assign(j->n, HcaStreamDev{});   // one entry per input stream: the device status array shares the index
+    std::vector<uint32_t> needed_frames(j->n, 0);
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
         const HcaInfo& h = infos[i];
@@ -132,29 +133,74 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         J.streams[i] = s;
         J.max_channels = std::max<uint32_t>(J.max_channels, h.channels);
         // the reference stops decoding once it has produced every output sample (hca.cpp:3401)
-        const uint32_t needed = (uint32_t)std::min<uint64_t>(h.frame_count, ((uint64_t)samples + h.delay + 1023) / 1024);
-        for (uint32_t f = 0; f < needed; f += run) {
-            HcaUnit u{i, f, std::min(run, needed - f)};
-            J.units.push_back(u);
-        }
-        j->units += needed;
+        needed_frames[i] = (uint32_t)std::min<uint64_t>(h.frame_count, ((uint64_t)samples + h.delay + 1023) / 1024);
+        j->units += needed_frames[i];
     }
-    while (J.units.size() % 32) J.units.push_back(HcaUnit{0, 0, 0});
-    // fast transform path: every decodable stream is mono (1) or stereo (2) with all 128 bands coded and no joint tools
+    // uniform batch: every decodable stream is mono (1) or stereo (2) with no joint tools (intensity pair, HFR)
     J.uniform = J.max_channels <= 2 ? J.max_channels : 0;
     for (uint32_t i = 0; i < j->n && J.uniform; i++) {
         if (j->status[i] != OK) continue;
         const HcaStreamDev& st = J.streams[i];
-        bool ok = st.channels == J.uniform && !st.joint;
-        for (unsigned ch = 0; ch < st.channels; ch++) ok = ok && st.coded[ch] == 128;
-        if (!ok) J.uniform = 0;
+        if (st.channels != J.uniform || st.joint) J.uniform = 0;
+    }
+    uint32_t max_frame = 8;
+    for (const auto& st : J.streams) max_frame = std::max(max_frame, st.frame_size);
+    J.scratch_words = ((max_frame + 15) / 16 + 4) * 4;             // whole 16-byte rows + zeroed slack rows for the prefetching reader
+    if (J.uniform && j->units > 0 && j->units < 0xFFFF0000ull && env_u32("CRI_HCA_GENERAL", 0) == 0) {
+        // fast path: flattened frame list cut into runs of run_len frames, one transform lane per (run, channel).
+        // run_len is chosen so that the transform kernel's CTAs fill the resident slots of the GPU in whole waves.
+        const uint64_t G = j->units;
+        const uint64_t cols_per_cta = hca_fast_threads_per_cta() / J.uniform;        // runs per CTA
+        const uint64_t slots = (uint64_t)std::max(1, c->sm_count) * hca_fast_ctas_per_sm();
+        uint32_t best = 1;
+        const uint32_t forced = env_u32("CRI_HCA_FAST_RUN", 0);
+        if (forced) {
+            best = forced;
+        } else {
+            const uint64_t one_wave = (G + cols_per_cta * slots - 1) / (cols_per_cta * slots);   // run_len that fits one wave
+            if (one_wave <= 32) {
+                best = (uint32_t)std::max<uint64_t>(1, one_wave);
+            } else {
+                double best_eff = 0.0;
+                for (uint32_t R = 12; R <= 32; R++) {
+                    const uint64_t runs = (G + R - 1) / R, ctas = (runs + cols_per_cta - 1) / cols_per_cta;
+                    const uint64_t waves = (ctas + slots - 1) / slots;
+                    const double eff = (double)ctas / (double)(waves * slots) * (1.0 - 1.0 / (8.0 * R));
+                    if (eff > best_eff) { best_eff = eff; best = R; }
+                }
+            }
+        }
+        J.run_len = best;
+        J.n_runs = (uint32_t)((G + best - 1) / best);
+        J.total_frames = G;
+        J.dec_prefix.assign(j->n + 1, 0);
+        for (uint32_t i = 0; i < j->n; i++) J.dec_prefix[i + 1] = J.dec_prefix[i] + needed_frames[i];
+        const uint64_t runs_per_warp = 32 / J.uniform;
+        const uint64_t warps = (J.n_runs + runs_per_warp - 1) / runs_per_warp;
+        J.spec_bytes = warps * J.run_len * 8 * 1024 * sizeof(float4);
+        J.s_bytes = (G + 1) * J.scratch_words * sizeof(uint32_t);
+        J.total_groups = 0;
+        J.max_steps = 0;
+        return OK;
+    }
+    for (uint32_t i = 0; i < j->n; i++) {
+        if (j->status[i] != OK) continue;
+        for (uint32_t f = 0; f < needed_frames[i]; f += run) {
+            HcaUnit u{i, f, std::min(run, needed_frames[i] - f)};
+            J.units.push_back(u);
+        }
+    }
+    while (J.units.size() % 32) J.units.push_back(HcaUnit{0, 0, 0});
+    // general transform kernel's shortcut: additionally all 128 bands coded in every channel
+    for (uint32_t i = 0; i < j->n && J.uniform; i++) {
+        if (j->status[i] != OK) continue;
+        const HcaStreamDev& st = J.streams[i];
+        for (unsigned ch = 0; ch < st.channels; ch++)
+            if (st.coded[ch] != 128) J.uniform = 0;
     }
     J.max_steps = run + 1;
     J.total_groups = (J.units.size() / 32) * J.max_steps;
     const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
-    uint32_t max_frame = 8;
-    for (const auto& st : J.streams) max_frame = std::max(max_frame, st.frame_size);
-    J.scratch_words = ((max_frame + 15) / 16 + 4) * 4;             // whole 16-byte rows + zeroed slack rows for the prefetching reader
     J.s_bytes = slots * J.scratch_words * sizeof(uint32_t);
     J.q_bytes = slots * J.max_channels * 8 * 16 * sizeof(uint4);
     J.g_bytes = slots * J.max_channels * 128 * sizeof(float);
@@ -308,6 +354,8 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     if (r == OK) r = upload(c, s, J.ath_tables, &J.d_ath);
     if (r == OK) r = upload(c, s, J.frame_prefix, &J.d_frame_prefix);
     if (r == OK) r = upload(c, s, J.crc_mul, &J.d_crc_mul);
+    if (r == OK) r = upload(c, s, J.dec_prefix, &J.d_dec_prefix);
+    if (r == OK && J.spec_bytes) r = pool_alloc(c, (void**)&J.d_spec, J.spec_bytes);
     if (r == OK && J.q_bytes) r = pool_alloc(c, (void**)&J.d_q, J.q_bytes);
     if (r == OK && J.g_bytes) r = pool_alloc(c, (void**)&J.d_g, J.g_bytes);
     if (r == OK && J.i_bytes) r = pool_alloc(c, (void**)&J.d_i, J.i_bytes);
@@ -336,10 +384,17 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.total_groups = J.total_groups;
         a.steps = J.max_steps;
         a.max_channels = J.max_channels;
+        a.dec_prefix = J.d_dec_prefix;
+        a.spec = reinterpret_cast<float4*>(J.d_spec);
+        a.total_frames = J.total_frames;
+        a.n_streams = j->n;
+        a.run_len = J.run_len;
+        a.n_runs = J.n_runs;
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
-        launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);
+        if (J.n_runs) launch_hca_decode_fast(a, j->stream, &c->launches, j->ev[2]);
+        else launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);
         CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));
-        *have_dominant = J.total_groups != 0;
+        *have_dominant = J.total_groups != 0 || J.n_runs != 0;
         return OK;
     }
     if (j->kind == CRI_JOB_HCA_CRYPT) {
@@ -385,7 +440,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
 void free_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
     for (void* p : {(void*)J.d_streams, (void*)J.d_units, (void*)J.d_s, (void*)J.d_frame_prefix, (void*)J.d_crc_mul,
-                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i})
+                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec})
         pool_free(c, p);
 }
 

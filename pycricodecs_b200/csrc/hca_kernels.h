@@ -28,11 +28,22 @@ struct HcaDecodeArgs {
     uint32_t max_channels;
     uint32_t scratch_words;     // multiple of 4
     uint32_t uniform;           // 0 mixed batch; 1 every stream is mono, 2 stereo: all bands coded, no HFR / intensity
+    // fast path (hca_fast_kernels.cu): frames flattened over the streams, cut into runs of run_len frames;
+    // scratch is then indexed by flattened frame and has one spare row
+    const uint32_t* dec_prefix; // [n_streams + 1] exclusive prefix of the frames decoded per stream
+    float4* spec;               // [transform warp][frame in run][subframe][32 chunks][32 lanes] dequantised spectra
+    uint64_t total_frames;
+    uint32_t n_streams;
+    uint32_t run_len;
+    uint32_t n_runs;            // 0 = not on the fast path
 };
 
 // `mid` (optional) is recorded between the unpack and the transform kernel.
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
 void launch_hca_imdct(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // second half of launch_hca_decode
+void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
+uint32_t hca_fast_threads_per_cta();
+uint32_t hca_fast_ctas_per_sm();
 
 struct HcaCryptArgs {
     const uint8_t* in;

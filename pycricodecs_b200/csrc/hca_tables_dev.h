@@ -68,6 +68,12 @@ struct HcaJob {
     std::vector<uint16_t> crc_mul;         // encode: [stream][32] CRC chunk multipliers
     uint16_t* d_crc_mul = nullptr;
     uint32_t uniform = 0;                  // decode: see HcaDecodeArgs::uniform
+    // decode fast path (hca_fast_kernels.cu)
+    std::vector<uint32_t> dec_prefix;      // [n + 1] exclusive prefix of the frames decoded per stream
+    uint32_t* d_dec_prefix = nullptr;
+    uint32_t run_len = 0, n_runs = 0;      // n_runs == 0: general path
+    uint64_t total_frames = 0, spec_bytes = 0;
+    uint8_t* d_spec = nullptr;
     uint8_t* d_s = nullptr;
     uint32_t max_channels = 1, max_steps = 0;
 

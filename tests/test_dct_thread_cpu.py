@@ -1,0 +1,65 @@
+"""The generated thread-resident IMDCT (pycricodecs_b200/csrc/hca_dct_thread_gen.inc, what hca_imdct_fast_kernel
+runs per lane) compiled for the host with the CUDA intrinsics mapped to plain, uncontracted fp32 arithmetic, against
+the oracle's imdct: PCM16 must be bit-equal, including the 32768 factor folded into the window constants."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = r'''
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+#include "hca_dct_thread_gen.inc"
+extern "C" void run(const float* spectra, int n, int16_t* pcm) {
+    float4 carry[16];
+    memset(carry, 0, sizeof carry);
+    for (int s = 0; s < n; s++) {
+        float x[128];
+        for (int i = 0; i < 128; i++) x[i] = spectra[s * 128 + i];
+        hca_dct4_dec(x);
+        hca_window_thread<1>(x, carry, [&](int i, float v) {
+            float t = truncf(v);                       // cvt.rzi.s16.f32: truncate, saturate
+            if (t > 32767.f) t = 32767.f;
+            if (t < -32768.f) t = -32768.f;
+            pcm[s * 128 + i] = (int16_t)t;
+        });
+    }
+}
+'''
+
+
+def test_generated_thread_imdct_matches_oracle(port):
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "shim.cpp")
+        with open(src, "w") as f:
+            f.write(SHIM)
+        so = os.path.join(tmp, "shim.so")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I",
+                        os.path.join(ROOT, "pycricodecs_b200", "csrc"), "-o", so, src], check=True)
+        lib = ctypes.CDLL(so)
+        rng = np.random.default_rng(7)
+        n = 48
+        for scale in (1e-30, 1e-4, 0.05, 1.0, 11.0):
+            spec = (rng.standard_normal((n, 128)) * scale).astype(np.float32)
+            spec[3] = 0
+            spec[4, ::3] = 0
+            pcm = np.zeros((n, 128), np.int16)
+            lib.run(spec.ctypes.data_as(ctypes.c_void_p), n, pcm.ctypes.data_as(ctypes.c_void_p))
+            prev = np.zeros(128, np.float32)
+            for s in range(n):
+                wave, prev, _ = port.imdct(spec[s].copy(), prev)
+                v = wave.astype(np.float32) * np.float32(32768.0)       # clHCA_ReadSamples16 (hca.cpp:339-360)
+                want = np.clip(np.trunc(v), -32768, 32767).astype(np.int16)
+                assert np.array_equal(pcm[s], want), f"scale {scale}, subframe {s}"

@@ -59,3 +59,35 @@ def test_class_surface(port):
     obj = HCA(h)
     assert obj.info()["FrameCount"] == 6 and obj.filetype == "hca"
     assert obj.decode() == port.hca_decode(h)[1]
+
+
+@pytest.mark.parametrize("run_len", [1, 2, 3, 5, 7, 64])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_fast_path_run_lengths(port, ctx, monkeypatch, run_len, channels):
+    """The fast path cuts the flattened frame list into runs: force run lengths that make runs start in the middle
+    of streams, cross from one stream into the next and end short, with more than one transform warp of runs."""
+    monkeypatch.setenv("CRI_HCA_FAST_RUN", str(run_len))
+    lengths = [5000, 1, 1024 * 3, 1024 * 9 + 17, 700, 1024 * 20, 2047, 1024 * 6 - 128, 31000, 900]
+    hcas = [port.hca_encode(synth.wav(s, channels, n), s % 2)[1] for s, n in enumerate(lengths)]   # Highest and High
+    hcas = hcas * 3
+    got = HCA.decode_batch(hcas, ctx=ctx)
+    want = {h: port.hca_decode(h)[1] for h in set(hcas)}
+    for h, g in zip(hcas, got):
+        assert _first_diff(g, want[h]) is None
+
+
+def test_fast_and_general_path_agree(port, ctx, monkeypatch):
+    hcas = [port.hca_encode(synth.wav(s, 2, 1024 * 11 + 3 * s), 1)[1] for s in range(5)]
+    fast = HCA.decode_batch(hcas, ctx=ctx)
+    monkeypatch.setenv("CRI_HCA_GENERAL", "1")
+    general = HCA.decode_batch(hcas, ctx=ctx)
+    assert fast == general
+
+
+def test_fast_path_bad_frame_in_the_middle_of_a_batch(port, ctx):
+    good = [port.hca_encode(synth.wav(s, 2, 9000), 1)[1] for s in range(4)]
+    bad = bytearray(good[1]); bad[96 + 682 * 2 + 50] ^= 0x10
+    res = HCA.decode_batch([good[0], bytes(bad), good[2], good[3]], ctx=ctx, raise_errors=False)
+    assert isinstance(res[1], Exception) and res[1].status == -202
+    for i in (0, 2, 3):
+        assert res[i] == port.hca_decode(good[i])[1]

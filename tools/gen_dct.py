@@ -98,6 +98,77 @@ def gen_imdct() -> list[str]:
     return out
 
 
+
+def gen_thread_window() -> list[str]:
+    """Window + overlap-add + carry for the thread-resident transform (hca_imdct_fast_kernel), straight to PCM.
+
+    The reference (hca.cpp:1983-1992) computes  wave[i] = w[i]*dct[64+i] + prev[i],  wave[64+i] = w[64+i]*dct[127-i]
+    - prev[64+i]  with  prev[i] = w[127-i]*dprev[63-i],  prev[64+i] = w[63-i]*dprev[i]  (dprev = the previous
+    subframe's dct[0..63]). Samples i and 127-i share dct[64+i] and dprev[63-i], so the code walks dprev in order,
+    four values (one 16-byte shared-memory word) at a time, and overwrites each carry word with this subframe's
+    dct[0..63] as soon as it has been consumed.
+
+    The window constants carry the PCM scale 32768 (an exact power-of-two bump of the exponent). Products and sums
+    scale exactly with it unless a product is subnormal, and a subnormal term cannot move the truncated integer
+    (|term| < 2^-111 against a sum that is either >= 2^-102 * 32768, where it is below half an ulp, or so small
+    that both versions truncate to 0), so  trunc(wave * 32768)  is unchanged.
+    """
+    win = T.window()
+    # register of dct[k] after hca_dct4_dec: replay the permutation bookkeeping of gen_imdct
+    phys = list(range(128))
+    half = 64
+    while half >= 1:
+        nxt = [None] * 128
+        for j in range(64 // half):
+            for k in range(half):
+                a, b = phys[j * 2 * half + 2 * k], phys[j * 2 * half + 2 * k + 1]
+                nxt[j * 2 * half + k], nxt[j * 2 * half + half + k] = a, b
+        phys = nxt
+        half //= 2
+    for stage in range(7):
+        half = 1 << stage
+        nxt = [None] * 128
+        for j in range(64 >> stage):
+            for k in range(half):
+                a, b = phys[j * 2 * half + k], phys[j * 2 * half + half + k]
+                nxt[j * 2 * half + k], nxt[j * 2 * half + 2 * half - 1 - k] = a, b
+        phys = nxt
+
+    def scaled(bits: int) -> str:
+        bits = int(bits)
+        e = (bits >> 23) & 0xFF
+        assert 1 <= e <= 200, "window constant must be a normal float"
+        return f(bits + (15 << 23))
+
+    out = []
+    out.append("// Window + overlap-add of one subframe held in registers after hca_dct4_dec, emitted as PCM-scaled floats:")
+    out.append("// emit(i, v) receives v = wave[i] * 32768 for every sample i (in the order the carry is walked). `carry` is")
+    out.append("// this thread's column of the shared carry array ([16][CARRY_STRIDE] float4 = dct[0..63] of the previous")
+    out.append("// subframe); it is replaced by this subframe's dct[0..63].")
+    out.append("template <int CARRY_STRIDE, class Emit>")
+    out.append("__device__ __forceinline__ void hca_window_thread(const float (&x)[128], float4* carry, Emit emit) {")
+    out.append("    float4 c;")
+    for q in range(16):
+        out.append(f"    c = carry[{q} * CARRY_STRIDE];")
+        for e, comp in enumerate("xyzw"):
+            k = 4 * q + e
+            i = 63 - k
+            d = f"x[{phys[64 + i]}]"
+            wa, wb = scaled(win[i]), scaled(win[127 - i])
+            out.append(f"    emit({i}, __fadd_rn(__fmul_rn({wa}, {d}), __fmul_rn({wb}, c.{comp})));")
+            out.append(f"    emit({127 - i}, __fsub_rn(__fmul_rn({wb}, {d}), __fmul_rn({wa}, c.{comp})));")
+        out.append(f"    carry[{q} * CARRY_STRIDE] = make_float4(x[{phys[4 * q]}], x[{phys[4 * q + 1]}], x[{phys[4 * q + 2]}], x[{phys[4 * q + 3]}]);")
+    out.append("}")
+    out.append("")
+    out.append("// Carry only (the look-back subframe in front of a run of frames).")
+    out.append("template <int CARRY_STRIDE>")
+    out.append("__device__ __forceinline__ void hca_carry_thread(const float (&x)[128], float4* carry) {")
+    for q in range(16):
+        out.append(f"    carry[{q} * CARRY_STRIDE] = make_float4(x[{phys[4 * q]}], x[{phys[4 * q + 1]}], x[{phys[4 * q + 2]}], x[{phys[4 * q + 3]}]);")
+    out.append("}")
+    return out
+
+
 def gen_mdct() -> list[str]:
     sin, cos = T.mdct_trig()
     sin = sin.reshape(8, 128)
@@ -254,6 +325,14 @@ def main():
     lines.append("")
     lines += gen_mdct_warp_tables()
     path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_gen.inc")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    print("wrote", path, len(lines), "lines")
+    # thread-resident decoder transform (hca_imdct_fast_kernel): only the DCT-IV of gen_imdct + the PCM window
+    dct = gen_imdct()
+    end = dct.index("}")                    # first function = hca_dct4_dec
+    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window()
+    path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_thread_gen.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
     print("wrote", path, len(lines), "lines")
