@@ -158,7 +158,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
             best = forced;
         } else {
             const uint64_t one_wave = (G + cols_per_cta * slots - 1) / (cols_per_cta * slots);   // run_len that fits one wave
-            if (one_wave <= 32) {
+            if (one_wave <= 96) {
                 best = (uint32_t)std::max<uint64_t>(1, one_wave);
             } else {
                 double best_eff = 0.0;

@@ -23,6 +23,7 @@
 // channel * (32 / NCH) + run % (32 / NCH) and chunk i holds coefficients 4i .. 4i+3. Both kernels touch it with
 // fully coalesced 512-byte rows. Algorithmic bytes per stereo frame: 8192 written + 8192 read, 4096 PCM written.
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "cri_tables.h"
@@ -40,7 +41,7 @@ __constant__ uint8_t c_max_bits[16] = CRI_TBL_MAX_BITS;
 
 #include "hca_dct_thread_gen.inc"
 
-constexpr int kFastThreads = 128;
+constexpr int kFastThreads = 128;             // unpack kernel
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -58,6 +59,7 @@ __device__ __forceinline__ uint32_t find_stream(const uint32_t* __restrict__ pre
 struct FastTables {
     float gain[1024];       // [scalefactor << 4 | resolution] = scaling[sf] * range[res]   (calculate_gain, hca.cpp:1498-1507)
     uint32_t code[128];     // resolutions 0..7, [res << 4 | 4 peeked bits]: float bits of the value | bits consumed
+    uint16_t crc[4][256];   // CRC-16 (poly 0x8005, MSB first) of byte v followed by k zero bytes
     uint8_t invert[68];
     uint8_t max_bits[16];
 };
@@ -66,6 +68,16 @@ __device__ __forceinline__ uint32_t crc16_step(uint32_t crc, uint32_t byte) {   
     const uint32_t v = ((crc >> 8) ^ byte) & 0xFF;
     const uint32_t t = (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u);
     return ((crc << 8) ^ t) & 0xFFFF;
+}
+
+// CRC-16 over four more message bytes (w = bytes in memory order): the register is folded into the first two bytes,
+// then the four table terms are independent (slice-by-4).
+__device__ __forceinline__ uint32_t crc16_word(const uint16_t (&T)[4][256], uint32_t c, uint32_t w) {
+    const uint32_t x = w ^ __byte_perm(c, 0, 0x4401);
+    return (uint32_t)T[3][x & 0xFF] ^ (uint32_t)T[2][(x >> 8) & 0xFF] ^ (uint32_t)T[1][(x >> 16) & 0xFF] ^ (uint32_t)T[0][x >> 24];
+}
+__device__ __forceinline__ uint32_t crc16_byte(const uint16_t (&T0)[256], uint32_t c, uint32_t byte) {
+    return ((c << 8) & 0xFFFF) ^ (uint32_t)T0[((c >> 8) ^ byte) & 0xFF];
 }
 
 // MSB-first reader over big-endian 32-bit words: 128 bits in registers (w3 holds the next bits), 2 x 64 more
@@ -126,6 +138,11 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
         tb.code[i] = __float_as_uint((float)(int)c_read_vals[i]) | (uint32_t)c_read_bits[i];
     for (int i = threadIdx.x; i < 66; i += kFastThreads) tb.invert[i] = c_invert[i];
     for (int i = threadIdx.x; i < 16; i += kFastThreads) tb.max_bits[i] = c_max_bits[i];
+    for (int i = threadIdx.x; i < 256; i += kFastThreads) {
+        uint32_t c = crc16_step(0, (uint32_t)i);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { tb.crc[k][i] = (uint16_t)c; c = crc16_step(c, 0); }
+    }
     __syncthreads();
 
     constexpr int RW = 32 / NCH;                              // runs per transform warp
@@ -152,7 +169,8 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     const int frame_size = active ? (int)S.frame_size : 0;
     const int nbits = frame_size * 8;
 
-    // ---- phase 1: CRC over the raw frame, cipher LUT, byte swap -> scratch row (16-byte loads, one row ahead)
+    // ---- phase 1: CRC over the raw frame (four bytes per step, slice-by-4 tables), cipher LUT, byte swap -> scratch
+    // row; 16-byte loads one row ahead
     if (active) {
         const uint8_t* src = a.in + S.in_off + (uint64_t)frame * S.frame_size;
         const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
@@ -161,39 +179,54 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
         const int wsel = lead >> 2, sh = (lead & 3) * 8;
         const uint8_t* cipher = S.cipher ? a.cipher + (size_t)S.cipher * 256 : nullptr;
         uint32_t crc = 0;
-        const int nrows = (frame_size + 15) >> 4;
+        const int nrows = (frame_size + 15) >> 4, full_rows = frame_size >> 4;
         uint4 cur = __ldg(ap), nxt = __ldg(ap + 1);
-        for (int row = 0; row < nrows; row++) {
-            const uint4 nn = __ldg(ap + row + 2);           // the input blob has 64 bytes of slack behind it
+        auto fetch_row = [&](int row, uint32_t (&raw)[4]) {      // the row's four words, frame bytes in memory order
+            const uint4 nn = __ldg(ap + row + 2);               // the input blob has 64 bytes of slack behind it
+            const uint32_t t[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
             uint32_t v[5];
-            {
-                const uint32_t t[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
 #pragma unroll
-                for (int k = 0; k < 5; k++) v[k] = wsel == 0 ? t[k] : wsel == 1 ? t[k + 1] : wsel == 2 ? t[k + 2] : t[k + 3];
-            }
-            uint32_t o[4];
+            for (int k = 0; k < 5; k++) v[k] = wsel == 0 ? t[k] : wsel == 1 ? t[k + 1] : wsel == 2 ? t[k + 2] : t[k + 3];
+#pragma unroll
+            for (int wq = 0; wq < 4; wq++) raw[wq] = __funnelshift_r(v[wq], v[wq + 1], sh);
+            cur = nxt; nxt = nn;
+        };
+        auto big_endian = [&](uint32_t w) -> uint32_t {          // deciphered, first frame byte in the top bits
+            if (!cipher) return __byte_perm(w, 0, 0x0123);
+            return ((uint32_t)__ldg(cipher + (w & 0xFF)) << 24) | ((uint32_t)__ldg(cipher + ((w >> 8) & 0xFF)) << 16) |
+                   ((uint32_t)__ldg(cipher + ((w >> 16) & 0xFF)) << 8) | (uint32_t)__ldg(cipher + (w >> 24));
+        };
+        for (int row = 0; row < full_rows; row++) {
+            uint32_t raw[4], o[4];
+            fetch_row(row, raw);
 #pragma unroll
             for (int wq = 0; wq < 4; wq++) {
-                const uint32_t raw = __funnelshift_r(v[wq], v[wq + 1], sh);
-                uint32_t be = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    uint32_t bb = (raw >> (8 * k)) & 0xFF;
-                    if (16 * row + 4 * wq + k < frame_size) crc = crc16_step(crc, bb); else bb = 0;
-                    if (cipher) bb = __ldg(cipher + bb);
-                    be = (be << 8) | bb;
-                }
-                o[wq] = be;
+                crc = crc16_word(tb.crc, crc, raw[wq]);
+                o[wq] = big_endian(raw[wq]);
             }
             reinterpret_cast<uint4*>(words)[row] = make_uint4(o[0], o[1], o[2], o[3]);
-            cur = nxt; nxt = nn;
         }
-        reinterpret_cast<uint4*>(words)[nrows] = make_uint4(0, 0, 0, 0);
+        if (frame_size & 15) {                                   // last, partial row: bytes past the frame read as 0
+            uint32_t raw[4], o[4];
+            fetch_row(full_rows, raw);
+            const int rem = frame_size & 15;
+#pragma unroll
+            for (int wq = 0; wq < 4; wq++) {
+                const int nb = min(4, max(0, rem - 4 * wq));
+                const uint32_t w = nb == 4 ? raw[wq] : nb == 0 ? 0u : raw[wq] & (0xFFFFFFFFu >> (32 - 8 * nb));
+                if (nb == 4) crc = crc16_word(tb.crc, crc, w);
+                else for (int k = 0; k < nb; k++) crc = crc16_byte(tb.crc[0], crc, (w >> (8 * k)) & 0xFF);
+                o[wq] = big_endian(w);                           // every cipher table maps 0 to 0
+            }
+            reinterpret_cast<uint4*>(words)[full_rows] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        reinterpret_cast<uint4*>(words)[nrows] = make_uint4(0, 0, 0, 0);     // slack for the prefetching reader
         reinterpret_cast<uint4*>(words)[nrows + 1] = make_uint4(0, 0, 0, 0);
-        if (crc != 0) bad = true;                           // a valid frame's CRC over all its bytes is 0 (hca.cpp:1166)
+        if (crc != 0) bad = true;                               // a valid frame's CRC over all its bytes is 0 (hca.cpp:1166)
     }
 
-    // ---- phase 2: frame header (hca.cpp:1162-1178), scalefactors, resolution (no HFR / intensity on this path)
+    // ---- phase 2: frame header (hca.cpp:1162-1178), then per channel scalefactors (:1290-1358) and, as each one is
+    // known, the band's resolution (:1444-1494). No HFR scales / intensity on this path.
     BitWindow br;
     br.init(words);
     uint32_t packed = 0;
@@ -202,58 +235,66 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
         const uint32_t noise_level = br.read(9, nbits), boundary = br.read(7, nbits);
         packed = (noise_level << 8) - boundary;
     }
-    const uint8_t* ath = a.ath + (size_t)(active ? S.ath : 0) * 128;
+    const bool has_ath = active && S.ath != 0;                   // v2.0 streams have no ATH curve
+    const uint8_t* ath = a.ath + (size_t)(has_ath ? S.ath : 0) * 128;
+    const uint32_t min_res = S.min_res, max_res = S.max_res;
     int run_bits[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        run_bits[c] = 0;
+    // A read that would cross the end of the frame yields 0 (hca.cpp:232-233). The per-read check is only compiled
+    // into the variant used when some lane's frame is too short to be sure its header ends inside it.
+    auto parse_channel = [&](int c, auto safe_tag) {
+        constexpr bool kSafe = decltype(safe_tag)::value;
         uint16_t* tc = tab + c * 128 * 32;
         const int coded = active && !bad ? (int)S.coded[c] : 0;
-        if (coded) {
-            // scalefactors (hca.cpp:1290-1358, v2.0 and older)
-            const uint32_t delta_bits = br.read(3, nbits);
-            if (delta_bits >= 6) {
-                for (int i = 0; i < coded; i++) tc[i * 32] = (uint16_t)br.read(6, nbits);
-            } else if (delta_bits > 0) {
-                const uint32_t escape = (1u << delta_bits) - 1;
-                uint32_t v = br.read(6, nbits);
-                tc[0] = (uint16_t)v;
-                for (int i = 1; i < coded; i++) {
-                    const uint32_t d = br.read((int)delta_bits, nbits);
-                    if (d == escape) {
-                        v = br.read(6, nbits);
-                    } else {
-                        const int test = (int)v + ((int)d - (int)(escape >> 1));
-                        if (test < 0 || test >= 64) { bad = true; break; }
-                        v = (v - (escape >> 1) + d) & 0x3F;
-                    }
-                    tc[i * 32] = (uint16_t)v;
-                }
-            } else {
-                for (int i = 0; i < coded; i++) tc[i * 32] = 0;
-            }
-        }
-        // resolution per band (hca.cpp:1444-1494); bands past the coded count decode to 0 from 0 bits
         int sum_bits = 0;
-        const int live = bad ? 0 : coded;
-        for (int i = 0; i < 128; i++) {
-            uint32_t word = 0;
-            if (i < live) {
-                const uint32_t sf = tc[i * 32];
+        if (coded) {
+            uint32_t db = br.peek(3);
+            if (!kSafe && br.position() + 3 > nbits) db = 0;
+            br.skip(3);
+            // delta_bits 0: all zero; 1..5: 6 raw bits, then deltas with escape (1 << db) - 1 to 6 raw bits; >= 6: raw
+            const int n_first = db == 0 ? 0 : 6;
+            const int n_rest = db >= 6 ? 6 : (int)db;
+            const bool delta = db >= 1 && db <= 5;
+            const uint32_t escape = (1u << db) - 1, half = escape >> 1;
+            uint32_t v = 0;
+            for (int i = 0; i < coded; i++) {
+                const int n1 = i == 0 ? n_first : n_rest;
+                uint32_t d = br.peek(n1);
+                uint32_t wide = br.peek(n1 + 6) & 63;            // the 6 raw bits behind an escape code
+                if (!kSafe) {
+                    const int pos = br.position();
+                    if (pos + n1 > nbits) d = 0;
+                    if (pos + n1 + 6 > nbits) wide = 0;
+                }
+                const bool rel = delta && i > 0;
+                const bool esc = rel && d == escape;
+                const int test = (int)v + (int)d - (int)half;
+                if (rel && !esc && (test < 0 || test >= 64)) bad = true;    // HCA_ERROR_UNPACK (hca.cpp:1330-1333)
+                v = esc ? wide : rel ? ((uint32_t)test & 63u) : d;
+                br.skip(n1 + (esc ? 6 : 0));
+                if ((i & 3) == 3) br.top_up();                   // at most 4 x 11 bits between refills
                 uint32_t res = 0;
-                if (sf > 0) {
-                    const int level = (int)ath[i] + (int)((packed + (uint32_t)i) >> 8);
-                    const int cp = level + 1 - (int)((5 * sf) >> 1);
+                if (v > 0) {
+                    const int level = (has_ath ? (int)ath[i] : 0) + (int)((packed + (uint32_t)i) >> 8);
+                    const int cp = level + 1 - (int)((5 * v) >> 1);
                     res = cp < 0 ? 15u : cp <= 65 ? (uint32_t)tb.invert[cp] : 0u;
-                    if (res > S.max_res) res = S.max_res; else if (res < S.min_res) res = S.min_res;
+                    res = min(max(res, min_res), max_res);
                 }
                 const uint32_t mb = tb.max_bits[res];
                 sum_bits += (int)mb;
-                word = mb | (res << 4) | (sf << 8);
+                tc[i * 32] = (uint16_t)(mb | (res << 4) | (v << 8));
             }
-            tc[i * 32] = (uint16_t)word;
+            br.top_up();
         }
+        for (int i = coded; i < 128; i++) tc[i * 32] = 0;       // bands past the coded count: 0 from 0 bits
         run_bits[c] = sum_bits;
+    };
+    const bool hdr_safe = !active || nbits >= 32 + NCH * (3 + 6 + 127 * 11);
+    if (__all_sync(kFull, hdr_safe)) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) parse_channel(c, std::true_type{});
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) parse_channel(c, std::false_type{});
     }
     if (bad) {                                               // nothing of a bad frame is decoded: every code is 0 bits
 #pragma unroll
@@ -300,7 +341,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
                         f[k] = __fmul_rn(gain_tab[t >> 4], q);                    // spectra = gain * q (hca.cpp:1568)
                     }
                     br.top_up();
-                    if (active) dst[chunk * 32] = make_float4(f[0], f[1], f[2], f[3]);
+                    if (active) __stcs(dst + chunk * 32, make_float4(f[0], f[1], f[2], f[3]));
                 }
             };
             if (any_careful) decode_run(std::true_type{}); else decode_run(std::false_type{});
@@ -335,8 +376,13 @@ __device__ __forceinline__ short pcm16_sat(float v) {
     return s;
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(kFastThreads, 3)
+// One CTA of THREADS = 256 per SM (2 warps per scheduler; the 252 registers per thread leave room for no more).
+// Measured on B200 (8192 stereo streams): 128 / 256 / 384 threads per SM all issue ~0.6 instructions per cycle and
+// scheduler while active, with "no instruction" the top stall: the body is ~70 KB of straight-line code that every
+// warp streams once per subframe, so instruction supply, not warp count, sets the pace. Barriers that keep the warps
+// of an SM (or of one scheduler) on the same cache lines did not change that.
+template <int NCH, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 hca_imdct_fast_kernel(HcaDecodeArgs a) {
     constexpr int RW = 32 / NCH;                 // runs (= tile rows) per warp
     constexpr int ROW_WORDS = 64 * NCH;          // 128 samples x NCH channels x int16
@@ -344,14 +390,13 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
     constexpr int WARP_WORDS = RW * PITCH + RW * 4;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* carry = reinterpret_cast<float4*>(s_dyn) + threadIdx.x;                                  // [16][kFastThreads]
-    uint32_t* tile = reinterpret_cast<uint32_t*>(s_dyn + 16 * kFastThreads * sizeof(float4)) + warp * WARP_WORDS;
+    float4* carry = reinterpret_cast<float4*>(s_dyn) + threadIdx.x;                                  // [16][THREADS]
+    uint32_t* tile = reinterpret_cast<uint32_t*>(s_dyn + 16 * THREADS * sizeof(float4)) + warp * WARP_WORDS;
     RowDesc* rows = reinterpret_cast<RowDesc*>(tile + RW * PITCH);
 
     const int rr = lane % RW, ch = lane / RW;
-    const uint32_t W = blockIdx.x * kFastWarps + warp;
+    const uint32_t W = blockIdx.x * (THREADS / 32) + warp;
     const uint32_t R = a.run_len;
-    if ((uint64_t)W * RW >= a.n_runs) return;    // whole warp
     const uint32_t r = W * RW + rr;
     const bool live = r < a.n_runs;
     const uint32_t G = (uint32_t)a.total_frames;
@@ -364,18 +409,19 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
         cnt = __ldg(a.dec_prefix + s + 1) - p0;
     }
 
+    float x[128];
     {   // look-back: the DCT output of the last subframe in front of the run (zero at the start of a stream)
         const bool lb = live && f > 0;
         const uint32_t r1 = lb ? r - 1 : 0;
         const float4* src = a.spec + (((uint64_t)(r1 / RW) * R + (R - 1)) * 8 + 7) * 1024 + ch * RW + (r1 % RW);
-        float x[128];
         load_spectra(x, src, lb);
         hca_dct4_dec(x);
-        hca_carry_thread<kFastThreads>(x, carry);
+        hca_carry_thread<THREADS>(x, carry);
     }
 
-    const float4* src_run = a.spec + (uint64_t)W * R * (8 * 1024) + lane;
+    const float4* src = a.spec + (uint64_t)W * R * (8 * 1024) + lane;     // block (j, sub) at + (j * 8 + sub) * 1024
     uint8_t* trow = reinterpret_cast<uint8_t*>(tile + rr * PITCH) + 2 * ch;
+    load_spectra(x, src, live && g < G);
     for (uint32_t j = 0; j < R; j++, g++) {
         const bool ok = live && g < G;
         bool fresh = false;
@@ -390,7 +436,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
         if (__any_sync(kFull, fresh)) {
             if (fresh) {
 #pragma unroll
-                for (int q = 0; q < 16; q++) carry[q * kFastThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 16; q++) carry[q * THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         long long out_off = 0;
@@ -401,9 +447,9 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
             out_samples = (int)S.out_samples;
             delay = (int)S.delay;
         }
+        const bool ok_next_frame = live && j + 1 < R && g + 1 < G;
+#pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
-            float x[128];
-            load_spectra(x, src_run + (uint64_t)(j * 8 + sub) * 1024, ok);
             hca_dct4_dec(x);
             if (ch == 0) {
                 const long long n0 = (long long)f * 1024 + sub * 128 - delay;     // stream sample index of the row's sample 0
@@ -413,9 +459,16 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
                 d.hi = ok ? (int)max(0ll, min(128ll, (long long)out_samples - n0)) : 0;
                 rows[rr] = d;
             }
-            hca_window_thread<kFastThreads>(x, carry, [&](int i, float v) {
-                *reinterpret_cast<short*>(trow + i * (2 * NCH)) = pcm16_sat(v);
-            });
+            // the next block of spectra is loaded into the registers the window frees, 16 bytes at a time
+            src += 1024;
+            const bool ok_next = sub < 7 ? ok : ok_next_frame;
+            hca_window_thread<THREADS>(x, carry,
+                [&](int i, float v) { *reinterpret_cast<short*>(trow + i * (2 * NCH)) = pcm16_sat(v); },
+                [&](int c) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok_next) v = __ldcs(src + c * 32);
+                    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                });
             __syncwarp();
             // ---- coalesced copy-out, one tile row (= 128 consecutive samples of one stream, all channels) at a time
 #pragma unroll 4
@@ -449,26 +502,33 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
     }
 }
 
+constexpr int kXfThreads = 256;
+
+template <int NCH, int THREADS>
+void launch_xf(const HcaDecodeArgs& a, cudaStream_t s) {
+    constexpr int RW = 32 / NCH;
+    const size_t smem_t = 16 * THREADS * sizeof(float4) + (size_t)(THREADS / 32) * (RW * (64 * NCH + 1) + RW * 4) * sizeof(uint32_t);
+    cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    const uint32_t warps = (a.n_runs + RW - 1) / RW, per_cta = THREADS / 32;
+    hca_imdct_fast_kernel<NCH, THREADS><<<(warps + per_cta - 1) / per_cta, THREADS, smem_t, s>>>(a);
+}
+
 template <int NCH>
 void launch_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
-    constexpr int RW = 32 / NCH;
     const size_t smem_u = (size_t)kFastWarps * NCH * 128 * 32 * sizeof(uint16_t);
-    const size_t smem_t = 16 * kFastThreads * sizeof(float4) + (size_t)kFastWarps * (RW * (64 * NCH + 1) + RW * 4) * sizeof(uint32_t);
     cudaFuncSetAttribute(hca_unpack_fast_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u);
-    cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
     const uint64_t unpack_warps = (uint64_t)((a.n_runs + 31) / 32) * a.run_len;
     hca_unpack_fast_kernel<NCH><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    const uint32_t imdct_warps = (a.n_runs + RW - 1) / RW;
-    hca_imdct_fast_kernel<NCH><<<(imdct_warps + kFastWarps - 1) / kFastWarps, kFastThreads, smem_t, s>>>(a);
+    launch_xf<NCH, kXfThreads>(a, s);
     ++*launches;
 }
 
 }  // namespace
 
-uint32_t hca_fast_threads_per_cta() { return kFastThreads; }
-uint32_t hca_fast_ctas_per_sm() { return 3; }
+uint32_t hca_fast_threads_per_cta() { return kXfThreads; }
+uint32_t hca_fast_ctas_per_sm() { return 1; }
 
 void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
     if (!a.n_runs) return;

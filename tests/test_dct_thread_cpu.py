@@ -34,7 +34,7 @@ extern "C" void run(const float* spectra, int n, int16_t* pcm) {
             if (t > 32767.f) t = 32767.f;
             if (t < -32768.f) t = -32768.f;
             pcm[s * 128 + i] = (int16_t)t;
-        });
+        }, [&](int c) { x[4 * c] = x[4 * c + 1] = x[4 * c + 2] = x[4 * c + 3] = 1e30f; });   // refilled registers must be dead
     }
 }
 '''

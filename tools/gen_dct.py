@@ -32,7 +32,9 @@ def f(bits: int) -> str:
     return f"__uint_as_float(0x{int(bits):08X}u)"
 
 
-def gen_imdct() -> list[str]:
+def gen_imdct(lockstep: int = 0) -> list[str]:
+    """lockstep > 0: the DCT takes a functor and calls it after every `lockstep` fp32 instructions (the transform
+    kernel uses it for a named barrier that keeps the warps of one scheduler on the same instruction-cache lines)."""
     sin, cos = T.imdct_trig()
     sin = sin.reshape(7, 64)
     cos = cos.reshape(7, 64)
@@ -41,8 +43,13 @@ def gen_imdct() -> list[str]:
     phys = list(range(128))  # phys[logical index] = register index
     out.append("// 128-point DCT-IV of the HCA decoder, in place on registers x[0..127].")
     out.append("// Input x[i] = spectra[i]; afterwards dct[i] lives in x[kImdctPerm[i]] (see hca_imdct_window).")
-    out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
+    if lockstep:
+        out.append("template <class Sync>")
+        out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128], Sync sync) {")
+    else:
+        out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
     out.append("    float t0, t1, t2, t3;")
+    since = 0
     # sum/difference passes, half = 64 .. 1  (hca.cpp:1907-1935)
     half = 64
     while half >= 1:
@@ -53,6 +60,10 @@ def gen_imdct() -> list[str]:
                 a = phys[j * 2 * half + 2 * k]
                 b = phys[j * 2 * half + 2 * k + 1]
                 out.append(f"    t0 = __fadd_rn(x[{a}], x[{b}]); x[{b}] = __fsub_rn(x[{a}], x[{b}]); x[{a}] = t0;")
+                since += 2
+                if lockstep and since >= lockstep:
+                    out.append("    sync();")
+                    since = 0
                 nxt[j * 2 * half + k] = a
                 nxt[j * 2 * half + half + k] = b
         phys = nxt
@@ -71,6 +82,10 @@ def gen_imdct() -> list[str]:
                 out.append(f"    t0 = __fmul_rn(x[{a}], {s}); t1 = __fmul_rn(x[{b}], {c}); "
                            f"t2 = __fmul_rn(x[{a}], {c}); t3 = __fmul_rn(x[{b}], {s}); "
                            f"x[{a}] = __fsub_rn(t0, t1); x[{b}] = __fadd_rn(t2, t3);")
+                since += 6
+                if lockstep and since >= lockstep:
+                    out.append("    sync();")
+                    since = 0
                 nxt[j * 2 * half + k] = a
                 nxt[j * 2 * half + 2 * half - 1 - k] = b
         phys = nxt
@@ -99,7 +114,7 @@ def gen_imdct() -> list[str]:
 
 
 
-def gen_thread_window() -> list[str]:
+def gen_thread_window(lockstep: int = 0) -> list[str]:
     """Window + overlap-add + carry for the thread-resident transform (hca_imdct_fast_kernel), straight to PCM.
 
     The reference (hca.cpp:1983-1992) computes  wave[i] = w[i]*dct[64+i] + prev[i],  wave[64+i] = w[64+i]*dct[127-i]
@@ -140,15 +155,32 @@ def gen_thread_window() -> list[str]:
         assert 1 <= e <= 200, "window constant must be a normal float"
         return f(bits + (15 << 23))
 
+    # which carry group (four consecutive dprev values = one float4) frees which register
+    inv = [0] * 128
+    for m, r in enumerate(phys):
+        inv[r] = m
+    group_of = [(inv[r] // 4) if inv[r] < 64 else ((127 - inv[r]) // 4) for r in range(128)]
     out = []
     out.append("// Window + overlap-add of one subframe held in registers after hca_dct4_dec, emitted as PCM-scaled floats:")
     out.append("// emit(i, v) receives v = wave[i] * 32768 for every sample i (in the order the carry is walked). `carry` is")
     out.append("// this thread's column of the shared carry array ([16][CARRY_STRIDE] float4 = dct[0..63] of the previous")
-    out.append("// subframe); it is replaced by this subframe's dct[0..63].")
-    out.append("template <int CARRY_STRIDE, class Emit>")
-    out.append("__device__ __forceinline__ void hca_window_thread(const float (&x)[128], float4* carry, Emit emit) {")
+    out.append("// subframe); it is replaced by this subframe's dct[0..63]. The carry groups are walked in the order 0, 15, 1, 14,")
+    out.append("// ...: after each pair exactly four aligned register quads x[4c..4c+3] are dead, and refill(c) is called for")
+    out.append("// each so that the caller can already load chunk c of the NEXT subframe's spectra into them (the registers")
+    out.append("// are full during the transform, so this is the only place a prefetch can live).")
+    if lockstep:
+        out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
+        out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill, Sync sync) {")
+    else:
+        out.append("template <int CARRY_STRIDE, class Emit, class Refill>")
+        out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill) {")
     out.append("    float4 c;")
-    for q in range(16):
+    done = set()
+    order = []
+    for p_ in range(8):
+        order += [p_, 15 - p_]
+    refilled = set()
+    for q in order:
         out.append(f"    c = carry[{q} * CARRY_STRIDE];")
         for e, comp in enumerate("xyzw"):
             k = 4 * q + e
@@ -158,6 +190,14 @@ def gen_thread_window() -> list[str]:
             out.append(f"    emit({i}, __fadd_rn(__fmul_rn({wa}, {d}), __fmul_rn({wb}, c.{comp})));")
             out.append(f"    emit({127 - i}, __fsub_rn(__fmul_rn({wb}, {d}), __fmul_rn({wa}, c.{comp})));")
         out.append(f"    carry[{q} * CARRY_STRIDE] = make_float4(x[{phys[4 * q]}], x[{phys[4 * q + 1]}], x[{phys[4 * q + 2]}], x[{phys[4 * q + 3]}]);")
+        done.add(q)
+        for ch in range(32):
+            if ch not in refilled and all(group_of[4 * ch + e] in done for e in range(4)):
+                out.append(f"    refill({ch});")
+                refilled.add(ch)
+        if lockstep and q in order[1::2]:
+            out.append("    sync();")
+    assert len(refilled) == 32
     out.append("}")
     out.append("")
     out.append("// Carry only (the look-back subframe in front of a run of frames).")
@@ -329,9 +369,11 @@ def main():
         fh.write("\n".join(lines) + "\n")
     print("wrote", path, len(lines), "lines")
     # thread-resident decoder transform (hca_imdct_fast_kernel): only the DCT-IV of gen_imdct + the PCM window
-    dct = gen_imdct()
+    LOCKSTEP = 0                            # > 0: call a functor every so many fp32 instructions (instruction-cache experiment,
+                                            # measured: no gain from keeping a scheduler's warps on the same lines)
+    dct = gen_imdct(LOCKSTEP)
     end = dct.index("}")                    # first function = hca_dct4_dec
-    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window()
+    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window(LOCKSTEP)
     path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_thread_gen.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
