@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t find_stream(const uint32_t* __restrict__ pre
 // ------------------------------------------------------------------------------------------------ unpack
 struct FastTables {
     float gain[1024];       // [scalefactor << 4 | resolution] = scaling[sf] * range[res]   (calculate_gain, hca.cpp:1498-1507)
-    uint32_t code[128];     // resolutions 0..7, [res << 4 | 4 peeked bits]: float bits of the value | bits consumed
+    float code[128];        // resolutions 0..7, [res << 4 | 4 peeked bits]: the value (read_val_table) as a float
     uint16_t crc[4][256];   // CRC-16 (poly 0x8005, MSB first) of byte v followed by k zero bytes
     uint8_t invert[68];
     uint8_t max_bits[16];
@@ -81,10 +81,11 @@ __device__ __forceinline__ uint32_t crc16_byte(const uint16_t (&T0)[256], uint32
 }
 
 // MSB-first reader over big-endian 32-bit words: 128 bits in registers (w3 holds the next bits), 2 x 64 more
-// requested ahead. top_up() must run at least once per 48 consumed bits.
+// requested ahead (the reader runs past the frame by up to 3 x 8 bytes: the scratch row has zeroed slack). top_up()
+// must run at least once per 48 consumed bits.
 struct BitWindow {
     uint32_t w3, w2, w1, w0;
-    uint2 ahead, ahead2;
+    uint2 ahead, ahead2, ahead3;    // the next 3 x 64 bits, already requested
     const uint2* next_ptr;
     int have;
     int loaded;
@@ -95,6 +96,7 @@ struct BitWindow {
         next_ptr = reinterpret_cast<const uint2*>(row + 4);
         ahead = *next_ptr++;
         ahead2 = *next_ptr++;
+        ahead3 = *next_ptr++;
         have = 128; loaded = 128;
     }
     __device__ __forceinline__ int position() const { return loaded - have; }
@@ -114,7 +116,8 @@ struct BitWindow {
             w3 = (uint32_t)(hi >> 32); w2 = (uint32_t)hi; w1 = (uint32_t)(lo >> 32); w0 = (uint32_t)lo;
             have += 64; loaded += 64;
             ahead = ahead2;
-            ahead2 = *next_ptr++;
+            ahead2 = ahead3;
+            ahead3 = *next_ptr++;
         }
     }
     __device__ __forceinline__ uint32_t read(int n, int nbits) {          // header fields (not the per-coefficient path)
@@ -125,32 +128,26 @@ struct BitWindow {
     }
 };
 
-// Per band and lane one 16-bit word: [3:0] code length (max_bit_table), [7:4] resolution, [13:8] scalefactor.
-// Bits [13:4] index FastTables::gain, bits [6:4] (with bit 7 clear) the prefix codebooks.
+// Per band and lane one 16-bit word: [5:2] resolution, [11:6] scalefactor, [15:12] code length (max_bit_table).
+// word & 0xFFC is the byte offset of the band's gain in FastTables::gain, word & 0x3C = 4 * resolution.
+//
+// Code lengths: a code of resolution r occupies max_bits[r] bits, or one bit less when its peeked value is below
+// kShortBelow[r] -- for the sign-magnitude family (r >= 8) that is the "zero gives the sign bit back" rule (code < 2),
+// for the prefix codebooks (r <= 7) it restates read_bit_table (hca.cpp:1513-1526; tests/test_tables.py checks the
+// restatement). So the bit position, the only serial dependency between codes, advances by a compare and a subtract;
+// the value lookups hang off the side of the chain.
+constexpr uint32_t kShortBelowLo = 0x26AE2620u;   // nibble r = threshold of resolution r, r = 0..7: 0,2,6,2,14,10,6,2
+constexpr uint32_t kShortBelowHi = 0x22222222u;   // r = 8..15: 2
 template <int NCH>
 __global__ void __launch_bounds__(kFastThreads, 3)
 hca_unpack_fast_kernel(HcaDecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ FastTables tb;
-    for (int i = threadIdx.x; i < 1024; i += kFastThreads)
-        tb.gain[i] = __fmul_rn(__uint_as_float(c_scaling[i >> 4]), __uint_as_float(c_range[i & 15]));
-    for (int i = threadIdx.x; i < 128; i += kFastThreads)
-        tb.code[i] = __float_as_uint((float)(int)c_read_vals[i]) | (uint32_t)c_read_bits[i];
-    for (int i = threadIdx.x; i < 66; i += kFastThreads) tb.invert[i] = c_invert[i];
-    for (int i = threadIdx.x; i < 16; i += kFastThreads) tb.max_bits[i] = c_max_bits[i];
-    for (int i = threadIdx.x; i < 256; i += kFastThreads) {
-        uint32_t c = crc16_step(0, (uint32_t)i);
-#pragma unroll
-        for (int k = 0; k < 4; k++) { tb.crc[k][i] = (uint16_t)c; c = crc16_step(c, 0); }
-    }
-    __syncthreads();
-
     constexpr int RW = 32 / NCH;                              // runs per transform warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t R = a.run_len;
     const uint32_t wid = blockIdx.x * kFastWarps + warp;     // (block of 32 runs, frame in run)
     const uint32_t rb = wid / R, j = wid - rb * R;
-    if ((uint64_t)rb * 32 >= a.n_runs) return;               // whole warp
     const uint32_t r = rb * 32 + lane;
     const uint64_t g64 = (uint64_t)r * R + j;
     const bool active = r < a.n_runs && g64 < a.total_frames;
@@ -160,6 +157,25 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
         stream = find_stream(a.dec_prefix, a.n_streams, g);
         frame = g - __ldg(a.dec_prefix + stream);
     }
+    if (active) {   // pull the frame towards L2 while the tables are built: each lane reads its own 682-byte frame
+        const HcaStreamDev& S0 = a.streams[stream];
+        const uint8_t* src = a.in + S0.in_off + (uint64_t)frame * S0.frame_size;
+        for (uint32_t k = 0; k < S0.frame_size + 127; k += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + k));
+    }
+    for (int i = threadIdx.x; i < 1024; i += kFastThreads)
+        tb.gain[i] = __fmul_rn(__uint_as_float(c_scaling[i >> 4]), __uint_as_float(c_range[i & 15]));
+    for (int i = threadIdx.x; i < 128; i += kFastThreads)
+        tb.code[i] = (float)(int)c_read_vals[i];
+    for (int i = threadIdx.x; i < 66; i += kFastThreads) tb.invert[i] = c_invert[i];
+    for (int i = threadIdx.x; i < 16; i += kFastThreads) tb.max_bits[i] = c_max_bits[i];
+    for (int i = threadIdx.x; i < 256; i += kFastThreads) {
+        uint32_t c = crc16_step(0, (uint32_t)i);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { tb.crc[k][i] = (uint16_t)c; c = crc16_step(c, 0); }
+    }
+    __syncthreads();
+
+    if ((uint64_t)rb * 32 >= a.n_runs) return;               // whole warp
     const HcaStreamDev& S = a.streams[stream];
 
     uint16_t* tab = reinterpret_cast<uint16_t*>(s_dyn) + (size_t)warp * (NCH * 128 * 32) + lane;   // + (c * 128 + band) * 32
@@ -281,7 +297,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
                 }
                 const uint32_t mb = tb.max_bits[res];
                 sum_bits += (int)mb;
-                tc[i * 32] = (uint16_t)(mb | (res << 4) | (v << 8));
+                tc[i * 32] = (uint16_t)((res << 2) | (v << 6) | (mb << 12));
             }
             br.top_up();
         }
@@ -307,7 +323,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     const uint32_t W = r / RW, rr = r % RW;
     float4* dst_frame = a.spec + ((uint64_t)W * R + j) * (8 * 1024) + rr;   // + sub * 1024 + (c * RW) + chunk * 32
     const float* gain_tab = tb.gain;
-    const uint32_t* code_tab = tb.code;
+    const float* code_tab = tb.code;
     for (int sub = 0; sub < 8; sub++) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
@@ -324,21 +340,18 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const uint32_t t = tp[(chunk * 4 + k) * 32];
-                        const int bits = (int)(t & 15);
+                        const int bits = (int)(t >> 12);
+                        const uint32_t res4 = t & 0x3C;
+                        const uint32_t short_below = __funnelshift_rc(kShortBelowLo, kShortBelowHi, res4) & 15;
                         uint32_t code = br.peek(bits);
                         if (kCareful && br.position() + bits > nbits) code = 0;   // reader rule, hca.cpp:232-233
-                        // sign-magnitude family (resolution >= 8): LSB is the sign, zero gives one bit back
-                        const uint32_t mag = code >> 1;
-                        const float f_hi = __uint_as_float(__float_as_uint((float)mag) | (code << 31));
-                        const int used_hi = bits - (mag == 0 ? 1 : 0);
-                        // prefix-codebook family (resolution <= 7)
-                        const uint32_t e = code_tab[(t & 0x70) | (code & 15)];
-                        const float f_lo = __uint_as_float(e & ~7u);
-                        const int used_lo = (int)(e & 7);
-                        const bool hi = (t & 0x80) != 0;
-                        const float q = hi ? f_hi : f_lo;
-                        br.skip(hi ? used_hi : used_lo);
-                        f[k] = __fmul_rn(gain_tab[t >> 4], q);                    // spectra = gain * q (hca.cpp:1568)
+                        br.skip(bits - (code < short_below ? 1 : 0));
+                        // value: sign-magnitude (resolution >= 8, LSB = sign) or prefix codebook (resolution <= 7)
+                        const float q_hi = __uint_as_float(__float_as_uint((float)(code >> 1)) | (code << 31));
+                        const float q_lo = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(code_tab) + ((res4 & 0x1C) << 4) + ((code & 15) << 2));
+                        const float q = (t & 0x20) ? q_hi : q_lo;
+                        const float gain = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(gain_tab) + (t & 0xFFC));
+                        f[k] = __fmul_rn(gain, q);                                // spectra = gain * q (hca.cpp:1568)
                     }
                     br.top_up();
                     if (active) __stcs(dst + chunk * 32, make_float4(f[0], f[1], f[2], f[3]));

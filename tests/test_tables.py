@@ -53,3 +53,34 @@ def test_tables_equal_reference_arrays(ref):
     assert np.array_equal(T["ENC_RES_CURVE"].astype(np.int32), ref.table("enc_res_curve", np.int32))
     assert np.array_equal(T["ENC_Q_BITS"].astype(np.int32), ref.table("enc_q_bits", np.int32))
     assert np.array_equal(T["ENC_Q_CODE"].astype(np.int8), ref.table("enc_q_value", np.int8))
+
+
+def test_code_length_threshold_restatement():
+    """hca_unpack_fast_kernel advances the bit position with  used = max_bits[r] - (code < short_below[r])  for both
+    code families; for the prefix codebooks (r <= 7) that must restate read_bit_table (hca.cpp:1513-1526), for the
+    sign-magnitude family it is the reference's 'zero gives the sign bit back' rule (hca.cpp:1554-1559)."""
+    T = {n: np.asarray(a).ravel() for n, _, a in G.all_tables()}
+    lo, hi = 0x26AE2620, 0x22222222
+    short_below = [(lo >> (4 * r)) & 15 for r in range(8)] + [(hi >> (4 * (r - 8))) & 15 for r in range(8, 16)]
+    for r in range(8):
+        mb = int(T["MAX_BITS"][r])
+        for code in range(1 << mb):
+            assert int(T["READ_BITS"][(r << 4) | code]) == mb - (1 if code < short_below[r] else 0), (r, code)
+    assert short_below[8:] == [2] * 8           # code >> 1 == 0  <=>  code < 2
+    # the slice-by-4 CRC tables are the byte table iterated over zero bytes (checked bit for bit on the GPU by the
+    # decode parity tests; here: the algebra)
+    t0 = [int(v) for v in G.crc16_table()]
+
+    def step(c, b):
+        return ((c << 8) & 0xFFFF) ^ t0[((c >> 8) ^ b) & 0xFF]
+    tk = [t0]
+    for _ in range(3):
+        tk.append([step(c, 0) for c in tk[-1]])
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        c = int(rng.integers(0, 1 << 16)); bs = [int(x) for x in rng.integers(0, 256, 4)]
+        want = c
+        for b in bs:
+            want = step(want, b)
+        x = (bs[0] | bs[1] << 8 | bs[2] << 16 | bs[3] << 24) ^ (((c >> 8) & 0xFF) | ((c & 0xFF) << 8))
+        assert tk[3][x & 0xFF] ^ tk[2][(x >> 8) & 0xFF] ^ tk[1][(x >> 16) & 0xFF] ^ tk[0][x >> 24] == want
