@@ -245,6 +245,18 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
         J.frame_prefix[i + 1] = J.frame_prefix[i] + frames;
     }
     finish_layout_public(j, sizes);   // out_off == in_off
+    {   // staged kernel: a warp stages up to 32 consecutive frames (<= 24 KB) of one stream in shared memory
+        uint32_t max_fs = 0;
+        for (const auto& st : J.streams) max_fs = std::max(max_fs, st.frame_size);
+        J.frames_per_group = 0;
+        if (max_fs >= 8 && max_fs <= 12288) {
+            J.frames_per_group = std::min(32u, std::max(1u, 24576u / max_fs));
+            J.group_bytes = ((J.frames_per_group * max_fs + 32 + 15) / 16) * 16;
+            J.group_prefix.assign(j->n + 1, 0);
+            for (uint32_t i = 0; i < j->n; i++)
+                J.group_prefix[i + 1] = J.group_prefix[i] + (J.streams[i].frame_count + J.frames_per_group - 1) / J.frames_per_group;
+        }
+    }
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
         const uint8_t* d = j->blob + j->in_off[i];
@@ -355,6 +367,7 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     if (r == OK) r = upload(c, s, J.frame_prefix, &J.d_frame_prefix);
     if (r == OK) r = upload(c, s, J.crc_mul, &J.d_crc_mul);
     if (r == OK) r = upload(c, s, J.dec_prefix, &J.d_dec_prefix);
+    if (r == OK) r = upload(c, s, J.group_prefix, &J.d_group_prefix);
     if (r == OK && J.spec_bytes) r = pool_alloc(c, (void**)&J.d_spec, J.spec_bytes);
     if (r == OK && J.q_bytes) r = pool_alloc(c, (void**)&J.d_q, J.q_bytes);
     if (r == OK && J.g_bytes) r = pool_alloc(c, (void**)&J.d_g, J.g_bytes);
@@ -407,6 +420,10 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_frames = J.frame_prefix.empty() ? 0 : J.frame_prefix.back();
         a.n_streams = j->n;
         a.n_tables = (uint32_t)(J.cipher_tables.size() / 256);
+        a.group_prefix = J.d_group_prefix;
+        a.n_groups = J.group_prefix.empty() ? 0 : J.group_prefix.back();
+        a.frames_per_group = J.frames_per_group;
+        a.group_bytes = J.group_bytes;
         CU_TRY(c, cudaEventRecord(j->ev[2], j->stream));
         launch_hca_crypt(a, j->stream, &c->launches);
         CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));
@@ -440,7 +457,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
 void free_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
     for (void* p : {(void*)J.d_streams, (void*)J.d_units, (void*)J.d_s, (void*)J.d_frame_prefix, (void*)J.d_crc_mul,
-                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec})
+                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec, (void*)J.d_group_prefix})
         pool_free(c, p);
 }
 
