@@ -40,6 +40,7 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1) {
     if (mode == 3) return raw + 1;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, co
 __global__ void __launch_bounds__(32 * (1 + kMovers))
 adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) uint32_t s_code[2][kCodeWords + 32];
+    __shared__ __align__(16) uint32_t s_code[3][kCodeWords + 32];        // tile t in stage t % 3: two tiles are in flight
     __shared__ __align__(16) int16_t s_pcm[2][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
     __shared__ StreamInfo s_info[32];
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,7 +114,14 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
             const uint32_t halfs = count * nch;
             if (((reinterpret_cast<uintptr_t>(dst) | (halfs * 2)) & 3) == 0) {
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(srow);
-                for (uint32_t e = lane; e < halfs / 2; e += 32) reinterpret_cast<uint32_t*>(dst)[e] = w[e];
+                const uint32_t words = halfs / 2;
+                uint32_t e = lane;
+                for (; e + 96 < words; e += 128) {          // four independent shared loads, then four stores
+                    const uint32_t v0 = w[e], v1 = w[e + 32], v2 = w[e + 64], v3 = w[e + 96];
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+                    d32[e] = v0; d32[e + 32] = v1; d32[e + 64] = v2; d32[e + 96] = v3;
+                }
+                for (; e < words; e += 32) reinterpret_cast<uint32_t*>(dst)[e] = w[e];
             } else {
                 for (uint32_t e = lane; e < halfs; e += 32) reinterpret_cast<int16_t*>(dst)[e] = srow[e];
             }
@@ -123,7 +131,9 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     if (role >= 1) {
         mover_request(&s_code[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, false, nch, lane, role - 1);
         cp_commit();
-        cp_wait_all();
+        if (ntiles > 1) mover_request(&s_code[1][0], row_words, in, s_info, nstreams, kTile, frame_bytes, false, nch, lane, role - 1);
+        cp_commit();
+        cp_wait_all_but_one();                              // tile 0 has landed, tile 1 is in flight
     }
     __syncthreads();
 
@@ -133,14 +143,14 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         const int buf = t & 1;
         const uint32_t b0 = t * kTile;
         if (role >= 1) {
-            if (t + 1 < ntiles) mover_request(&s_code[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, false, nch, lane, role - 1);
+            if (t + 2 < ntiles) mover_request(&s_code[(t + 2) % 3][0], row_words, in, s_info, nstreams, b0 + 2 * kTile, frame_bytes, false, nch, lane, role - 1);
             cp_commit();
             if (t >= 1) store_tile(t - 1);
-            cp_wait_all();
+            cp_wait_all_but_one();                          // tile t + 1 has landed (tile t + 2 may still be in flight)
         } else {
             const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
             // byte 0 of this lane's first frame inside its stream's row
-            const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[buf][slot * row_words]) +
+            const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[t % 3][slot * row_words]) +
                                  (int)((ch.eof_off + (uint64_t)b0 * frame_bytes) & 3);
             int16_t* my_pcm = &s_pcm[buf][slot * out_row + ch.channel];
             for (uint32_t tb = 0; tb < nb; tb++) {
@@ -159,18 +169,53 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
 #pragma unroll
                 for (int k = 0; k < kBlk; k++) blk[k] = src[k];
                 const int scale = decode_scale((blk[0] << 8) | blk[1], ch.mode, c0, c1);
+                // Speculative pass without the int16 clamp (adx.cpp:209): as long as no sample leaves the int16 range
+                // the clamp is the identity, and without it the recurrence can be regrouped so that only a multiply-add
+                // and a shift per sample sit on the serial path:
+                //   s_n = a_n + x_n,  x_n = q_n*scale + (c1*s_{n-2} >> 12),  a_{n+1} = (c0*a_n + c0*x_n) >> 12 = c0*s_n >> 12
+                // (the two floor shifts stay separate, exactly as in the reference). Every product stays below 2^31 for
+                // scales up to 0x2000 and |c| <= 0x2000; `range` ORs the biased samples, so any excursion shows in its
+                // high bits and the block is then redone with the reference's clamped recurrence from the saved history.
+                bool exact = scale > 0x2000 || abs(c0) > 0x2000 || abs(c1) > 0x2000;
+                if (!exact) {
+                    const int o1 = h1, o2 = h2;
+                    int a1 = (c0 * h1) >> 12;                 // a_n
+                    int range = 0;
+                    int sm1 = h1, sm2 = h2;                   // s_{n-1}, s_{n-2}
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const int byte = blk[2 + k];
-                    const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
-                    int s = (q_hi * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);   // same sum, h1 term last (critical path)
-                    s = clamp16(s);
-                    h2 = h1; h1 = s;
-                    dst[(2 * k) * nch] = (int16_t)s;
-                    s = (q_lo * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);
-                    s = clamp16(s);
-                    h2 = h1; h1 = s;
-                    dst[(2 * k + 1) * nch] = (int16_t)s;
+                    for (int k = 0; k < 16; k++) {
+                        const int byte = blk[2 + k];
+                        const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
+                        int x = q_hi * scale + ((c1 * sm2) >> 12);
+                        int sn = a1 + x;
+                        a1 = (c0 * a1 + c0 * x) >> 12;
+                        dst[(2 * k) * nch] = (int16_t)sn;
+                        sm2 = sm1; sm1 = sn;
+                        const int r0 = sn + 32768;
+                        x = q_lo * scale + ((c1 * sm2) >> 12);
+                        sn = a1 + x;
+                        a1 = (c0 * a1 + c0 * x) >> 12;
+                        dst[(2 * k + 1) * nch] = (int16_t)sn;
+                        sm2 = sm1; sm1 = sn;
+                        range |= r0 | (sn + 32768);
+                    }
+                    h1 = sm1; h2 = sm2;
+                    if ((unsigned)range > 0xFFFFu) { exact = true; h1 = o1; h2 = o2; }
+                }
+                if (exact) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const int byte = blk[2 + k];
+                        const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
+                        int s = (q_hi * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);
+                        s = clamp16(s);
+                        h2 = h1; h1 = s;
+                        dst[(2 * k) * nch] = (int16_t)s;
+                        s = (q_lo * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);
+                        s = clamp16(s);
+                        h2 = h1; h1 = s;
+                        dst[(2 * k + 1) * nch] = (int16_t)s;
+                    }
                 }
             }
         }
@@ -348,23 +393,59 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 dst[1] = (uint8_t)sc.word;
                 const int scale = sc.scale ? sc.scale : 1;  // adx.cpp:256-257
                 const int half = scale >> 1;
-                const uint32_t magic = div_magic(scale);
+                // pass 2 (adx.cpp:254-266), speculative form. With t = (s << 12) - c0*h1 - c1*h2 the reference computes
+                //   delta = trunc((t >> 12 -+ half) / scale) clamped to [-8, 7],  h1' = clamp16(((delta << 12) * scale + pred) >> 12).
+                // (delta << 12) * scale is a multiple of 4096, so h1' = clamp16(delta * scale + (pred >> 12)), and
+                // pred >> 12 = s - ceil(t / 4096). The int16 clamp does not fire on ordinary audio: the block is first run
+                // without it (9 dependent operations per sample instead of 14; `range_s` collects the biased values), and
+                // redone with the reference's own sequence from the saved history if a value left the int16 range. (The
+                // delta clamp stays: the scale comes from residuals against RAW history, so it fires in ~1 block of 8.)
+                // Division: q = ((2*|r| + 2*half) * ceil(2^31 / scale)) >> 32 is exact while (|r| + half) * scale < 2^31.
+                bool exact = abs(c0) > 0x2000 || abs(c1) > 0x2000 || scale > 0x1000;
                 h1 = o1; h2 = o2;
+                if (!exact) {
+                    const uint32_t magic31 = 0x7FFFFFFFu / (uint32_t)scale + 1u;      // ceil(2^31 / scale), scale >= 1
+                    const int half2 = 2 * half;
+                    int range_s = 0;
+                    int g1 = h1, g2 = h2;
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    int byte = 0;
+                    for (int k = 0; k < 16; k++) {
+                        int byte = 0;
 #pragma unroll
-                    for (int n = 0; n < 2; n++) {
-                        const int pred = c0 * h1 + c1 * h2;
-                        int d = (smp[2 * k + n] * 4096 - pred) >> 12;
-                        d = d > 0 ? d + half : d - half;
-                        d = div_trunc(d, magic, scale);
-                        d = min(max(d, -8), 7);
-                        const int sim = clamp16((d * 4096 * scale + pred) >> 12);
-                        h2 = h1; h1 = sim;
-                        byte = (byte << 4) | (d & 0xF);
+                        for (int n = 0; n < 2; n++) {
+                            const int sm = smp[2 * k + n];
+                            const int t = (sm * 4096 - c1 * g2) - c0 * g1;
+                            const int r = t >> 12;
+                            const int q = (int)__umulhi((uint32_t)(2 * abs(r) + half2), magic31);
+                            const int d = min(max(r < 0 ? -q : q, -8), 7);
+                            const int sim = d * scale + (sm - ((t + 4095) >> 12));
+                            range_s |= sim + 32768;
+                            g2 = g1; g1 = sim;
+                            byte = (byte << 4) | (d & 0xF);
+                        }
+                        dst[2 + k] = (uint8_t)byte;
                     }
-                    dst[2 + k] = (uint8_t)byte;
+                    if ((unsigned)range_s > 0xFFFFu) exact = true;
+                    else { h1 = g1; h2 = g2; }
+                }
+                if (exact) {
+                    const uint32_t magic = div_magic(scale);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        int byte = 0;
+#pragma unroll
+                        for (int n = 0; n < 2; n++) {
+                            const int pred = c0 * h1 + c1 * h2;
+                            int d = (smp[2 * k + n] * 4096 - pred) >> 12;
+                            d = d > 0 ? d + half : d - half;
+                            d = div_trunc(d, magic, scale);
+                            d = min(max(d, -8), 7);
+                            const int sim = clamp16((d * 4096 * scale + pred) >> 12);
+                            h2 = h1; h1 = sim;
+                            byte = (byte << 4) | (d & 0xF);
+                        }
+                        dst[2 + k] = (uint8_t)byte;
+                    }
                 }
             }
         }

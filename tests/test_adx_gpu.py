@@ -94,3 +94,34 @@ def test_eof_marker_stops_decode(port, ctx):
     a[hdr + 36 * 10: hdr + 36 * 10 + 2] = b"\x80\x01"   # EOF marker at frame 10
     got = ADX.decode_batch([bytes(a)], ctx)[0]
     assert got == port.adx_decode(bytes(a))[1]
+
+
+def _loud_wav(seed, ch, n):
+    """Full-scale material: square bursts, white noise at +-32767 and rail-to-rail steps. It drives the decoder's
+    int16 clamp and the encoder's [-8, 7] delta clamp, i.e. the exact fallback behind the kernels' speculative
+    (clamp-free) recurrences."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(-32768, 32768, size=(n, ch)).astype(np.int16)
+    x[n // 4: n // 2] = np.where((np.arange(n // 4, n // 2) // 3 % 2)[:, None] == 0, 32767, -32768)
+    x[n // 2: n // 2 + 64] = 0
+    x[:64] = (x[:64].astype(np.int32) * np.arange(64)[:, None] // 64 // 64).astype(np.int16)   # quiet start: scale of block 0 < 256
+    return synth.wav_header(ch, n) + x.tobytes()
+
+
+def test_clipping_material_takes_the_exact_path(port, ctx):
+    wavs = [_loud_wav(s, c, 32 * 200) for s in range(4) for c in (1, 2)]
+    enc = ADX.encode_batch(wavs, ctx)
+    for w, g in zip(wavs, enc):
+        assert g == port.adx_encode(w)[1]
+    dec = ADX.decode_batch(enc, ctx, raise_errors=False)
+    for a, g in zip(enc, dec):
+        r, want = port.adx_decode(a)
+        assert (g == want) if r == 0 else (g.status == r)
+    # a decoder-side stress the encoder never produces: huge scales on every block
+    a = bytearray(enc[1])
+    hdr = int.from_bytes(a[2:4], "big") + 4
+    for b in range(hdr, len(a) - 18, 18):
+        a[b] = 0x3F
+    r, want = port.adx_decode(bytes(a))
+    got = ADX.decode_batch([bytes(a)], ctx, raise_errors=False)[0]
+    assert (got == want) if r == 0 else (got.status == r)
