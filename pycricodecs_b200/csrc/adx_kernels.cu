@@ -31,7 +31,16 @@ constexpr int kPcmRow = kTile * kSpb + 2;            // int16 per chain in the P
 constexpr int kCodeWords = (kTile * 32 * kBlk + 3) / 4 + 1;     // covering words of 32 chains x kTile blocks
 constexpr int kPcmWords = (kTile * 32 * kSpb * 2 + 3) / 4 + 1;  // covering words of 32 chains x kTile x 32 samples
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kMovers = 3;               // mover warps per CTA (warp 0 is the worker)
+constexpr int kMovers = 3;               // mover warps per worker warp
+// A CTA holds kGroups independent worker + movers groups: warp w belongs to group w % kGroups with role w / kGroups
+// (0 = worker). Warps map to the SM's four schedulers by warp index, so the four workers of a CTA sit on four
+// different schedulers -- with one 4-warp CTA per group, every resident CTA's worker landed on scheduler 0 and three
+// to four serial recurrences shared one issue port while the other three schedulers idled with the movers.
+constexpr int kGroups = 4;
+constexpr int kGroupThreads = 32 * (1 + kMovers);
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kGroupThreads) : "memory");
+}
 
 __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
 
@@ -54,7 +63,7 @@ __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1)
 
 // Warp specialisation: a CTA is two warps working on the same 32 chains. Warp 0 ("worker") runs the 32 serial
 // recurrences out of shared memory; warp 1 ("mover") keeps the next input tile arriving (cp.async) and drains the
-// previous output tile to HBM, so the recurrence never waits for memory. One __syncthreads per tile hands the
+// previous output tile to HBM, so the recurrence never waits for memory. One group barrier per tile hands the
 // double-buffered tiles over.
 struct StreamInfo {
     uint64_t in_base;    // first byte of the stream's payload in the input blob (decode: frame 0, encode: sample 0)
@@ -80,14 +89,22 @@ __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, co
 }
 
 // ------------------------------------------------------------ decode, fast
-__global__ void __launch_bounds__(32 * (1 + kMovers))
+struct alignas(16) DecodeStage {
+    uint32_t code[3][kCodeWords + 32];        // tile t in stage t % 3: two tiles are in flight
+    int16_t pcm[2][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
+    StreamInfo info[32];
+};
+
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) uint32_t s_code[3][kCodeWords + 32];        // tile t in stage t % 3: two tiles are in flight
-    __shared__ __align__(16) int16_t s_pcm[2][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
-    __shared__ StreamInfo s_info[32];
-    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t first = blockIdx.x * 32u;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const int group = (threadIdx.x >> 5) % kGroups, role = (threadIdx.x >> 5) / kGroups, lane = threadIdx.x & 31;
+    DecodeStage& stage = reinterpret_cast<DecodeStage*>(s_dyn)[group];
+    auto& s_code = stage.code;
+    auto& s_pcm = stage.pcm;
+    StreamInfo* s_info = stage.info;
+    const uint32_t first = (blockIdx.x * kGroups + group) * 32u;
     if (first >= n_chains) return;
     const AdxChain ch = chains[first + lane];               // the list is padded to whole warps (idle: blocks == 0)
     const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
@@ -100,7 +117,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(kFull, warp_blocks, o));
     const int slot = lane / nch;                            // this lane's stream within the CTA
     if (role == 0 && ch.channel == 0) s_info[slot] = StreamInfo{ch.eof_off, ch.out_off, ch.blocks, ch.samples};
-    __syncthreads();
+    group_sync(group);
     const uint32_t ntiles = (warp_blocks + kTile - 1) / kTile;
 
     auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is one contiguous run in the WAV
@@ -135,7 +152,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         cp_commit();
         cp_wait_all_but_one();                              // tile 0 has landed, tile 1 is in flight
     }
-    __syncthreads();
+    group_sync(group);
 
     int h1 = ch.hist1, h2 = ch.hist2, c0 = ch.coef0, c1 = ch.coef1;
     bool ended = false;   // EOF block seen (adx.cpp:405-406): the rest of the stream stays silent
@@ -219,7 +236,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 }
             }
         }
-        __syncthreads();
+        group_sync(group);
     }
     if (role >= 1 && ntiles) store_tile(ntiles - 1);
 }
@@ -301,14 +318,22 @@ __device__ __forceinline__ int div_trunc(int v, uint32_t magic, int d) {
 }
 
 // ------------------------------------------------------------ encode, fast
-__global__ void __launch_bounds__(32 * (1 + kMovers))
+struct alignas(16) EncodeStage {
+    uint32_t pcm[2][kPcmWords + 32];
+    uint8_t code[2][32 * kTile * kBlk + 128];   // per stream: blocks in file order
+    StreamInfo info[32];
+};
+
+__global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
 adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
-    __shared__ __align__(16) uint32_t s_pcm[2][kPcmWords + 32];
-    __shared__ __align__(16) uint8_t s_code[2][32 * kTile * kBlk + 128];   // per stream: blocks in file order
-    __shared__ StreamInfo s_info[32];
-    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t first = blockIdx.x * 32u;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const int group = (threadIdx.x >> 5) % kGroups, role = (threadIdx.x >> 5) / kGroups, lane = threadIdx.x & 31;
+    EncodeStage& stage = reinterpret_cast<EncodeStage*>(s_dyn)[group];
+    auto& s_pcm = stage.pcm;
+    auto& s_code = stage.code;
+    StreamInfo* s_info = stage.info;
+    const uint32_t first = (blockIdx.x * kGroups + group) * 32u;
     if (first >= n_chains) return;
     const AdxChain ch = chains[first + lane];
     const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
@@ -322,7 +347,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     const int slot = lane / nch;
     const uint64_t stream_base = ch.in_off - 2ull * ch.channel;   // first PCM sample of the stream
     if (role == 0 && ch.channel == 0) s_info[slot] = StreamInfo{stream_base, ch.out_off, ch.blocks, ch.samples};
-    __syncthreads();
+    group_sync(group);
     const uint32_t ntiles = (warp_blocks + kTile - 1) / kTile;
 
     auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is contiguous in the ADX image
@@ -347,7 +372,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         cp_commit();
         cp_wait_all();
     }
-    __syncthreads();
+    group_sync(group);
 
     int h1 = ch.hist1, h2 = ch.hist2;
     const int c0 = ch.coef0, c1 = ch.coef1;
@@ -449,7 +474,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 }
             }
         }
-        __syncthreads();
+        group_sync(group);
     }
     if (role >= 1 && ntiles) store_tile(ntiles - 1);
 }
@@ -517,7 +542,9 @@ __global__ void scatter_patches_kernel(uint8_t* __restrict__ out, const uint8_t*
 void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
-        adx_decode_fast_kernel<<<(n_fast + 31) / 32, 32 * (1 + kMovers), 0, s>>>(d_in, d_out, d_chains, n_fast);
+        const unsigned groups = (n_fast + 31) / 32;
+        cudaFuncSetAttribute(adx_decode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroups * sizeof(DecodeStage)));
+        adx_decode_fast_kernel<<<(groups + kGroups - 1) / kGroups, kGroups * kGroupThreads, kGroups * sizeof(DecodeStage), s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
@@ -529,7 +556,9 @@ void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_ch
 void launch_adx_encode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
-        adx_encode_fast_kernel<<<(n_fast + 31) / 32, 32 * (1 + kMovers), 0, s>>>(d_in, d_out, d_chains, n_fast);
+        const unsigned groups = (n_fast + 31) / 32;
+        cudaFuncSetAttribute(adx_encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroups * sizeof(EncodeStage)));
+        adx_encode_fast_kernel<<<(groups + kGroups - 1) / kGroups, kGroups * kGroupThreads, kGroups * sizeof(EncodeStage), s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
