@@ -45,7 +45,7 @@ WORKLOADS = {
 DOMINANT = {
     # fast path transform kernel: reads 2 x 8 x 128 fp32 spectra (8192 B), writes 2048 PCM16 samples (4096 B) per stereo frame
     "hca_decode": ("hca_imdct_fast_kernel", 12288), "hca_decrypt_decode": ("hca_imdct_fast_kernel", 12288),
-    "hca_decrypt": ("hca_crypt_kernel", None), "hca_encode": ("hca_encode_kernel", None),
+    "hca_decrypt": ("hca_crypt_staged_kernel", None), "hca_encode": ("hca_encode_kernel", None),
     "adx_encode": ("adx_encode_fast_kernel", 82), "adx_decode": ("adx_decode_fast_kernel", 82),
 }
 

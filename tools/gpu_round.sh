@@ -31,9 +31,9 @@ cat $OUT/${TAG}_bench_reference.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'hca_|adx_|scatter_' -c 400 --csv \
     --log-file $OUT/${TAG}_launches_hca_decode.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/${TAG}_ncu_bench.log 2>&1
 # full captures of the two decode kernels (one launch each, after the warm-up launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:hca_imdct -s 4 -c 1 -o $OUT/${TAG}_prof_imdct -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:hca_imdct_fast -s 4 -c 1 -o $OUT/${TAG}_prof_imdct -f \
     python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/${TAG}_ncu_imdct.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:hca_unpack -s 4 -c 1 -o $OUT/${TAG}_prof_unpack -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:hca_unpack_fast -s 4 -c 1 -o $OUT/${TAG}_prof_unpack -f \
     python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/${TAG}_ncu_unpack.log 2>&1
 for w in adx_encode adx_decode hca_encode hca_decrypt; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${w%%_*}_.*${w##*_}|hca_crypt" -s 4 -c 1 -o $OUT/${TAG}_prof_$w -f \
