@@ -80,23 +80,36 @@ __device__ __forceinline__ uint32_t crc16_byte(const uint16_t (&T0)[256], uint32
     return ((c << 8) & 0xFFFF) ^ (uint32_t)T0[((c >> 8) ^ byte) & 0xFF];
 }
 
-// MSB-first reader over big-endian 32-bit words: 128 bits in registers (w3 holds the next bits), 2 x 64 more
-// requested ahead (the reader runs past the frame by up to 3 x 8 bytes: the scratch row has zeroed slack). top_up()
-// must run at least once per 48 consumed bits.
+// MSB-first reader over big-endian 32-bit words: 128 bits in registers (w3 holds the next bits). Refills come from a
+// per-lane ring of 2 x 16 bytes in shared memory that cp.async keeps filled from the frame's scratch row: a refill is
+// then a shared-memory load, and the copy that replaces a consumed slot is in flight for at least three top_up()
+// calls before its data is needed (the other slot holds 128 bits; a call consumes at most 64), which is what
+// `wait_group 2` in front of the refill checks. (A register prefetch does not work here: refills are per-lane
+// events, but a register written by one lane's load is a scoreboard dependency for the whole warp, so the warp
+// waited on L2 in nearly every iteration.) The reader runs past the frame by up to 48 bytes: the scratch row has
+// slack. top_up() must run at least once per 48 consumed bits.
 struct BitWindow {
     uint32_t w3, w2, w1, w0;
-    uint2 ahead, ahead2, ahead3;    // the next 3 x 64 bits, already requested
-    const uint2* next_ptr;
+    uint32_t ring;              // shared-memory byte address of this lane's slot 0 (slot 1 is kRingSlotStride above)
+    const uint4* next16;        // next 16-byte chunk of the row to request
+    int rd;                     // next 8-byte half to consume: slot rd >> 1, half rd & 1
     int have;
     int loaded;
+    static constexpr uint32_t kRingSlotStride = 32 * 16;
 
-    __device__ __forceinline__ void init(const uint32_t* row) {
+    __device__ __forceinline__ void request(uint32_t slot) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + slot * kRingSlotStride), "l"(next16));
+        next16++;
+    }
+    __device__ __forceinline__ void init(const uint32_t* row, uint32_t ring_addr) {
         const uint4 a = *reinterpret_cast<const uint4*>(row);
         w3 = a.x; w2 = a.y; w1 = a.z; w0 = a.w;
-        next_ptr = reinterpret_cast<const uint2*>(row + 4);
-        ahead = *next_ptr++;
-        ahead2 = *next_ptr++;
-        ahead3 = *next_ptr++;
+        ring = ring_addr;
+        next16 = reinterpret_cast<const uint4*>(row) + 1;
+        request(0);
+        request(1);
+        asm volatile("cp.async.commit_group;");
+        rd = 0;
         have = 128; loaded = 128;
     }
     __device__ __forceinline__ int position() const { return loaded - have; }
@@ -109,16 +122,20 @@ struct BitWindow {
         have -= n;
     }
     __device__ __forceinline__ void top_up() {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
         if (have <= 64) {
-            const uint64_t n64 = ((uint64_t)ahead.x << 32) | ahead.y;
+            uint2 v;
+            const uint32_t slot = (uint32_t)rd >> 1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(ring + slot * kRingSlotStride + ((uint32_t)rd & 1) * 8));
+            const uint64_t n64 = ((uint64_t)v.x << 32) | v.y;
             const uint64_t hi = (((uint64_t)w3 << 32) | w2) | ((n64 >> 1) >> (have - 1));
             const uint64_t lo = n64 << (64 - have);
             w3 = (uint32_t)(hi >> 32); w2 = (uint32_t)hi; w1 = (uint32_t)(lo >> 32); w0 = (uint32_t)lo;
             have += 64; loaded += 64;
-            ahead = ahead2;
-            ahead2 = ahead3;
-            ahead3 = *next_ptr++;
+            if (rd & 1) request(slot);          // both halves of the slot are consumed: refill it
+            rd = (rd + 1) & 3;
         }
+        asm volatile("cp.async.commit_group;");
     }
     __device__ __forceinline__ uint32_t read(int n, int nbits) {          // header fields (not the per-coefficient path)
         const uint32_t v = position() + n <= nbits ? peek(n) : 0u;
@@ -244,7 +261,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     // ---- phase 2: frame header (hca.cpp:1162-1178), then per channel scalefactors (:1290-1358) and, as each one is
     // known, the band's resolution (:1444-1494). No HFR scales / intensity on this path.
     BitWindow br;
-    br.init(words);
+    br.init(words, (uint32_t)__cvta_generic_to_shared(s_dyn + (size_t)kFastWarps * (NCH * 128 * 32 * sizeof(uint16_t)) + (size_t)warp * 1024 + lane * 16));
     uint32_t packed = 0;
     if (active) {
         if (br.read(16, nbits) != 0xFFFF) bad = true;
@@ -394,7 +411,7 @@ __device__ __forceinline__ short pcm16_sat(float v) {
 // scheduler while active, with "no instruction" the top stall: the body is ~70 KB of straight-line code that every
 // warp streams once per subframe, so instruction supply, not warp count, sets the pace. Barriers that keep the warps
 // of an SM (or of one scheduler) on the same cache lines did not change that.
-template <int NCH, int THREADS>
+template <int NCH, int THREADS, int CONVOY>
 __global__ void __launch_bounds__(THREADS, 1)
 hca_imdct_fast_kernel(HcaDecodeArgs a) {
     constexpr int RW = 32 / NCH;                 // runs (= tile rows) per warp
@@ -422,13 +439,18 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
         cnt = __ldg(a.dec_prefix + s + 1) - p0;
     }
 
+    // CONVOY > 0: all warps of the CTA meet every CONVOY-th sync point of the generated code (one per 128 fp32
+    // instructions), so they fetch the same instruction-cache lines at the same time
+    auto convoy = [&](int k) {
+        if (CONVOY > 0 && k % CONVOY == 0) __syncthreads();
+    };
     float x[128];
     {   // look-back: the DCT output of the last subframe in front of the run (zero at the start of a stream)
         const bool lb = live && f > 0;
         const uint32_t r1 = lb ? r - 1 : 0;
         const float4* src = a.spec + (((uint64_t)(r1 / RW) * R + (R - 1)) * 8 + 7) * 1024 + ch * RW + (r1 % RW);
         load_spectra(x, src, lb);
-        hca_dct4_dec(x);
+        hca_dct4_dec(x, convoy);
         hca_carry_thread<THREADS>(x, carry);
     }
 
@@ -463,7 +485,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
         const bool ok_next_frame = live && j + 1 < R && g + 1 < G;
 #pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
-            hca_dct4_dec(x);
+            hca_dct4_dec(x, convoy);
             if (ch == 0) {
                 const long long n0 = (long long)f * 1024 + sub * 128 - delay;     // stream sample index of the row's sample 0
                 RowDesc d;
@@ -481,7 +503,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok_next) v = __ldcs(src + c * 32);
                     x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-                });
+                }, convoy);
             __syncwarp();
             // ---- coalesced copy-out, one tile row (= 128 consecutive samples of one stream, all channels) at a time
 #pragma unroll 4
@@ -517,24 +539,30 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
 
 constexpr int kXfThreads = 256;
 
-template <int NCH, int THREADS>
+template <int NCH, int THREADS, int CONVOY>
 void launch_xf(const HcaDecodeArgs& a, cudaStream_t s) {
     constexpr int RW = 32 / NCH;
     const size_t smem_t = 16 * THREADS * sizeof(float4) + (size_t)(THREADS / 32) * (RW * (64 * NCH + 1) + RW * 4) * sizeof(uint32_t);
-    cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH, THREADS, CONVOY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
     const uint32_t warps = (a.n_runs + RW - 1) / RW, per_cta = THREADS / 32;
-    hca_imdct_fast_kernel<NCH, THREADS><<<(warps + per_cta - 1) / per_cta, THREADS, smem_t, s>>>(a);
+    hca_imdct_fast_kernel<NCH, THREADS, CONVOY><<<(warps + per_cta - 1) / per_cta, THREADS, smem_t, s>>>(a);
 }
 
 template <int NCH>
 void launch_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
-    const size_t smem_u = (size_t)kFastWarps * NCH * 128 * 32 * sizeof(uint16_t);
+    const size_t smem_u = (size_t)kFastWarps * (NCH * 128 * 32 * sizeof(uint16_t) + 1024);   // band tables + the bit readers' rings
     cudaFuncSetAttribute(hca_unpack_fast_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u);
     const uint64_t unpack_warps = (uint64_t)((a.n_runs + 31) / 32) * a.run_len;
     hca_unpack_fast_kernel<NCH><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    launch_xf<NCH, kXfThreads>(a, s);
+    static const int convoy = [] { const char* v = getenv("CRI_XF_CONVOY"); return v ? atoi(v) : 0; }();
+    if (convoy == 1) launch_xf<NCH, kXfThreads, 1>(a, s);
+    else if (convoy == 2) launch_xf<NCH, kXfThreads, 2>(a, s);
+    else if (convoy == 4) launch_xf<NCH, kXfThreads, 4>(a, s);
+    else if (convoy == 8) launch_xf<NCH, kXfThreads, 8>(a, s);
+    else if (convoy == 0 && getenv("CRI_XF_CONVOY")) launch_xf<NCH, kXfThreads, 0>(a, s);
+    else launch_xf<NCH, kXfThreads, 2>(a, s);       // default: meet every 256 fp32 instructions (measured: -5 %)
     ++*launches;
 }
 

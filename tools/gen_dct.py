@@ -50,6 +50,10 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
         out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
     out.append("    float t0, t1, t2, t3;")
     since = 0
+    nsync = [0]
+    def sync_line():
+        nsync[0] += 1
+        return f"    sync({nsync[0]});"
     # sum/difference passes, half = 64 .. 1  (hca.cpp:1907-1935)
     half = 64
     while half >= 1:
@@ -62,7 +66,7 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
                 out.append(f"    t0 = __fadd_rn(x[{a}], x[{b}]); x[{b}] = __fsub_rn(x[{a}], x[{b}]); x[{a}] = t0;")
                 since += 2
                 if lockstep and since >= lockstep:
-                    out.append("    sync();")
+                    out.append(sync_line())
                     since = 0
                 nxt[j * 2 * half + k] = a
                 nxt[j * 2 * half + half + k] = b
@@ -84,7 +88,7 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
                            f"x[{a}] = __fsub_rn(t0, t1); x[{b}] = __fadd_rn(t2, t3);")
                 since += 6
                 if lockstep and since >= lockstep:
-                    out.append("    sync();")
+                    out.append(sync_line())
                     since = 0
                 nxt[j * 2 * half + k] = a
                 nxt[j * 2 * half + 2 * half - 1 - k] = b
@@ -196,7 +200,7 @@ def gen_thread_window(lockstep: int = 0) -> list[str]:
                 out.append(f"    refill({ch});")
                 refilled.add(ch)
         if lockstep and q in order[1::2]:
-            out.append("    sync();")
+            out.append(f"    sync({100 + order.index(q) // 2});")
     assert len(refilled) == 32
     out.append("}")
     out.append("")
@@ -369,8 +373,7 @@ def main():
         fh.write("\n".join(lines) + "\n")
     print("wrote", path, len(lines), "lines")
     # thread-resident decoder transform (hca_imdct_fast_kernel): only the DCT-IV of gen_imdct + the PCM window
-    LOCKSTEP = 0                            # > 0: call a functor every so many fp32 instructions (instruction-cache experiment,
-                                            # measured: no gain from keeping a scheduler's warps on the same lines)
+    LOCKSTEP = 128                          # the transform calls sync(k) every so many fp32 instructions (instruction-cache convoy)
     dct = gen_imdct(LOCKSTEP)
     end = dct.index("}")                    # first function = hca_dct4_dec
     lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window(LOCKSTEP)
