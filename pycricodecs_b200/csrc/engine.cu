@@ -390,7 +390,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     }
     if (rc == OK) rc = [&]() -> int {
         for (auto& e : j->ev) CU_TRY(c, cudaEventCreate(&e));
-        int r = pool_alloc(c, (void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 64);  // slack: kernels read whole 16-byte rows
+        int r = pool_alloc(c, (void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 128);  // slack: kernels read whole 16-byte rows, up to four rows ahead
         if (r == OK) r = pool_alloc(c, (void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16);
         if (r == OK) r = pool_alloc(c, (void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1));
         if (r != OK) return r;

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t find_stream(const uint32_t* __restrict__ pre
 // ------------------------------------------------------------------------------------------------ unpack
 struct FastTables {
     float gain[1024];       // [scalefactor << 4 | resolution] = scaling[sf] * range[res]   (calculate_gain, hca.cpp:1498-1507)
-    float code[128];        // resolutions 0..7, [res << 4 | 4 peeked bits]: the value (read_val_table) as a float
+    float code[128];        // resolutions 0..7, [4 peeked bits << 3 | res]: the value (read_val_table) as a float
     uint16_t crc[4][256];   // CRC-16 (poly 0x8005, MSB first) of byte v followed by k zero bytes
     uint8_t invert[68];
     uint8_t max_bits[16];
@@ -182,7 +182,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     for (int i = threadIdx.x; i < 1024; i += kFastThreads)
         tb.gain[i] = __fmul_rn(__uint_as_float(c_scaling[i >> 4]), __uint_as_float(c_range[i & 15]));
     for (int i = threadIdx.x; i < 128; i += kFastThreads)
-        tb.code[i] = (float)(int)c_read_vals[i];
+        tb.code[((i & 15) << 3) | (i >> 4)] = (float)(int)c_read_vals[i];
     for (int i = threadIdx.x; i < 66; i += kFastThreads) tb.invert[i] = c_invert[i];
     for (int i = threadIdx.x; i < 16; i += kFastThreads) tb.max_bits[i] = c_max_bits[i];
     for (int i = threadIdx.x; i < 256; i += kFastThreads) {
@@ -213,16 +213,16 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
         const uint8_t* cipher = S.cipher ? a.cipher + (size_t)S.cipher * 256 : nullptr;
         uint32_t crc = 0;
         const int nrows = (frame_size + 15) >> 4, full_rows = frame_size >> 4;
-        uint4 cur = __ldg(ap), nxt = __ldg(ap + 1);
+        uint4 cur = __ldg(ap), nxt = __ldg(ap + 1), nx2 = __ldg(ap + 2), nx3 = __ldg(ap + 3);
         auto fetch_row = [&](int row, uint32_t (&raw)[4]) {      // the row's four words, frame bytes in memory order
-            const uint4 nn = __ldg(ap + row + 2);               // the input blob has 64 bytes of slack behind it
+            const uint4 nn = __ldg(ap + row + 4);               // four rows in flight; the input blob has 64 bytes of slack behind it
             const uint32_t t[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
             uint32_t v[5];
 #pragma unroll
             for (int k = 0; k < 5; k++) v[k] = wsel == 0 ? t[k] : wsel == 1 ? t[k + 1] : wsel == 2 ? t[k + 2] : t[k + 3];
 #pragma unroll
             for (int wq = 0; wq < 4; wq++) raw[wq] = __funnelshift_r(v[wq], v[wq + 1], sh);
-            cur = nxt; nxt = nn;
+            cur = nxt; nxt = nx2; nx2 = nx3; nx3 = nn;
         };
         auto big_endian = [&](uint32_t w) -> uint32_t {          // deciphered, first frame byte in the top bits
             if (!cipher) return __byte_perm(w, 0, 0x0123);
@@ -365,8 +365,8 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
                         br.skip(bits - (code < short_below ? 1 : 0));
                         // value: sign-magnitude (resolution >= 8, LSB = sign) or prefix codebook (resolution <= 7)
                         const float q_hi = __uint_as_float(__float_as_uint((float)(code >> 1)) | (code << 31));
-                        const float q_lo = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(code_tab) + ((res4 & 0x1C) << 4) + ((code & 15) << 2));
-                        const float q = (t & 0x20) ? q_hi : q_lo;
+                        float q = q_hi;                                           // codes of the prefix family are < 16
+                        if (!(t & 0x20)) q = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(code_tab) + (code << 5) + (res4 & 0x1C));
                         const float gain = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(gain_tab) + (t & 0xFFC));
                         f[k] = __fmul_rn(gain, q);                                // spectra = gain * q (hca.cpp:1568)
                     }
