@@ -121,6 +121,24 @@ __device__ __forceinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_
     }
 }
 
+// Bits of one band's eight coefficients at resolution r (the per-coefficient terms of CalculateUsedBits, hca.cpp:2772-2787).
+__device__ __forceinline__ int band_cost(const EncTables& tb, const float* sp_band, int r) {
+    int len = 0;
+    if (r >= 8) {
+        const int bits = tb.max_bits[r] - 1;
+        const float dz = tb.dead_zone[r];
+#pragma unroll
+        for (int j = 0; j < 8; j++) len += bits + (fabsf(sp_band[j * kSpecRow]) >= dz ? 1 : 0);
+    } else {
+        const float inv = tb.inv_step[r];
+        const float up = __fadd_rn(inv, 1.0f);
+        const uint8_t* qb = tb.qbits + r * 16 - (r - 7);                   // - (int)(inv + 0.5 - 8)
+#pragma unroll
+        for (int j = 0; j < 8; j++) len += qb[__float2int_rz(__fadd_rn(__fmul_rn(sp_band[j * kSpecRow], inv), up))];
+    }
+    return len;
+}
+
 // Total frame bits for (noise level, evaluation boundary): CalculateUsedBits, hca.cpp:2763-2790.
 __device__ __forceinline__ int used_bits(const EncTables& tb, const FrameSmem& fs, const HcaStreamDev& S, int lane, int noise_level,
                                          int boundary) {
@@ -131,28 +149,52 @@ __device__ __forceinline__ int used_bits(const EncTables& tb, const FrameSmem& f
         const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
         for (int b = lane; b < coded; b += 32) {
             const int noise = b < boundary ? noise_level - 1 : noise_level;
-            const int r = enc_resolution(tb, fs.sf[c * 128 + b], noise);
-            if (r >= 8) {
-                const int bits = tb.max_bits[r] - 1;
-                const float dz = tb.dead_zone[r];
-#pragma unroll
-                for (int j = 0; j < 8; j++) len += bits + (fabsf(sp[j * kSpecRow + b]) >= dz ? 1 : 0);
-            } else {
-                const float inv = tb.inv_step[r];
-                const float up = __fadd_rn(inv, 1.0f);
-                const int down = r - 7;                                  // (int)(inv + 0.5 - 8)
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int q = __float2int_rz(__fadd_rn(__fmul_rn(sp[j * kSpecRow + b], inv), up)) - down;
-                    len += tb.qbits[r * 16 + q];
-                }
-            }
+            len += band_cost(tb, sp + b, enc_resolution(tb, fs.sf[c * 128 + b], noise));
         }
     }
     len = warp_sum(len);
     int hdr = 48;
     for (int c = 0; c < nch; c++) hdr += fs.header_bits[c];
     return len + hdr;
+}
+
+// The boundary search (BinarySearchBoundary, hca.cpp:2834-2850) only ever compares two noise levels per band: bands
+// below the boundary use noise_level - 1, the others noise_level. With hi[b] / lo[b] = bits of band b (all channels)
+// at noise_level / noise_level - 1,  used_bits(noise_level, m) = header + sum(hi) + sum over b < m of (lo[b] - hi[b])
+// -- the same integers added in another order. One pass fills pre[m] = that value for m = 0..128; every probe of the
+// search is then a lookup instead of a pass over the 2048 coefficients.
+__device__ __forceinline__ void boundary_table(const EncTables& tb, const FrameSmem& fs, const HcaStreamDev& S, int lane, int noise_level,
+                                               int* pre) {
+    const int nch = S.channels;
+    int diff[4] = {0, 0, 0, 0};
+    int tot = 0;
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = lane + 32 * k;
+            if (b < coded) {
+                const int sfv = fs.sf[c * 128 + b];
+                const int r_hi = enc_resolution(tb, sfv, noise_level), r_lo = enc_resolution(tb, sfv, noise_level - 1);
+                const int c_hi = band_cost(tb, sp + b, r_hi);
+                const int c_lo = r_lo == r_hi ? c_hi : band_cost(tb, sp + b, r_lo);
+                tot += c_hi;
+                diff[k] += c_lo - c_hi;
+            }
+        }
+    }
+    int base = warp_sum(tot) + 48;
+    for (int c = 0; c < nch; c++) base += fs.header_bits[c];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int total;
+        const int excl = warp_excl_scan(diff[k], lane, &total);
+        pre[lane + 32 * k] = base + excl;              // boundary m = lane + 32k: bands below m switched to the lower level
+        base += total;
+    }
+    if (lane == 0) pre[128] = base;
+    __syncwarp();
 }
 
 // CalculateOptimalDeltaLength + CalculateFrameHeaderLength, hca.cpp:2708-2750 (warp-collective).
@@ -491,14 +533,16 @@ hca_encode_kernel(HcaEncodeArgs a) {
         }
     }
     if (!failed && noise_level != 0) {                        // BinarySearchBoundary
+        int* pre = reinterpret_cast<int*>(fs.pcm);            // the PCM stage (>= 576 words) is dead after the MDCT: 129 words of scratch
+        boundary_table(tb, fs, S, lane, noise_level, pre);
         int lo_b = 0, hi_b = 127;
         while (abs(hi_b - lo_b) > 1) {
             const int mid = (lo_b + hi_b) / 2;
-            const int v = used_bits(tb, fs, S, lane, noise_level, mid);
+            const int v = pre[mid];
             if (avail < v) hi_b = mid - 1; else lo_b = mid;
         }
         if (lo_b == hi_b) boundary = lo_b < 127 ? lo_b : -1;
-        else boundary = used_bits(tb, fs, S, lane, noise_level, hi_b) > avail ? lo_b : hi_b;
+        else boundary = pre[hi_b] > avail ? lo_b : hi_b;
         if (boundary < 0) failed = true;
     }
     if (failed) {                                             // EncodeFrame gives up: HcaErrorCode, hca.cpp:2976-2984
