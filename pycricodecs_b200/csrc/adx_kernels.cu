@@ -28,8 +28,9 @@ constexpr int kTile = 8;                 // blocks per chain per tile
 constexpr int kSpb = 32;                 // samples per block on the fast path
 constexpr int kBlk = 18;                 // bytes per block on the fast path
 constexpr int kPcmRow = kTile * kSpb + 2;            // int16 per chain in the PCM tile: odd word stride
-constexpr int kCodeWords = (kTile * 32 * kBlk + 3) / 4 + 1;     // covering words of 32 chains x kTile blocks
-constexpr int kPcmWords = (kTile * 32 * kSpb * 2 + 3) / 4 + 1;  // covering words of 32 chains x kTile x 32 samples
+// input stages: per stream one row of whole 16-byte chunks covering its tile (+ one chunk for the misalignment)
+constexpr int kCodeWords = 32 * ((kTile * kBlk + 15) / 16 + 1) * 4;        // 32 chains x kTile blocks
+constexpr int kPcmWords = 32 * ((kTile * kSpb * 2 + 15) / 16 + 1) * 4;     // 32 chains x kTile x 32 samples
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMovers = 3;               // mover warps per worker warp
 // A CTA holds kGroups independent worker + movers groups: warp w belongs to group w % kGroups with role w / kGroups
@@ -44,8 +45,8 @@ __device__ __forceinline__ void group_sync(int group) {
 
 __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -72,7 +73,8 @@ struct StreamInfo {
     uint32_t samples;    // valid samples per channel
 };
 
-// mover: request the aligned words that cover bytes [in_base + lo, in_base + hi) of every stream into its stage row
+// mover: request the aligned 16-byte chunks that cover bytes [in_base + lo, in_base + hi) of every stream into its stage
+// row (the blob starts 256-byte aligned and has slack behind it, so the chunks may overhang the stream on both sides)
 __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, const uint8_t* blob, const StreamInfo* info,
                                               int nstreams, uint32_t b0, int unit_bytes, bool clip_samples, int nch, int lane,
                                               int mover) {
@@ -82,15 +84,15 @@ __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, co
         uint64_t lo = (uint64_t)b0 * unit_bytes, hi = lo + (uint64_t)nb * unit_bytes;
         if (clip_samples) hi = min(hi, (uint64_t)si.samples * nch * 2);   // encode: PCM ends with the stream, the rest is padding
         if (hi <= lo) continue;
-        const uint64_t first = (si.in_base + lo) & ~(uint64_t)3;
-        const int words = (int)(((si.in_base + hi + 3) & ~(uint64_t)3) - first) >> 2;
-        for (int w = lane; w < words; w += 32) cp_async4(stage + s * row_words + w, blob + first + 4ull * w);
+        const uint64_t first = (si.in_base + lo) & ~(uint64_t)15;
+        const int chunks = (int)(((si.in_base + hi + 15) & ~(uint64_t)15) - first) >> 4;
+        for (int w = lane; w < chunks; w += 32) cp_async16(stage + s * row_words + 4 * w, blob + first + 16ull * w);
     }
 }
 
 // ------------------------------------------------------------ decode, fast
 struct alignas(16) DecodeStage {
-    uint32_t code[3][kCodeWords + 32];        // tile t in stage t % 3: two tiles are in flight
+    uint32_t code[3][kCodeWords];             // tile t in stage t % 3: two tiles are in flight
     int16_t pcm[2][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
     StreamInfo info[32];
 };
@@ -110,7 +112,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
     const int nstreams = 32 / nch;
     const int frame_bytes = nch * kBlk;
-    const int row_words = (kTile * frame_bytes + 3) / 4 + 1;
+    const int row_words = ((kTile * frame_bytes + 15) / 16 + 1) * 4;   // whole 16-byte chunks
     const int out_row = kTile * kSpb * nch + 2;             // int16 per stream in the PCM tile (odd word stride)
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
@@ -168,7 +170,7 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
             const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
             // byte 0 of this lane's first frame inside its stream's row
             const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[t % 3][slot * row_words]) +
-                                 (int)((ch.eof_off + (uint64_t)b0 * frame_bytes) & 3);
+                                 (int)((ch.eof_off + (uint64_t)b0 * frame_bytes) & 15);
             int16_t* my_pcm = &s_pcm[buf][slot * out_row + ch.channel];
             for (uint32_t tb = 0; tb < nb; tb++) {
                 int16_t* dst = my_pcm + tb * kSpb * nch;      // sample i of this block -> dst[i * nch]
@@ -319,7 +321,7 @@ __device__ __forceinline__ int div_trunc(int v, uint32_t magic, int d) {
 
 // ------------------------------------------------------------ encode, fast
 struct alignas(16) EncodeStage {
-    uint32_t pcm[2][kPcmWords + 32];
+    uint32_t pcm[2][kPcmWords];
     uint8_t code[2][32 * kTile * kBlk + 128];   // per stream: blocks in file order
     StreamInfo info[32];
 };
@@ -339,7 +341,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     const int nch = __shfl_sync(kFull, (int)ch.channels, 0);
     const int nstreams = 32 / nch;
     const int frame_bytes = nch * kSpb * 2;                  // PCM bytes of one block of every channel
-    const int row_words = (kTile * frame_bytes + 3) / 4 + 1;
+    const int row_words = ((kTile * frame_bytes + 15) / 16 + 1) * 4;   // whole 16-byte chunks
     const int code_row = kTile * nch * kBlk + 4;             // bytes per stream in the block tile (odd word stride)
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
@@ -388,7 +390,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         } else {
             const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
             const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_pcm[buf][slot * row_words]) +
-                                 (int)((stream_base + (uint64_t)b0 * frame_bytes) & 3);
+                                 (int)((stream_base + (uint64_t)b0 * frame_bytes) & 15);
             for (uint32_t tb = 0; tb < nb; tb++) {
                 uint8_t* dst = &s_code[buf][slot * code_row + (tb * nch + ch.channel) * kBlk];
                 // this block's samples; past the end of the stream the reference pads with silence (adx.cpp:450-460)
