@@ -32,6 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 KEY = 0xCF222F1FE0748978
+QUALITY = 1          # HCA quality of the synthetic streams: 0 Highest, 1 High (BASELINE configs), 2 Middle, 3 Low (--quality)
 METRIC = "audio frames/sec (48kHz stereo) HCA-decode + ADX-encode at 1/2/4/8 B200 vs CPU ref"
 WORKLOADS = {
     "hca_decode": "8192 x 48kHz stereo HCA v2.0 decode (keyless, High), 2 s streams",
@@ -98,7 +99,7 @@ def make_inputs(workload, streams, rank, ctx, device):
     if workload == "adx_decode":
         out, off = run_job_to_pinned(ctx, _lib.JOB_ADX_ENCODE, wav.numpy(), woff, adx=engine.adx_params())
         return out, off, wav, woff
-    hca, hoff = run_job_to_pinned(ctx, _lib.JOB_HCA_ENCODE, wav.numpy(), woff, quality=1, adx=engine.adx_params())
+    hca, hoff = run_job_to_pinned(ctx, _lib.JOB_HCA_ENCODE, wav.numpy(), woff, quality=QUALITY, adx=engine.adx_params())
     if workload == "hca_decode":
         return hca, hoff, wav, woff
     keys = np.full(streams, KEY, np.uint64)
@@ -192,7 +193,7 @@ def run_ours(a):
     if kind in (_lib.JOB_ADX_ENCODE, _lib.JOB_HCA_ENCODE):
         kw["adx"] = engine.adx_params()
     if kind == _lib.JOB_HCA_ENCODE:
-        kw["quality"] = 1
+        kw["quality"] = QUALITY
     if kind == _lib.JOB_HCA_CRYPT:
         kw.update(encrypt=0, ciph_type=0)
     blob_np = pin_in.numpy()[:in_bytes]
@@ -242,7 +243,7 @@ def run_ours(a):
     elif a.workload == "adx_decode":
         want0 = port.adx_decode(in0)[1]
     elif a.workload == "hca_encode":
-        want0 = port.hca_encode(in0, 1)[1]
+        want0 = port.hca_encode(in0, QUALITY)[1]
     elif a.workload == "hca_decrypt":
         want0 = port.hca_crypt(in0, 0, 0, KEY)[1]
     else:
@@ -339,7 +340,8 @@ def run_ours(a):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (no FMA, bit-exact) + int16/u8 bitstream" if hca else "int32",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[a.workload], "name": a.workload, "streams_per_gpu": a.streams,
+            "config": {"workload": WORKLOADS[a.workload] if QUALITY == 1 or not hca else WORKLOADS[a.workload].replace("High", ["Highest", "High", "Middle", "Low"][QUALITY]),
+                       "name": a.workload, "streams_per_gpu": a.streams,
                        "unique_streams_per_gpu": a.streams, "stream_seconds": 2.0, "sample_rate": 48000, "channels": 2,
                        "input_synthesis": "pycricodecs_b200.synth PCM; compressed inputs made once, untimed, by this repo's own GPU encoders",
                        "l2": "inputs and outputs exceed the 126 MB L2 (no flush needed)" if in_bytes + out_bytes > 3e8 else "working set near L2 size",
@@ -375,7 +377,7 @@ def _cpu_one(workload, data, key):
     elif workload == "hca_decrypt":
         impl.hca_crypt(data, 0, 0, key)
     elif workload == "hca_encode":
-        impl.hca_encode(data, 1)
+        impl.hca_encode(data, QUALITY)
     elif workload == "adx_encode":
         impl.adx_encode(data)
     else:
@@ -435,7 +437,7 @@ def reference_inputs(workload, count):
         elif workload == "adx_decode":
             out.append(impl.adx_encode(w)[1])
         else:
-            h = impl.hca_encode(w, 1)[1]
+            h = impl.hca_encode(w, QUALITY)[1]
             if workload in ("hca_decrypt_decode", "hca_decrypt"):
                 h = bytes(impl.hca_crypt(h, 1, 56, KEY)) if cpu_kind() == "reference" else impl.hca_crypt(h, 1, 56, KEY)[1]
             out.append(h)
@@ -489,7 +491,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-companion", action="store_true", help="skip the ADX-encode companion measurement of the default workload")
+    ap.add_argument("--quality", type=int, default=1, choices=[0, 1, 2, 3], help="HCA quality of the synthetic streams (default High)")
     a = ap.parse_args()
+    global QUALITY
+    QUALITY = a.quality
     if a.impl == "reference":
         run_reference(a)
     else:
