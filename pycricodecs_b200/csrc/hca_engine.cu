@@ -136,13 +136,18 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         needed_frames[i] = (uint32_t)std::min<uint64_t>(h.frame_count, ((uint64_t)samples + h.delay + 1023) / 1024);
         j->units += needed_frames[i];
     }
-    // uniform batch: every decodable stream is mono (1) or stereo (2) with no joint tools (intensity pair, HFR)
+    // uniform batch: every decodable stream is mono (1) or stereo (2): discrete channels or one primary/secondary pair
     J.uniform = J.max_channels <= 2 ? J.max_channels : 0;
+    bool any_joint = false;
     for (uint32_t i = 0; i < j->n && J.uniform; i++) {
         if (j->status[i] != OK) continue;
         const HcaStreamDev& st = J.streams[i];
-        if (st.channels != J.uniform || st.joint) J.uniform = 0;
+        const bool types_ok = st.channels == 1 ? st.type[0] == 0
+                                               : (st.type[0] == 0 && st.type[1] == 0) || (st.type[0] == 1 && st.type[1] == 2);
+        if (st.channels != J.uniform || !types_ok) J.uniform = 0;
+        any_joint = any_joint || st.joint;
     }
+    J.any_joint = any_joint;
     uint32_t max_frame = 8;
     for (const auto& st : J.streams) max_frame = std::max(max_frame, st.frame_size);
     J.scratch_words = ((max_frame + 15) / 16 + 4) * 4;             // whole 16-byte rows + zeroed slack rows for the prefetching reader
@@ -179,6 +184,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         const uint64_t warps = (J.n_runs + runs_per_warp - 1) / runs_per_warp;
         J.spec_bytes = warps * J.run_len * 8 * 1024 * sizeof(float4);
         J.s_bytes = (G + 1) * J.scratch_words * sizeof(uint32_t);
+        J.i_bytes = (G + 1) * sizeof(uint32_t);                      // intensity nibbles of the frame's secondary channel
         J.total_groups = 0;
         J.max_steps = 0;
         return OK;
@@ -191,7 +197,8 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         }
     }
     while (J.units.size() % 32) J.units.push_back(HcaUnit{0, 0, 0});
-    // general transform kernel's shortcut: additionally all 128 bands coded in every channel
+    // general transform kernel's shortcut: no joint tools and all 128 bands coded in every channel
+    if (any_joint) J.uniform = 0;
     for (uint32_t i = 0; i < j->n && J.uniform; i++) {
         if (j->status[i] != OK) continue;
         const HcaStreamDev& st = J.streams[i];
@@ -403,6 +410,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_streams = j->n;
         a.run_len = J.run_len;
         a.n_runs = J.n_runs;
+        a.joint = J.any_joint ? 1u : 0u;
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
         if (J.n_runs) launch_hca_decode_fast(a, j->stream, &c->launches, j->ev[2]);
         else launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);

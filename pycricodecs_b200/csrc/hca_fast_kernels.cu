@@ -1,5 +1,5 @@
-// HCA decode, fast path: every stream of the job is mono or stereo, v <= 2.0, with no joint-stereo tools (no
-// intensity pair, no high-frequency reconstruction) -- what the reference encoder emits at quality High and Highest.
+// HCA decode, fast path: every stream of the job is mono or stereo (discrete channels or one intensity-stereo pair,
+// with or without high-frequency reconstruction), v <= 2.0 -- everything the reference encoder emits.
 //
 // Work is laid out over the FLATTENED frame list of the job (frame g = 0 .. G-1 in stream order, dec_prefix[s] =
 // first g of stream s) cut into runs of `run_len` consecutive frames:
@@ -38,6 +38,8 @@ __constant__ uint32_t c_range[16] = CRI_TBL_DEC_RANGE;
 __constant__ uint8_t c_read_bits[128] = CRI_TBL_READ_BITS;
 __constant__ int8_t c_read_vals[128] = CRI_TBL_READ_VALS;
 __constant__ uint8_t c_max_bits[16] = CRI_TBL_MAX_BITS;
+__constant__ uint32_t c_conv[128] = CRI_TBL_SCALE_CONV;          // HFR: scale_conversion_table (hca.cpp:1579-1598)
+__constant__ uint32_t c_intensity[16] = CRI_TBL_INTENSITY_RATIO;  // intensity stereo ratios (hca.cpp:1689-1693)
 
 #include "hca_dct_thread_gen.inc"
 
@@ -155,7 +157,9 @@ struct BitWindow {
 // the value lookups hang off the side of the chain.
 constexpr uint32_t kShortBelowLo = 0x26AE2620u;   // nibble r = threshold of resolution r, r = 0..7: 0,2,6,2,14,10,6,2
 constexpr uint32_t kShortBelowHi = 0x22222222u;   // r = 8..15: 2
-template <int NCH>
+// JOINT: some stream of the batch has an intensity-stereo pair or HFR bands (their header fields and the HFR pass are
+// compiled out otherwise)
+template <int NCH, bool JOINT>
 __global__ void __launch_bounds__(kFastThreads, 3)
 hca_unpack_fast_kernel(HcaDecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -271,7 +275,11 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     const bool has_ath = active && S.ath != 0;                   // v2.0 streams have no ATH curve
     const uint8_t* ath = a.ath + (size_t)(has_ath ? S.ath : 0) * 128;
     const uint32_t min_res = S.min_res, max_res = S.max_res;
+    const int hfr_groups = JOINT && active ? (int)S.hfr_groups : 0;
+    uint64_t hfr_sf[NCH];                                        // 6-bit HFR scalefactors of the channel, group g at bit 6g
     int run_bits[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) hfr_sf[c] = 0;
     // A read that would cross the end of the frame yields 0 (hca.cpp:232-233). The per-read check is only compiled
     // into the variant used when some lane's frame is too short to be sure its header ends inside it.
     auto parse_channel = [&](int c, auto safe_tag) {
@@ -317,11 +325,44 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
                 tc[i * 32] = (uint16_t)((res << 2) | (v << 6) | (mb << 12));
             }
             br.top_up();
+            // intensity indices of a secondary channel, HFR scales of the others (unpack_intensity, hca.cpp:1361-1441, v <= 2.0)
+            if (!JOINT) {
+            } else if (S.type[c] == 2) {
+                uint32_t v0 = br.peek(4);
+                if (!kSafe && br.position() + 4 > nbits) v0 = 0;
+                uint32_t inten = v0;
+                if (v0 < 15) {
+                    br.skip(4);
+                    for (int i = 1; i < 8; i++) {
+                        uint32_t v = br.peek(4);
+                        if (!kSafe && br.position() + 4 > nbits) v = 0;
+                        br.skip(4);
+                        inten |= v << (4 * i);
+                    }
+                    br.top_up();
+                }
+                a.inten[g] = inten;
+            } else {
+                uint64_t packed_sf = 0;
+                for (int grp = 0; grp < hfr_groups; grp++) {
+                    uint32_t v = br.peek(6);
+                    if (!kSafe && br.position() + 6 > nbits) v = 0;
+                    br.skip(6);
+                    if ((grp & 3) == 3) br.top_up();
+                    packed_sf |= (uint64_t)v << (6 * grp);
+                }
+                br.top_up();
+                hfr_sf[c] = packed_sf;
+            }
         }
         for (int i = coded; i < 128; i++) tc[i * 32] = 0;       // bands past the coded count: 0 from 0 bits
         run_bits[c] = sum_bits;
     };
-    const bool hdr_safe = !active || nbits >= 32 + NCH * (3 + 6 + 127 * 11);
+    int hdr_bound = 32;                                          // most bits the header can take for this stream's geometry
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+        hdr_bound += 3 + 6 + 11 * max((int)S.coded[c] - 1, 0) + (!JOINT ? 0 : S.type[c] == 2 ? 32 : 6 * hfr_groups);
+    const bool hdr_safe = !active || nbits >= hdr_bound;
     if (__all_sync(kFull, hdr_safe)) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) parse_channel(c, std::true_type{});
@@ -341,6 +382,10 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     float4* dst_frame = a.spec + ((uint64_t)W * R + j) * (8 * 1024) + rr;   // + sub * 1024 + (c * RW) + chunk * 32
     const float* gain_tab = tb.gain;
     const float* code_tab = tb.code;
+    // HFR geometry (clHCA_DecodeHeader, hca.cpp:872-874): bands [start, start + room) mirror [start - room, start)
+    const int hfr_start = (int)S.base_bands + (int)S.stereo_bands;
+    const bool hfr_on = JOINT && active && S.bands_per_hfr != 0;
+    const int hfr_room = hfr_on ? max(0, min(min((int)S.total_bands - hfr_start, hfr_groups * (int)S.bands_per_hfr), hfr_start)) : 0;
     for (int sub = 0; sub < 8; sub++) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
@@ -375,6 +420,26 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
                 }
             };
             if (any_careful) decode_run(std::true_type{}); else decode_run(std::false_type{});
+            // high-frequency reconstruction (hca.cpp:1638-1683): band start + n = conv[hfr scale - sf(low) + 63] * band
+            // start - 1 - n, from this lane's own freshly stored row (intensity scaling happens later, in the transform
+            // kernel, so the row still holds the unscaled spectra the reference mirrors)
+            if (JOINT && __any_sync(kFull, hfr_on && S.type[c] != 2 && !bad)) {
+                if (hfr_on && S.type[c] != 2 && !bad) {
+                    float* row = reinterpret_cast<float*>(dst);
+                    auto at = [&](int band) -> float* { return row + (size_t)(band >> 2) * 128 + (band & 3); };
+                    const int bph = (int)S.bands_per_hfr;
+                    int grp = 0, in_grp = 0;
+                    for (int n = 0; n < hfr_room; n++) {
+                        const int low = hfr_start - 1 - n, high = hfr_start + n;
+                        const int sf_low = (int)((tp[low * 32] >> 6) & 63);
+                        int k = (int)((hfr_sf[c] >> (6 * grp)) & 63) - sf_low + 63;
+                        k = max(k, 0);
+                        *at(high) = __fmul_rn(__uint_as_float(c_conv[k]), *at(low));
+                        if (++in_grp == bph) { in_grp = 0; grp++; }
+                    }
+                    if (hfr_start + hfr_room >= 1) *at(hfr_start + hfr_room - 1) = 0.f;   // hca.cpp:1681 (band start - 1 if nothing was mirrored)
+                }
+            }
         }
     }
     if (bad && active) a.status[stream] = ERR_HCA_DECODE;
@@ -411,7 +476,7 @@ __device__ __forceinline__ short pcm16_sat(float v) {
 // scheduler while active, with "no instruction" the top stall: the body is ~70 KB of straight-line code that every
 // warp streams once per subframe, so instruction supply, not warp count, sets the pace. Barriers that keep the warps
 // of an SM (or of one scheduler) on the same cache lines did not change that.
-template <int NCH, int THREADS, int CONVOY>
+template <int NCH, int THREADS, int CONVOY, bool JOINT>
 __global__ void __launch_bounds__(THREADS, 1)
 hca_imdct_fast_kernel(HcaDecodeArgs a) {
     constexpr int RW = 32 / NCH;                 // runs (= tile rows) per warp
@@ -444,12 +509,30 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
     auto convoy = [&](int k) {
         if (CONVOY > 0 && k % CONVOY == 0) __syncthreads();
     };
+    // intensity stereo (apply_intensity_stereo, hca.cpp:1696-1714): bands [base, total) of both channels are the PRIMARY
+    // channel's spectra times ratio / (2 - ratio); the primary sits NCH-pair lanes below (lane & (RW - 1)). HFR has
+    // already been applied by the unpack kernel, on the unscaled spectra, as in the reference's order.
+    auto intensity = [&](float (&x)[128], bool pair_joint, uint32_t inten, int sub, int base, int total) {
+        if (!JOINT || NCH != 2 || !__any_sync(kFull, pair_joint)) return;
+        const float rl = __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]);
+        const float mine = ch == 0 ? rl : __fsub_rn(2.0f, rl);
+#pragma unroll
+        for (int i = 0; i < 128; i++) {
+            const float left = __shfl_sync(kFull, x[i], lane & (RW - 1));
+            if (pair_joint && i >= base && i < total) x[i] = __fmul_rn(left, mine);
+        }
+    };
     float x[128];
     {   // look-back: the DCT output of the last subframe in front of the run (zero at the start of a stream)
         const bool lb = live && f > 0;
         const uint32_t r1 = lb ? r - 1 : 0;
         const float4* src = a.spec + (((uint64_t)(r1 / RW) * R + (R - 1)) * 8 + 7) * 1024 + ch * RW + (r1 % RW);
         load_spectra(x, src, lb);
+        {
+            const HcaStreamDev& S = a.streams[s];
+            const bool pj = JOINT && lb && S.type[ch] != 0;
+            intensity(x, pj, pj ? __ldg(a.inten + g - 1) : 0u, 7, (int)S.base_bands, (int)S.total_bands);
+        }
         hca_dct4_dec(x, convoy);
         hca_carry_thread<THREADS>(x, carry);
     }
@@ -476,15 +559,24 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
         }
         long long out_off = 0;
         int out_samples = 0, delay = 0;
+        bool pair_joint = false;
+        uint32_t inten = 0;
+        int jbase = 0, jtotal = 0;
         if (ok) {
             const HcaStreamDev& S = a.streams[s];
             out_off = (long long)S.out_off;
             out_samples = (int)S.out_samples;
             delay = (int)S.delay;
+            if (JOINT && NCH == 2 && S.type[ch] != 0) {
+                pair_joint = true;
+                inten = __ldg(a.inten + g);
+                jbase = (int)S.base_bands; jtotal = (int)S.total_bands;
+            }
         }
         const bool ok_next_frame = live && j + 1 < R && g + 1 < G;
 #pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
+            intensity(x, pair_joint, inten, sub, jbase, jtotal);
             hca_dct4_dec(x, convoy);
             if (ch == 0) {
                 const long long n0 = (long long)f * 1024 + sub * 128 - delay;     // stream sample index of the row's sample 0
@@ -539,30 +631,24 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
 
 constexpr int kXfThreads = 256;
 
-template <int NCH, int THREADS, int CONVOY>
+template <int NCH, int THREADS, int CONVOY, bool JOINT>
 void launch_xf(const HcaDecodeArgs& a, cudaStream_t s) {
     constexpr int RW = 32 / NCH;
     const size_t smem_t = 16 * THREADS * sizeof(float4) + (size_t)(THREADS / 32) * (RW * (64 * NCH + 1) + RW * 4) * sizeof(uint32_t);
-    cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH, THREADS, CONVOY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH, THREADS, CONVOY, JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
     const uint32_t warps = (a.n_runs + RW - 1) / RW, per_cta = THREADS / 32;
-    hca_imdct_fast_kernel<NCH, THREADS, CONVOY><<<(warps + per_cta - 1) / per_cta, THREADS, smem_t, s>>>(a);
+    hca_imdct_fast_kernel<NCH, THREADS, CONVOY, JOINT><<<(warps + per_cta - 1) / per_cta, THREADS, smem_t, s>>>(a);
 }
 
-template <int NCH>
+template <int NCH, bool JOINT>
 void launch_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
     const size_t smem_u = (size_t)kFastWarps * (NCH * 128 * 32 * sizeof(uint16_t) + 1024);   // band tables + the bit readers' rings
-    cudaFuncSetAttribute(hca_unpack_fast_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u);
+    cudaFuncSetAttribute(hca_unpack_fast_kernel<NCH, JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u);
     const uint64_t unpack_warps = (uint64_t)((a.n_runs + 31) / 32) * a.run_len;
-    hca_unpack_fast_kernel<NCH><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
+    hca_unpack_fast_kernel<NCH, JOINT><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    static const int convoy = [] { const char* v = getenv("CRI_XF_CONVOY"); return v ? atoi(v) : 0; }();
-    if (convoy == 1) launch_xf<NCH, kXfThreads, 1>(a, s);
-    else if (convoy == 2) launch_xf<NCH, kXfThreads, 2>(a, s);
-    else if (convoy == 4) launch_xf<NCH, kXfThreads, 4>(a, s);
-    else if (convoy == 8) launch_xf<NCH, kXfThreads, 8>(a, s);
-    else if (convoy == 0 && getenv("CRI_XF_CONVOY")) launch_xf<NCH, kXfThreads, 0>(a, s);
-    else launch_xf<NCH, kXfThreads, 2>(a, s);       // default: meet every 256 fp32 instructions (measured: -5 %)
+    launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
     ++*launches;
 }
 
@@ -573,8 +659,11 @@ uint32_t hca_fast_ctas_per_sm() { return 1; }
 
 void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
     if (!a.n_runs) return;
-    if (a.uniform == 2) launch_fast<2>(a, s, launches, mid);
-    else launch_fast<1>(a, s, launches, mid);
+    if (a.uniform == 2) {
+        if (a.joint) launch_fast<2, true>(a, s, launches, mid); else launch_fast<2, false>(a, s, launches, mid);
+    } else {
+        if (a.joint) launch_fast<1, true>(a, s, launches, mid); else launch_fast<1, false>(a, s, launches, mid);
+    }
 }
 
 }  // namespace cri

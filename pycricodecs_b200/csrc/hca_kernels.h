@@ -36,6 +36,7 @@ struct HcaDecodeArgs {
     uint32_t n_streams;
     uint32_t run_len;
     uint32_t n_runs;            // 0 = not on the fast path
+    uint32_t joint;             // fast path: some stream has an intensity-stereo pair or HFR bands
 };
 
 // `mid` (optional) is recorded between the unpack and the transform kernel.

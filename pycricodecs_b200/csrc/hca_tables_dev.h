@@ -75,6 +75,7 @@ struct HcaJob {
     std::vector<uint32_t> dec_prefix;      // [n + 1] exclusive prefix of the frames decoded per stream
     uint32_t* d_dec_prefix = nullptr;
     uint32_t run_len = 0, n_runs = 0;      // n_runs == 0: general path
+    bool any_joint = false;                // some stream has an intensity-stereo pair or HFR bands
     uint64_t total_frames = 0, spec_bytes = 0;
     uint8_t* d_spec = nullptr;
     uint8_t* d_s = nullptr;

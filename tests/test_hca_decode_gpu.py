@@ -91,3 +91,20 @@ def test_fast_path_bad_frame_in_the_middle_of_a_batch(port, ctx):
     assert isinstance(res[1], Exception) and res[1].status == -202
     for i in (0, 2, 3):
         assert res[i] == port.hca_decode(good[i])[1]
+
+
+@pytest.mark.parametrize("run_len", [0, 3, 8])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_fast_path_mixed_qualities(port, ctx, monkeypatch, run_len, channels):
+    """One batch with discrete-channel streams (Highest, High), intensity-stereo streams (Middle) and intensity + HFR
+    streams (Low): all of it is on the fast path (JOINT kernels), with lanes of a warp on different kinds of stream."""
+    if run_len:
+        monkeypatch.setenv("CRI_HCA_FAST_RUN", str(run_len))
+    lengths = [4000, 1024 * 5 + 1, 9000, 1500, 1024 * 12, 333, 7777, 1024 * 3]
+    hcas = [port.hca_encode(synth.wav(20 + s, channels, n), s % 4)[1] for s, n in enumerate(lengths)] * 2
+    got = HCA.decode_batch(hcas, ctx=ctx)
+    want = {h: port.hca_decode(h)[1] for h in set(hcas)}
+    for i, (h, g) in enumerate(zip(hcas, got)):
+        assert _first_diff(g, want[h]) is None, f"stream {i} (quality {i % 4})"
+    monkeypatch.setenv("CRI_HCA_GENERAL", "1")
+    assert HCA.decode_batch(hcas, ctx=ctx) == got
