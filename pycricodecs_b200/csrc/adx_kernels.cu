@@ -17,6 +17,7 @@
 //
 // Anything else (other bit depths / block sizes / channel counts, odd PCM alignment) takes the generic kernels:
 // same arithmetic, one thread per chain straight on global memory.
+#include <algorithm>
 #include <cstdint>
 
 #include "kernels.h"
@@ -539,7 +540,63 @@ __global__ void scatter_patches_kernel(uint8_t* __restrict__ out, const uint8_t*
     for (uint32_t i = threadIdx.x & 31; i < pt.bytes; i += 32) out[pt.dst_off + i] = bytes[pt.src_off + i];
 }
 
+// ------------------------------------------------------------ WAV ingest
+// One CTA per (stream, chunk of kConvChunk samples); conversion rules of the reference: PCM8_to_PCM16, PCM_to_PCM16,
+// Float_to_PCM (pcm.cpp:455-527), with the x86 (int) cast of an out-of-range float (INT_MIN) restated explicitly.
+constexpr uint32_t kConvChunk = 8192;
+__global__ void pcm_convert_kernel(uint8_t* blob, const PcmConv* __restrict__ conv, uint32_t n) {
+    const uint32_t s = blockIdx.y;
+    if (s >= n) return;
+    const PcmConv c = conv[s];
+    const uint32_t begin = blockIdx.x * kConvChunk;
+    if (begin >= c.count) return;
+    const uint32_t end = min(begin + kConvChunk, c.count);
+    const uint8_t* src = blob + c.src_off;
+    int16_t* dst = reinterpret_cast<int16_t*>(blob + c.dst_off);
+    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+        int v;
+        if (c.format == 1) {
+            v = ((int)src[i] - (1 << (c.shift - 1))) << 8;
+        } else if (c.format == 2) {
+            const uint8_t* p = src + 3ull * i;
+            int w = (int)p[0] | ((int)p[1] << 8) | ((int)p[2] << 16);
+            if (w & 0x800000) w |= ~0xFFFFFF;
+            v = w >> c.shift;
+        } else if (c.format == 3) {
+            const uint8_t* p = src + 4ull * i;
+            const int w = (int)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+            v = w >> 16;
+        } else if (c.format == 4) {
+            const uint8_t* p = src + 4ull * i;
+            const float f = __uint_as_float((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+            const float x = __fmul_rn(f, 32767.0f);
+            v = fabsf(x) < 2147483648.0f ? __float2int_rz(x) : INT_MIN;
+            v = clamp16(v);
+        } else {
+            const uint8_t* p = src + 8ull * i;
+            unsigned long long bits = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) bits |= (unsigned long long)p[k] << (8 * k);
+            const double x = __dmul_rn(__longlong_as_double((long long)bits), 32767.0);
+            v = fabs(x) < 2147483648.0 ? __double2int_rz(x) : INT_MIN;
+            v = clamp16(v);
+        }
+        dst[i] = (int16_t)v;
+    }
+}
+
 }  // namespace
+
+void launch_pcm_convert(uint8_t* d_blob, const PcmConv* d_conv, uint32_t n, uint32_t max_count, cudaStream_t s, uint64_t* launches) {
+    if (!n) return;
+    // grid.x covers the longest stream; CTAs past the end of a shorter one return at once
+    const uint32_t chunks = std::max<uint32_t>(1, (max_count + kConvChunk - 1) / kConvChunk);
+    for (uint32_t first = 0; first < n; first += 65535) {
+        const uint32_t cnt = std::min<uint32_t>(65535, n - first);
+        pcm_convert_kernel<<<dim3(chunks, cnt), 256, 0, s>>>(d_blob, d_conv + first, cnt);
+    }
+    ++*launches;
+}
 
 void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches) {

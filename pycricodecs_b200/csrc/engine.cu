@@ -282,6 +282,24 @@ static void plan_adx_decode(cri_job* j) {
     lists.finish(j);
 }
 
+namespace cri {
+uint64_t pcm16_offset(cri_job* j, uint32_t i, const WavInfo& w) {
+    const uint64_t data = j->in_off[i] + w.data_offset;
+    if (w.format == WAV_S16) return data;
+    if (!j->conv_base) j->conv_base = (j->in_bytes + 128 + 255) & ~(uint64_t)255;      // behind the blob and its read slack
+    PcmConv c{};
+    c.src_off = data;
+    c.dst_off = j->conv_base + j->conv_bytes;
+    c.count = w.total_samples;
+    c.format = w.format;
+    c.shift = w.shift;
+    j->conv.push_back(c);
+    j->conv_bytes += ((uint64_t)w.total_samples * 2 + 255) & ~(uint64_t)255;
+    j->conv_max_count = std::max(j->conv_max_count, w.total_samples);
+    return c.dst_off;
+}
+}  // namespace cri
+
 static void plan_adx_encode(cri_job* j) {
     std::vector<uint64_t> sizes(j->n, 0);
     std::vector<WavInfo> wavs(j->n);
@@ -307,16 +325,14 @@ static void plan_adx_encode(cri_job* j) {
         const AdxEncPlan& p = plans[i];
         one.clear();
         const uint8_t* d = j->blob + j->in_off[i];
-        const int16_t* pcm = reinterpret_cast<const int16_t*>(d + wavs[i].data_offset);
         int16_t firsts[256];
-        for (int c = 0; c < p.channels; c++) memcpy(&firsts[c], d + wavs[i].data_offset + 2 * (size_t)c, 2);
-        (void)pcm;
+        for (int c = 0; c < p.channels; c++) firsts[c] = wav_sample_s16(wavs[i], d + wavs[i].data_offset, (size_t)c);
         // header + EOF block are host-built patches; block payload comes from the kernel
         tmp.assign(p.out_size, 0);
         write_adx_frame(tmp.data(), p, firsts);
         add_patch(j, j->out_off[i], tmp.data(), (uint32_t)p.header_size);
         add_patch(j, j->out_off[i] + p.out_size - p.block_size, tmp.data() + p.out_size - p.block_size, (uint32_t)p.block_size);
-        const uint64_t pcm0 = j->in_off[i] + wavs[i].data_offset;
+        const uint64_t pcm0 = pcm16_offset(j, i, wavs[i]);
         const bool is_fast = (pcm0 & 1) == 0 && p.bit_depth == 4 && p.block_size == 18;
         for (int c = 0; c < p.channels; c++) {
             AdxChain ch{};
@@ -390,12 +406,15 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     }
     if (rc == OK) rc = [&]() -> int {
         for (auto& e : j->ev) CU_TRY(c, cudaEventCreate(&e));
-        int r = pool_alloc(c, (void**)&j->d_in, std::max<uint64_t>(j->in_bytes, 16) + 128);  // slack: kernels read whole 16-byte rows, up to four rows ahead
+        // slack: kernels read whole 16-byte rows, up to four rows ahead; then the WAV ingest's conversion region
+        const uint64_t in_alloc = j->conv_bytes ? j->conv_base + j->conv_bytes + 128 : std::max<uint64_t>(j->in_bytes, 16) + 128;
+        int r = pool_alloc(c, (void**)&j->d_in, in_alloc);
         if (r == OK) r = pool_alloc(c, (void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16);
         if (r == OK) r = pool_alloc(c, (void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1));
         if (r != OK) return r;
         CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes + 16, stream));
         r = upload_vec(c, stream, j->adx_chains, &j->d_adx_chains);
+        if (r == OK) r = upload_vec(c, stream, j->conv, &j->d_conv);
         if (r == OK) r = upload_vec(c, stream, j->patches, &j->d_patches);
         if (r == OK) r = upload_vec(c, stream, j->patch_bytes, &j->d_patch_bytes);
         if (r == OK) r = upload_hca_tables(c, j);
@@ -437,6 +456,7 @@ static int job_enqueue_run(cri_ctx* c, cri_job* j) {
     CU_TRY(c, cudaMemsetAsync(j->d_status, 0, sizeof(int32_t) * std::max<uint32_t>(j->n, 1), s));
     if (j->needs_clear) CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes, s));
     CU_TRY(c, cudaEventRecord(j->ev[0], s));
+    launch_pcm_convert(j->d_in, j->d_conv, (uint32_t)j->conv.size(), j->conv_max_count, s, &c->launches);
     launch_scatter_patches(j->d_out, j->d_patch_bytes, j->d_patches, (uint32_t)j->patches.size(), s, &c->launches);
     j->have_dominant = false;
     switch (j->kind) {
@@ -519,7 +539,7 @@ extern "C" void cri_job_destroy(cri_ctx* c, cri_job* j) {
     if (c) cudaSetDevice(c->device);
     for (auto& e : j->ev)
         if (e) cudaEventDestroy(e);
-    for (void* p : {(void*)j->d_in, (void*)j->d_out, (void*)j->d_status, (void*)j->d_adx_chains, (void*)j->d_patches,
+    for (void* p : {(void*)j->d_in, (void*)j->d_out, (void*)j->d_status, (void*)j->d_adx_chains, (void*)j->d_conv, (void*)j->d_patches,
                     (void*)j->d_patch_bytes})
         pool_free(c, p);
     free_hca_tables(c, j);

@@ -66,6 +66,11 @@ struct cri_job {
     uint8_t* d_out = nullptr;
     int32_t* d_status = nullptr;
 
+    // WAV ingest: streams whose samples are not PCM16 get a converted copy behind the input blob (region starts at conv_base)
+    std::vector<cri::PcmConv> conv;
+    cri::PcmConv* d_conv = nullptr;
+    uint64_t conv_base = 0, conv_bytes = 0;
+    uint32_t conv_max_count = 0;
     std::vector<cri::Patch> patches;          // host-built headers / trailers, scattered on every run
     std::vector<uint8_t> patch_bytes;
     cri::Patch* d_patches = nullptr;
@@ -86,6 +91,9 @@ void pool_free(cri_ctx* c, void* p);
 void pool_trim(cri_ctx* c);
 void finish_layout_public(cri_job* j, const std::vector<uint64_t>& sizes);
 void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n);
+// offset (into the device input blob) of stream i's PCM16 samples: the WAV data itself, or a converted copy that the
+// conversion kernel fills before the encode kernels run
+uint64_t pcm16_offset(cri_job* j, uint32_t i, const cri::WavInfo& w);
 int plan_hca_decode(cri_ctx* c, cri_job* j);
 int plan_hca_crypt(cri_ctx* c, cri_job* j);
 int plan_hca_encode(cri_ctx* c, cri_job* j);

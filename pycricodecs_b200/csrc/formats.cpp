@@ -32,7 +32,7 @@ int parse_wav(const uint8_t* d, size_t n, WavInfo* w) {
     size_t at = 12;
     uint32_t walked = 4;  // the reference counts the "WAVE" tag first (pcm.cpp:296)
     bool got_fmt = false, got_data = false;
-    uint32_t format = 0, align = 0, bits = 0, data_bytes = 0;
+    uint32_t format = 0, align = 0, bits = 0, data_bytes = 0, valid_bits = 0, sub_format = 0;
     while (walked < riff_size) {
         if (at + 8 > n) return -7;
         const uint32_t tag = le32(d + at);
@@ -47,6 +47,11 @@ int parse_wav(const uint8_t* d, size_t n, WavInfo* w) {
             align = le16(d + at + 20);
             bits = le16(d + at + 22);
             if (format != 1 && format != 3 && format != 0xFFFE) return -3;
+            if (format == 0xFFFE) {                       // WAVE_FORMAT_EXTENSIBLE: valid bits + sub-format GUID (pcm.cpp:204-215)
+                if (body < 40 || at + 48 > n) return -8;      // no valid-bits field: the reference sees bit depth 0
+                valid_bits = le16(d + at + 26);
+                sub_format = le32(d + at + 32);
+            }
             got_fmt = true;
         } else if (tag == fourcc('s', 'm', 'p', 'l')) {
             if (body < 36 || at + 44 > n) return -4;
@@ -69,11 +74,56 @@ int parse_wav(const uint8_t* d, size_t n, WavInfo* w) {
     }
     if (!got_fmt) return -2;
     if (!got_data) return -6;
-    // Only 16-bit integer PCM reaches the kernels (other depths: SURVEY.md §8f row 2).
-    if (format != 1 || bits != 16 || w->channels < 1 || align / (uint32_t)w->channels != 2) return -8;
+    // PCM::load_WAVE (pcm.cpp:291-327): bit depth / container combinations the reference can turn into PCM16; the
+    // combinations it mishandles (null source pointer, unconverted buffer) are rejected with its -8
+    if (w->channels < 1) return -8;
+    const uint32_t depth = format == 0xFFFE ? valid_bits : bits;
+    const uint32_t mode = format == 0xFFFE ? (sub_format == 0xFFFE ? 1u : sub_format) : format;
+    const uint32_t sample_bytes = align / (uint32_t)w->channels;
+    if (mode == 3) {
+        if ((depth != 32 && depth != 64) || sample_bytes != depth / 8) return -8;
+        w->format = depth == 32 ? WAV_F32 : WAV_F64;
+    } else if (mode == 1) {
+        if (depth >= 1 && depth <= 8 && sample_bytes == 1) { w->format = WAV_U8; w->shift = (uint8_t)depth; }
+        else if (depth >= 9 && depth <= 16 && sample_bytes == 2) w->format = WAV_S16;
+        else if (depth >= 17 && depth <= 24 && sample_bytes == 3) { w->format = WAV_S24; w->shift = (uint8_t)(depth - 16); }
+        else if (depth == 32 && sample_bytes == 4) w->format = WAV_S32;
+        else return -8;
+    } else {
+        return -3;
+    }
+    w->sample_bytes = (uint8_t)sample_bytes;
     if (w->data_offset + data_bytes > n) return -7;
-    w->total_samples = data_bytes / 2;
+    w->total_samples = data_bytes / sample_bytes;
     return 0;
+}
+
+static int16_t clamp_like_reference(int v) {               // Clamp<int>(value, 32767), pcm.cpp:155-161
+    return (int16_t)(v > 32767 ? 32767 : v < -32768 ? -32768 : v);
+}
+
+int16_t wav_sample_s16(const WavInfo& w, const uint8_t* data, size_t index) {
+    const uint8_t* p = data + index * w.sample_bytes;
+    switch (w.format) {
+        case WAV_U8: return (int16_t)(((int)p[0] - (1 << (w.shift - 1))) << 8);
+        case WAV_S24: {
+            int v = (int)p[0] | ((int)p[1] << 8) | ((int)p[2] << 16);
+            if (v & 0x800000) v |= ~0xFFFFFF;
+            return (int16_t)((v >> w.shift) & 0xFFFF);
+        }
+        case WAV_S32: { int32_t v; memcpy(&v, p, 4); return (int16_t)((v >> 16) & 0xFFFF); }
+        case WAV_F32: {
+            float f; memcpy(&f, p, 4);
+            const float s = f * 32767.0f;
+            return clamp_like_reference(std::fabs(s) < 2147483648.0f ? (int)s : INT32_MIN);   // cvttss2si: out of range -> INT_MIN
+        }
+        case WAV_F64: {
+            double f; memcpy(&f, p, 8);
+            const double s = f * 32767.0;
+            return clamp_like_reference(std::fabs(s) < 2147483648.0 ? (int)s : INT32_MIN);
+        }
+        default: { int16_t v; memcpy(&v, p, 2); return v; }
+    }
 }
 
 size_t wav_header_size(bool looping) { return looping ? 0x70 : 0x2C; }

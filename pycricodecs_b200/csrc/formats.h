@@ -44,12 +44,26 @@ inline void put_le32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_
 uint16_t crc16(const uint8_t* p, size_t n);
 
 // ---------------------------------------------------------------- WAV
+// Sample encodings the reference converts to PCM16 before encoding (PCM::load_WAVE / Get_PCM16, pcm.cpp:291-327, 455-545)
+enum WavSampleFormat : uint8_t {
+    WAV_S16 = 0,   // 9..16 valid bits in 2 bytes: used as they are
+    WAV_U8 = 1,    // <= 8 valid bits in 1 byte:   (u8 - (1 << (bits - 1))) << 8
+    WAV_S24 = 2,   // 17..24 valid bits in 3 bytes: sign-extended >> (bits - 16)
+    WAV_S32 = 3,   // 32 bits in 4 bytes:          >> 16
+    WAV_F32 = 4,   // IEEE float:  clamp((int)(x * 32767))
+    WAV_F64 = 5,   // IEEE double: clamp((int)(x * 32767))
+};
 struct WavInfo {
     int channels = 0, rate = 0, looping = 0;
     uint32_t loop_start = 0, loop_end = 0;
     size_t data_offset = 0;      // byte offset of the first PCM sample in the image
     uint32_t total_samples = 0;  // over all channels (the reference's ColumnSize)
+    uint8_t format = WAV_S16;    // WavSampleFormat
+    uint8_t sample_bytes = 2;
+    uint8_t shift = 0;           // WAV_U8: valid bits; WAV_S24: bits - 16
 };
+// the reference's conversion of sample `index` (over all channels) to PCM16
+int16_t wav_sample_s16(const WavInfo& w, const uint8_t* data, size_t index);
 int parse_wav(const uint8_t* d, size_t n, WavInfo* w);  // 0 or pcm.cpp code (-1..-8)
 size_t wav_header_size(bool looping);
 void write_wav_header(uint8_t* out, uint32_t samples_per_channel, int channels, int rate, bool looping,

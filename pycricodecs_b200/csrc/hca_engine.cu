@@ -291,7 +291,7 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
         if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
         // loop points (smpl chunk -> loop chunk, pre/post audio, hca.cpp:2292-2321, 3000-3053) are a later row
         if (wavs[i].looping && !j->adx.force_not_looping) { j->status[i] = ERR_UNSUPPORTED; continue; }
-        if ((j->in_off[i] + wavs[i].data_offset) & 1) { j->status[i] = ERR_UNSUPPORTED; continue; }   // PCM must be 2-byte aligned in the blob
+        if (wavs[i].format == WAV_S16 && ((j->in_off[i] + wavs[i].data_offset) & 1)) { j->status[i] = ERR_UNSUPPORTED; continue; }   // PCM must be 2-byte aligned in the blob
         if (plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels,
                             j->quality, &plans[i]) < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; continue; }
         sizes[i] = (uint64_t)plans[i].header_size + (uint64_t)plans[i].frame_count * plans[i].frame_size;
@@ -309,7 +309,7 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
         if (j->status[i] == OK) {
             const HcaEncPlan& p = plans[i];
             HcaStreamDev s{};
-            s.in_off = j->in_off[i] + wavs[i].data_offset;
+            s.in_off = pcm16_offset(j, i, wavs[i]);
             s.out_off = j->out_off[i] + p.header_size;
             s.frame_size = p.frame_size;
             s.frame_count = p.frame_count;

@@ -31,6 +31,18 @@ void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_ch
 void launch_adx_encode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_chains, uint32_t n_fast, uint32_t n_generic,
                        cudaStream_t s, uint64_t* launches);
 
+// WAV ingest: samples of other encodings are converted to PCM16 into a spare region of the input blob before the encode
+// kernels run (the reference's PCM::Get_PCM16, pcm.cpp:530-545).
+struct PcmConv {
+    uint64_t src_off;     // first sample in the input blob
+    uint64_t dst_off;     // first int16 of the converted copy (2-byte aligned, inside the blob's conversion region)
+    uint32_t count;       // samples over all channels
+    uint8_t format;       // WavSampleFormat
+    uint8_t shift;
+    uint8_t pad[2];
+};
+void launch_pcm_convert(uint8_t* d_blob, const PcmConv* d_conv, uint32_t n, uint32_t max_count, cudaStream_t s, uint64_t* launches);
+
 // Scatter host-built header/trailer bytes into the output blob (one patch per stream piece).
 struct Patch {
     uint64_t dst_off;
