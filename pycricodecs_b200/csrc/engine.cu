@@ -310,9 +310,11 @@ static void plan_adx_encode(cri_job* j) {
         const size_t len = j->in_off[i + 1] - j->in_off[i];
         int r = parse_wav(d, len, &wavs[i]);
         if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
-        // A looping WAV (smpl chunk) encodes a loop header unless version 5 + force flag (adx.cpp:421); not built yet.
-        if (wavs[i].looping && !(q.force_not_looping && q.version == 5)) { j->status[i] = ERR_UNSUPPORTED; continue; }
-        r = plan_adx_encode(wavs[i], q.bit_depth, q.block_size, q.encoding, q.highpass, q.filter, q.version, &plans[i]);
+        // A looping WAV (smpl chunk) encodes a loop table unless version 5 + force flag (adx.cpp:421). One loop is what every
+        // tool writes; the reference's multi-loop / zero-loop paths read past its own arrays and stay unsupported.
+        const bool looping = wavs[i].looping && !(q.force_not_looping && q.version == 5);
+        if (looping && wavs[i].loop_count != 1) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        r = plan_adx_encode(wavs[i], q.bit_depth, q.block_size, q.encoding, q.highpass, q.filter, q.version, &plans[i], looping);
         if (r < 0) { j->status[i] = r; continue; }
         sizes[i] = plans[i].out_size;
     }
@@ -686,8 +688,11 @@ extern "C" int cri_adx_encode_sizes(const uint8_t* blob, const uint64_t* off, ui
         sizes[i] = 0;
         int r = parse_wav(blob + off[i], off[i + 1] - off[i], &w);
         if (r < 0) r += ERR_WAV_BASE;
-        else if (w.looping && !(p->force_not_looping && p->version == 5)) r = ERR_UNSUPPORTED;
-        else r = plan_adx_encode(w, p->bit_depth, p->block_size, p->encoding, p->highpass, p->filter, p->version, &pl);
+        else {
+            const bool looping = w.looping && !(p->force_not_looping && p->version == 5);
+            if (looping && w.loop_count != 1) r = ERR_UNSUPPORTED;
+            else r = plan_adx_encode(w, p->bit_depth, p->block_size, p->encoding, p->highpass, p->filter, p->version, &pl, looping);
+        }
         if (r == OK) sizes[i] = pl.out_size;
         if (status) status[i] = r;
     }

@@ -57,6 +57,7 @@ int parse_wav(const uint8_t* d, size_t n, WavInfo* w) {
             if (body < 36 || at + 44 > n) return -4;
             const uint32_t loops = le32(d + at + 36), extra = le32(d + at + 40);
             if ((uint64_t)body < (uint64_t)loops * 24 + extra + 36) return -5;
+            w->loop_count = loops;
             if (loops) {
                 if (at + 68 > n) return -5;
                 w->loop_start = le32(d + at + 52);
@@ -226,7 +227,7 @@ static int round_up_to(int v, int m) {  // IO.hpp:30-36
 }
 
 int plan_adx_encode(const WavInfo& w, unsigned bit_depth, unsigned block_size, unsigned mode, unsigned highpass,
-                    unsigned filter, unsigned version, AdxEncPlan* p) {
+                    unsigned filter, unsigned version, AdxEncPlan* p, bool looping) {
     *p = AdxEncPlan{};
     const unsigned ch = (unsigned)w.channels & 0xFFu;  // the reference narrows to unsigned char (adx.cpp:418)
     if (ch < 1) return -10;
@@ -254,6 +255,12 @@ int plan_adx_encode(const WavInfo& w, unsigned bit_depth, unsigned block_size, u
         p->frames = p->samples / p->samples_per_block;
     int hs = 20 + 6;
     if (version != 3) hs += ch > 1 ? 4 * (int)ch : 8;
+    if (looping) {                       // one loop: alignment + count words and a 20-byte ADXLoop (adx.cpp:483-484)
+        hs += 4 + 20;
+        p->looping = 1;
+        p->loop_start = w.loop_start;
+        p->loop_end = w.loop_end;
+    }
     p->header_size = (hs + 15) / 16 * 16;
     p->out_size = (size_t)p->header_size + (size_t)p->frames * ch * block_size + block_size;
     if (mode == 2) {
@@ -283,6 +290,21 @@ void write_adx_frame(uint8_t* out, const AdxEncPlan& p, const int16_t* first) {
             put_be16(out + 24 + 4 * c, (uint16_t)first[c]);
             put_be16(out + 26 + 4 * c, (uint16_t)first[c]);
         }
+    if (p.looping) {                     // Loop::writeLoops + ADXLoop::writeLoop, adx.cpp:94-107, 133-143
+        uint8_t* l = out + 20 + (p.version != 3 ? 4 + (p.channels > 1 ? 4 * p.channels : 8) : 0);
+        const uint32_t in_frame = (uint32_t)(p.block_size - 2) * 2;
+        const uint32_t align = (uint32_t)round_up_to((int)p.loop_start, (int)(p.channels == 1 ? in_frame * 2 : in_frame)) & 0xFFFFu;
+        const uint32_t spf = p.samples_per_block, bs = (uint32_t)p.block_size, ch = (uint32_t)p.channels;
+        const uint32_t start = p.loop_start + align, end = p.loop_end + align;
+        put_be16(l, align);
+        put_be16(l + 2, 1);
+        put_be16(l + 4, 0);
+        put_be16(l + 6, 1);
+        put_be32(l + 8, start);
+        put_be32(l + 12, (uint32_t)p.header_size + ((start / spf) * bs) * ch);
+        put_be32(l + 16, end);
+        put_be32(l + 20, (uint32_t)p.header_size + (uint32_t)round_up_to((int)((end / spf) * bs + (end % spf) / bs), (int)bs) * ch);
+    }
     memcpy(out + p.header_size - 6, "(c)CRI", 6);
     uint8_t* eof = out + p.out_size - p.block_size;
     put_be16(eof, 0x8001);

@@ -56,6 +56,7 @@ enum WavSampleFormat : uint8_t {
 struct WavInfo {
     int channels = 0, rate = 0, looping = 0;
     uint32_t loop_start = 0, loop_end = 0;
+    uint32_t loop_count = 0;     // NumberofSampleLoops of the smpl chunk (loop_start / loop_end are loop 0)
     size_t data_offset = 0;      // byte offset of the first PCM sample in the image
     uint32_t total_samples = 0;  // over all channels (the reference's ColumnSize)
     uint8_t format = WAV_S16;    // WavSampleFormat
@@ -90,10 +91,12 @@ struct AdxEncPlan {
     int header_size = 0;
     size_t out_size = 0;
     int coef[2] = {0, 0};
+    int looping = 0;                 // the WAV carries a sampler loop: the header gets a loop table (adx.cpp:94-143)
+    uint32_t loop_start = 0, loop_end = 0;
 };
 // Validation order and codes as ADX::Encode (adx.cpp:424-442): -10..-18.
 int plan_adx_encode(const WavInfo& w, unsigned bit_depth, unsigned block_size, unsigned mode, unsigned highpass,
-                    unsigned filter, unsigned version, AdxEncPlan* p);
+                    unsigned filter, unsigned version, AdxEncPlan* p, bool looping = false);
 // Writes the header (incl. initial history, "(c)CRI") and the EOF block; block payload is the kernel's job.
 void write_adx_frame(uint8_t* out, const AdxEncPlan& p, const int16_t* first_samples);
 

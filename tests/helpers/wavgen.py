@@ -50,3 +50,18 @@ def wav_as(kind: str, sid: int, channels: int, n: int, rate: int = 48000) -> byt
 
 KINDS = ("u8", "s24", "s20in3", "s32", "f32", "f64", "ext24")
 CASES = [(k, 40 + i, 1 + i % 2, 32 * 40 + 1024 * (i % 3)) for i, k in enumerate(KINDS)]
+
+
+def loop_wav(sid: int, channels: int, n: int, loop_start: int, loop_end: int, rate: int = 48000) -> bytes:
+    """16-bit WAV with a one-loop `smpl` chunk in front of the data (what PCM::GetWaveBuffer itself writes, pcm.cpp:258-265)."""
+    pcm = synth.pcm(sid, channels, n).tobytes()
+    fmt = struct.pack("<HHIIHH", 1, channels, rate, rate * channels * 2, channels * 2, 16)
+    smpl = struct.pack("<9I", 0, 0, 0, 60, 0, 0, 0, 1, 0) + struct.pack("<6I", 0, 0, loop_start, loop_end, 0, 0)
+    body = (b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"smpl" + struct.pack("<I", len(smpl)) + smpl +
+            b"data" + struct.pack("<I", len(pcm)) + pcm)
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+# (sid, channels, samples, loop start, loop end, ADX version)
+LOOP_CASES = [(50, 1, 32 * 100, 1000, 3000, 4), (51, 2, 32 * 100, 1000, 3000, 4), (52, 2, 32 * 90 + 7, 33, 2800, 3),
+              (53, 2, 32 * 64, 0, 2047, 5)]

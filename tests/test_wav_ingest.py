@@ -59,3 +59,18 @@ def test_every_sample_encoding_encodes_like_the_reference(ctx):
     plain = synth.wav(3, 2, 2048)
     got = engine.adx_encode_batch([plain, wavs[1], plain, wavs[4]], ctx=ctx)
     assert got[0] == got[2] and h(got[1]) == d["s24"]["adx"] and h(got[3]) == d["f32"]["adx"]
+
+
+@pytest.mark.gpu
+def test_looping_wav_to_adx_and_back(ctx):
+    """A WAV with a sampler loop encodes an ADX loop table (Loop::writeLoops, adx.cpp:94-143); decoding that ADX gives
+    a WAV with the loop in a smpl chunk again. Expected values: the compiled reference (adx_loops in the fixture)."""
+    from pycricodecs_b200 import engine
+    d = json.load(open(GOLD))["adx_loops"]
+    for (sid, ch, n, ls, le, ver), want in zip(wavgen.LOOP_CASES, d):
+        w = wavgen.loop_wav(sid, ch, n, ls, le)
+        assert h(w) == want["wav"]
+        a = engine.adx_encode_batch([w], ctx=ctx, AdxVersion=ver)[0]
+        assert (h(a), len(a)) == (want["adx"], want["adx_len"]), f"encode, case {sid}"
+        if not want["adx_decoded"].startswith("error"):
+            assert h(engine.adx_decode_batch([a], ctx=ctx)[0]) == want["adx_decoded"], f"decode, case {sid}"

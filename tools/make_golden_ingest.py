@@ -25,6 +25,17 @@ def main():
         r, x = R.hca_encode(w, 1)
         assert r == 0, (kind, r)
         out[kind] = {"wav": h(w), "adx": h(a), "adx_len": len(a), "hca": h(x), "hca_len": len(x)}
+    loops = []
+    for sid, ch, n, ls, le, ver in wavgen.LOOP_CASES:
+        w = wavgen.loop_wav(sid, ch, n, ls, le)
+        r, a = R.adx_encode(w, version=ver)
+        assert r == 0, (sid, r)
+        try:
+            dec = h(R.adx_decode(a))                    # the reference may refuse its own output (copyright check quirk)
+        except Exception as e:                          # noqa: BLE001
+            dec = "error: " + str(e)
+        loops.append({"wav": h(w), "adx": h(a), "adx_len": len(a), "adx_decoded": dec})
+    out["adx_loops"] = loops
     json.dump(out, open(os.path.join(ROOT, "tests", "golden", "ingest_digests.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1))
 
