@@ -116,6 +116,11 @@ CRI_API int cri_hca_crypt_batch(cri_ctx* ctx, const uint8_t* blob, const uint64_
  *    enum's Lowest = 5 falls back to High, chunk.py:73). ---------------------- */
 CRI_API int cri_hca_encode_sizes(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t quality,
                          uint64_t* out_sizes, int32_t* status);
+/*    A WAV with a sampler loop (smpl chunk) encodes a loop chunk plus pre / post audio frames unless
+ *    force_not_looping is set (hca.cpp:2440-2449, 3469): its size depends on the flag. cri_hca_encode_sizes
+ *    answers for force_not_looping = 0, the default of HCA.encode (hca.py:255). */
+CRI_API int cri_hca_encode_sizes_ex(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t quality,
+                            uint32_t force_not_looping, uint64_t* out_sizes, int32_t* status);
 CRI_API int cri_hca_encode_batch(cri_ctx* ctx, const uint8_t* blob, const uint64_t* offsets, uint32_t n,
                          uint32_t quality, uint32_t force_not_looping,
                          uint8_t* out_blob, const uint64_t* out_offsets, int32_t* status);

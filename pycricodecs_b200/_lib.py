@@ -54,6 +54,7 @@ SIGNATURES = {
     "cri_hca_decode_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cri_hca_crypt_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "cri_hca_encode_sizes": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),
+    "cri_hca_encode_sizes_ex": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),
     "cri_hca_encode_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp, c_vp]),
     "cri_job_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JobDesc), ctypes.POINTER(c_vp)]),
     "cri_job_out_bytes": (ctypes.c_uint64, [c_vp]),

@@ -553,9 +553,13 @@ __global__ void pcm_convert_kernel(uint8_t* blob, const PcmConv* __restrict__ co
     const uint32_t end = min(begin + kConvChunk, c.count);
     const uint8_t* src = blob + c.src_off;
     int16_t* dst = reinterpret_cast<int16_t*>(blob + c.dst_off);
-    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    for (uint32_t j = begin + threadIdx.x; j < end; j += blockDim.x) {
+        if (c.kind == 2) { dst[j] = 0; continue; }
+        const uint32_t i = c.kind == 1 ? j % c.channels : j;
         int v;
-        if (c.format == 1) {
+        if (c.format == 0) {
+            v = (int)(int16_t)((uint32_t)src[2ull * i] | ((uint32_t)src[2ull * i + 1] << 8));
+        } else if (c.format == 1) {
             v = ((int)src[i] - (1 << (c.shift - 1))) << 8;
         } else if (c.format == 2) {
             const uint8_t* p = src + 3ull * i;
@@ -581,7 +585,7 @@ __global__ void pcm_convert_kernel(uint8_t* blob, const PcmConv* __restrict__ co
             v = fabs(x) < 2147483648.0 ? __double2int_rz(x) : INT_MIN;
             v = clamp16(v);
         }
-        dst[i] = (int16_t)v;
+        dst[j] = (int16_t)v;
     }
 }
 

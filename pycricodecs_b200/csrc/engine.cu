@@ -298,6 +298,35 @@ uint64_t pcm16_offset(cri_job* j, uint32_t i, const WavInfo& w) {
     j->conv_max_count = std::max(j->conv_max_count, w.total_samples);
     return c.dst_off;
 }
+uint64_t hca_loop_input_offset(cri_job* j, uint32_t i, const WavInfo& w, const HcaEncPlan& p) {
+    const uint64_t data = j->in_off[i] + w.data_offset;
+    if (!j->conv_base) j->conv_base = (j->in_bytes + 128 + 255) & ~(uint64_t)255;
+    const uint64_t dst0 = j->conv_base + j->conv_bytes;
+    const uint32_t ch = (uint32_t)w.channels;
+    uint64_t frames_done = 0;
+    auto piece = [&](uint8_t kind, uint64_t first_frame, uint32_t frames) {
+        if (!frames) return;
+        PcmConv c{};
+        c.src_off = data + first_frame * ch * w.sample_bytes;
+        c.dst_off = dst0 + frames_done * ch * 2;
+        c.count = frames * ch;
+        c.format = w.format;
+        c.shift = w.shift;
+        c.kind = kind;
+        c.channels = (uint8_t)ch;
+        j->conv.push_back(c);
+        j->conv_max_count = std::max(j->conv_max_count, c.count);
+        frames_done += frames;
+    };
+    const uint32_t total = p.frame_count * 1024;
+    piece(2, 0, p.pre_zero);
+    piece(1, 0, p.pre_first);
+    piece(0, 0, p.main_samples);
+    piece(0, p.loop_start, p.post_samples);
+    if (frames_done < total) piece(2, 0, (uint32_t)(total - frames_done));
+    j->conv_bytes += ((uint64_t)total * ch * 2 + 255) & ~(uint64_t)255;
+    return dst0;
+}
 }  // namespace cri
 
 static void plan_adx_encode(cri_job* j) {
@@ -736,16 +765,25 @@ extern "C" int cri_hca_crypt_batch(cri_ctx* c, const uint8_t* blob, const uint64
     return run_batch(c, d, out, off, status);
 }
 
+extern "C" int cri_hca_encode_sizes_ex(const uint8_t* blob, const uint64_t* off, uint32_t n, uint32_t quality,
+                                       uint32_t force_not_looping, uint64_t* sizes, int32_t* status);
 extern "C" int cri_hca_encode_sizes(const uint8_t* blob, const uint64_t* off, uint32_t n, uint32_t quality, uint64_t* sizes,
                                     int32_t* status) {
+    return cri_hca_encode_sizes_ex(blob, off, n, quality, 0, sizes, status);
+}
+
+extern "C" int cri_hca_encode_sizes_ex(const uint8_t* blob, const uint64_t* off, uint32_t n, uint32_t quality,
+                                       uint32_t force_not_looping, uint64_t* sizes, int32_t* status) {
     for (uint32_t i = 0; i < n; i++) {
         WavInfo w;
         HcaEncPlan pl;
         sizes[i] = 0;
         int r = parse_wav(blob + off[i], off[i + 1] - off[i], &w);
         if (r < 0) r += ERR_WAV_BASE;
-        else if (w.looping) r = ERR_UNSUPPORTED;
-        else if (plan_hca_encode((unsigned)w.channels, (unsigned)w.rate, w.total_samples / (unsigned)w.channels, quality, &pl) < 0)
+        else if (w.looping && !force_not_looping) {
+            r = plan_hca_encode_loop(w, quality, &pl);
+            if (r < 0 && r != ERR_UNSUPPORTED) r = ERR_HCA_CHANNELS;
+        } else if (plan_hca_encode((unsigned)w.channels, (unsigned)w.rate, w.total_samples / (unsigned)w.channels, quality, &pl) < 0)
             r = ERR_HCA_CHANNELS;
         if (r == OK) sizes[i] = (uint64_t)pl.header_size + (uint64_t)pl.frame_count * pl.frame_size;
         if (status) status[i] = r;

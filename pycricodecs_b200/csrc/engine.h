@@ -94,6 +94,8 @@ void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n
 // offset (into the device input blob) of stream i's PCM16 samples: the WAV data itself, or a converted copy that the
 // conversion kernel fills before the encode kernels run
 uint64_t pcm16_offset(cri_job* j, uint32_t i, const cri::WavInfo& w);
+// the same for a looping HCA encode: the virtual input of the reference's frame feeder, assembled on the device
+uint64_t hca_loop_input_offset(cri_job* j, uint32_t i, const cri::WavInfo& w, const cri::HcaEncPlan& p);
 int plan_hca_decode(cri_ctx* c, cri_job* j);
 int plan_hca_crypt(cri_ctx* c, cri_job* j);
 int plan_hca_encode(cri_ctx* c, cri_job* j);

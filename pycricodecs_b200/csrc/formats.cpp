@@ -588,7 +588,51 @@ int plan_hca_encode(unsigned channels, unsigned rate, unsigned samples, unsigned
     return 0;
 }
 
-void write_hca_header(uint8_t* hd, const HcaEncPlan& p) {  // PackHeader, hca.cpp:3109-3164 (no loop chunk yet)
+int plan_hca_encode_loop(const WavInfo& w, unsigned quality, HcaEncPlan* p) {
+    const unsigned ch = (unsigned)w.channels, column = w.total_samples, n = column / (ch ? ch : 1);
+    const int r = plan_hca_encode(ch, (unsigned)w.rate, n, quality, p);
+    if (r < 0) return r;
+    const unsigned ls = w.loop_start, le = w.loop_end;
+    if (w.loop_count != 1 || ls >= le || le > n) return ERR_UNSUPPORTED;
+    const unsigned sc = std::min(le, column);                                  // hca.cpp:2443 (compares with ColumnSize)
+    unsigned delay = 128 + ((unsigned)round_up_to((int)ls, 1024) - ls);       // :2444
+    unsigned lstart = ls + delay, lend = le + delay;                           // CalculateLoopInfo, :2292-2305
+    p->loop_start_frame = lstart / 1024;
+    p->loop_start_delay = lstart % 1024;
+    p->loop_end_frame = lend / 1024;
+    p->loop_end_padding = 1024 - lend % 1024;
+    if (p->loop_end_padding == 1024) { p->loop_end_frame--; p->loop_end_padding = 0; }
+    unsigned input = std::min((unsigned)round_up_to((int)sc, 128), column) + 256;   // :2446-2447
+    p->post_samples = input - sc;
+    // CalculateHeaderSize, :2307-2321: the loop start frame is moved to a 2048-byte boundary with extra delay frames
+    p->header_size = 96;
+    {
+        const unsigned off = p->header_size + p->frame_size * p->loop_start_frame;
+        const unsigned pad_bytes = (unsigned)round_up_to((int)off, 2048) - off;
+        const unsigned pad_frames = pad_bytes / p->frame_size;
+        delay += pad_frames * 1024;
+        p->loop_start_frame += pad_frames;
+        p->loop_end_frame += pad_frames;
+        p->header_size += pad_bytes % p->frame_size;
+    }
+    p->delay = delay;
+    p->frame_count = ceil_div_float((int)(input + delay), 1024);
+    p->padding = p->frame_count * 1024 - delay - input;
+    p->loop_flag = 1;
+    p->loop_start = ls;
+    p->main_samples = sc;
+    const unsigned pre = delay - 128;                                          // BufferPreSamples; PreEncode, :3000-3012
+    p->pre_zero = pre ? ((pre - 1) / 1024) * 1024 : 0;
+    p->pre_first = pre - p->pre_zero;
+    // SaveLoopAudio (:3014-3022) copies from 1024-sample input chunks while the main audio is being fed: everything it
+    // wants must lie inside the input and inside the chunks visited before the loop end is reached
+    const unsigned visited = std::min(n, ((sc + 1023) / 1024) * 1024);
+    if (ls + p->post_samples > visited) return ERR_UNSUPPORTED;
+    p->samples = sc;
+    return 0;
+}
+
+void write_hca_header(uint8_t* hd, const HcaEncPlan& p) {  // PackHeader, hca.cpp:3109-3164
     memset(hd, 0, p.header_size);
     put_be32(hd, tag4('H', 'C', 'A', 0));
     put_be16(hd + 4, 0x0200);
@@ -609,8 +653,17 @@ void write_hca_header(uint8_t* hd, const HcaEncPlan& p) {  // PackHeader, hca.cp
     hd[35] = (uint8_t)p.base_bands;
     hd[36] = (uint8_t)p.stereo_bands;
     hd[37] = (uint8_t)p.bands_per_hfr;
-    put_be32(hd + 40, tag4('c', 'i', 'p', 'h'));
-    put_be32(hd + 46, tag4('p', 'a', 'd', 0));
+    unsigned at = 40;
+    if (p.loop_flag) {
+        put_be32(hd + 40, tag4('l', 'o', 'o', 'p'));
+        put_be32(hd + 44, p.loop_start_frame);
+        put_be32(hd + 48, p.loop_end_frame);
+        put_be16(hd + 52, p.loop_start_delay);
+        put_be16(hd + 54, p.loop_end_padding);
+        at = 56;
+    }
+    put_be32(hd + at, tag4('c', 'i', 'p', 'h'));
+    put_be32(hd + at + 6, tag4('p', 'a', 'd', 0));
     put_be16(hd + p.header_size - 2, crc16(hd, p.header_size - 2));
 }
 

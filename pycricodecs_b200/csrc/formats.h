@@ -123,8 +123,15 @@ struct HcaEncPlan {
     unsigned channel_config = 0;
     uint8_t type[16] = {};
     unsigned coded[16] = {};
+    // looping input (initHCAEncode / CalculateLoopInfo / CalculateHeaderSize, hca.cpp:2292-2321, 2440-2449): the encoder
+    // is fed  pre_zero x silence, pre_first x the first sample frame, main_samples input frames, post_samples frames
+    // from the loop start, then silence
+    unsigned loop_flag = 0, loop_start_frame = 0, loop_end_frame = 0, loop_start_delay = 0, loop_end_padding = 0;
+    unsigned loop_start = 0, pre_zero = 0, pre_first = 0, main_samples = 0, post_samples = 0;
 };
 int plan_hca_encode(unsigned channels, unsigned rate, unsigned samples_per_channel, unsigned quality, HcaEncPlan* p);
+// the same for a WAV with a sampler loop; -300 where the reference itself reads outside its buffers
+int plan_hca_encode_loop(const WavInfo& w, unsigned quality, HcaEncPlan* p);
 void write_hca_header(uint8_t* out, const HcaEncPlan& p);
 
 }  // namespace cri

@@ -289,11 +289,13 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         const int r = parse_wav(d, len, &wavs[i]);
         if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
-        // loop points (smpl chunk -> loop chunk, pre/post audio, hca.cpp:2292-2321, 3000-3053) are a later row
-        if (wavs[i].looping && !j->adx.force_not_looping) { j->status[i] = ERR_UNSUPPORTED; continue; }
-        if (wavs[i].format == WAV_S16 && ((j->in_off[i] + wavs[i].data_offset) & 1)) { j->status[i] = ERR_UNSUPPORTED; continue; }   // PCM must be 2-byte aligned in the blob
-        if (plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels,
-                            j->quality, &plans[i]) < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; continue; }
+        const bool looping = wavs[i].looping && !j->adx.force_not_looping;
+        if (!looping && wavs[i].format == WAV_S16 && ((j->in_off[i] + wavs[i].data_offset) & 1)) { j->status[i] = ERR_UNSUPPORTED; continue; }   // PCM must be 2-byte aligned in the blob
+        int pr;
+        if (looping) pr = plan_hca_encode_loop(wavs[i], j->quality, &plans[i]);   // loop chunk + pre / post audio (hca.cpp:2292-2321, 3000-3053)
+        else pr = plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels, j->quality, &plans[i]);
+        if (pr == ERR_UNSUPPORTED) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        if (pr < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; continue; }
         sizes[i] = (uint64_t)plans[i].header_size + (uint64_t)plans[i].frame_count * plans[i].frame_size;
     }
     finish_layout_public(j, sizes);
@@ -309,11 +311,11 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
         if (j->status[i] == OK) {
             const HcaEncPlan& p = plans[i];
             HcaStreamDev s{};
-            s.in_off = pcm16_offset(j, i, wavs[i]);
+            s.in_off = p.loop_flag ? hca_loop_input_offset(j, i, wavs[i], p) : pcm16_offset(j, i, wavs[i]);
             s.out_off = j->out_off[i] + p.header_size;
             s.frame_size = p.frame_size;
             s.frame_count = p.frame_count;
-            s.out_samples = p.samples;
+            s.out_samples = p.loop_flag ? p.frame_count * 1024 : p.samples;   // looping: the assembled feeder input, all of it
             s.channels = (uint8_t)p.channels;
             s.total_bands = (uint8_t)p.total_bands;
             s.base_bands = (uint8_t)p.base_bands;

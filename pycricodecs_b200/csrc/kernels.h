@@ -39,7 +39,8 @@ struct PcmConv {
     uint32_t count;       // samples over all channels
     uint8_t format;       // WavSampleFormat
     uint8_t shift;
-    uint8_t pad[2];
+    uint8_t kind;         // 0: convert samples src[i]; 1: repeat the first sample frame (src[i % channels]); 2: silence
+    uint8_t channels;
 };
 void launch_pcm_convert(uint8_t* d_blob, const PcmConv* d_conv, uint32_t n, uint32_t max_count, cudaStream_t s, uint64_t* launches);
 

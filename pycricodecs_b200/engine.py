@@ -194,7 +194,7 @@ def batch_blob(kind: int, blob: np.ndarray, offsets: np.ndarray, ctx: Optional[C
     elif kind == _lib.JOB_HCA_DECODE:
         L.cri_hca_decode_sizes(bp, op, n, sizes.ctypes.data, status.ctypes.data)
     elif kind == _lib.JOB_HCA_ENCODE:
-        L.cri_hca_encode_sizes(bp, op, n, int(quality), sizes.ctypes.data, status.ctypes.data)
+        L.cri_hca_encode_sizes_ex(bp, op, n, int(quality), int(adx.force_not_looping), sizes.ctypes.data, status.ctypes.data)
     elif kind == _lib.JOB_HCA_CRYPT:
         sizes[:n] = offsets[1:] - offsets[:-1]
     else:

@@ -65,3 +65,7 @@ def loop_wav(sid: int, channels: int, n: int, loop_start: int, loop_end: int, ra
 # (sid, channels, samples, loop start, loop end, ADX version)
 LOOP_CASES = [(50, 1, 32 * 100, 1000, 3000, 4), (51, 2, 32 * 100, 1000, 3000, 4), (52, 2, 32 * 90 + 7, 33, 2800, 3),
               (53, 2, 32 * 64, 0, 2047, 5)]
+
+# looping HCA encode: (sid, channels, samples, loop start, loop end, quality)
+HCA_LOOP_CASES = [(60, 2, 1024 * 12, 3000, 11000, 1), (61, 1, 1024 * 9 + 500, 100, 9000, 1), (62, 2, 1024 * 20, 1024, 1024 * 19, 3),
+                  (63, 2, 5000, 0, 4500, 0), (64, 2, 1024 * 40, 17000, 40000, 2)]

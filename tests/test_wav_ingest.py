@@ -74,3 +74,24 @@ def test_looping_wav_to_adx_and_back(ctx):
         assert (h(a), len(a)) == (want["adx"], want["adx_len"]), f"encode, case {sid}"
         if not want["adx_decoded"].startswith("error"):
             assert h(engine.adx_decode_batch([a], ctx=ctx)[0]) == want["adx_decoded"], f"decode, case {sid}"
+
+
+@pytest.mark.gpu
+def test_looping_wav_to_hca_and_back(ctx):
+    """Looping HCA encode: loop chunk in the header, the loop start frame moved to a 2048-byte boundary with extra
+    delay frames, and the reference's frame feeder (silence / first-sample pre-roll, main audio up to the loop end,
+    post-roll taken from the loop start; hca.cpp:2292-2321, 2440-2449, 3000-3107) -- assembled on the device in front of
+    the encode kernel. Decoding that stream puts the loop back into a smpl chunk."""
+    from pycricodecs_b200 import engine
+    d = json.load(open(GOLD))["hca_loops"]
+    wavs = [wavgen.loop_wav(sid, ch, n, ls, le) for sid, ch, n, ls, le, q in wavgen.HCA_LOOP_CASES]
+    for (sid, ch, n, ls, le, q), w, want in zip(wavgen.HCA_LOOP_CASES, wavs, d):
+        assert h(w) == want["wav"]
+        x = engine.hca_encode_batch([w], quality=q, ctx=ctx)[0]
+        assert (h(x), len(x)) == (want["hca"], want["hca_len"]), f"encode, case {sid}"
+        assert h(engine.hca_decode_batch([x], ctx=ctx)[0]) == want["hca_decoded"], f"decode, case {sid}"
+    # force_not_looping ignores the smpl chunk: same stream as the loop-free WAV
+    from pycricodecs_b200 import synth
+    sid, ch, n, ls, le, q = wavgen.HCA_LOOP_CASES[0]
+    assert engine.hca_encode_batch([wavs[0]], quality=q, force_not_looping=True, ctx=ctx)[0] == \
+        engine.hca_encode_batch([synth.wav(sid, ch, n)], quality=q, ctx=ctx)[0]

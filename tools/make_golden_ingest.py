@@ -36,6 +36,13 @@ def main():
             dec = "error: " + str(e)
         loops.append({"wav": h(w), "adx": h(a), "adx_len": len(a), "adx_decoded": dec})
     out["adx_loops"] = loops
+    hloops = []
+    for sid, ch, n, ls, le, q in wavgen.HCA_LOOP_CASES:
+        w = wavgen.loop_wav(sid, ch, n, ls, le)
+        r, x = R.hca_encode(w, q)
+        assert r == 0, (sid, r)
+        hloops.append({"wav": h(w), "hca": h(x), "hca_len": len(x), "hca_decoded": h(R.hca_decode(x))})
+    out["hca_loops"] = hloops
     json.dump(out, open(os.path.join(ROOT, "tests", "golden", "ingest_digests.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1))
 
