@@ -413,6 +413,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.run_len = J.run_len;
         a.n_runs = J.n_runs;
         a.joint = J.any_joint ? 1u : 0u;
+        a.force_careful = env_u32("CRI_HCA_CAREFUL", 0);
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
         if (J.n_runs) launch_hca_decode_fast(a, j->stream, &c->launches, j->ev[2]);
         else launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);

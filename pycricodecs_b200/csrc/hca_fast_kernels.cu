@@ -362,7 +362,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
 #pragma unroll
     for (int c = 0; c < NCH; c++)
         hdr_bound += 3 + 6 + 11 * max((int)S.coded[c] - 1, 0) + (!JOINT ? 0 : S.type[c] == 2 ? 32 : 6 * hfr_groups);
-    const bool hdr_safe = !active || nbits >= hdr_bound;
+    const bool hdr_safe = !a.force_careful && (!active || nbits >= hdr_bound);
     if (__all_sync(kFull, hdr_safe)) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) parse_channel(c, std::true_type{});
@@ -390,7 +390,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             // can this run cross the end of the frame? (only corrupt / wrongly keyed frames do)
-            const bool careful = br.position() + run_bits[c] > nbits;
+            const bool careful = a.force_careful || br.position() + run_bits[c] > nbits;
             const bool any_careful = __any_sync(kFull, careful);
             const uint16_t* tp = tab + c * 128 * 32;
             float4* dst = dst_frame + sub * 1024 + c * RW;

@@ -37,6 +37,7 @@ struct HcaDecodeArgs {
     uint32_t run_len;
     uint32_t n_runs;            // 0 = not on the fast path
     uint32_t joint;             // fast path: some stream has an intensity-stereo pair or HFR bands
+    uint32_t force_careful;     // tests: take the end-of-frame-checked reader variants everywhere (CRI_HCA_CAREFUL=1)
 };
 
 // `mid` (optional) is recorded between the unpack and the transform kernel.

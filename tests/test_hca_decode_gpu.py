@@ -108,3 +108,36 @@ def test_fast_path_mixed_qualities(port, ctx, monkeypatch, run_len, channels):
         assert _first_diff(g, want[h]) is None, f"stream {i} (quality {i % 4})"
     monkeypatch.setenv("CRI_HCA_GENERAL", "1")
     assert HCA.decode_batch(hcas, ctx=ctx) == got
+
+
+def test_checked_reader_variants_agree(port, ctx, monkeypatch):
+    """The unpack kernel has two variants of its header parser and of its code loop: one without per-read end-of-frame
+    checks (used when a frame is long enough that no read can reach its end) and one with the reference reader's rule
+    (a read that would cross the end yields 0, hca.cpp:232-233). Valid streams never need the second; force it."""
+    hcas = [port.hca_encode(synth.wav(30 + s, 1 + s % 2, 6000 + 500 * s), s % 4)[1] for s in range(8)]
+    want = HCA.decode_batch(hcas, ctx=ctx)
+    monkeypatch.setenv("CRI_HCA_CAREFUL", "1")
+    assert HCA.decode_batch(hcas, ctx=ctx) == want
+    for h, g in zip(hcas[:4], want[:4]):
+        assert g == port.hca_decode(h)[1]
+
+
+def test_truncated_last_frame_matches_reference_reader(port, ctx):
+    """A frame whose CRC is valid but whose code runs reach past its end: reads past the end are zeros. Built by
+    shrinking frame_size in the header and re-stamping every frame's CRC; the oracle decodes the same bytes."""
+    import struct
+    from pycricodecs_b200 import engine
+    src = port.hca_encode(synth.wav(5, 2, 4096), 0)[1]                     # Highest: 1024-byte frames, dense
+    fs_old = struct.unpack(">H", src[28:30])[0]
+    fs_new = fs_old - 300
+    hdr = bytearray(src[:96])
+    hdr[28:30] = struct.pack(">H", fs_new)
+    hdr[94:96] = struct.pack(">H", engine.crc16(bytes(hdr[:94])))
+    frames = []
+    for f in range(struct.unpack(">I", src[16:20])[0]):
+        body = bytearray(src[96 + f * fs_old: 96 + f * fs_old + fs_new - 2])
+        frames.append(bytes(body) + struct.pack(">H", engine.crc16(bytes(body))))
+    cut = bytes(hdr) + b"".join(frames)
+    r, want = port.hca_decode(cut)
+    got = HCA.decode_batch([cut], ctx=ctx, raise_errors=False)[0]
+    assert (got == want) if r == 0 else (got.status == -202)
