@@ -22,6 +22,7 @@
 //     reference's order; the fp64 corners (sqrt(2), 1.0/avg) are evaluated in fp64;
 //   * the bitstream is assembled with warp prefix sums of code lengths and
 //     shared-memory atomicOr, 32 bands per step in band order.
+#include <algorithm>
 #include <cstdint>
 
 #include "cri_tables.h"
@@ -263,18 +264,23 @@ hca_encode_kernel(HcaEncodeArgs a) {
     {
         uint8_t* p = s_dyn + (size_t)warp * a.smem_per_warp;
         fs.spec = reinterpret_cast<float*>(p); p += (size_t)MC * 8 * kSpecRow * 4;
-        fs.bits = reinterpret_cast<uint32_t*>(p); p += (size_t)a.frame_words * 4;
         fs.hfr_avg = reinterpret_cast<float*>(p); p += (size_t)MC * 8 * 4;
         fs.hfr_scale = reinterpret_cast<int*>(p); p += (size_t)MC * 8 * 4;
         fs.header_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
         fs.delta_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
-        fs.pcm = reinterpret_cast<int16_t*>(p); p += (size_t)MC * 1152 * 2 + 16;
+        // PCM stage; after the MDCT the same bytes hold the boundary table, then the packed frame (a frame is at most
+        // the size of the PCM it encodes at the lowest compression ratio the planner picks, 4:1)
+        fs.pcm = reinterpret_cast<int16_t*>(p);
+        fs.bits = reinterpret_cast<uint32_t*>(p);
+        {
+            const size_t pcm_bytes = (size_t)MC * 1152 * 2 + 16, bit_bytes = (size_t)a.frame_words * 4;
+            p += pcm_bytes > bit_bytes ? pcm_bytes : bit_bytes;
+        }
         fs.sf = p; p += (size_t)MC * 128;
         fs.res = p; p += (size_t)MC * 128;
         fs.inten = p;
     }
     const int frame_size = (int)S.frame_size;
-    for (uint32_t i = lane; i < a.frame_words; i += 32) fs.bits[i] = 0;
 
     // ---- PCM: previous 128 + this frame's 1024 sample frames, interleaved as in the WAV; silence outside the stream
     // (hca.cpp:3035-3053). The aligned 32-bit words covering the run are copied as they are (coalesced); `pcm` then
@@ -558,6 +564,8 @@ hca_encode_kernel(HcaEncodeArgs a) {
     }
     __syncwarp();
 
+    for (uint32_t i = lane; i < a.frame_words; i += 32) fs.bits[i] = 0;   // the PCM stage / boundary table are dead now
+    __syncwarp();
     // ---- pack (hca.cpp:2894-2963): sync word, noise level, boundary, per-channel headers, spectra, CRC
     const int limit_bits = (frame_size - 2) * 8 + 16;         // writer buffer = frame_size - 2 bytes after the sync word
     int cursor = 0;
@@ -666,8 +674,9 @@ hca_encode_kernel(HcaEncodeArgs a) {
 }  // namespace
 
 size_t hca_encode_smem_per_warp(uint32_t max_channels, uint32_t frame_words) {
-    size_t n = (size_t)max_channels * 8 * kSpecRow * 4 + (size_t)frame_words * 4 + (size_t)max_channels * 8 * 4 * 2 +
-               (size_t)max_channels * 4 * 2 + (size_t)max_channels * 1152 * 2 + 16 + (size_t)max_channels * 128 * 2 + (size_t)max_channels * 8;
+    size_t n = (size_t)max_channels * 8 * kSpecRow * 4 + (size_t)max_channels * 8 * 4 * 2 + (size_t)max_channels * 4 * 2 +
+               std::max((size_t)max_channels * 1152 * 2 + 16, (size_t)frame_words * 4) + (size_t)max_channels * 128 * 2 +
+               (size_t)max_channels * 8;
     return (n + 15) / 16 * 16;
 }
 
