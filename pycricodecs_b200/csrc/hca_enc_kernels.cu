@@ -268,13 +268,12 @@ hca_encode_kernel(HcaEncodeArgs a) {
         fs.hfr_scale = reinterpret_cast<int*>(p); p += (size_t)MC * 8 * 4;
         fs.header_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
         fs.delta_bits = reinterpret_cast<int*>(p); p += (size_t)MC * 4;
-        // PCM stage; after the MDCT the same bytes hold the boundary table, then the packed frame (a frame is at most
-        // the size of the PCM it encodes at the lowest compression ratio the planner picks, 4:1)
+        // scratch: the boundary table (129 words) during the bit allocation, then the packed frame
         fs.pcm = reinterpret_cast<int16_t*>(p);
         fs.bits = reinterpret_cast<uint32_t*>(p);
         {
-            const size_t pcm_bytes = (size_t)MC * 1152 * 2 + 16, bit_bytes = (size_t)a.frame_words * 4;
-            p += pcm_bytes > bit_bytes ? pcm_bytes : bit_bytes;
+            const size_t tab_bytes = 129 * 4 + 12, bit_bytes = (size_t)a.frame_words * 4;
+            p += (tab_bytes > bit_bytes ? tab_bytes : bit_bytes + 15) / 16 * 16;
         }
         fs.sf = p; p += (size_t)MC * 128;
         fs.res = p; p += (size_t)MC * 128;
@@ -282,46 +281,17 @@ hca_encode_kernel(HcaEncodeArgs a) {
     }
     const int frame_size = (int)S.frame_size;
 
-    // ---- PCM: previous 128 + this frame's 1024 sample frames, interleaved as in the WAV; silence outside the stream
-    // (hca.cpp:3035-3053). The aligned 32-bit words covering the run are copied as they are (coalesced); `pcm` then
-    // points at the first sample inside them.
-    const int16_t* pcm;
-    {
-        const long long n0 = (long long)frame * 1024 - 128;            // first sample frame wanted
-        const long long lo = n0 < 0 ? 0 : n0;
-        const long long hi = min((long long)S.out_samples, n0 + 1152);  // exclusive
-        uint32_t* stage = reinterpret_cast<uint32_t*>(fs.pcm);
-        const int total_words = (1152 * nch * 2) / 4 + 2;
-        for (int w = lane; w < total_words; w += 32) stage[w] = 0;      // silence for everything not covered below
-        __syncwarp();
-        const uint64_t first_byte = S.in_off + (uint64_t)lo * nch * 2;   // of the first real sample in the blob
-        const uint64_t abase = first_byte & ~(uint64_t)3;
-        // sample frame n0 sits at byte `lead` of the stage; real data starts (lo - n0) sample frames later
-        const int lead = (int)(first_byte & 3);
-        const int skip_bytes = (int)(lo - n0) * nch * 2;                 // multiple of 4 only if nch*2*(lo-n0) is
-        // keep 4-byte copies possible: shift the whole stage so that real data keeps its blob alignment
-        const int data_at = skip_bytes + lead;                           // byte offset of the first real sample in the stage
-        const int word0 = data_at >> 2;                                  // stage word that receives blob word `abase`
-        if (hi > lo && (skip_bytes & 3) == 0) {
-            const int nwords = (int)((((first_byte + (uint64_t)(hi - lo) * nch * 2) + 3) & ~(uint64_t)3) - abase) >> 2;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.in + abase);
-            for (int w = lane; w < nwords; w += 32) stage[word0 + w] = __ldg(src + w);
-            __syncwarp();
-            // the covering words may carry up to 3 foreign bytes in front of / behind the run: blank them
-            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
-            const int end_at = data_at + (int)(hi - lo) * nch * 2;
-            if (lane < 4 && (word0 * 4 + lane) < data_at) sb[word0 * 4 + lane] = 0;
-            if (lane < 4 && end_at + lane < (word0 + nwords) * 4) sb[end_at + lane] = 0;
-        } else if (hi > lo) {                                            // odd geometry (3, 5, 7 channels at a stream start)
-            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
-            const uint8_t* src = a.in + first_byte;
-            const int nbytes = (int)(hi - lo) * nch * 2;
-            for (int k = lane; k < nbytes; k += 32) sb[data_at + k] = src[k];
-        }
-        pcm = reinterpret_cast<const int16_t*>(reinterpret_cast<const uint8_t*>(stage) + lead);
-    }
-    __syncwarp();
-
+    // ---- PCM: the MDCT of subframe `sub` reads sample frames [1024 * frame - 128 + 128 * sub, + 256) straight from the
+    // blob (previous 128 + current 128; 2-byte loads that L1 serves after the first touch of a line); outside the
+    // stream there is silence (hca.cpp:3035-3053)
+    const int16_t* pcm_base = reinterpret_cast<const int16_t*>(a.in + S.in_off);
+    const long long pcm_n0 = (long long)frame * 1024 - 128;             // stream index of the frame's first wanted sample frame
+    const long long pcm_end = (long long)S.out_samples;
+    auto sample = [&](int idx /* sample frame inside the 1152-frame window */, int c) -> float {
+        const long long n = pcm_n0 + idx;
+        const int v = (n >= 0 && n < pcm_end) ? (int)__ldg(pcm_base + n * nch + c) : 0;
+        return (float)v;
+    };
     // ---- MDCT: 8 subframes x channels (hca.cpp:2470-2559)
     {
         const float w0 = __uint_as_float(kMdctWin[4 * lane]), w1 = __uint_as_float(kMdctWin[4 * lane + 1]);
@@ -335,13 +305,12 @@ hca_encode_kernel(HcaEncodeArgs a) {
         const float k = 1.0f / 32768.0f;
         for (int c = 0; c < nch; c++) {
             for (int sub = 0; sub < 8; sub++) {
-                const int16_t* cur = pcm + (size_t)(128 + sub * 128) * nch + c;   // sample i of the subframe: cur[i * nch]
-                const int16_t* prv = cur - 128 * nch;
-                const int i0 = 2 * lane * nch, i1 = (63 - 2 * lane) * nch, i2 = (64 + 2 * lane) * nch, i3 = (127 - 2 * lane) * nch;
-                const float c0 = __fmul_rn((float)cur[i0], k), c1 = __fmul_rn((float)cur[i1], k);
-                const float c2 = __fmul_rn((float)cur[i2], k), c3 = __fmul_rn((float)cur[i3], k);
-                const float p0 = __fmul_rn((float)prv[i0], k), p1 = __fmul_rn((float)prv[i1], k);
-                const float p2 = __fmul_rn((float)prv[i2], k), p3 = __fmul_rn((float)prv[i3], k);
+                const int cur = 128 + sub * 128, prv = sub * 128;          // window positions of the subframe / the one before it
+                const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
+                const float c0 = __fmul_rn(sample(cur + i0, c), k), c1 = __fmul_rn(sample(cur + i1, c), k);
+                const float c2 = __fmul_rn(sample(cur + i2, c), k), c3 = __fmul_rn(sample(cur + i3, c), k);
+                const float p0 = __fmul_rn(sample(prv + i0, c), k), p1 = __fmul_rn(sample(prv + i1, c), k);
+                const float p2 = __fmul_rn(sample(prv + i2, c), k), p3 = __fmul_rn(sample(prv + i3, c), k);
                 // windowing (hca.cpp:2537-2546): in[i] = W[63-i]*(-cur[64+i]) - (-W[64+i])*cur[63-i],
                 //                               in[64+i] = W[i]*prv[i] - (-W[127-i])*prv[127-i]
                 const float in_a = __fsub_rn(__fmul_rn(w1, -c2), __fmul_rn(-w2, c1));   // in[2l]
@@ -539,7 +508,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         }
     }
     if (!failed && noise_level != 0) {                        // BinarySearchBoundary
-        int* pre = reinterpret_cast<int*>(fs.pcm);            // the PCM stage (>= 576 words) is dead after the MDCT: 129 words of scratch
+        int* pre = reinterpret_cast<int*>(fs.pcm);            // scratch shared with the frame buffer, which is filled later
         boundary_table(tb, fs, S, lane, noise_level, pre);
         int lo_b = 0, hi_b = 127;
         while (abs(hi_b - lo_b) > 1) {
@@ -675,7 +644,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
 
 size_t hca_encode_smem_per_warp(uint32_t max_channels, uint32_t frame_words) {
     size_t n = (size_t)max_channels * 8 * kSpecRow * 4 + (size_t)max_channels * 8 * 4 * 2 + (size_t)max_channels * 4 * 2 +
-               std::max((size_t)max_channels * 1152 * 2 + 16, (size_t)frame_words * 4) + (size_t)max_channels * 128 * 2 +
+               (std::max((size_t)129 * 4 + 12, (size_t)frame_words * 4) + 15) / 16 * 16 + (size_t)max_channels * 128 * 2 +
                (size_t)max_channels * 8;
     return (n + 15) / 16 * 16;
 }
