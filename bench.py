@@ -358,6 +358,19 @@ def run_ours(a):
             "clocks": clocks,
             "parity_spot_check": bool(parity),
         }
+        if dom_name == "hca_imdct_fast_kernel" and dom > 0:
+            # the transform is bounded by fp32 issue before HBM -- 16 transforms x 3968 separately rounded
+            # fp32 operations per stereo frame (no FMA: the reference rounds every product and sum) against one fp32
+            # instruction per lane and clock
+            sm = 148
+            try:
+                sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            except Exception:
+                pass
+            ops = per_rank_units * 16 * 3968 / (dom * 1e-3)
+            peak_ops = sm * 128 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+            line["roofline"]["fp32_issue"] = {"achieved_tops": ops / 1e12, "peak_tops": peak_ops / 1e12, "frac": ops / peak_ops,
+                                              "note": "separately rounded fp32 mul/add per second vs SMs x 128 lanes x SM clock"}
         if companion is not None:
             line["adx_encode"] = companion
         if not a.no_cpu:
