@@ -434,20 +434,30 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 if (!exact) {
                     const uint32_t magic31 = 0x7FFFFFFFu / (uint32_t)scale + 1u;      // ceil(2^31 / scale), scale >= 1
                     const int half2 = 2 * half;
+                    // Serial path per sample: t -> r -> |r| -> 2|r| + half2 -> q -> min(q, limit) -> t'. The next t is
+                    //   s'*4096 - c1*sim_{n-1} - c0*sim_n  with  sim_n = delta*scale + P  =  B - (c0*scale) * delta,
+                    // where B = s'*4096 - c1*sim_{n-1} - c0*P and the sign of delta (known from r, early) is folded into
+                    // the multiplier, so neither the sign nor the simulated sample itself sits on the path.
+                    const int a_pos = c0 * scale;
                     int range_s = 0;
-                    int g1 = h1, g2 = h2;
+                    int g1 = h1, g2 = h2;                                             // sim_{n-1}, sim_{n-2}
+                    int t = (smp[0] * 4096 - c1 * g2) - c0 * g1;
 #pragma unroll
                     for (int k = 0; k < 16; k++) {
                         int byte = 0;
 #pragma unroll
                         for (int n = 0; n < 2; n++) {
-                            const int sm = smp[2 * k + n];
-                            const int t = (sm * 4096 - c1 * g2) - c0 * g1;
+                            const int i = 2 * k + n;
+                            const int sm = smp[i];
                             const int r = t >> 12;
+                            const bool neg = r < 0;
                             const int q = (int)__umulhi((uint32_t)(2 * abs(r) + half2), magic31);
-                            const int d = min(max(r < 0 ? -q : q, -8), 7);
-                            const int sim = d * scale + (sm - ((t + 4095) >> 12));
+                            const int qc = min(q, neg ? 8 : 7);                       // clamp of delta to [-8, 7], on the magnitude
+                            const int pshift = sm - ((t + 4095) >> 12);               // pred >> 12
+                            const int d = neg ? -qc : qc;
+                            const int sim = d * scale + pshift;
                             range_s |= sim + 32768;
+                            if (i < kSpb - 1) t = (smp[i + 1] * 4096 - c1 * g1 - c0 * pshift) - (neg ? -a_pos : a_pos) * qc;
                             g2 = g1; g1 = sim;
                             byte = (byte << 4) | (d & 0xF);
                         }
