@@ -589,11 +589,13 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
             // the next block of spectra is loaded into the registers the window frees, 16 bytes at a time
             src += 1024;
             const bool ok_next = sub < 7 ? ok : ok_next_frame;
+            // lanes without a next block (end of the run / of the job, idle lanes) read block 0 instead: their rows are
+            // never stored, so the values do not matter, and the loads need no predicate and no zero fill
+            const float4* nsrc = ok_next ? src : a.spec + lane;
             hca_window_thread<THREADS>(x, carry,
                 [&](int i, float v) { *reinterpret_cast<short*>(trow + i * (2 * NCH)) = pcm16_sat(v); },
                 [&](int c) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok_next) v = __ldcs(src + c * 32);
+                    const float4 v = __ldcs(nsrc + c * 32);
                     x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
                 }, convoy);
             __syncwarp();
