@@ -193,18 +193,21 @@ hca_unpack_kernel(HcaDecodeArgs a) {
     }
     const uint8_t* ath = a.ath + (size_t)(active ? S.ath : 0) * 128;
     int run_bits[kHcaMaxChannels];                           // worst-case bits of one 128-code run per channel
+    uint32_t frame_draws = 0;                                // noise generator draws per subframe, all channels
     for (int c = 0; c < nch && !bad; c++) {
         const int coded = S.coded[c];
         const int type = S.type[c];
-        // scalefactors (hca.cpp:1290-1358, v2.0 and older)
+        // scalefactors (hca.cpp:1290-1358); v3.0 appends one per HFR group to every non-secondary channel
+        const int extra = (S.v3 && type != 2) ? (int)S.hfr_groups : 0;
+        const int n_sf = coded + extra;                      // <= 127 - extra (plan_hca_decode, v3_supported)
         const uint32_t delta_bits = br.read(3, nbits);
         if (delta_bits >= 6) {
-            for (int i = 0; i < coded; i++) s_sf[i * 32] = (uint8_t)br.read(6, nbits);
+            for (int i = 0; i < n_sf; i++) s_sf[i * 32] = (uint8_t)br.read(6, nbits);
         } else if (delta_bits > 0) {
             const uint32_t escape = (1u << delta_bits) - 1;
             uint32_t v = br.read(6, nbits);
             s_sf[0] = (uint8_t)v;
-            for (int i = 1; i < coded; i++) {
+            for (int i = 1; i < n_sf; i++) {
                 const uint32_t d = br.read((int)delta_bits, nbits);
                 if (d == escape) {
                     v = br.read(6, nbits);
@@ -219,24 +222,63 @@ hca_unpack_kernel(HcaDecodeArgs a) {
             for (int i = 0; i < 128; i++) s_sf[i * 32] = 0;
         }
         if (bad) break;
+        // v3.0: the HFR scales are the extra scalefactors, copied to the top of the table starting ONE entry past the
+        // last one read (hca.cpp:1353-1355); that entry is never written in a supported stream, so it reads as zero
+        if (extra > 0 && delta_bits > 0) {
+            s_sf[127 * 32] = 0;
+            for (int i = 1; i < extra; i++) s_sf[(127 - i) * 32] = s_sf[(n_sf - i) * 32];
+        }
         // intensity (secondary channel) or HFR scales (others), hca.cpp:1361-1441
         if (type == 2) {
             const uint32_t v0 = br.position() + 4 <= nbits ? br.peek(4) : 0u;
             uint32_t inten = v0;
-            if (v0 < 15) {
+            if (!S.v3) {
+                if (v0 < 15) {
+                    br.skip(4);
+                    br.top_up();
+                    for (int i = 1; i < 8; i++) inten |= br.read(4, nbits) << (4 * i);
+                }
+            } else {                                         // hca.cpp:1382-1424
                 br.skip(4);
                 br.top_up();
-                for (int i = 1; i < 8; i++) inten |= br.read(4, nbits) << (4 * i);
+                if (v0 < 15) {
+                    const uint32_t db = br.read(2, nbits);
+                    if (db == 3) {
+                        for (int i = 1; i < 8; i++) inten |= br.read(4, nbits) << (4 * i);
+                    } else {
+                        const uint32_t escape = (2u << db) - 1;
+                        uint32_t v = v0;
+                        for (int i = 1; i < 8; i++) {
+                            const uint32_t d = br.read((int)db + 1, nbits);
+                            if (d == escape) {
+                                v = br.read(4, nbits);
+                            } else {
+                                v = (v - (escape >> 1) + d) & 0xFF;
+                                // the reference stops here and keeps the PREVIOUS frame's remaining intensities
+                                // (its caller ignores the error); only corrupt data gets here: the stream fails
+                                if (v > 15) { bad = true; break; }
+                            }
+                            inten |= v << (4 * i);
+                        }
+                    }
+                } else {
+                    inten = 0x77777777u;
+                }
             }
             a.inten[slot * a.max_channels + c] = inten;
-        } else {
+        } else if (!S.v3) {
             for (int g = 0; g < S.hfr_groups; g++) s_sf[(128 - S.hfr_groups + g) * 32] = (uint8_t)br.read(6, nbits);
         }
+        if (bad) break;
         // resolution + gain per band (hca.cpp:1444-1507)
         float4* gdst = reinterpret_cast<float4*>(a.gain + (slot * a.max_channels + c) * 128);
+        const bool noise = S.noise && a.sfres != nullptr;
+        uint32_t* cls = reinterpret_cast<uint32_t*>(a.sfres + (noise ? (slot * a.max_channels + c) * 128 : 0));
+        int n_noise = 0, n_valid = 0;
         int sum_bits = 0;
         for (int i0 = 0; i0 < 128; i0 += 4) {
             float g[4];
+            uint32_t cls4 = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int i = i0 + k;
@@ -244,12 +286,16 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                 g[k] = 0.f;
                 if (i < coded) {
                     const uint32_t sf = s_sf[i * 32];
+                    uint32_t tag = sf;
                     if (sf > 0) {
                         const int level = (int)ath[i] + (int)((packed + (uint32_t)i) >> 8);
                         const int cp = level + 1 - (int)((5 * sf) >> 1);
                         r = cp < 0 ? 15u : cp <= 65 ? (uint32_t)tb.invert[cp] : 0u;
                         if (r > S.max_res) r = S.max_res; else if (r < S.min_res) r = S.min_res;
+                        // hca.cpp:1479-1487: bands with a scalefactor are "noise" (resolution 0) or "valid"
+                        if (r < 1) { tag |= 0x40; n_noise++; } else { tag |= 0x80; n_valid++; }
                     }
+                    cls4 |= tag << (8 * k);
                     g[k] = __fmul_rn(tb.scaling[sf], tb.range[r]);
                 }
                 const uint32_t mb = i < coded ? tb.max_bits[r] : 0u;
@@ -257,22 +303,38 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                 s_rb[(c * 128 + i) * 32] = (uint8_t)(r | (mb << 4));     // bands past `coded`: r = 0, 0 bits
             }
             gdst[i0 >> 2] = make_float4(g[0], g[1], g[2], g[3]);
+            if (noise) cls[i0 >> 2] = cls4;
         }
         run_bits[c] = sum_bits;
+        if (noise) {
+            // the generator runs only in channels that have both kinds of band (hca.cpp:1605-1606)
+            const uint32_t d = (n_noise > 0 && n_valid > 0) ? (uint32_t)n_noise : 0u;
+            a.draws[slot * a.max_channels + c] = d;
+            frame_draws += d;
+        }
         // HFR multipliers for the bands above the coded ones (hca.cpp:1638-1683, v2.0 rule)
         if (S.bands_per_hfr && type != 2) {
             const int start = S.base_bands + S.stereo_bands;
             int high = start, low = start - 1;
             float* gflat = a.gain + (slot * a.max_channels + c) * 128;
+            // v3.0: the low band stops moving down after the first half of the groups (hca.cpp:1652-1661)
+            const int moving = S.v3 ? (int)S.hfr_groups >> 1 : (int)S.hfr_groups;
             for (int g = 0; g < S.hfr_groups; g++)
                 for (int i = 0; i < S.bands_per_hfr; i++) {
                     if (high >= S.total_bands || low < 0) break;
                     int k = (int)s_sf[(128 - S.hfr_groups + g) * 32] - (int)s_sf[low * 32] + 63;
                     k &= ~(k >> 31);
                     gflat[high] = tb.conv[k];
-                    high++; low--;
+                    high++;
+                    if (g < moving) low--;
                 }
         }
+    }
+
+    if (active && S.noise && a.sfres != nullptr) {
+        if (step != 0) a.frame_draws[S.frame_base + frame] = bad ? 0u : frame_draws;
+        if (bad)                                             // a failed frame draws nothing (its stream is reported as failed)
+            for (int c = 0; c < nch; c++) a.draws[slot * a.max_channels + c] = 0;
     }
 
     // ---- spectra: subframe-major, channel-minor runs of codes (hca.cpp:1540-1571). The loops are warp-uniform
@@ -354,6 +416,7 @@ void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launche
     const uint64_t groups_per_cta = kUnpackThreads / 32;
     hca_unpack_kernel<<<(unsigned)((a.total_groups + groups_per_cta - 1) / groups_per_cta), kUnpackThreads, smem, s>>>(a);
     ++*launches;
+    if (a.sfres) launch_hca_noise_scan(a, s, launches);
     if (mid) cudaEventRecord(mid, s);
     launch_hca_imdct(a, s, launches);
 }

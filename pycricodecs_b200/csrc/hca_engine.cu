@@ -82,6 +82,19 @@ static void fill_stream(HcaStreamDev* s, const HcaInfo& h) {
         if (h.type[c]) joint = true;
     }
     s->joint = joint ? 1 : 0;
+    s->v3 = h.version > 0x0200 ? 1 : 0;
+    s->noise = s->v3 && h.min_res == 0 ? 1 : 0;
+}
+
+// v3.0 reads hfr_groups extra scalefactors per non-secondary channel and copies them to the top of the table starting
+// one entry past the last one read (hca.cpp:1353-1355). That entry is always zero as long as the copies cannot reach
+// it, i.e. coded + 2 * hfr_groups < 128; otherwise it carries a value over from the previous frame, which a
+// frame-parallel decoder cannot reproduce.
+static bool v3_supported(const HcaInfo& h) {
+    if (h.version <= 0x0200 || h.hfr_groups == 0) return true;
+    for (unsigned c = 0; c < h.channels; c++)
+        if (h.type[c] != 2 && h.coded[c] + 2 * h.hfr_groups >= 128) return false;
+    return true;
 }
 
 int plan_hca_decode(cri_ctx* c, cri_job* j) {
@@ -95,11 +108,10 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         HcaInfo& h = infos[i];
         if (parse_hca(d, len, &h) != OK) { j->status[i] = ERR_HCA_HEADER; continue; }
         if ((uint64_t)h.header_size + (uint64_t)h.frame_count * h.frame_size > len) { j->status[i] = ERR_HCA_HEADER; continue; }
-        // v3.0 streams (delta-coded intensity, derived HFR scales, noise fill with a cross-frame LCG) are a later row
-        if (h.version > 0x0200) { j->status[i] = ERR_UNSUPPORTED; continue; }
         const uint64_t total = (uint64_t)h.frame_count * 1024;
         if (total < (uint64_t)h.delay + h.padding) { j->status[i] = ERR_HCA_HEADER; continue; }
-        sizes[i] = wav_header_size(h.loop_flag) + (total - h.delay - h.padding) * h.channels * 2;
+        sizes[i] = wav_header_size(h.loop_flag) + (total - h.delay - h.padding) * h.channels * 2;   // as cri_hca_decode_sizes
+        if (!v3_supported(h)) j->status[i] = ERR_UNSUPPORTED;                                        // region stays zero
     }
     finish_layout_public(j, sizes);
 
@@ -109,6 +121,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     J.max_channels = 1;
     J.streams.assign(j->n, HcaStreamDev{});   // one entry per input stream: the device status array shares the index
     std::vector<uint32_t> needed_frames(j->n, 0);
+    bool any_v3 = false, any_noise = false;
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
         const HcaInfo& h = infos[i];
@@ -134,6 +147,9 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         J.max_channels = std::max<uint32_t>(J.max_channels, h.channels);
         // the reference stops decoding once it has produced every output sample (hca.cpp:3401)
         needed_frames[i] = (uint32_t)std::min<uint64_t>(h.frame_count, ((uint64_t)samples + h.delay + 1023) / 1024);
+        J.streams[i].frame_base = (uint32_t)j->units;
+        any_v3 = any_v3 || s.v3;
+        any_noise = any_noise || s.noise;
         j->units += needed_frames[i];
     }
     // uniform batch: every decodable stream is mono (1) or stereo (2): discrete channels or one primary/secondary pair
@@ -151,6 +167,9 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     uint32_t max_frame = 8;
     for (const auto& st : J.streams) max_frame = std::max(max_frame, st.frame_size);
     J.scratch_words = ((max_frame + 15) / 16 + 4) * 4;             // whole 16-byte rows + zeroed slack rows for the prefetching reader
+    J.n_bytes = 0;
+    J.noise_frames = 0;
+    if (any_v3) J.uniform = 0;        // v3.0 streams take the general kernels
     if (J.uniform && j->units > 0 && j->units < 0xFFFF0000ull && env_u32("CRI_HCA_GENERAL", 0) == 0) {
         // fast path: flattened frame list cut into runs of run_len frames, one transform lane per (run, channel).
         // run_len is chosen so that the transform kernel's CTAs fill the resident slots of the GPU in whole waves.
@@ -212,6 +231,10 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     J.q_bytes = slots * J.max_channels * 8 * 16 * sizeof(uint4);
     J.g_bytes = slots * J.max_channels * 128 * sizeof(float);
     J.i_bytes = slots * J.max_channels * sizeof(uint32_t);
+    if (any_noise && j->units < 0xFFFF0000ull) {
+        J.noise_frames = j->units;
+        J.n_bytes = slots * J.max_channels * (128 + sizeof(uint32_t)) + 2 * J.noise_frames * sizeof(uint32_t);
+    }
     return OK;
 }
 
@@ -382,6 +405,7 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     if (r == OK && J.g_bytes) r = pool_alloc(c, (void**)&J.d_g, J.g_bytes);
     if (r == OK && J.i_bytes) r = pool_alloc(c, (void**)&J.d_i, J.i_bytes);
     if (r == OK && J.s_bytes) r = pool_alloc(c, (void**)&J.d_s, J.s_bytes);
+    if (r == OK && J.n_bytes) r = pool_alloc(c, (void**)&J.d_n, J.n_bytes);
     return r;
 }
 
@@ -414,6 +438,13 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_runs = J.n_runs;
         a.joint = J.any_joint ? 1u : 0u;
         a.force_careful = env_u32("CRI_HCA_CAREFUL", 0);
+        if (J.d_n) {
+            const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
+            a.sfres = J.d_n;
+            a.draws = reinterpret_cast<uint32_t*>(J.d_n + slots * J.max_channels * 128);
+            a.frame_draws = a.draws + slots * J.max_channels;
+            a.frame_state = a.frame_draws + J.noise_frames;
+        }
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
         if (J.n_runs) launch_hca_decode_fast(a, j->stream, &c->launches, j->ev[2]);
         else launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);
@@ -468,7 +499,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
 void free_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
     for (void* p : {(void*)J.d_streams, (void*)J.d_units, (void*)J.d_s, (void*)J.d_frame_prefix, (void*)J.d_crc_mul,
-                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec, (void*)J.d_group_prefix})
+                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec, (void*)J.d_group_prefix, (void*)J.d_n})
         pool_free(c, p);
 }
 

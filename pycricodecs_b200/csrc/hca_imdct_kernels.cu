@@ -21,6 +21,20 @@ namespace cri {
 namespace {
 
 __constant__ uint32_t c_intensity[16] = CRI_TBL_INTENSITY_RATIO;
+__constant__ uint32_t c_noise_conv[128] = CRI_TBL_SCALE_CONV;
+
+// The v3.0 noise generator is rand()'s LCG, state' = 0x343FD * state + 0x269EC3 (hca.cpp:1616), run once per
+// resolution-0 band in stream order. n steps at once: compose the affine map with itself by squaring.
+__device__ __forceinline__ uint32_t lcg_jump(uint32_t state, uint32_t n) {
+    uint32_t mul = 1, add = 0, m = 0x343FDu, c = 0x269EC3u;
+    while (n) {
+        if (n & 1) { mul *= m; add = add * m + c; }
+        c = c * m + c;
+        m *= m;
+        n >>= 1;
+    }
+    return mul * state + add;
+}
 
 #include "hca_dct_gen.inc"
 
@@ -120,13 +134,16 @@ hca_imdct_kernel(HcaDecodeArgs a) {
     const int nch = NCH ? NCH : (int)S.channels;
     const int MC = (int)a.max_channels;
     // per-warp shared: 2 input stages (256 B spectra + 512 B gains), PCM tile [MC][128] int16, then (general path)
-    // overlap carry [MC][32] float2 and HFR scratch [128] float
-    const size_t per_warp = 2 * 768 + (size_t)MC * 256 + (NCH ? 0 : (size_t)MC * 256 + 512);
+    // overlap carry [MC][32] float2, HFR / noise scratch [128] float, and for the noise generator the band of every
+    // valid rank [128] and the scalefactors [128]
+    const size_t per_warp = 2 * 768 + (size_t)MC * 256 + (NCH ? 0 : (size_t)MC * 256 + 512 + 256);
     uint8_t* base = s_dyn + (size_t)warp * per_warp;
     uint8_t* stage = base;
     int16_t* tile = reinterpret_cast<int16_t*>(base + 2 * 768);
     float2* carry = reinterpret_cast<float2*>(base + 2 * 768 + MC * 256);
     float* xs = reinterpret_cast<float*>(base + 2 * 768 + MC * 512);
+    uint8_t* vmap = base + 2 * 768 + MC * 512 + 512;
+    uint8_t* sfb = vmap + 128;
 
     LaneConsts k;
     k.wa0 = __uint_as_float(kWinA[2 * lane]); k.wa1 = __uint_as_float(kWinA[2 * lane + 1]);
@@ -144,8 +161,13 @@ hca_imdct_kernel(HcaDecodeArgs a) {
         for (int c = 0; c < nch; c++) carry[c * 32 + lane] = make_float2(0.f, 0.f);
     const int total = S.total_bands, basebands = S.base_bands;
     const int start = S.base_bands + S.stereo_bands;
-    const int room = min(min(total - start, (int)S.hfr_groups * (int)S.bands_per_hfr), start);
+    // HFR band start + n copies low band start - 1 - min(n, lim): v3.0 stops moving down after half of the groups
+    // (hca.cpp:1652-1676); the copying ends at the top band, after the last group, or when the low band would pass 0
+    const int lim = (S.v3 ? (int)S.hfr_groups >> 1 : (int)S.hfr_groups) * (int)S.bands_per_hfr;
+    int room = min(total - start, (int)S.hfr_groups * (int)S.bands_per_hfr);
+    if (lim >= start) room = min(room, start);
     const bool joint = !NCH && S.joint;
+    const bool noise_on = !NCH && S.noise && a.sfres != nullptr;
     const uint64_t slot0 = (uint64_t)unit * a.steps;
 
     // block index -> (step, subframe, channel); a unit has 1 look-back block set (subframe 7 of the frame in front
@@ -192,6 +214,55 @@ hca_imdct_kernel(HcaDecodeArgs a) {
 #pragma unroll
                     for (int r = 0; r < 4; r++)
                         if (4 * lane + r >= coded) x[r] = 0.f;
+                    if (noise_on) {
+                        // ---- noise fill (hca.cpp:1602-1635): resolution-0 band number i of this channel takes a
+                        // random VALID band's value, rescaled by the difference of their scalefactors; draw i of
+                        // the channel is draw (subframes before) + (channels before) + i + 1 of the frame
+                        const uint32_t* dr = a.draws + slot * MC;
+                        const uint32_t mine = dr[c];
+                        if (mine) {
+                            uint32_t all = 0, before = 0;
+                            for (int cc = 0; cc < nch; cc++) {
+                                const uint32_t d = dr[cc];
+                                all += d;
+                                if (cc < c) before += d;
+                            }
+                            const uint32_t state0 = lcg_jump(a.frame_state[S.frame_base + frame], (uint32_t)sub * all + before);
+                            const uint32_t cls4 = reinterpret_cast<const uint32_t*>(a.sfres + (slot * MC + c) * 128)[lane];
+                            const uint32_t below = (1u << lane) - 1;
+                            int n_rank = 0, v_rank = 0, valid = 0;
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                const uint32_t nm = __ballot_sync(kFull, (cls4 >> (8 * r)) & 0x40);
+                                const uint32_t vm = __ballot_sync(kFull, (cls4 >> (8 * r)) & 0x80);
+                                n_rank += __popc(nm & below);
+                                v_rank += __popc(vm & below);
+                                valid += __popc(vm);
+                            }
+                            valid = max(valid, 1);           // (a channel that draws has valid bands; keeps bad data in bounds)
+                            __syncwarp();
+                            reinterpret_cast<float4*>(xs)[lane] = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                const uint32_t b = (cls4 >> (8 * r)) & 0xFF;
+                                sfb[4 * lane + r] = (uint8_t)(b & 0x3F);
+                                if (b & 0x80) vmap[v_rank++] = (uint8_t)(4 * lane + r);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                const uint32_t b = (cls4 >> (8 * r)) & 0xFF;
+                                if (b & 0x40) {
+                                    const uint32_t rnd = lcg_jump(state0, (uint32_t)(++n_rank));
+                                    const int pick = valid - 1 - (int)(((rnd & 0x7FFF) * (uint32_t)valid) >> 15);
+                                    const int vi = vmap[pick] & 127;
+                                    int k = (int)(b & 0x3F) - (int)sfb[vi] + 62;
+                                    k &= ~(k >> 31);
+                                    x[r] = __fmul_rn(__uint_as_float(c_noise_conv[k]), xs[vi]);
+                                }
+                            }
+                        }
+                    }
                     if (joint) {
                         // ---- HFR: mirrored low bands scaled into the high bands (hca.cpp:1638-1683)
                         if (S.bands_per_hfr && type != 2) {
@@ -202,7 +273,7 @@ hca_imdct_kernel(HcaDecodeArgs a) {
 #pragma unroll
                             for (int r = 0; r < 4; r++) {
                                 const int p = 4 * lane + r;
-                                if (p >= start && p < start + room) x[r] = __fmul_rn(gg[r], xs[2 * start - 1 - p]);
+                                if (p >= start && p < start + room) x[r] = __fmul_rn(gg[r], xs[start - 1 - min(p - start, lim)]);
                                 if (p == start + room - 1) x[r] = 0.f;
                             }
                         }
@@ -271,15 +342,36 @@ hca_imdct_kernel(HcaDecodeArgs a) {
     }
 }
 
+// Generator state at the start of every frame: one thread walks one stream's per-frame draw counts.
+__global__ void hca_noise_scan_kernel(HcaDecodeArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_streams) return;
+    const HcaStreamDev& S = a.streams[i];
+    if (!S.noise || a.status[i] != 0) return;
+    const uint64_t need = ((uint64_t)S.out_samples + S.delay + 1023) / 1024;          // as plan_hca_decode
+    const uint32_t frames = (uint32_t)(need < S.frame_count ? need : S.frame_count);
+    uint32_t state = 1;                                                                // HCA_DEFAULT_RANDOM, hca.cpp:62
+    for (uint32_t f = 0; f < frames; f++) {
+        a.frame_state[S.frame_base + f] = state;
+        state = lcg_jump(state, 8u * a.frame_draws[S.frame_base + f]);
+    }
+}
+
 template <int NCH>
 void launch_one(const HcaDecodeArgs& a, cudaStream_t s) {
-    const size_t per_warp = 2 * 768 + (size_t)a.max_channels * 256 + (NCH ? 0 : (size_t)a.max_channels * 256 + 512);
+    const size_t per_warp = 2 * 768 + (size_t)a.max_channels * 256 + (NCH ? 0 : (size_t)a.max_channels * 256 + 512 + 256);
     const size_t smem = per_warp * kWarps;
     cudaFuncSetAttribute(hca_imdct_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     hca_imdct_kernel<NCH><<<(a.n_units + kWarps - 1) / kWarps, kWarps * 32, smem, s>>>(a);
 }
 
 }  // namespace
+
+void launch_hca_noise_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches) {
+    if (!a.sfres || !a.n_streams) return;
+    hca_noise_scan_kernel<<<(a.n_streams + 127) / 128, 128, 0, s>>>(a);
+    ++*launches;
+}
 
 void launch_hca_imdct(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches) {
     if (!a.n_units) return;

@@ -37,11 +37,19 @@ struct HcaDecodeArgs {
     uint32_t run_len;
     uint32_t n_runs;            // 0 = not on the fast path
     uint32_t joint;             // fast path: some stream has an intensity-stereo pair or HFR bands
+    // v3.0 noise generator (null when no stream needs it): the unpack kernel leaves, per frame slot and channel, the
+    // band classes and the number of generator draws per subframe; a scan turns the per-frame totals into the
+    // generator state at the start of every frame (the state runs through the whole stream, hca.cpp:1602-1635)
+    uint8_t* sfres;             // [slot][channel][128] scalefactor | 0x40 noise band | 0x80 valid band
+    uint32_t* draws;            // [slot][channel] draws per subframe
+    uint32_t* frame_draws;      // [job frame] draws per subframe, all channels
+    uint32_t* frame_state;      // [job frame] generator state at the start of the frame
     uint32_t force_careful;     // tests: take the end-of-frame-checked reader variants everywhere (CRI_HCA_CAREFUL=1)
 };
 
 // `mid` (optional) is recorded between the unpack and the transform kernel.
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
+void launch_hca_noise_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // between the two, when a.sfres
 void launch_hca_imdct(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // second half of launch_hca_decode
 void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
 uint32_t hca_fast_threads_per_cta();

@@ -25,12 +25,15 @@ struct HcaStreamDev {
     uint32_t delay;         // decode: samples dropped at the start (encoder delay)
     uint32_t cipher;        // index into the cipher-table array (0 = identity)
     uint32_t ath;           // index into the ATH-curve array (0 = all zero)
+    uint32_t frame_base;    // decode: index of the stream's frame 0 in the job-wide per-frame arrays (noise generator)
     uint8_t channels, total_bands, base_bands, stereo_bands;
     uint8_t bands_per_hfr, hfr_groups, min_res, max_res;
     uint8_t type[kHcaMaxChannels];    // 0 discrete, 1 stereo primary, 2 stereo secondary
     uint8_t coded[kHcaMaxChannels];   // coded band count per channel
     uint8_t joint;          // 1 if any HFR / intensity reconstruction is needed
-    uint8_t pad[3];
+    uint8_t v3;             // version 3.0 bitstream: extra scalefactors for the HFR scales, delta-coded intensities
+    uint8_t noise;          // v3.0 with min_res == 0: resolution-0 bands are rebuilt by the noise generator
+    uint8_t pad;
 };
 
 struct HcaUnit {
@@ -61,6 +64,9 @@ struct HcaJob {
     std::vector<uint8_t> cipher_tables;    // 256 bytes each, [0] identity
     std::vector<uint8_t> ath_tables;       // 128 bytes each, [0] zero
     uint64_t q_bytes = 0, g_bytes = 0, i_bytes = 0, s_bytes = 0;
+    uint64_t n_bytes = 0;                  // noise generator side arrays (v3.0 streams with min_res == 0), see run_hca
+    uint64_t noise_frames = 0;             // frames of the job-wide per-frame arrays
+    uint8_t* d_n = nullptr;
     uint32_t scratch_words = 0;
     std::vector<uint64_t> frame_prefix;    // crypt: exclusive prefix of frame counts per stream
     uint64_t* d_frame_prefix = nullptr;
