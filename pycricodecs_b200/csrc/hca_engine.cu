@@ -438,6 +438,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_runs = J.n_runs;
         a.joint = J.any_joint ? 1u : 0u;
         a.force_careful = env_u32("CRI_HCA_CAREFUL", 0);
+        a.one2 = 0x3F8000003F800000ull;
         if (J.d_n) {
             const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
             a.sfres = J.d_n;

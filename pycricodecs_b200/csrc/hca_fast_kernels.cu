@@ -41,6 +41,27 @@ __constant__ uint8_t c_max_bits[16] = CRI_TBL_MAX_BITS;
 __constant__ uint32_t c_conv[128] = CRI_TBL_SCALE_CONV;          // HFR: scale_conversion_table (hca.cpp:1579-1598)
 __constant__ uint32_t c_intensity[16] = CRI_TBL_INTENSITY_RATIO;  // intensity stereo ratios (hca.cpp:1689-1693)
 
+// Two-wide fp32 helpers of the generated transform (sm_100a f32x2: one instruction, two separately rounded results).
+// hca_bfly2: (a, b) <- (a + b, a - b) on two register pairs. hca_sum2: d = p + q, written as fma(q, one, p) with `one`
+// = {1.0f, 1.0f} read from the kernel arguments: ptxas contracts a packed add of products into FFMA2 even under
+// -fmad=false, which would drop the rounding of the products; it cannot contract through a multiplier it does not know.
+__device__ __forceinline__ void hca_bfly2(float& a0, float& a1, float& b0, float& b1) {
+    unsigned long long a, b, s, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(a), "l"(b));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(s));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(d));
+}
+__device__ __forceinline__ void hca_sum2(unsigned long long one, float p0, float p1, float q0, float q1, float& d0, float& d1) {
+    unsigned long long p, q, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(p0), "f"(p1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(q0), "f"(q1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(q), "l"(one), "l"(p));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 #include "hca_dct_thread_gen.inc"
 
 constexpr int kFastThreads = 128;             // unpack kernel
@@ -533,7 +554,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
             const bool pj = JOINT && lb && S.type[ch] != 0;
             intensity(x, pj, pj ? __ldg(a.inten + g - 1) : 0u, 7, (int)S.base_bands, (int)S.total_bands);
         }
-        hca_dct4_dec(x, convoy);
+        hca_dct4_dec(x, a.one2, convoy);
         hca_carry_thread<THREADS>(x, carry);
     }
 
@@ -577,7 +598,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
 #pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
             intensity(x, pair_joint, inten, sub, jbase, jtotal);
-            hca_dct4_dec(x, convoy);
+            hca_dct4_dec(x, a.one2, convoy);
             if (ch == 0) {
                 const long long n0 = (long long)f * 1024 + sub * 128 - delay;     // stream sample index of the row's sample 0
                 RowDesc d;
@@ -592,7 +613,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
             // lanes without a next block (end of the run / of the job, idle lanes) read block 0 instead: their rows are
             // never stored, so the values do not matter, and the loads need no predicate and no zero fill
             const float4* nsrc = ok_next ? src : a.spec + lane;
-            hca_window_thread<THREADS>(x, carry,
+            hca_window_thread<THREADS>(x, carry, a.one2,
                 [&](int i, float v) { *reinterpret_cast<short*>(trow + i * (2 * NCH)) = pcm16_sat(v); },
                 [&](int c) {
                     const float4 v = __ldcs(nsrc + c * 32);

@@ -44,6 +44,7 @@ struct HcaDecodeArgs {
     uint32_t* draws;            // [slot][channel] draws per subframe
     uint32_t* frame_draws;      // [job frame] draws per subframe, all channels
     uint32_t* frame_state;      // [job frame] generator state at the start of the frame
+    uint64_t one2;              // {1.0f, 1.0f}: the multiplier of the transform kernel's two-wide sums (hca_sum2)
     uint32_t force_careful;     // tests: take the end-of-frame-checked reader variants everywhere (CRI_HCA_CAREFUL=1)
 };
 

@@ -21,6 +21,14 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+// the two-wide helpers of hca_fast_kernels.cu, as the scalar operations they stand for
+static inline void hca_bfly2(float& a0, float& a1, float& b0, float& b1) {
+    float s0 = __fadd_rn(a0, b0), s1 = __fadd_rn(a1, b1), d0 = __fsub_rn(a0, b0), d1 = __fsub_rn(a1, b1);
+    a0 = s0; a1 = s1; b0 = d0; b1 = d1;
+}
+static inline void hca_sum2(unsigned long long, float p0, float p1, float q0, float q1, float& d0, float& d1) {
+    d0 = __fadd_rn(p0, q0); d1 = __fadd_rn(p1, q1);
+}
 #include "hca_dct_thread_gen.inc"
 extern "C" void run(const float* spectra, int n, int16_t* pcm) {
     float4 carry[16];
@@ -28,8 +36,8 @@ extern "C" void run(const float* spectra, int n, int16_t* pcm) {
     for (int s = 0; s < n; s++) {
         float x[128];
         for (int i = 0; i < 128; i++) x[i] = spectra[s * 128 + i];
-        hca_dct4_dec(x, [](int) {});
-        hca_window_thread<1>(x, carry, [&](int i, float v) {
+        hca_dct4_dec(x, 0ull, [](int) {});
+        hca_window_thread<1>(x, carry, 0ull, [&](int i, float v) {
             float t = truncf(v);                       // cvt.rzi.s16.f32: truncate, saturate
             if (t > 32767.f) t = 32767.f;
             if (t < -32768.f) t = -32768.f;

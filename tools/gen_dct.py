@@ -32,9 +32,18 @@ def f(bits: int) -> str:
     return f"__uint_as_float(0x{int(bits):08X}u)"
 
 
-def gen_imdct(lockstep: int = 0) -> list[str]:
+def neg(bits: int) -> int:
+    return int(bits) ^ 0x80000000
+
+
+def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
     """lockstep > 0: the DCT takes a functor and calls it after every `lockstep` fp32 instructions (the transform
-    kernel uses it for a named barrier that keeps the warps of one scheduler on the same instruction-cache lines)."""
+    kernel uses it for a named barrier that keeps the warps of one scheduler on the same instruction-cache lines).
+
+    packed: butterflies whose two registers differ in a bit above bit 0 come in pairs (a, b), (a + 1, b + 1); their
+    sums and differences are emitted as two-wide operations on the register pairs (hca_bfly2 / hca_sum2, f32x2 on
+    sm_100a: half the instructions for the same, separately rounded, results). Products stay scalar multiplies by
+    immediates; a difference t0 - t1 becomes t0 + (x * -c), which is the same number."""
     sin, cos = T.imdct_trig()
     sin = sin.reshape(7, 64)
     cos = cos.reshape(7, 64)
@@ -45,10 +54,15 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
     out.append("// Input x[i] = spectra[i]; afterwards dct[i] lives in x[kImdctPerm[i]] (see hca_imdct_window).")
     if lockstep:
         out.append("template <class Sync>")
-        out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128], Sync sync) {")
+        if packed:
+            out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128], const unsigned long long one, Sync sync) {")
+        else:
+            out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128], Sync sync) {")
     else:
         out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
     out.append("    float t0, t1, t2, t3;")
+    if packed:
+        out.append("    float u0, u1, u2, u3;")
     since = 0
     nsync = [0]
     def sync_line():
@@ -59,17 +73,26 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
     while half >= 1:
         blocks = 64 // half
         nxt = [None] * 128
+        pairs = set()
+        for j in range(blocks):
+            for k in range(half):
+                pairs.add((phys[j * 2 * half + 2 * k], phys[j * 2 * half + 2 * k + 1]))
         for j in range(blocks):
             for k in range(half):
                 a = phys[j * 2 * half + 2 * k]
                 b = phys[j * 2 * half + 2 * k + 1]
-                out.append(f"    t0 = __fadd_rn(x[{a}], x[{b}]); x[{b}] = __fsub_rn(x[{a}], x[{b}]); x[{a}] = t0;")
+                nxt[j * 2 * half + k] = a
+                nxt[j * 2 * half + half + k] = b
+                if packed and a % 2 == 0 and b % 2 == 0 and (a + 1, b + 1) in pairs:
+                    out.append(f"    hca_bfly2(x[{a}], x[{a + 1}], x[{b}], x[{b + 1}]);")
+                elif packed and a % 2 == 1 and b % 2 == 1 and (a - 1, b - 1) in pairs:
+                    continue                                   # done with its even partner
+                else:
+                    out.append(f"    t0 = __fadd_rn(x[{a}], x[{b}]); x[{b}] = __fsub_rn(x[{a}], x[{b}]); x[{a}] = t0;")
                 since += 2
                 if lockstep and since >= lockstep:
                     out.append(sync_line())
                     since = 0
-                nxt[j * 2 * half + k] = a
-                nxt[j * 2 * half + half + k] = b
         phys = nxt
         half //= 2
     # rotation passes, half = 1 .. 64  (hca.cpp:1937-1972)
@@ -77,21 +100,36 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
         half = 1 << stage
         blocks = 64 >> stage
         nxt = [None] * 128
+        rot = {}
+        for j in range(blocks):
+            for k in range(half):
+                rot[(phys[j * 2 * half + k], phys[j * 2 * half + half + k])] = (sin[stage, j * half + k], cos[stage, j * half + k])
         for j in range(blocks):
             for k in range(half):
                 a = phys[j * 2 * half + k]
                 b = phys[j * 2 * half + half + k]
-                s = f(sin[stage, j * half + k])
-                c = f(cos[stage, j * half + k])
-                out.append(f"    t0 = __fmul_rn(x[{a}], {s}); t1 = __fmul_rn(x[{b}], {c}); "
-                           f"t2 = __fmul_rn(x[{a}], {c}); t3 = __fmul_rn(x[{b}], {s}); "
-                           f"x[{a}] = __fsub_rn(t0, t1); x[{b}] = __fadd_rn(t2, t3);")
-                since += 6
+                nxt[j * 2 * half + k] = a
+                nxt[j * 2 * half + 2 * half - 1 - k] = b
+                sb, cb = rot[(a, b)]
+                if packed and a % 2 == 0 and b % 2 == 0 and (a + 1, b + 1) in rot:
+                    sb2, cb2 = rot[(a + 1, b + 1)]
+                    out.append(f"    t0 = __fmul_rn(x[{a}], {f(sb)}); t1 = __fmul_rn(x[{b}], {f(neg(cb))}); "
+                               f"t2 = __fmul_rn(x[{a}], {f(cb)}); t3 = __fmul_rn(x[{b}], {f(sb)});")
+                    out.append(f"    u0 = __fmul_rn(x[{a + 1}], {f(sb2)}); u1 = __fmul_rn(x[{b + 1}], {f(neg(cb2))}); "
+                               f"u2 = __fmul_rn(x[{a + 1}], {f(cb2)}); u3 = __fmul_rn(x[{b + 1}], {f(sb2)});")
+                    out.append(f"    hca_sum2(one, t0, u0, t1, u1, x[{a}], x[{a + 1}]); hca_sum2(one, t2, u2, t3, u3, x[{b}], x[{b + 1}]);")
+                    since += 10
+                elif packed and a % 2 == 1 and b % 2 == 1 and (a - 1, b - 1) in rot:
+                    continue
+                else:
+                    s_, c_ = f(sb), f(cb)
+                    out.append(f"    t0 = __fmul_rn(x[{a}], {s_}); t1 = __fmul_rn(x[{b}], {c_}); "
+                               f"t2 = __fmul_rn(x[{a}], {c_}); t3 = __fmul_rn(x[{b}], {s_}); "
+                               f"x[{a}] = __fsub_rn(t0, t1); x[{b}] = __fadd_rn(t2, t3);")
+                    since += 6
                 if lockstep and since >= lockstep:
                     out.append(sync_line())
                     since = 0
-                nxt[j * 2 * half + k] = a
-                nxt[j * 2 * half + 2 * half - 1 - k] = b
         phys = nxt
     out.append("}")
     out.append("")
@@ -118,7 +156,7 @@ def gen_imdct(lockstep: int = 0) -> list[str]:
 
 
 
-def gen_thread_window(lockstep: int = 0) -> list[str]:
+def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
     """Window + overlap-add + carry for the thread-resident transform (hca_imdct_fast_kernel), straight to PCM.
 
     The reference (hca.cpp:1983-1992) computes  wave[i] = w[i]*dct[64+i] + prev[i],  wave[64+i] = w[64+i]*dct[127-i]
@@ -172,7 +210,11 @@ def gen_thread_window(lockstep: int = 0) -> list[str]:
     out.append("// ...: after each pair exactly four aligned register quads x[4c..4c+3] are dead, and refill(c) is called for")
     out.append("// each so that the caller can already load chunk c of the NEXT subframe's spectra into them (the registers")
     out.append("// are full during the transform, so this is the only place a prefetch can live).")
-    if lockstep:
+    if lockstep and packed:
+        out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
+        out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, const unsigned long long one, Emit emit, Refill refill, Sync sync) {")
+        out.append("    float p0, p1, q0, q1, v0, v1;")
+    elif lockstep:
         out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
         out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill, Sync sync) {")
     else:
@@ -191,8 +233,14 @@ def gen_thread_window(lockstep: int = 0) -> list[str]:
             i = 63 - k
             d = f"x[{phys[64 + i]}]"
             wa, wb = scaled(win[i]), scaled(win[127 - i])
-            out.append(f"    emit({i}, __fadd_rn(__fmul_rn({wa}, {d}), __fmul_rn({wb}, c.{comp})));")
-            out.append(f"    emit({127 - i}, __fsub_rn(__fmul_rn({wb}, {d}), __fmul_rn({wa}, c.{comp})));")
+            if packed:
+                # (wave[i], wave[127-i]) = (wa*d, wb*d) + (wb*c, -wa*c): two products each, one two-wide sum
+                wan = scaled(neg(win[i]))
+                out.append(f"    p0 = __fmul_rn({wa}, {d}); p1 = __fmul_rn({wb}, {d}); q0 = __fmul_rn({wb}, c.{comp}); q1 = __fmul_rn({wan}, c.{comp});")
+                out.append(f"    hca_sum2(one, p0, p1, q0, q1, v0, v1); emit({i}, v0); emit({127 - i}, v1);")
+            else:
+                out.append(f"    emit({i}, __fadd_rn(__fmul_rn({wa}, {d}), __fmul_rn({wb}, c.{comp})));")
+                out.append(f"    emit({127 - i}, __fsub_rn(__fmul_rn({wb}, {d}), __fmul_rn({wa}, c.{comp})));")
         out.append(f"    carry[{q} * CARRY_STRIDE] = make_float4(x[{phys[4 * q]}], x[{phys[4 * q + 1]}], x[{phys[4 * q + 2]}], x[{phys[4 * q + 3]}]);")
         done.add(q)
         for ch in range(32):
@@ -374,9 +422,9 @@ def main():
     print("wrote", path, len(lines), "lines")
     # thread-resident decoder transform (hca_imdct_fast_kernel): only the DCT-IV of gen_imdct + the PCM window
     LOCKSTEP = 128                          # the transform calls sync(k) every so many fp32 instructions (instruction-cache convoy)
-    dct = gen_imdct(LOCKSTEP)
+    dct = gen_imdct(LOCKSTEP, packed=True)
     end = dct.index("}")                    # first function = hca_dct4_dec
-    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window(LOCKSTEP)
+    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window(LOCKSTEP, packed=True)
     path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_thread_gen.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
