@@ -62,7 +62,8 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
         out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
     out.append("    float t0, t1, t2, t3;")
     if packed:
-        out.append("    float u0, u1, u2, u3;")
+        out.append("    float u0, u1, u2, u3, r0, r1, r2, r3, w0, w1, w2, w3;")
+    pending, flip = [None], [True]
     since = 0
     nsync = [0]
     def sync_line():
@@ -113,11 +114,18 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
                 sb, cb = rot[(a, b)]
                 if packed and a % 2 == 0 and b % 2 == 0 and (a + 1, b + 1) in rot:
                     sb2, cb2 = rot[(a + 1, b + 1)]
-                    out.append(f"    t0 = __fmul_rn(x[{a}], {f(sb)}); t1 = __fmul_rn(x[{b}], {f(neg(cb))}); "
-                               f"t2 = __fmul_rn(x[{a}], {f(cb)}); t3 = __fmul_rn(x[{b}], {f(sb)});")
-                    out.append(f"    u0 = __fmul_rn(x[{a + 1}], {f(sb2)}); u1 = __fmul_rn(x[{b + 1}], {f(neg(cb2))}); "
-                               f"u2 = __fmul_rn(x[{a + 1}], {f(cb2)}); u3 = __fmul_rn(x[{b + 1}], {f(sb2)});")
-                    out.append(f"    hca_sum2(one, t0, u0, t1, u1, x[{a}], x[{a + 1}]); hca_sum2(one, t2, u2, t3, u3, x[{b}], x[{b + 1}]);")
+                    # software pipelining in the source: the sums of a group are emitted after the NEXT group's
+                    # products (alternating temporaries), so no sum directly follows the products it waits for
+                    t, u = ("t", "u") if flip[0] else ("r", "w")
+                    flip[0] = not flip[0]
+                    out.append(f"    {t}0 = __fmul_rn(x[{a}], {f(sb)}); {t}1 = __fmul_rn(x[{b}], {f(neg(cb))}); "
+                               f"{t}2 = __fmul_rn(x[{a}], {f(cb)}); {t}3 = __fmul_rn(x[{b}], {f(sb)});")
+                    out.append(f"    {u}0 = __fmul_rn(x[{a + 1}], {f(sb2)}); {u}1 = __fmul_rn(x[{b + 1}], {f(neg(cb2))}); "
+                               f"{u}2 = __fmul_rn(x[{a + 1}], {f(cb2)}); {u}3 = __fmul_rn(x[{b + 1}], {f(sb2)});")
+                    if pending[0]:
+                        out.append(pending[0])
+                    pending[0] = (f"    hca_sum2(one, {t}0, {u}0, {t}1, {u}1, x[{a}], x[{a + 1}]); "
+                                  f"hca_sum2(one, {t}2, {u}2, {t}3, {u}3, x[{b}], x[{b + 1}]);")
                     since += 10
                 elif packed and a % 2 == 1 and b % 2 == 1 and (a - 1, b - 1) in rot:
                     continue
@@ -130,6 +138,9 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
                 if lockstep and since >= lockstep:
                     out.append(sync_line())
                     since = 0
+        if pending[0]:
+            out.append(pending[0])
+            pending[0] = None
         phys = nxt
     out.append("}")
     out.append("")
