@@ -62,8 +62,8 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
         out.append("__device__ __forceinline__ void hca_dct4_dec(float (&x)[128]) {")
     out.append("    float t0, t1, t2, t3;")
     if packed:
-        out.append("    float u0, u1, u2, u3, r0, r1, r2, r3, w0, w1, w2, w3;")
-    pending, flip = [None], [True]
+        out.append("    float u0, u1, u2, u3, r0, r1, r2, r3, w0, w1, w2, w3, y0, y1, y2, y3, z0, z1, z2, z3;")
+    pending, flip, DEPTH = [], [0], 2
     since = 0
     nsync = [0]
     def sync_line():
@@ -116,16 +116,16 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
                     sb2, cb2 = rot[(a + 1, b + 1)]
                     # software pipelining in the source: the sums of a group are emitted after the NEXT group's
                     # products (alternating temporaries), so no sum directly follows the products it waits for
-                    t, u = ("t", "u") if flip[0] else ("r", "w")
-                    flip[0] = not flip[0]
+                    t, u = (("t", "u"), ("r", "w"), ("y", "z"))[flip[0] % 3]
+                    flip[0] += 1
                     out.append(f"    {t}0 = __fmul_rn(x[{a}], {f(sb)}); {t}1 = __fmul_rn(x[{b}], {f(neg(cb))}); "
                                f"{t}2 = __fmul_rn(x[{a}], {f(cb)}); {t}3 = __fmul_rn(x[{b}], {f(sb)});")
                     out.append(f"    {u}0 = __fmul_rn(x[{a + 1}], {f(sb2)}); {u}1 = __fmul_rn(x[{b + 1}], {f(neg(cb2))}); "
                                f"{u}2 = __fmul_rn(x[{a + 1}], {f(cb2)}); {u}3 = __fmul_rn(x[{b + 1}], {f(sb2)});")
-                    if pending[0]:
-                        out.append(pending[0])
-                    pending[0] = (f"    hca_sum2(one, {t}0, {u}0, {t}1, {u}1, x[{a}], x[{a + 1}]); "
-                                  f"hca_sum2(one, {t}2, {u}2, {t}3, {u}3, x[{b}], x[{b + 1}]);")
+                    if len(pending) >= DEPTH:
+                        out.append(pending.pop(0))
+                    pending.append(f"    hca_sum2(one, {t}0, {u}0, {t}1, {u}1, x[{a}], x[{a + 1}]); "
+                                   f"hca_sum2(one, {t}2, {u}2, {t}3, {u}3, x[{b}], x[{b + 1}]);")
                     since += 10
                 elif packed and a % 2 == 1 and b % 2 == 1 and (a - 1, b - 1) in rot:
                     continue
@@ -138,9 +138,8 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
                 if lockstep and since >= lockstep:
                     out.append(sync_line())
                     since = 0
-        if pending[0]:
-            out.append(pending[0])
-            pending[0] = None
+        out += pending
+        del pending[:]
         phys = nxt
     out.append("}")
     out.append("")
@@ -224,7 +223,7 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
     if lockstep and packed:
         out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
         out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, const unsigned long long one, Emit emit, Refill refill, Sync sync) {")
-        out.append("    float p0, p1, q0, q1, v0, v1;")
+        out.append("    float p0, p1, q0, q1, v0, v1, v2, v3;")
     elif lockstep:
         out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
         out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill, Sync sync) {")
@@ -232,6 +231,7 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
         out.append("template <int CARRY_STRIDE, class Emit, class Refill>")
         out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill) {")
     out.append("    float4 c;")
+    wpend, wflip = [], [True]
     done = set()
     order = []
     for p_ in range(8):
@@ -248,10 +248,16 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
                 # (wave[i], wave[127-i]) = (wa*d, wb*d) + (wb*c, -wa*c): two products each, one two-wide sum
                 wan = scaled(neg(win[i]))
                 out.append(f"    p0 = __fmul_rn({wa}, {d}); p1 = __fmul_rn({wb}, {d}); q0 = __fmul_rn({wb}, c.{comp}); q1 = __fmul_rn({wan}, c.{comp});")
-                out.append(f"    hca_sum2(one, p0, p1, q0, q1, v0, v1); emit({i}, v0); emit({127 - i}, v1);")
+                out.append(f"    hca_sum2(one, p0, p1, q0, q1, {'v0, v1' if wflip[0] else 'v2, v3'});")
+                if wpend:
+                    out.append(wpend.pop(0))
+                wpend.append(f"    emit({i}, {'v0' if wflip[0] else 'v2'}); emit({127 - i}, {'v1' if wflip[0] else 'v3'});")
+                wflip[0] = not wflip[0]
             else:
                 out.append(f"    emit({i}, __fadd_rn(__fmul_rn({wa}, {d}), __fmul_rn({wb}, c.{comp})));")
                 out.append(f"    emit({127 - i}, __fsub_rn(__fmul_rn({wb}, {d}), __fmul_rn({wa}, c.{comp})));")
+        out += wpend
+        del wpend[:]
         out.append(f"    carry[{q} * CARRY_STRIDE] = make_float4(x[{phys[4 * q]}], x[{phys[4 * q + 1]}], x[{phys[4 * q + 2]}], x[{phys[4 * q + 3]}]);")
         done.add(q)
         for ch in range(32):
