@@ -614,7 +614,8 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
             // never stored, so the values do not matter, and the loads need no predicate and no zero fill
             const float4* nsrc = ok_next ? src : a.spec + lane;
             hca_window_thread<THREADS>(x, carry, a.one2,
-                [&](int i, float v) { *reinterpret_cast<short*>(trow + i * (2 * NCH)) = pcm16_sat(v); },
+                [](float v) { return pcm16_sat(v); },
+                [&](int i, short v) { *reinterpret_cast<short*>(trow + i * (2 * NCH)) = v; },
                 [&](int c) {
                     const float4 v = __ldcs(nsrc + c * 32);
                     x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;

@@ -37,12 +37,12 @@ extern "C" void run(const float* spectra, int n, int16_t* pcm) {
         float x[128];
         for (int i = 0; i < 128; i++) x[i] = spectra[s * 128 + i];
         hca_dct4_dec(x, 0ull, [](int) {});
-        hca_window_thread<1>(x, carry, 0ull, [&](int i, float v) {
+        hca_window_thread<1>(x, carry, 0ull, [](float v) {
             float t = truncf(v);                       // cvt.rzi.s16.f32: truncate, saturate
             if (t > 32767.f) t = 32767.f;
             if (t < -32768.f) t = -32768.f;
-            pcm[s * 128 + i] = (int16_t)t;
-        }, [&](int c) { x[4 * c] = x[4 * c + 1] = x[4 * c + 2] = x[4 * c + 3] = 1e30f; },   // refilled registers must be dead
+            return (int16_t)t;
+        }, [&](int i, int16_t v) { pcm[s * 128 + i] = v; }, [&](int c) { x[4 * c] = x[4 * c + 1] = x[4 * c + 2] = x[4 * c + 3] = 1e30f; },   // refilled registers must be dead
             [](int) {});
     }
 }

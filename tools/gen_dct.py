@@ -166,6 +166,9 @@ def gen_imdct(lockstep: int = 0, packed: bool = False) -> list[str]:
 
 
 
+WSLOTS, CVT_LAG, STORE_LAG = 6, 2, 2
+
+
 def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
     """Window + overlap-add + carry for the thread-resident transform (hca_imdct_fast_kernel), straight to PCM.
 
@@ -221,9 +224,12 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
     out.append("// each so that the caller can already load chunk c of the NEXT subframe's spectra into them (the registers")
     out.append("// are full during the transform, so this is the only place a prefetch can live).")
     if lockstep and packed:
-        out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
-        out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, const unsigned long long one, Emit emit, Refill refill, Sync sync) {")
-        out.append("    float p0, p1, q0, q1, v0, v1, v2, v3;")
+        out.append("// Packed form: cvt(v) turns a PCM-scaled float into the value emit(i, s) stores.")
+        out.append("template <int CARRY_STRIDE, class Cvt, class Emit, class Refill, class Sync>")
+        out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, const unsigned long long one, Cvt cvt, Emit emit, Refill refill, Sync sync) {")
+        out.append("    float p0, p1, q0, q1;")
+        out.append("    float " + ", ".join(f"va{k}, vb{k}" for k in range(WSLOTS)) + ";")
+        out.append("    decltype(cvt(0.f)) " + ", ".join(f"sa{k}, sb{k}" for k in range(WSLOTS)) + ";")
     elif lockstep:
         out.append("template <int CARRY_STRIDE, class Emit, class Refill, class Sync>")
         out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill, Sync sync) {")
@@ -231,7 +237,7 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
         out.append("template <int CARRY_STRIDE, class Emit, class Refill>")
         out.append("__device__ __forceinline__ void hca_window_thread(float (&x)[128], float4* carry, Emit emit, Refill refill) {")
     out.append("    float4 c;")
-    wpend, wflip = [], [True]
+    wpend, wcount = [], [0]
     done = set()
     order = []
     for p_ in range(8):
@@ -248,16 +254,21 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
                 # (wave[i], wave[127-i]) = (wa*d, wb*d) + (wb*c, -wa*c): two products each, one two-wide sum
                 wan = scaled(neg(win[i]))
                 out.append(f"    p0 = __fmul_rn({wa}, {d}); p1 = __fmul_rn({wb}, {d}); q0 = __fmul_rn({wb}, c.{comp}); q1 = __fmul_rn({wan}, c.{comp});")
-                out.append(f"    hca_sum2(one, p0, p1, q0, q1, {'v0, v1' if wflip[0] else 'v2, v3'});")
-                if wpend:
-                    out.append(wpend.pop(0))
-                wpend.append(f"    emit({i}, {'v0' if wflip[0] else 'v2'}); emit({127 - i}, {'v1' if wflip[0] else 'v3'});")
-                wflip[0] = not wflip[0]
+                # the conversion to int16 (F2I, a long-latency unit) runs CVT_LAG elements behind the sums and the
+                # shared-memory stores STORE_LAG elements behind the conversions, on rotating temporaries
+                slot = wcount[0] % WSLOTS
+                wcount[0] += 1
+                out.append(f"    hca_sum2(one, p0, p1, q0, q1, va{slot}, vb{slot});")
+                wpend.append((i, slot))
+                if len(wpend) > CVT_LAG:
+                    j, sl = wpend[-1 - CVT_LAG]
+                    out.append(f"    sa{sl} = cvt(va{sl}); sb{sl} = cvt(vb{sl});")
+                if len(wpend) > CVT_LAG + STORE_LAG:
+                    j, sl = wpend[-1 - CVT_LAG - STORE_LAG]
+                    out.append(f"    emit({j}, sa{sl}); emit({127 - j}, sb{sl});")
             else:
                 out.append(f"    emit({i}, __fadd_rn(__fmul_rn({wa}, {d}), __fmul_rn({wb}, c.{comp})));")
                 out.append(f"    emit({127 - i}, __fsub_rn(__fmul_rn({wb}, {d}), __fmul_rn({wa}, c.{comp})));")
-        out += wpend
-        del wpend[:]
         out.append(f"    carry[{q} * CARRY_STRIDE] = make_float4(x[{phys[4 * q]}], x[{phys[4 * q + 1]}], x[{phys[4 * q + 2]}], x[{phys[4 * q + 3]}]);")
         done.add(q)
         for ch in range(32):
@@ -267,6 +278,14 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
         if lockstep and q in order[1::2]:
             out.append(f"    sync({100 + order.index(q) // 2});")
     assert len(refilled) == 32
+    if packed:                                   # drain the conversion / store pipeline
+        n = len(wpend)
+        for k in range(n - CVT_LAG, n):
+            j, sl = wpend[k]
+            out.append(f"    sa{sl} = cvt(va{sl}); sb{sl} = cvt(vb{sl});")
+        for k in range(n - CVT_LAG - STORE_LAG, n):
+            j, sl = wpend[k]
+            out.append(f"    emit({j}, sa{sl}); emit({127 - j}, sb{sl});")
     out.append("}")
     out.append("")
     out.append("// Carry only (the look-back subframe in front of a run of frames).")
