@@ -333,6 +333,22 @@ def run_ours(a):
         dom_name, dom_bytes = DOMINANT[a.workload]
         if dom_bytes is None:
             dom_bytes = path_bytes            # single-kernel workloads: the kernel IS the path
+        kernels = None
+        if dom_name == "hca_imdct_fast_kernel" and dom > 0:
+            # the decode step is two kernels: the unpack kernel (frame bytes in, 2 x 8 x 128 fp32 spectra out) takes the
+            # rest of the step's device time (plus one ~10 us header-patch launch). Both are reported; the top-level
+            # roofline is the one with the larger share of the step.
+            xf = {"kernel": dom_name, "kernel_ms": dom, "algorithmic_bytes_per_unit": dom_bytes}
+            un = {"kernel": "hca_unpack_fast_kernel", "kernel_ms": ms - dom, "algorithmic_bytes_per_unit": in_bytes / per_rank_units + 8192}
+            kernels = []
+            for k in (un, xf):
+                k["share_of_step"] = k["kernel_ms"] / ms
+                k["achieved"] = per_rank_units * k["algorithmic_bytes_per_unit"] / (k["kernel_ms"] * 1e-3) / 1e9
+                k["frac"] = k["achieved"] / peak
+                k["traffic"] = traffic_of(k["kernel"], a.streams)
+                kernels.append(k)
+            if un["kernel_ms"] > dom:
+                dom_name, dom_bytes, dom = un["kernel"], un["algorithmic_bytes_per_unit"], un["kernel_ms"]
         achieved = per_rank_units * dom_bytes / (dom * 1e-3) / 1e9 if dom > 0 else None
         line = {
             "metric": METRIC, "value": total_units / (ms * 1e-3), "unit": unit,
@@ -349,6 +365,7 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": traffic_of(dom_name, a.streams),
                          "kernel": dom_name, "kernel_ms": dom, "algorithmic_bytes_per_unit": dom_bytes, "peak_source": peak_src,
+                         **({"kernels": kernels} if kernels else {}),
                          "whole_path": {"algorithmic_bytes_per_unit": path_bytes,
                                         "achieved_gbs": per_rank_units * path_bytes / (ms * 1e-3) / 1e9,
                                         "frac": per_rank_units * path_bytes / (ms * 1e-3) / 1e9 / peak}},
@@ -358,7 +375,8 @@ def run_ours(a):
             "clocks": clocks,
             "parity_spot_check": bool(parity),
         }
-        if dom_name == "hca_imdct_fast_kernel" and dom > 0:
+        if kernels:
+            dom_xf = kernels[1]["kernel_ms"]
             # the transform is bounded by fp32 issue before HBM -- 16 transforms x 3968 separately rounded
             # fp32 operations per stereo frame (no FMA: the reference rounds every product and sum) against one fp32
             # instruction per lane and clock
@@ -367,9 +385,10 @@ def run_ours(a):
                 sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
             except Exception:
                 pass
-            ops = per_rank_units * 16 * 3968 / (dom * 1e-3)
+            ops = per_rank_units * 16 * 3968 / (dom_xf * 1e-3)
             peak_ops = sm * 128 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
             line["roofline"]["fp32_issue"] = {"achieved_tops": ops / 1e12, "peak_tops": peak_ops / 1e12, "frac": ops / peak_ops,
+                                              "kernel": "hca_imdct_fast_kernel",
                                               "note": "separately rounded fp32 mul/add per second vs SMs x 128 lanes x SM clock"}
         if companion is not None:
             line["adx_encode"] = companion
