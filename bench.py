@@ -395,7 +395,7 @@ def run_ours(a):
         if not a.no_cpu:
             sample = [bytes(blob_np[int(offsets[i]):int(offsets[i + 1])]) for i in range(min(64, a.streams))]
             line["cpu_baseline"] = cpu_baseline(a.workload, sample, keyed, a.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -498,7 +498,7 @@ def run_reference(a):
     hca = is_hca(a.workload)
     unit = "HCA frames/s (1024 samples x 2 ch)" if hca else "ADX blocks/s (32 samples x 1 ch)"
     v = units_step / dt
-    print(json.dumps({
+    emit_line({
         "impl": "reference", "metric": METRIC, "value": v, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 scalar SSE2 (no FMA)" if hca else "int32", "data": "synthetic",
@@ -508,10 +508,30 @@ def run_reference(a):
         "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": cpu_kind(),
                          "sample": f"{per_step} streams of 2 s per step over a {cores}-process pool"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: native libraries write banners to file descriptor 1 (NCCL prints its version
+    there at the first collective), so the descriptor is pointed at stderr for the run and the line goes to a saved copy."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
