@@ -493,10 +493,14 @@ __device__ __forceinline__ short pcm16_sat(float v) {
 }
 
 // One CTA of THREADS = 256 per SM (2 warps per scheduler; the 252 registers per thread leave room for no more).
-// Measured on B200 (8192 stereo streams): 128 / 256 / 384 threads per SM all issue ~0.6 instructions per cycle and
-// scheduler while active, with "no instruction" the top stall: the body is ~70 KB of straight-line code that every
-// warp streams once per subframe, so instruction supply, not warp count, sets the pace. Barriers that keep the warps
-// of an SM (or of one scheduler) on the same cache lines did not change that.
+// Measured on B200 (8192 stereo streams): with every sum a scalar instruction, 128 / 256 / 384 threads per SM all
+// issued ~0.6 instructions per cycle and scheduler with "no instruction" the top stall -- the body is ~70 KB of
+// straight-line code that every warp streams once per subframe, and instruction supply set the pace whatever the
+// warp count. Issuing the paired sums two-wide (FADD2 / FFMA2, see hca_bfly2 / hca_sum2) cut the instruction count
+// by a fifth and removed that stall; what remains is the fp32 pipe itself (two-wide forms take two pipe cycles:
+// tools/ubench/fp32_rates.cu) and fixed-latency waits that two warps per scheduler cannot hide. The CTA-wide convoy
+// barrier (warps fetch the same instruction-cache lines together) is worth ~5 %; barriers among the warps of one
+// scheduler added nothing.
 template <int NCH, int THREADS, int CONVOY, bool JOINT>
 __global__ void __launch_bounds__(THREADS, 1)
 hca_imdct_fast_kernel(HcaDecodeArgs a) {
