@@ -144,20 +144,31 @@ struct BitWindow {
         w0 <<= n;
         have -= n;
     }
+    // Branch-free: in nearly every call some lane of the warp needs its refill, so the warp would walk the refill
+    // path anyway; predicated, it needs no reconvergence barrier and its loads and shifts interleave with the
+    // value lookups of the codes around it.
     __device__ __forceinline__ void top_up() {
         asm volatile("cp.async.wait_group 2;" ::: "memory");
-        if (have <= 64) {
-            uint2 v;
-            const uint32_t slot = (uint32_t)rd >> 1;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(ring + slot * kRingSlotStride + ((uint32_t)rd & 1) * 8));
-            const uint64_t n64 = ((uint64_t)v.x << 32) | v.y;
-            const uint64_t hi = (((uint64_t)w3 << 32) | w2) | ((n64 >> 1) >> (have - 1));
-            const uint64_t lo = n64 << (64 - have);
-            w3 = (uint32_t)(hi >> 32); w2 = (uint32_t)hi; w1 = (uint32_t)(lo >> 32); w0 = (uint32_t)lo;
-            have += 64; loaded += 64;
-            if (rd & 1) request(slot);          // both halves of the slot are consumed: refill it
-            rd = (rd + 1) & 3;
-        }
+        const bool need = have <= 64;
+        const uint32_t slot = (uint32_t)rd >> 1;
+        uint32_t vx = 0, vy = 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
+                     : "+r"(vx), "+r"(vy) : "r"(ring + slot * kRingSlotStride + ((uint32_t)rd & 1) * 8), "r"((uint32_t)need));
+        const int h = need ? have : 64;                               // keeps the shift counts in range when nothing is loaded
+        const uint64_t n64 = ((uint64_t)vx << 32) | vy;
+        const uint64_t hi = (((uint64_t)w3 << 32) | w2) | ((n64 >> 1) >> (h - 1));
+        const uint64_t lo = n64 << (64 - h);
+        w3 = need ? (uint32_t)(hi >> 32) : w3;
+        w2 = need ? (uint32_t)hi : w2;
+        w1 = need ? (uint32_t)(lo >> 32) : w1;
+        w0 = need ? (uint32_t)lo : w0;
+        have += need ? 64 : 0;
+        loaded += need ? 64 : 0;
+        const bool refill = need && (rd & 1);                         // both halves of the slot are consumed: refill it
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                     ::"r"(ring + slot * kRingSlotStride), "l"(next16), "r"((uint32_t)refill) : "memory");
+        next16 += refill ? 1 : 0;
+        rd = need ? (rd + 1) & 3 : rd;
         asm volatile("cp.async.commit_group;");
     }
     __device__ __forceinline__ uint32_t read(int n, int nbits) {          // header fields (not the per-coefficient path)
