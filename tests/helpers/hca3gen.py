@@ -67,7 +67,8 @@ def stream(seed, frames=8, channels=2, frame_size=1024, total=128, base=40, ster
     """One v3.0 stream. Channel pairs are primary/secondary when stereo > 0 (hca.cpp:909-960, 2 channels per track)."""
     rng = np.random.default_rng(seed)
     out = header(version, channels, rate, frames, delay, 0, frame_size, min_res, max_res, 1, 0, total, base, stereo, bands_per_hfr)
-    paired = stereo > 0 and channels == 2
+    # channel roles for one track and channel_config 0 (hca.cpp:909-960): 1 primary, 2 secondary, 0 discrete
+    roles = {1: [0], 2: [1, 2], 3: [1, 2, 0], 4: [1, 2, 1, 2]}[channels] if stereo > 0 else [0] * channels
     rest = total - base - stereo
     groups = 0 if bands_per_hfr == 0 else (rest + bands_per_hfr - 1) // bands_per_hfr
     for _ in range(frames):
@@ -76,7 +77,7 @@ def stream(seed, frames=8, channels=2, frame_size=1024, total=128, base=40, ster
         b.put(int(rng.integers(level[0], level[1])), 9)
         b.put(int(rng.integers(0, 128)), 7)
         for c in range(channels):
-            secondary = paired and c == 1
+            secondary = roles[c] == 2
             count = base if secondary else base + stereo
             if not secondary and groups > 0 and version > 0x0200:
                 count += groups

@@ -28,6 +28,8 @@ CASES = [   # wider than the committed fixtures; expected = oracle port (pinned 
     dict(seed=9, frame_size=4096, min_res=2, max_res=12, sf_max=60),
     dict(seed=10, frame_size=4096, frames=37, delay=300),
     dict(seed=11, frame_size=4096, version=0x0200, min_res=1),
+    dict(seed=12, frame_size=8192, channels=4, frames=6),                  # two primary / secondary pairs
+    dict(seed=13, frame_size=6144, channels=3, frames=6, base=50, stereo=20, bands_per_hfr=5, total=110),
 ]
 
 
