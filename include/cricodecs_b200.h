@@ -13,8 +13,9 @@
  *  -101 .. -110  WAV ingest errors = -100 + pcm.cpp code (pcm.cpp:22-33)
  *  -201 .. -204  HCA errors = -200 + py_codec_err code (hca.cpp:3252-3268):
  *                header / frame decode (wrong key) / channel config / encode
- *  -300          valid input this build does not handle (looping WAV encode,
- *                HCA v3.0 noise fill, non-16-bit PCM)
+ *  -300          valid input this build does not handle (WAVs with several
+ *                sampler loops; HCA v3.0 layouts whose derived HFR scales
+ *                depend on the previous frame)
  *  -301          truncated input or output buffer too small
  *  -400          CUDA failure (no device, launch or copy error); the library
  *                never falls back to a CPU path
