@@ -35,7 +35,6 @@ namespace {
 __constant__ uint8_t c_invert[66] = CRI_TBL_INVERT;
 __constant__ uint32_t c_scaling[64] = CRI_TBL_DEC_SCALING;
 __constant__ uint32_t c_range[16] = CRI_TBL_DEC_RANGE;
-__constant__ uint8_t c_read_bits[128] = CRI_TBL_READ_BITS;
 __constant__ int8_t c_read_vals[128] = CRI_TBL_READ_VALS;
 __constant__ uint8_t c_max_bits[16] = CRI_TBL_MAX_BITS;
 __constant__ uint32_t c_conv[128] = CRI_TBL_SCALE_CONV;          // HFR: scale_conversion_table (hca.cpp:1579-1598)
