@@ -427,7 +427,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
             float4* dst = dst_frame + sub * 1024 + c * RW;
             auto decode_run = [&](auto careful_tag) {
                 constexpr bool kCareful = decltype(careful_tag)::value;
-#pragma unroll 4
+#pragma unroll 2
                 for (int chunk = 0; chunk < 32; chunk++) {
                     float f[4];
 #pragma unroll
