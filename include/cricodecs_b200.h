@@ -142,6 +142,12 @@ typedef struct cri_job_desc {
     uint32_t quality;            /* HCA encode */
     int encrypt;                 /* HCA crypt */
     uint32_t ciph_type;          /* HCA crypt */
+    /* Device-resident I/O (optional, all NULL for host blobs): `d_blob` is the input blob in the GPU's memory
+     * (`blob` is then ignored), `d_out` receives the packed output blob in place of a library-owned buffer, and
+     * `stream` (a cudaStream_t) orders every copy and kernel of the job. */
+    const uint8_t* d_blob;
+    uint8_t* d_out;
+    void* stream;
 } cri_job_desc;
 CRI_API int cri_job_create(cri_ctx* ctx, const cri_job_desc* desc, cri_job** job); /* parses, plans, uploads the input */
 CRI_API uint64_t cri_job_out_bytes(const cri_job* job);
@@ -151,6 +157,29 @@ CRI_API int cri_job_upload(cri_ctx* ctx, cri_job* job);                         
 CRI_API int cri_job_run(cri_ctx* ctx, cri_job* job);                                /* kernels only, inputs resident */
 CRI_API int cri_job_download(cri_ctx* ctx, cri_job* job, uint8_t* out_blob, int32_t* status); /* HBM -> host (D2H) + status */
 CRI_API void cri_job_destroy(cri_ctx* ctx, cri_job* job);
+
+/* -- Device-pointer batch calls: SURVEY.md section 8(b) item (2), `..._batch(..., cudaStream_t)`. Same meaning
+ *    as the host-buffer calls above, but `d_blob` and `d_out` are DEVICE pointers on the context's GPU and every
+ *    copy and kernel is ordered on `stream` (a cudaStream_t passed as void*; NULL = the context's own stream), so a
+ *    GPU-resident producer / consumer never crosses PCIe with the payload. `offsets`, `out_offsets`, keys and
+ *    `status` are HOST arrays. `out_offsets` must be the packed layout that *_sizes() describes (-301 otherwise);
+ *    the *_sizes_dev variants read the headers from the device blob. The calls fetch the stream headers (a few
+ *    hundred bytes per stream) for planning, enqueue the work and return after `stream` has finished it. ---------- */
+CRI_API int cri_sizes_dev(cri_ctx* ctx, int job_kind, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n,
+                          const cri_adx_params* adx, uint32_t quality, uint64_t* out_sizes, int32_t* status, void* stream);
+CRI_API int cri_adx_decode_batch_dev(cri_ctx* ctx, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n,
+                             uint8_t* d_out, const uint64_t* out_offsets, int32_t* status, void* stream);
+CRI_API int cri_adx_encode_batch_dev(cri_ctx* ctx, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n,
+                             const cri_adx_params* p, uint8_t* d_out, const uint64_t* out_offsets, int32_t* status, void* stream);
+CRI_API int cri_hca_decode_batch_dev(cri_ctx* ctx, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n,
+                             const uint64_t* keys, const uint16_t* subkeys,
+                             uint8_t* d_out, const uint64_t* out_offsets, int32_t* status, void* stream);
+CRI_API int cri_hca_crypt_batch_dev(cri_ctx* ctx, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n,
+                            int encrypt, uint32_t ciph_type, const uint64_t* keys, const uint16_t* subkeys,
+                            uint8_t* d_out, int32_t* status, void* stream);
+CRI_API int cri_hca_encode_batch_dev(cri_ctx* ctx, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n,
+                             uint32_t quality, uint32_t force_not_looping,
+                             uint8_t* d_out, const uint64_t* out_offsets, int32_t* status, void* stream);
 
 /* -- Single-stream conveniences with library-owned output (cri_free). These
  *    are what a 1:1 replacement of the five CriCodecs callables binds. ------- */

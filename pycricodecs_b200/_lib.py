@@ -29,7 +29,7 @@ class AdxParams(ctypes.Structure):
 class JobDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("blob", c_vp), ("offsets", c_vp), ("n", ctypes.c_uint32), ("keys", c_vp),
                 ("subkeys", c_vp), ("adx", AdxParams), ("quality", ctypes.c_uint32), ("encrypt", ctypes.c_int),
-                ("ciph_type", ctypes.c_uint32)]
+                ("ciph_type", ctypes.c_uint32), ("d_blob", c_vp), ("d_out", c_vp), ("stream", c_vp)]
 
 
 JOB_ADX_DECODE, JOB_ADX_ENCODE, JOB_HCA_DECODE, JOB_HCA_CRYPT, JOB_HCA_ENCODE = 1, 2, 3, 4, 5
@@ -56,6 +56,12 @@ SIGNATURES = {
     "cri_hca_encode_sizes": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),
     "cri_hca_encode_sizes_ex": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),
     "cri_hca_encode_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp, c_vp]),
+    "cri_sizes_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint32, ctypes.POINTER(AdxParams), ctypes.c_uint32, c_vp, c_vp, c_vp]),
+    "cri_adx_decode_batch_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
+    "cri_adx_encode_batch_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.POINTER(AdxParams), c_vp, c_vp, c_vp, c_vp]),
+    "cri_hca_decode_batch_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cri_hca_crypt_batch_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cri_hca_encode_batch_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "cri_job_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JobDesc), ctypes.POINTER(c_vp)]),
     "cri_job_out_bytes": (ctypes.c_uint64, [c_vp]),
     "cri_job_out_offsets": (c_u64p, [c_vp]),

@@ -550,6 +550,14 @@ __global__ void scatter_patches_kernel(uint8_t* __restrict__ out, const uint8_t*
     for (uint32_t i = threadIdx.x & 31; i < pt.bytes; i += 32) out[pt.dst_off + i] = bytes[pt.src_off + i];
 }
 
+__global__ void gather_segments_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                       const Segment* __restrict__ segs, uint32_t n) {
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const Segment sg = segs[p];
+    for (uint32_t i = threadIdx.x & 31; i < sg.bytes; i += 32) dst[sg.dst_off + i] = src[sg.src_off + i];
+}
+
 // ------------------------------------------------------------ WAV ingest
 // One CTA per (stream, chunk of kConvChunk samples); conversion rules of the reference: PCM8_to_PCM16, PCM_to_PCM16,
 // Float_to_PCM (pcm.cpp:455-527), with the x86 (int) cast of an out-of-range float (INT_MIN) restated explicitly.
@@ -644,6 +652,13 @@ void launch_scatter_patches(uint8_t* d_out, const uint8_t* d_bytes, const Patch*
                             uint64_t* launches) {
     if (!n) return;
     scatter_patches_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_out, d_bytes, d_patches, n);
+    ++*launches;
+}
+
+void launch_gather_segments(uint8_t* d_dst, const uint8_t* d_src, const Segment* d_segs, uint32_t n, cudaStream_t s,
+                            uint64_t* launches) {
+    if (!n) return;
+    gather_segments_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_dst, d_src, d_segs, n);
     ++*launches;
 }
 

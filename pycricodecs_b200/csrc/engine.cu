@@ -3,6 +3,7 @@
 // is in formats.cpp. There is deliberately no CPU fallback anywhere in this
 // file: without a CUDA device every compute entry point returns -400.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -46,6 +47,8 @@ extern "C" int cri_ctx_create(int device, cri_ctx** out) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     const char* t = getenv("CRI_TRACE");
     c->trace = t && *t && *t != '0';
+    const char* pz = getenv("CRI_POISON");
+    c->poison = pz && *pz && *pz != '0';
     *out = c;
     return OK;
 }
@@ -57,6 +60,8 @@ extern "C" void cri_ctx_destroy(cri_ctx* c) {
     for (auto& kv : c->pool.live) cudaFree(kv.first);   // blocks of jobs the caller never destroyed
     for (auto& s : c->pipe) cudaStreamDestroy(s);
     for (auto& p : c->pin_status) cudaFreeHost(p);
+    for (auto& e : c->idle_events) cudaEventDestroy(e);
+    if (c->pin_stage) cudaFreeHost(c->pin_stage);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -406,10 +411,150 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Plan on the host, take HBM from the context's cache, and enqueue every upload on `stream`. Nothing here waits for the GPU.
-static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream, cri_job** out) {
+// ---------------------------------------------------------- device-resident input
+// A device-pointer job plans from headers like every other job; the headers are fetched from the caller's HBM into a
+// sparse host shadow of the blob (anonymous mapping: untouched pages cost nothing). Round 0 takes the first kHeadBytes
+// of every stream; later rounds take what a stream's own header says is still missing (long HCA / ADX headers, WAV
+// chunks in front of or behind the sample data).
+namespace {
+constexpr uint32_t kHeadBytes = 1024;
+
+struct Valid {            // fetched byte ranges of one stream: a prefix and (WAVs) chunk headers / bodies further in
+    uint64_t prefix = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> extra;     // [first, last)
+    bool has(uint64_t off, uint64_t n) const {
+        if (off + n <= prefix) return true;
+        for (const auto& e : extra)
+            if (off >= e.first && off + n <= e.second) return true;
+        return false;
+    }
+};
+
+constexpr uint32_t fourcc_le(char a, char b, char c, char d) {
+    return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24);
+}
+
+// What does stream (d, len) still need, given `v`? Appends one [off, off + n) range (stream-relative); nothing = complete.
+void missing_ranges(int kind, const uint8_t* d, uint64_t len, const Valid& v, std::vector<std::pair<uint64_t, uint64_t>>* need) {
+    auto want = [&](uint64_t from, uint64_t upto) {              // grows the prefix when contiguous with it
+        upto = std::min(upto, len);
+        if (from <= v.prefix) from = v.prefix;
+        if (upto > from) need->emplace_back(from, upto - from);
+    };
+    if (kind == CRI_JOB_HCA_DECODE || kind == CRI_JOB_HCA_CRYPT) {
+        if (v.prefix >= 8) want(0, be16(d + 6));                           // header size field
+        return;
+    }
+    if (kind == CRI_JOB_ADX_DECODE) {
+        if (v.prefix >= 4) want(0, (uint64_t)be16(d + 2) + 4 + 4);         // data offset: header, copyright text, first bytes
+        return;
+    }
+    // WAV: the chunk walk of parse_wav (pcm.cpp:291-342): every chunk header, the fmt / smpl bodies, the first sample frame
+    if (v.prefix < 12 || le32(d) != fourcc_le('R', 'I', 'F', 'F')) return;
+    const uint64_t riff_size = le32(d + 4);
+    uint64_t at = 12, walked = 4;
+    while (walked < riff_size && at + 8 <= len) {
+        if (!v.has(at, 8)) { want(at, at + 512); return; }               // next chunk header (and, likely, its small body)
+        const uint32_t tag = le32(d + at), body = le32(d + at + 4);
+        uint64_t span = (uint64_t)body + 8;
+        if ((span & 1) && span + walked + 1 <= riff_size) span += 1;
+        uint64_t n = 8;
+        if (tag == fourcc_le('f', 'm', 't', ' ') || tag == fourcc_le('s', 'm', 'p', 'l')) n = std::min<uint64_t>(span, 128);
+        else if (tag == fourcc_le('d', 'a', 't', 'a')) n = 8 + 2048;       // first sample frame (<= 255 channels x 8 bytes)
+        n = std::min(n, len - at);
+        if (!v.has(at, n)) { want(at, at + n); return; }
+        at += span;
+        walked += span;
+    }
+}
+}  // namespace
+
+static int fetch_segments(cri_ctx* c, cudaStream_t stream, const uint8_t* d_blob, std::vector<Segment>& segs, uint64_t total,
+                          uint8_t* shadow, const std::vector<uint64_t>& shadow_off) {
+    if (segs.empty()) return OK;
+    if (c->pin_stage_cap < total) {
+        if (c->pin_stage) cudaFreeHost(c->pin_stage);
+        c->pin_stage = nullptr;
+        c->pin_stage_cap = 0;
+        const size_t cap = std::max<size_t>(total + total / 2, size_t(1) << 20);
+        CU_TRY(c, cudaHostAlloc((void**)&c->pin_stage, cap, cudaHostAllocDefault));
+        c->pin_stage_cap = cap;
+    }
+    uint8_t* d_stage = nullptr;
+    Segment* d_segs = nullptr;
+    int r = pool_alloc(c, (void**)&d_stage, total);
+    if (r == OK) r = pool_alloc(c, (void**)&d_segs, segs.size() * sizeof(Segment));
+    if (r == OK) r = [&]() -> int {
+        CU_TRY(c, cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream));
+        launch_gather_segments(d_stage, d_blob, d_segs, (uint32_t)segs.size(), stream, &c->launches);
+        CU_TRY(c, cudaMemcpyAsync(c->pin_stage, d_stage, total, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(c, cudaStreamSynchronize(stream));
+        return OK;
+    }();
+    pool_free(c, d_stage);
+    pool_free(c, d_segs);
+    if (r != OK) return r;
+    for (size_t k = 0; k < segs.size(); k++) memcpy(shadow + shadow_off[k], c->pin_stage + segs[k].dst_off, segs[k].bytes);
+    return OK;
+}
+
+// Builds the host shadow of a device blob: *shadow (munmap it with *bytes) holds every header byte planning reads.
+static int build_shadow(cri_ctx* c, int kind, const uint8_t* d_blob, const uint64_t* off, uint32_t n, cudaStream_t stream,
+                        uint8_t** shadow, size_t* bytes) {
+    const uint64_t base0 = n ? off[0] : 0, total_in = n ? off[n] : 0;
+    *bytes = (size_t)std::max<uint64_t>(total_in, 1) + 64;
+    void* m = mmap(nullptr, *bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (m == MAP_FAILED) { *shadow = nullptr; return ERR_BUFFER; }
+    *shadow = (uint8_t*)m;
+    (void)base0;
+    std::vector<Valid> valid(n);
+    std::vector<Segment> segs;
+    std::vector<uint64_t> shadow_off;
+    std::vector<std::pair<uint64_t, uint64_t>> need;
+    for (int round = 0; round < 12; round++) {
+        segs.clear();
+        shadow_off.clear();
+        uint64_t total = 0;
+        std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> got;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint64_t len = off[i + 1] - off[i];
+            need.clear();
+            if (round == 0) { if (len) need.emplace_back(0, std::min<uint64_t>(len, kHeadBytes)); }
+            else missing_ranges(kind, *shadow + off[i], len, valid[i], &need);
+            for (auto& rg : need) {
+                if (!rg.second) continue;
+                Segment sg{off[i] + rg.first, total, (uint32_t)rg.second, 0};
+                segs.push_back(sg);
+                shadow_off.push_back(off[i] + rg.first);
+                total += (rg.second + 15) & ~(uint64_t)15;
+                got.push_back({i, rg});
+            }
+        }
+        if (segs.empty()) break;
+        const int r = fetch_segments(c, stream, d_blob, segs, total, *shadow, shadow_off);
+        if (r != OK) return r;
+        for (auto& g : got) {
+            Valid& v = valid[g.first];
+            if (g.second.first == v.prefix) v.prefix += g.second.second;
+            else v.extra.emplace_back(g.second.first, g.second.first + g.second.second);
+        }
+    }
+    return OK;
+}
+
+static int take_events(cri_ctx* c, cri_job* j) {
+    for (auto& e : j->ev) {
+        if (!c->idle_events.empty()) { e = c->idle_events.back(); c->idle_events.pop_back(); }
+        else CU_TRY(c, cudaEventCreate(&e));
+    }
+    return OK;
+}
+
+// Plan on the host, take HBM from the context's cache, and enqueue every upload on `stream`. Nothing here waits for the GPU
+// (a device-pointer job waits for its header fetches).
+static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream, cri_job** out, const uint64_t* expect_out = nullptr) {
     *out = nullptr;
-    if (!c || !d || (!d->blob && d->n) || !d->offsets) return ERR_BUFFER;
+    if (!c || !d || (!d->blob && !d->d_blob && d->n) || !d->offsets) return ERR_BUFFER;
     CU_TRY(c, cudaSetDevice(c->device));
     cri_job* j = new (std::nothrow) cri_job();
     if (!j) return ERR_BUFFER;
@@ -427,7 +572,16 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     if (d->keys) j->keys.assign(d->keys, d->keys + d->n);
     if (d->subkeys) j->subkeys.assign(d->subkeys, d->subkeys + d->n);
     int rc = OK;
-    switch (d->kind) {
+    if (d->d_blob) {
+        j->d_src = d->d_blob;
+        rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, stream, &j->shadow, &j->shadow_bytes);
+        j->blob = j->shadow;
+    }
+    if (d->d_out) {
+        j->d_out = d->d_out;
+        j->own_out = false;
+    }
+    if (rc == OK) switch (d->kind) {
         case CRI_JOB_ADX_DECODE: plan_adx_decode(j); break;
         case CRI_JOB_ADX_ENCODE: plan_adx_encode(j); break;
         case CRI_JOB_HCA_DECODE: rc = plan_hca_decode(c, j); break;
@@ -435,22 +589,31 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         case CRI_JOB_HCA_ENCODE: rc = plan_hca_encode(c, j); break;
         default: rc = ERR_UNSUPPORTED;
     }
+    if (rc == OK && expect_out)      // the caller's buffer is laid out by *_sizes(): it must be the packed layout planned here
+        for (uint32_t i = 0; i <= j->n && rc == OK; i++)
+            if (expect_out[i] - expect_out[0] != j->out_off[i]) rc = ERR_BUFFER;
     if (rc == OK) rc = [&]() -> int {
-        for (auto& e : j->ev) CU_TRY(c, cudaEventCreate(&e));
+        int r = take_events(c, j);
+        if (r != OK) return r;
         // slack: kernels read whole 16-byte rows, up to four rows ahead; then the WAV ingest's conversion region
         const uint64_t in_alloc = j->conv_bytes ? j->conv_base + j->conv_bytes + 128 : std::max<uint64_t>(j->in_bytes, 16) + 128;
-        int r = pool_alloc(c, (void**)&j->d_in, in_alloc);
-        if (r == OK) r = pool_alloc(c, (void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16);
+        r = pool_alloc(c, (void**)&j->d_in, in_alloc);
+        if (r == OK && j->own_out) r = pool_alloc(c, (void**)&j->d_out, std::max<uint64_t>(j->out_bytes, 16) + 16);
         if (r == OK) r = pool_alloc(c, (void**)&j->d_status, sizeof(int32_t) * std::max<uint32_t>(j->n, 1));
         if (r != OK) return r;
-        CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes + 16, stream));
+        // Every byte of the output blob is written by a kernel or a patch on every run; a job that leaves gaps (streams
+        // cut short, unsupported layouts) sets needs_clear and is zero-filled at the start of each run instead.
+        if (c->poison && j->out_bytes) CU_TRY(c, cudaMemsetAsync(j->d_out, 0xA5, j->out_bytes, stream));
         r = upload_vec(c, stream, j->adx_chains, &j->d_adx_chains);
         if (r == OK) r = upload_vec(c, stream, j->conv, &j->d_conv);
         if (r == OK) r = upload_vec(c, stream, j->patches, &j->d_patches);
         if (r == OK) r = upload_vec(c, stream, j->patch_bytes, &j->d_patch_bytes);
         if (r == OK) r = upload_hca_tables(c, j);
         if (r != OK) return r;
-        if (j->in_bytes) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, stream));
+        if (j->in_bytes) {
+            if (j->d_src) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->d_src, j->in_bytes, cudaMemcpyDeviceToDevice, stream));
+            else CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, stream));
+        }
         return OK;
     }();
     if (rc != OK) {
@@ -476,7 +639,10 @@ extern "C" uint64_t cri_job_units(const cri_job* j) { return j->units; }
 
 extern "C" int cri_job_upload(cri_ctx* c, cri_job* j) {
     CU_TRY(c, cudaSetDevice(c->device));
-    if (j->in_bytes) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, j->stream));
+    if (j->in_bytes) {
+        if (j->d_src) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->d_src, j->in_bytes, cudaMemcpyDeviceToDevice, j->stream));
+        else CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, j->stream));
+    }
     CU_TRY(c, cudaStreamSynchronize(j->stream));
     return OK;
 }
@@ -511,6 +677,8 @@ static int job_enqueue_run(cri_ctx* c, cri_job* j) {
             break;
         }
     }
+    for (const auto& dc : j->dev_copies)
+        CU_TRY(c, cudaMemcpyAsync(j->d_out + dc.dst_off, j->d_in + dc.src_off, dc.bytes, cudaMemcpyDeviceToDevice, s));
     CU_TRY(c, cudaEventRecord(j->ev[1], s));
     CU_TRY(c, cudaGetLastError());
     return OK;
@@ -569,7 +737,9 @@ extern "C" void cri_job_destroy(cri_ctx* c, cri_job* j) {
     if (!j) return;
     if (c) cudaSetDevice(c->device);
     for (auto& e : j->ev)
-        if (e) cudaEventDestroy(e);
+        if (e) { if (c) c->idle_events.push_back(e); else cudaEventDestroy(e); }
+    if (!j->own_out) j->d_out = nullptr;
+    if (j->shadow) munmap(j->shadow, j->shadow_bytes);
     for (void* p : {(void*)j->d_in, (void*)j->d_out, (void*)j->d_status, (void*)j->d_adx_chains, (void*)j->d_conv, (void*)j->d_patches,
                     (void*)j->d_patch_bytes})
         pool_free(c, p);
@@ -797,6 +967,103 @@ extern "C" int cri_hca_encode_batch(cri_ctx* c, const uint8_t* blob, const uint6
     d.quality = quality;
     d.adx.force_not_looping = force_not_looping;
     return run_batch(c, d, out, out_off, status);
+}
+
+// ------------------------------------------------- device-pointer batch calls
+// One job for the whole batch (there is no PCIe transfer to hide, so no chunking): headers are fetched for planning,
+// the payload is copied once inside HBM into the engine's padded input buffer (kernels read whole 16-byte rows past
+// the last stream), kernels write straight into the caller's output buffer.
+static int run_batch_dev(cri_ctx* c, cri_job_desc d, const uint64_t* out_offsets, int32_t* status) {
+    if (!c) return ERR_CUDA;
+    if (!d.offsets || (d.n && (!d.d_blob || !d.d_out))) return ERR_BUFFER;
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = d.stream ? (cudaStream_t)d.stream : c->stream;
+    if (out_offsets) d.d_out += out_offsets[0];
+    c->last_ms = c->last_dominant_ms = 0.f;
+    cri_job* j = nullptr;
+    int rc = job_create_on(c, &d, st, &j, out_offsets);
+    if (rc != OK) return rc;
+    rc = job_enqueue_run(c, j);
+    if (rc == OK) rc = job_wait_run(c, j, false);
+    if (rc == OK) rc = job_enqueue_download(c, j, nullptr, status, nullptr);
+    if (rc == OK) rc = job_wait_download(c, j);
+    if (rc == OK) {
+        bool any = false;
+        for (uint32_t i = 0; i < j->n; i++)       // a stream that failed on the device leaves silence, not garbage
+            if (j->status[i] == OK && j->h_status[i] != OK && j->out_off[i + 1] > j->out_off[i]) {
+                cudaMemsetAsync(j->d_out + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i], st);
+                any = true;
+            }
+        if (any) CU_TRY(c, cudaStreamSynchronize(st));
+    }
+    cri_job_destroy(c, j);
+    return rc;
+}
+
+static cri_job_desc make_desc_dev(int kind, const uint8_t* d_blob, const uint64_t* offsets, uint32_t n, uint8_t* d_out, void* stream) {
+    cri_job_desc d = make_desc(kind, nullptr, offsets, n);
+    d.d_blob = d_blob;
+    d.d_out = d_out;
+    d.stream = stream;
+    return d;
+}
+
+extern "C" int cri_sizes_dev(cri_ctx* c, int kind, const uint8_t* d_blob, const uint64_t* off, uint32_t n, const cri_adx_params* adx,
+                             uint32_t quality, uint64_t* sizes, int32_t* status, void* stream) {
+    if (!c) return ERR_CUDA;
+    if (!off || (n && !d_blob)) return ERR_BUFFER;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (kind == CRI_JOB_HCA_CRYPT) {
+        for (uint32_t i = 0; i < n; i++) { sizes[i] = off[i + 1] - off[i]; if (status) status[i] = OK; }
+        return OK;
+    }
+    uint8_t* shadow = nullptr;
+    size_t bytes = 0;
+    int rc = build_shadow(c, kind, d_blob, off, n, stream ? (cudaStream_t)stream : c->stream, &shadow, &bytes);
+    if (rc == OK) switch (kind) {
+        case CRI_JOB_ADX_DECODE: rc = cri_adx_decode_sizes(shadow, off, n, sizes, status); break;
+        case CRI_JOB_ADX_ENCODE: rc = adx ? cri_adx_encode_sizes(shadow, off, n, adx, sizes, status) : ERR_BUFFER; break;
+        case CRI_JOB_HCA_DECODE: rc = cri_hca_decode_sizes(shadow, off, n, sizes, status); break;
+        case CRI_JOB_HCA_ENCODE: rc = cri_hca_encode_sizes_ex(shadow, off, n, quality, adx ? adx->force_not_looping : 0, sizes, status); break;
+        default: rc = ERR_UNSUPPORTED;
+    }
+    if (shadow) munmap(shadow, bytes);
+    return rc;
+}
+
+extern "C" int cri_adx_decode_batch_dev(cri_ctx* c, const uint8_t* d_blob, const uint64_t* off, uint32_t n, uint8_t* d_out,
+                                        const uint64_t* out_off, int32_t* status, void* stream) {
+    return run_batch_dev(c, make_desc_dev(CRI_JOB_ADX_DECODE, d_blob, off, n, d_out, stream), out_off, status);
+}
+extern "C" int cri_adx_encode_batch_dev(cri_ctx* c, const uint8_t* d_blob, const uint64_t* off, uint32_t n, const cri_adx_params* p,
+                                        uint8_t* d_out, const uint64_t* out_off, int32_t* status, void* stream) {
+    cri_job_desc d = make_desc_dev(CRI_JOB_ADX_ENCODE, d_blob, off, n, d_out, stream);
+    d.adx = *p;
+    return run_batch_dev(c, d, out_off, status);
+}
+extern "C" int cri_hca_decode_batch_dev(cri_ctx* c, const uint8_t* d_blob, const uint64_t* off, uint32_t n, const uint64_t* keys,
+                                        const uint16_t* subkeys, uint8_t* d_out, const uint64_t* out_off, int32_t* status, void* stream) {
+    cri_job_desc d = make_desc_dev(CRI_JOB_HCA_DECODE, d_blob, off, n, d_out, stream);
+    d.keys = keys;
+    d.subkeys = subkeys;
+    return run_batch_dev(c, d, out_off, status);
+}
+extern "C" int cri_hca_crypt_batch_dev(cri_ctx* c, const uint8_t* d_blob, const uint64_t* off, uint32_t n, int encrypt,
+                                       uint32_t ciph_type, const uint64_t* keys, const uint16_t* subkeys, uint8_t* d_out,
+                                       int32_t* status, void* stream) {
+    cri_job_desc d = make_desc_dev(CRI_JOB_HCA_CRYPT, d_blob, off, n, d_out, stream);
+    d.keys = keys;
+    d.subkeys = subkeys;
+    d.encrypt = encrypt;
+    d.ciph_type = ciph_type;
+    return run_batch_dev(c, d, off, status);
+}
+extern "C" int cri_hca_encode_batch_dev(cri_ctx* c, const uint8_t* d_blob, const uint64_t* off, uint32_t n, uint32_t quality,
+                                        uint32_t force_not_looping, uint8_t* d_out, const uint64_t* out_off, int32_t* status, void* stream) {
+    cri_job_desc d = make_desc_dev(CRI_JOB_HCA_ENCODE, d_blob, off, n, d_out, stream);
+    d.quality = quality;
+    d.adx.force_not_looping = force_not_looping;
+    return run_batch_dev(c, d, out_off, status);
 }
 
 // ------------------------------------------------------ single-stream API

@@ -32,6 +32,10 @@ struct cri_ctx {
     int32_t* pin_status[kPipeDepth] = {};       // page-locked landing buffers of the chunks' status words (a copy to
     size_t pin_status_cap[kPipeDepth] = {};     //  pageable memory would block the host until the chunk's kernels end)
     DevPool pool;
+    std::vector<cudaEvent_t> idle_events;       // events of finished jobs, reused by the next ones
+    uint8_t* pin_stage = nullptr;               // page-locked landing buffer of the header fetches of device-pointer jobs
+    size_t pin_stage_cap = 0;
+    bool poison = false;                        // CRI_POISON=1 (tests): output blobs start as 0xA5 so that a byte no kernel writes shows
     bool trace = false;                         // CRI_TRACE=1: phase times of every batch call on stderr
     uint64_t launches = 0;
     float last_ms = 0.f, last_dominant_ms = 0.f;
@@ -65,6 +69,15 @@ struct cri_job {
     uint8_t* d_in = nullptr;
     uint8_t* d_out = nullptr;
     int32_t* d_status = nullptr;
+
+    // device-pointer jobs (cri_*_batch_dev): the input blob lives in the caller's HBM; `blob` then points at a sparse
+    // host shadow that holds only the fetched header bytes, and d_out is the caller's buffer
+    const uint8_t* d_src = nullptr;
+    uint8_t* shadow = nullptr;
+    size_t shadow_bytes = 0;
+    bool own_out = true;
+    struct DevCopy { uint64_t src_off, dst_off, bytes; };
+    std::vector<DevCopy> dev_copies;          // input bytes that pass through unchanged (in place of host-built patches)
 
     // WAV ingest: streams whose samples are not PCM16 get a converted copy behind the input blob (region starts at conv_base)
     std::vector<cri::PcmConv> conv;

@@ -13,7 +13,10 @@
 // frame works on it in shared memory: substitution table (shared), CRC16 four bytes per step (slice-by-4 tables,
 // shared). HBM traffic is the compulsory 2 x frame_size per frame. hca_crypt_kernel is the any-size path: one lane
 // per frame straight on global memory.
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <type_traits>
 
 #include "hca_kernels.h"
 
@@ -168,10 +171,210 @@ hca_crypt_staged_kernel(HcaCryptArgs a) {
     for (uint32_t k = max(r1 * 16, head_end) + lane; k < end; k += 32) a.out[base + k] = buf[k];
 }
 
+
+// ---- LUT kernel: the streaming path (frames of 128 bytes .. 12 KB, i.e. every real stream)
+//
+// Persistent CTAs of 8 warps. A warp takes one group (up to 32 consecutive frames of one stream = one contiguous byte
+// range of the blob) at a time: a single elected lane moves it HBM -> shared memory with one bulk copy (cp.async.bulk,
+// completion on an mbarrier) and back with one bulk store, so moving the data costs no issue slots; between the two,
+// one LANE per frame works in place. Per 32-bit word of the frame:
+//   * substitution: four lookups in a copy of the stream's 256-byte table that is replicated once per shared-memory
+//     bank ([byte value][lane], 32 KB), so the 32 lanes' data-dependent lookups never conflict;
+//   * CRC16 without tables. P = x^16 + x^15 + x^2 + 1 = (x + 1)(x^15 + x + 1). Modulo x + 1 the message reduces to its
+//     parity (one XOR per word). Modulo Q = x^15 + x + 1 squaring gives x^(15 * 2^j) = x^(2^j) + 1, in particular
+//     x^480 = x^32 + 1: the message is taken in blocks of fifteen 32-bit words and the running value A (15 words in
+//     registers) advances by A * x^480 + B = (A << 32) ^ A ^ B, i.e. ONE three-input XOR per word plus two for the
+//     word that overflows. A is reduced to 15 bits once per frame (x^30 = x^2 + 1, x^15 = x + 1), the two residues
+//     are recombined (R = E ^ (parity(E) ^ parity(M) ? 0x8003 : 0)) and written into the frame's last two bytes.
+// tools/crc_model.py restates the arithmetic in Python and checks it against the bitwise CRC.
+constexpr int kLutWarps = 8;
+constexpr uint32_t kLutTableBytes = 256 * 32 * 4;
+constexpr uint32_t kLutFront = 16;                 // bytes in front of a warp's staging area (words read before a frame's start)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// running value r (< 2^17) times x^32 plus the next big-endian message word, modulo Q (result < 2^16)
+__device__ __forceinline__ uint32_t modq_word(uint32_t r, uint32_t o) {
+    uint32_t v = (r << 4) ^ (r << 2) ^ o;                              // x^32 = x^4 + x^2  (x^30 = x^2 + 1)
+    uint32_t h = v >> 30; v = (v & 0x3FFFFFFFu) ^ h ^ (h << 2);
+    h = v >> 15; v = (v & 0x7FFFu) ^ h ^ (h << 1);
+    return v;
+}
+// the same for one more message byte (r < 2^17; result < 2^15: fully reduced)
+__device__ __forceinline__ uint32_t modq_byte(uint32_t r, uint32_t m) {
+    const uint32_t v = (r << 8) ^ m, h = v >> 15;
+    return (v & 0x7FFFu) ^ h ^ (h << 1);
+}
+
+__global__ void __launch_bounds__(kLutWarps * 32, 1)
+hca_crypt_lut_kernel(HcaCryptArgs a) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint32_t* lut = reinterpret_cast<uint32_t*>(s_dyn);                                   // [256][32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + kLutTableBytes);                 // [kLutWarps]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_bytes = kLutFront + a.group_bytes;
+    uint8_t* dat = s_dyn + kLutTableBytes + 64 + (size_t)warp * warp_bytes + kLutFront;   // 16-byte aligned
+    const uint8_t* lut_src = a.tables + (size_t)a.lut_table * 256;
+    for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x) lut[i] = lut_src[i >> 5];
+    const uint32_t bar = smem_u32(bars + warp);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t* lut_lane = lut + lane;
+    uint32_t phase = 0;
+    for (uint64_t gid = (uint64_t)blockIdx.x * kLutWarps + warp; gid < a.n_groups; gid += (uint64_t)gridDim.x * kLutWarps) {
+        uint32_t lo = 0, hi = a.n_streams;                  // group -> stream
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(a.group_prefix + mid) <= gid) lo = mid; else hi = mid;
+        }
+        const HcaStreamDev& S = a.streams[lo];
+        const uint32_t fs = S.frame_size;
+        const uint32_t f0 = (uint32_t)(gid - __ldg(a.group_prefix + lo)) * a.frames_per_group;
+        const uint32_t cnt = min(a.frames_per_group, S.frame_count - f0);
+        const uint64_t off0 = S.in_off + (uint64_t)f0 * fs;  // same offset in both blobs
+        const uint32_t bytes = cnt * fs;
+        const uint32_t lead = (uint32_t)(off0 & 15);
+        const uint64_t base = off0 - lead;
+        const uint32_t nrows = (lead + bytes + 15) >> 4;
+        // ---- in: whole 16-byte rows (the blob starts 256-byte aligned and has 64 bytes of slack behind it)
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the previous group's store has read the buffer
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nrows * 16) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(dat)), "l"(a.in + base), "r"(nrows * 16), "r"(bar) : "memory");
+        }
+        {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        // ---- one lane per frame, in place
+        if ((uint32_t)lane < cnt) {
+            const bool fast = S.cipher == a.lut_table;
+            const uint8_t* gtab = a.tables + (size_t)S.cipher * 256;
+            const uint32_t q0 = lead + (uint32_t)lane * fs;            // frame start, bytes from `dat`
+            const uint32_t e1 = q0 + fs - 3;                            // last byte covered by the CRC (hca.cpp:3326)
+            const uint32_t wE = e1 >> 2, k_tail = (e1 & 3) + 1;         // word of that byte; CRC-covered bytes in it
+            const uint32_t N = ((fs - 3) >> 2) + 1;                     // full words in front of it, same for every lane
+            uint32_t* wp = reinterpret_cast<uint32_t*>(dat) + (int)(wE - N);   // may start one word in front of the frame
+            auto run = [&](auto fast_tag) {
+                constexpr bool kFast = decltype(fast_tag)::value;
+                auto map4 = [&](uint32_t w) -> uint32_t {               // four substitutions, memory order kept
+                    uint32_t x0, x1, x2, x3;
+                    if (kFast) {
+                        x0 = lut_lane[(w & 0xFF) << 5]; x1 = lut_lane[((w >> 8) & 0xFF) << 5];
+                        x2 = lut_lane[((w >> 16) & 0xFF) << 5]; x3 = lut_lane[(w >> 24) << 5];
+                    } else {
+                        x0 = __ldg(gtab + (w & 0xFF)); x1 = __ldg(gtab + ((w >> 8) & 0xFF));
+                        x2 = __ldg(gtab + ((w >> 16) & 0xFF)); x3 = __ldg(gtab + (w >> 24));
+                    }
+                    return __byte_perm(__byte_perm(x0, x1, 0x3340), __byte_perm(x2, x3, 0x4033), 0x7610);
+                };
+                uint32_t par = 0, r = 0;
+                // words 0 and 1: bytes in front of the frame belong to the neighbour (not stored, zero for the CRC)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t addr = (wE - N + i) * 4;             // may wrap below zero for i = 0: then drop >= 4
+                    const uint32_t drop = (int32_t)(q0 - addr) <= 0 ? 0u : min(q0 - addr, 4u);
+                    uint32_t o = map4(wp[i]);
+                    o = drop >= 4 ? 0u : o & (0xFFFFFFFFu << (8 * drop));
+                    if (drop == 0) wp[i] = o;
+                    else for (uint32_t b = drop; b < 4; b++) reinterpret_cast<uint8_t*>(wp + i)[b] = (uint8_t)(o >> (8 * b));
+                    par ^= o;
+                    r = modq_word(r, __byte_perm(o, 0, 0x0123));
+                }
+                const uint32_t blocks = (N - 2) / 15, rest = (N - 2) % 15;
+                uint32_t* p = wp + 2;
+                if (blocks) {
+                    uint32_t acc[15];
+#pragma unroll
+                    for (int i = 0; i < 14; i++) acc[i] = 0;
+                    acc[14] = r;
+                    for (uint32_t b = 0; b < blocks; b++, p += 15) {
+                        const uint32_t a0 = acc[0];
+#pragma unroll
+                        for (int i = 0; i < 15; i++) {
+                            const uint32_t o = map4(p[i]);
+                            p[i] = o;
+                            par ^= o;
+                            const uint32_t be = __byte_perm(o, 0, 0x0123);
+                            if (i < 13) acc[i] = acc[i] ^ acc[i + 1] ^ be;
+                            else if (i == 13) acc[13] = acc[13] ^ acc[14] ^ be ^ a0;
+                            else acc[14] = acc[14] ^ a0 ^ be;
+                        }
+                    }
+                    r = 0;
+#pragma unroll
+                    for (int i = 0; i < 15; i++) r = modq_word(r, acc[i]);
+                }
+                for (uint32_t i = 0; i < rest; i++) {
+                    const uint32_t o = map4(p[i]);
+                    p[i] = o;
+                    par ^= o;
+                    r = modq_word(r, __byte_perm(o, 0, 0x0123));
+                }
+                // the word with the last CRC-covered byte: byte stores (what follows is the CRC field and the next frame)
+                {
+                    const uint32_t o = map4(p[rest]);
+                    uint8_t* pb = reinterpret_cast<uint8_t*>(p + rest);
+                    for (uint32_t b = 0; b < k_tail; b++) {
+                        const uint32_t m = (o >> (8 * b)) & 0xFF;
+                        pb[b] = (uint8_t)m;
+                        par ^= m;
+                        r = modq_byte(r, m);
+                    }
+                }
+                r = modq_byte(modq_byte(r, 0), 0);                      // message * x^16
+                const uint32_t t = (__popc(r) ^ __popc(par)) & 1;
+                const uint32_t crc = r ^ (t ? 0x8003u : 0u);
+                dat[q0 + fs - 2] = (uint8_t)(crc >> 8);
+                dat[q0 + fs - 1] = (uint8_t)crc;
+            };
+            if (fast) run(std::true_type{}); else run(std::false_type{});
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the lanes' writes, before the bulk store reads them
+        __syncwarp();
+        // ---- out: interior rows in one bulk store, the group's first and last partial rows byte by byte
+        const uint32_t end = lead + bytes;
+        const uint32_t head_end = lead ? min(16u, end) : 0u;
+        const uint32_t r0 = lead ? 1u : 0u;
+        const uint32_t r1 = max(end >> 4, r0);
+        if (lane == 0 && r1 > r0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(a.out + base + (uint64_t)r0 * 16), "r"(smem_u32(dat + r0 * 16)), "r"((r1 - r0) * 16) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        for (uint32_t k = lead + lane; k < head_end; k += 32) a.out[base + k] = dat[k];
+        for (uint32_t k = max(r1 * 16, head_end) + lane; k < end; k += 32) a.out[base + k] = dat[k];
+        __syncwarp();                                                   // every lane is done with the buffer
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
+}
+
 }  // namespace
 
 void launch_hca_crypt(const HcaCryptArgs& a, cudaStream_t s, uint64_t* launches) {
     if (!a.n_frames) return;
+    static const bool force_staged = [] { const char* e = getenv("CRI_HCA_CRYPT_STAGED"); return e && *e && *e != '0'; }();
+    if (a.n_groups && a.min_frame >= 128 && !force_staged) {
+        const size_t smem = kLutTableBytes + 64 + (size_t)kLutWarps * (kLutFront + a.group_bytes);
+        if (smem <= 227 * 1024) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(hca_crypt_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const uint64_t ctas = std::min<uint64_t>((a.n_groups + kLutWarps - 1) / kLutWarps, (uint64_t)sms);
+            hca_crypt_lut_kernel<<<(unsigned)ctas, kLutWarps * 32, smem, s>>>(a);
+            ++*launches;
+            return;
+        }
+    }
     if (a.n_groups) {
         const size_t smem = (size_t)kStageWarps * a.group_bytes;
         cudaFuncSetAttribute(hca_crypt_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

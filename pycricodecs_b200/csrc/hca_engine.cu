@@ -111,7 +111,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         const uint64_t total = (uint64_t)h.frame_count * 1024;
         if (total < (uint64_t)h.delay + h.padding) { j->status[i] = ERR_HCA_HEADER; continue; }
         sizes[i] = wav_header_size(h.loop_flag) + (total - h.delay - h.padding) * h.channels * 2;   // as cri_hca_decode_sizes
-        if (!v3_supported(h)) j->status[i] = ERR_UNSUPPORTED;                                        // region stays zero
+        if (!v3_supported(h)) { j->status[i] = ERR_UNSUPPORTED; j->needs_clear = true; }           // region stays zero
     }
     finish_layout_public(j, sizes);
 
@@ -276,8 +276,20 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
     }
     finish_layout_public(j, sizes);   // out_off == in_off
     {   // staged kernel: a warp stages up to 32 consecutive frames (<= 24 KB) of one stream in shared memory
-        uint32_t max_fs = 0;
-        for (const auto& st : J.streams) max_fs = std::max(max_fs, st.frame_size);
+        uint32_t max_fs = 0, min_fs = 0xFFFFFFFFu;
+        std::map<uint32_t, uint64_t> table_use;                       // frames per cipher table
+        for (const auto& st : J.streams) {
+            max_fs = std::max(max_fs, st.frame_size);
+            if (st.frame_count) {
+                min_fs = std::min(min_fs, st.frame_size);
+                table_use[st.cipher] += st.frame_count;
+            }
+        }
+        J.min_frame = min_fs == 0xFFFFFFFFu ? 0 : min_fs;
+        J.lut_table = 0;
+        uint64_t most = 0;
+        for (const auto& kv : table_use)
+            if (kv.second > most) { most = kv.second; J.lut_table = kv.first; }
         J.frames_per_group = 0;
         if (max_fs >= 8 && max_fs <= 12288) {
             J.frames_per_group = std::min(32u, std::max(1u, 24576u / max_fs));
@@ -296,7 +308,10 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
         crypt_header(hdr.data(), hs, j->encrypt ? j->ciph_type : 0);
         add_patch_public(j, j->out_off[i], hdr.data(), hs);
         const uint64_t body_end = (uint64_t)hs + (uint64_t)J.streams[i].frame_count * J.streams[i].frame_size;
-        if (body_end < len) add_patch_public(j, j->out_off[i] + body_end, d + body_end, (uint32_t)(len - body_end));
+        if (body_end < len) {        // bytes behind the last frame pass through unchanged
+            if (j->d_src) j->dev_copies.push_back({j->in_off[i] + body_end, j->out_off[i] + body_end, len - body_end});
+            else add_patch_public(j, j->out_off[i] + body_end, d + body_end, (uint32_t)(len - body_end));
+        }
     }
     return OK;
 }
@@ -467,6 +482,8 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_groups = J.group_prefix.empty() ? 0 : J.group_prefix.back();
         a.frames_per_group = J.frames_per_group;
         a.group_bytes = J.group_bytes;
+        a.lut_table = J.lut_table;
+        a.min_frame = J.min_frame;
         CU_TRY(c, cudaEventRecord(j->ev[2], j->stream));
         launch_hca_crypt(a, j->stream, &c->launches);
         CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));

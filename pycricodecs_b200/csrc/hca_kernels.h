@@ -70,6 +70,8 @@ struct HcaCryptArgs {
     uint64_t n_groups;             // 0 = lane-per-frame kernel (frames too large to stage)
     uint32_t frames_per_group;
     uint32_t group_bytes;          // shared-memory bytes per group (multiple of 16, >= frames_per_group * frame_size + 32)
+    uint32_t lut_table;            // the cipher table most streams use: the LUT kernel keeps a bank-replicated copy of it
+    uint32_t min_frame;            // smallest frame size of the job (the LUT kernel wants >= 128 bytes)
 };
 void launch_hca_crypt(const HcaCryptArgs& a, cudaStream_t s, uint64_t* launches);
 

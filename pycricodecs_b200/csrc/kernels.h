@@ -53,4 +53,15 @@ struct Patch {
 void launch_scatter_patches(uint8_t* d_out, const uint8_t* d_patch_bytes, const Patch* d_patches, uint32_t n,
                             cudaStream_t s, uint64_t* launches);
 
+// Gather byte ranges of a device blob into a packed device buffer (the device-pointer entry points fetch the
+// stream headers this way: the host plans from headers only).
+struct Segment {
+    uint64_t src_off;
+    uint64_t dst_off;
+    uint32_t bytes;
+    uint32_t pad;
+};
+void launch_gather_segments(uint8_t* d_dst, const uint8_t* d_src, const Segment* d_segs, uint32_t n, cudaStream_t s,
+                            uint64_t* launches);
+
 }  // namespace cri

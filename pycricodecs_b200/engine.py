@@ -224,6 +224,59 @@ def batch_blob(kind: int, blob: np.ndarray, offsets: np.ndarray, ctx: Optional[C
     return out, out_offsets, status[:n]
 
 
+def batch_device(kind: int, blob, offsets: np.ndarray, ctx: Optional[Context] = None, out=None, stream=None, *, keys=None,
+                 subkeys=None, adx: Optional[AdxParams] = None, quality: int = 1, encrypt: int = 0, ciph_type: int = 0):
+    """Device-resident batch: `blob` is a CUDA uint8 tensor on the context's GPU (anything with `data_ptr()`), the result
+    is a CUDA uint8 tensor too -- the payload never crosses PCIe (the `cri_*_batch_dev` calls of the C-ABI).
+
+    Returns (out, out_offsets, status). `out` may be passed in (a CUDA uint8 tensor of at least the packed output
+    size); `stream` is a torch.cuda.Stream (default: the current stream of the blob's device). Headers are fetched from
+    the device blob for planning (a few hundred bytes per stream).
+    """
+    import torch
+    ctx = ctx or default_context()
+    L = ctx._lib
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    if stream is None:
+        stream = torch.cuda.current_stream(blob.device)
+    sp_ = ctypes.c_void_p(stream.cuda_stream)
+    sizes = np.zeros(max(n, 1), dtype=np.uint64)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    keys = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+    subkeys = None if subkeys is None else np.ascontiguousarray(subkeys, dtype=np.uint16)
+    kp = None if keys is None else keys.ctypes.data
+    sp = None if subkeys is None else subkeys.ctypes.data
+    adx = adx if adx is not None else adx_params()
+    bp, op = blob.data_ptr(), offsets.ctypes.data
+    ctx.check(L.cri_sizes_dev(ctx.handle, kind, bp, op, n, ctypes.byref(adx), int(quality), sizes.ctypes.data, status.ctypes.data, sp_))
+    out_offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(sizes[:n], out=out_offsets[1:])
+    if kind == _lib.JOB_HCA_CRYPT:
+        out_offsets = offsets
+    total = int(out_offsets[-1])
+    if out is None:
+        out = torch.empty(max(total, 1), dtype=torch.uint8, device=blob.device)
+    elif out.numel() < total:
+        raise ValueError("output buffer too small")
+    oo = out_offsets.ctypes.data
+    if kind == _lib.JOB_ADX_DECODE:
+        rc = L.cri_adx_decode_batch_dev(ctx.handle, bp, op, n, out.data_ptr(), oo, status.ctypes.data, sp_)
+    elif kind == _lib.JOB_ADX_ENCODE:
+        rc = L.cri_adx_encode_batch_dev(ctx.handle, bp, op, n, ctypes.byref(adx), out.data_ptr(), oo, status.ctypes.data, sp_)
+    elif kind == _lib.JOB_HCA_DECODE:
+        rc = L.cri_hca_decode_batch_dev(ctx.handle, bp, op, n, kp, sp, out.data_ptr(), oo, status.ctypes.data, sp_)
+    elif kind == _lib.JOB_HCA_ENCODE:
+        rc = L.cri_hca_encode_batch_dev(ctx.handle, bp, op, n, int(quality), int(adx.force_not_looping), out.data_ptr(), oo,
+                                        status.ctypes.data, sp_)
+    elif kind == _lib.JOB_HCA_CRYPT:
+        rc = L.cri_hca_crypt_batch_dev(ctx.handle, bp, op, n, int(encrypt), int(ciph_type), kp, sp, out.data_ptr(), status.ctypes.data, sp_)
+    else:
+        raise ValueError(f"unknown job kind {kind}")
+    ctx.check(rc)
+    return out, out_offsets, status[:n]
+
+
 def _run_streams(kind: int, streams: Sequence[bytes], ctx: Optional[Context], raise_errors: bool, **kw):
     blob, offsets = pack(streams)
     out, offs, status = batch_blob(kind, blob, offsets, ctx, **kw)
