@@ -190,9 +190,11 @@ extern "C" const char* cri_strerror(int st) {
 
 namespace cri {
 void finish_layout_public(cri_job* j, const std::vector<uint64_t>& sizes) {
-    j->out_off.assign(j->n + 1, 0);
+    j->out_off.assign(j->n + 1, j->out_delta);
     for (uint32_t i = 0; i < j->n; i++) j->out_off[i + 1] = j->out_off[i] + sizes[i];
-    j->out_bytes = j->out_off[j->n];
+    j->out_off_pub.resize(j->n + 1);
+    for (uint32_t i = 0; i <= j->n; i++) j->out_off_pub[i] = j->out_off[i] - j->out_delta;
+    j->out_bytes = j->out_off_pub[j->n];
 }
 
 void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n) {
@@ -577,8 +579,10 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, stream, &j->shadow, &j->shadow_bytes);
         j->blob = j->shadow;
     }
-    if (d->d_out) {
-        j->d_out = d->d_out;
+    if (d->d_out) {      // kernels take a 256-byte aligned blob start: align the pointer down and shift every offset instead
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(d->d_out);
+        j->out_delta = addr & 255;
+        j->d_out = reinterpret_cast<uint8_t*>(addr - j->out_delta);
         j->own_out = false;
     }
     if (rc == OK) switch (d->kind) {
@@ -591,7 +595,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     }
     if (rc == OK && expect_out)      // the caller's buffer is laid out by *_sizes(): it must be the packed layout planned here
         for (uint32_t i = 0; i <= j->n && rc == OK; i++)
-            if (expect_out[i] - expect_out[0] != j->out_off[i]) rc = ERR_BUFFER;
+            if (expect_out[i] - expect_out[0] != j->out_off_pub[i]) rc = ERR_BUFFER;
     if (rc == OK) rc = [&]() -> int {
         int r = take_events(c, j);
         if (r != OK) return r;
@@ -603,7 +607,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         if (r != OK) return r;
         // Every byte of the output blob is written by a kernel or a patch on every run; a job that leaves gaps (streams
         // cut short, unsupported layouts) sets needs_clear and is zero-filled at the start of each run instead.
-        if (c->poison && j->out_bytes) CU_TRY(c, cudaMemsetAsync(j->d_out, 0xA5, j->out_bytes, stream));
+        if (c->poison && j->out_bytes) CU_TRY(c, cudaMemsetAsync(j->d_out + j->out_delta, 0xA5, j->out_bytes, stream));
         r = upload_vec(c, stream, j->adx_chains, &j->d_adx_chains);
         if (r == OK) r = upload_vec(c, stream, j->conv, &j->d_conv);
         if (r == OK) r = upload_vec(c, stream, j->patches, &j->d_patches);
@@ -634,7 +638,7 @@ extern "C" int cri_job_create(cri_ctx* c, const cri_job_desc* d, cri_job** out) 
 }
 
 extern "C" uint64_t cri_job_out_bytes(const cri_job* j) { return j->out_bytes; }
-extern "C" const uint64_t* cri_job_out_offsets(const cri_job* j) { return j->out_off.data(); }
+extern "C" const uint64_t* cri_job_out_offsets(const cri_job* j) { return j->out_off_pub.data(); }
 extern "C" uint64_t cri_job_units(const cri_job* j) { return j->units; }
 
 extern "C" int cri_job_upload(cri_ctx* c, cri_job* j) {
@@ -651,7 +655,7 @@ extern "C" int cri_job_upload(cri_ctx* c, cri_job* j) {
 static int job_enqueue_run(cri_ctx* c, cri_job* j) {
     cudaStream_t s = j->stream;
     CU_TRY(c, cudaMemsetAsync(j->d_status, 0, sizeof(int32_t) * std::max<uint32_t>(j->n, 1), s));
-    if (j->needs_clear) CU_TRY(c, cudaMemsetAsync(j->d_out, 0, j->out_bytes, s));
+    if (j->needs_clear && j->out_bytes) CU_TRY(c, cudaMemsetAsync(j->d_out + j->out_delta, 0, j->out_bytes, s));
     CU_TRY(c, cudaEventRecord(j->ev[0], s));
     launch_pcm_convert(j->d_in, j->d_conv, (uint32_t)j->conv.size(), j->conv_max_count, s, &c->launches);
     launch_scatter_patches(j->d_out, j->d_patch_bytes, j->d_patches, (uint32_t)j->patches.size(), s, &c->launches);
@@ -711,7 +715,7 @@ static int job_enqueue_download(cri_ctx* c, cri_job* j, uint8_t* out_blob, int32
     j->dl_out = out_blob;
     j->dl_status = status;
     if (j->n) CU_TRY(c, cudaMemcpyAsync(landing, j->d_status, sizeof(int32_t) * j->n, cudaMemcpyDeviceToHost, j->stream));
-    if (out_blob && j->out_bytes) CU_TRY(c, cudaMemcpyAsync(out_blob, j->d_out, j->out_bytes, cudaMemcpyDeviceToHost, j->stream));
+    if (out_blob && j->out_bytes) CU_TRY(c, cudaMemcpyAsync(out_blob, j->d_out + j->out_delta, j->out_bytes, cudaMemcpyDeviceToHost, j->stream));
     return OK;
 }
 
@@ -721,7 +725,7 @@ static int job_wait_download(cri_ctx* c, cri_job* j) {
         const int32_t st = j->status[i] != OK ? j->status[i] : j->h_status[i];
         if (j->dl_status) j->dl_status[i] = st;
         if (st != OK && j->dl_out && j->status[i] == OK)  // a stream that failed on the device leaves silence, not garbage
-            memset(j->dl_out + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i]);
+            memset(j->dl_out + j->out_off_pub[i], 0, j->out_off_pub[i + 1] - j->out_off_pub[i]);
     }
     return OK;
 }
@@ -766,10 +770,10 @@ static int chunk_finish(cri_ctx* c, ChunkRun& r, uint8_t* out_blob, const uint64
     if (rc == OK) rc = job_wait_download(c, j);
     if (rc == OK && !r.packed)       // caller chose a different layout: place each stream from the staging blob
         for (uint32_t i = 0; i < j->n; i++) {
-            const uint64_t sz = j->out_off[i + 1] - j->out_off[i];
+            const uint64_t sz = j->out_off_pub[i + 1] - j->out_off_pub[i];
             const uint64_t* oo = out_offsets + r.s0;
             if (oo[i + 1] - oo[i] < sz) { if (status) status[r.s0 + i] = ERR_BUFFER; continue; }
-            memcpy(out_blob + oo[i], j->staging.data() + j->out_off[i], sz);
+            memcpy(out_blob + oo[i], j->staging.data() + j->out_off_pub[i], sz);
         }
     cri_job_destroy(c, j);
     r.job = nullptr;
@@ -820,7 +824,7 @@ static int run_batch(cri_ctx* c, cri_job_desc d, uint8_t* out_blob, const uint64
         if (rc != OK) break;
         r.packed = true;
         if (out_offsets)
-            for (uint32_t i = 0; i <= m && r.packed; i++) r.packed = out_offsets[r.s0 + i] - out_offsets[r.s0] == j->out_off[i];
+            for (uint32_t i = 0; i <= m && r.packed; i++) r.packed = out_offsets[r.s0 + i] - out_offsets[r.s0] == j->out_off_pub[i];
         uint8_t* dst;
         if (r.packed) {
             dst = out_blob ? out_blob + (out_offsets ? out_offsets[r.s0] : 0) : nullptr;

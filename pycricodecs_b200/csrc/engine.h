@@ -46,8 +46,11 @@ struct cri_job {
     int kind = 0;
     uint32_t n = 0;
     const uint8_t* blob = nullptr;            // caller's host input (borrowed for the job's lifetime)
-    std::vector<uint64_t> in_off, out_off;
-    uint64_t in_bytes = 0, out_bytes = 0, units = 0;
+    std::vector<uint64_t> in_off, out_off;    // out_off: offsets from d_out (start at out_delta)
+    std::vector<uint64_t> out_off_pub;        // the same from the start of the output blob (what callers see)
+    uint64_t in_bytes = 0, out_bytes = 0, units = 0;   // out_bytes: size of the output blob (without out_delta)
+    uint64_t out_delta = 0;                   // device-pointer jobs: the caller's buffer starts this many bytes behind the
+                                              //  256-byte aligned address the kernels take as the blob's start
     std::vector<int32_t> status;              // host-side (header / parameter) status per stream
     std::vector<uint64_t> keys;
     std::vector<uint16_t> subkeys;

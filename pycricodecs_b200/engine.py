@@ -224,6 +224,23 @@ def batch_blob(kind: int, blob: np.ndarray, offsets: np.ndarray, ctx: Optional[C
     return out, out_offsets, status[:n]
 
 
+def sizes_device(kind: int, blob, offsets: np.ndarray, ctx: Optional[Context] = None, stream=None, *, adx: Optional[AdxParams] = None,
+                 quality: int = 1, **_ignored):
+    """Exact output size of every stream of a device-resident blob (`cri_sizes_dev`): (sizes uint64[n], status int32[n])."""
+    import torch
+    ctx = ctx or default_context()
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    if stream is None:
+        stream = torch.cuda.current_stream(blob.device)
+    sizes = np.zeros(max(n, 1), dtype=np.uint64)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    adx = adx if adx is not None else adx_params()
+    ctx.check(ctx._lib.cri_sizes_dev(ctx.handle, kind, blob.data_ptr(), offsets.ctypes.data, n, ctypes.byref(adx), int(quality),
+                                     sizes.ctypes.data, status.ctypes.data, ctypes.c_void_p(stream.cuda_stream)))
+    return sizes[:n], status[:n]
+
+
 def batch_device(kind: int, blob, offsets: np.ndarray, ctx: Optional[Context] = None, out=None, stream=None, *, keys=None,
                  subkeys=None, adx: Optional[AdxParams] = None, quality: int = 1, encrypt: int = 0, ciph_type: int = 0):
     """Device-resident batch: `blob` is a CUDA uint8 tensor on the context's GPU (anything with `data_ptr()`), the result
