@@ -86,7 +86,8 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
     """Run one batch over all ranks of the process group.
 
     `blob` is the WHOLE batch (host numpy uint8 array, or a torch tensor on any device; a rank only touches the bytes of
-    its own pieces), `offsets` the n + 1 stream offsets. Per-stream keyword arrays (`keys`, `subkeys`) are global and are
+    its own pieces) or a callable `blob(lo, hi)` that returns the device tensor with streams lo .. hi - 1 of one of this
+    rank's pieces; `offsets` are the n + 1 stream offsets. Per-stream keyword arrays (`keys`, `subkeys`) are global and are
     sliced per piece.
 
     Returns (out, out_offsets, status); `out_offsets` (n + 1) and `status` (n) are global:
@@ -136,7 +137,9 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
     def piece_input(lo, hi):
         if (lo, hi) not in inputs:
             b0, b1 = int(offsets[lo]), int(offsets[hi])
-            if isinstance(blob, torch.Tensor):
+            if callable(blob):                                   # the caller hands out pieces itself (e.g. already in HBM)
+                inputs[(lo, hi)] = blob(lo, hi)
+            elif isinstance(blob, torch.Tensor):
                 t = blob[b0:b1]
                 inputs[(lo, hi)] = t if t.device == device else t.to(device, non_blocking=True)
             else:
