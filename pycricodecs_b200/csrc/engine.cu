@@ -62,6 +62,7 @@ extern "C" void cri_ctx_destroy(cri_ctx* c) {
     for (auto& p : c->pin_status) cudaFreeHost(p);
     for (auto& e : c->idle_events) cudaEventDestroy(e);
     if (c->pin_stage) cudaFreeHost(c->pin_stage);
+    for (auto& sh : c->idle_shadows) munmap(sh.first, sh.second);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -501,14 +502,34 @@ static int fetch_segments(cri_ctx* c, cudaStream_t stream, const uint8_t* d_blob
 }
 
 // Builds the host shadow of a device blob: *shadow (munmap it with *bytes) holds every header byte planning reads.
+// The shadow is an all-zero anonymous mapping of the blob's size; only fetched ranges are ever written, `dirty` lists them
+// and release_shadow zeroes them again, so a context can hand the same mapping (its pages already faulted in) to the
+// next job: a fresh mapping costs one page fault per stream.
+static void release_shadow(cri_ctx* c, uint8_t* shadow, size_t bytes, const std::vector<std::pair<uint64_t, uint32_t>>& dirty) {
+    if (!shadow) return;
+    if (!c || c->idle_shadows.size() >= 2) { munmap(shadow, bytes); return; }
+    for (const auto& d : dirty) memset(shadow + d.first, 0, d.second);
+    c->idle_shadows.emplace_back(shadow, bytes);
+}
+
 static int build_shadow(cri_ctx* c, int kind, const uint8_t* d_blob, const uint64_t* off, uint32_t n, cudaStream_t stream,
-                        uint8_t** shadow, size_t* bytes) {
-    const uint64_t base0 = n ? off[0] : 0, total_in = n ? off[n] : 0;
-    *bytes = (size_t)std::max<uint64_t>(total_in, 1) + 64;
-    void* m = mmap(nullptr, *bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    if (m == MAP_FAILED) { *shadow = nullptr; return ERR_BUFFER; }
-    *shadow = (uint8_t*)m;
-    (void)base0;
+                        uint8_t** shadow, size_t* bytes, std::vector<std::pair<uint64_t, uint32_t>>* dirty) {
+    const uint64_t total_in = n ? off[n] : 0;
+    const size_t want = (size_t)std::max<uint64_t>(total_in, 1) + 64;
+    *shadow = nullptr;
+    for (size_t k = 0; k < c->idle_shadows.size(); k++)
+        if (c->idle_shadows[k].second >= want) {
+            *shadow = c->idle_shadows[k].first;
+            *bytes = c->idle_shadows[k].second;
+            c->idle_shadows.erase(c->idle_shadows.begin() + k);
+            break;
+        }
+    if (!*shadow) {
+        *bytes = want;
+        void* m = mmap(nullptr, *bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) return ERR_BUFFER;
+        *shadow = (uint8_t*)m;
+    }
     std::vector<Valid> valid(n);
     std::vector<Segment> segs;
     std::vector<uint64_t> shadow_off;
@@ -534,6 +555,7 @@ static int build_shadow(cri_ctx* c, int kind, const uint8_t* d_blob, const uint6
         }
         if (segs.empty()) break;
         const int r = fetch_segments(c, stream, d_blob, segs, total, *shadow, shadow_off);
+        for (size_t k = 0; k < segs.size(); k++) dirty->emplace_back(shadow_off[k], segs[k].bytes);
         if (r != OK) return r;
         for (auto& g : got) {
             Valid& v = valid[g.first];
@@ -576,7 +598,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     int rc = OK;
     if (d->d_blob) {
         j->d_src = d->d_blob;
-        rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, stream, &j->shadow, &j->shadow_bytes);
+        rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, stream, &j->shadow, &j->shadow_bytes, &j->shadow_dirty);
         j->blob = j->shadow;
     }
     if (d->d_out) {      // kernels take a 256-byte aligned blob start: align the pointer down and shift every offset instead
@@ -743,7 +765,7 @@ extern "C" void cri_job_destroy(cri_ctx* c, cri_job* j) {
     for (auto& e : j->ev)
         if (e) { if (c) c->idle_events.push_back(e); else cudaEventDestroy(e); }
     if (!j->own_out) j->d_out = nullptr;
-    if (j->shadow) munmap(j->shadow, j->shadow_bytes);
+    release_shadow(c, j->shadow, j->shadow_bytes, j->shadow_dirty);
     for (void* p : {(void*)j->d_in, (void*)j->d_out, (void*)j->d_status, (void*)j->d_adx_chains, (void*)j->d_conv, (void*)j->d_patches,
                     (void*)j->d_patch_bytes})
         pool_free(c, p);
@@ -1023,7 +1045,8 @@ extern "C" int cri_sizes_dev(cri_ctx* c, int kind, const uint8_t* d_blob, const 
     }
     uint8_t* shadow = nullptr;
     size_t bytes = 0;
-    int rc = build_shadow(c, kind, d_blob, off, n, stream ? (cudaStream_t)stream : c->stream, &shadow, &bytes);
+    std::vector<std::pair<uint64_t, uint32_t>> dirty;
+    int rc = build_shadow(c, kind, d_blob, off, n, stream ? (cudaStream_t)stream : c->stream, &shadow, &bytes, &dirty);
     if (rc == OK) switch (kind) {
         case CRI_JOB_ADX_DECODE: rc = cri_adx_decode_sizes(shadow, off, n, sizes, status); break;
         case CRI_JOB_ADX_ENCODE: rc = adx ? cri_adx_encode_sizes(shadow, off, n, adx, sizes, status) : ERR_BUFFER; break;
@@ -1031,7 +1054,7 @@ extern "C" int cri_sizes_dev(cri_ctx* c, int kind, const uint8_t* d_blob, const 
         case CRI_JOB_HCA_ENCODE: rc = cri_hca_encode_sizes_ex(shadow, off, n, quality, adx ? adx->force_not_looping : 0, sizes, status); break;
         default: rc = ERR_UNSUPPORTED;
     }
-    if (shadow) munmap(shadow, bytes);
+    release_shadow(c, shadow, bytes, dirty);
     return rc;
 }
 

@@ -33,6 +33,7 @@ struct cri_ctx {
     size_t pin_status_cap[kPipeDepth] = {};     //  pageable memory would block the host until the chunk's kernels end)
     DevPool pool;
     std::vector<cudaEvent_t> idle_events;       // events of finished jobs, reused by the next ones
+    std::vector<std::pair<uint8_t*, size_t>> idle_shadows;   // header shadows of finished device-pointer jobs (all zero again)
     uint8_t* pin_stage = nullptr;               // page-locked landing buffer of the header fetches of device-pointer jobs
     size_t pin_stage_cap = 0;
     bool poison = false;                        // CRI_POISON=1 (tests): output blobs start as 0xA5 so that a byte no kernel writes shows
@@ -78,6 +79,7 @@ struct cri_job {
     const uint8_t* d_src = nullptr;
     uint8_t* shadow = nullptr;
     size_t shadow_bytes = 0;
+    std::vector<std::pair<uint64_t, uint32_t>> shadow_dirty;   // fetched ranges: zeroed again when the shadow goes back to the context
     bool own_out = true;
     struct DevCopy { uint64_t src_off, dst_off, bytes; };
     std::vector<DevCopy> dev_copies;          // input bytes that pass through unchanged (in place of host-built patches)

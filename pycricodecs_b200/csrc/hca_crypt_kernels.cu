@@ -222,16 +222,13 @@ struct CryptGroup {          // one group = up to 32 consecutive frames of one s
     uint64_t base;           // 16-byte aligned start in both blobs
 };
 __device__ __forceinline__ CryptGroup crypt_group(const HcaCryptArgs& a, uint64_t gid) {
-    uint32_t lo = 0, hi = a.n_streams;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(a.group_prefix + mid) <= gid) lo = mid; else hi = mid;
-    }
+    const uint2 e = __ldg(a.group_table + gid);              // host-built: no search (a search is ~13 dependent loads per group)
+    const uint32_t lo = e.x;
     const HcaStreamDev& S = a.streams[lo];
     CryptGroup g;
     g.stream = lo;
     g.fs = S.frame_size;
-    const uint32_t f0 = (uint32_t)(gid - __ldg(a.group_prefix + lo)) * a.frames_per_group;
+    const uint32_t f0 = e.y;
     g.cnt = min(a.frames_per_group, S.frame_count - f0);
     const uint64_t off0 = S.in_off + (uint64_t)f0 * g.fs;     // same offset in both blobs
     g.bytes = g.cnt * g.fs;

@@ -297,6 +297,9 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
             J.group_prefix.assign(j->n + 1, 0);
             for (uint32_t i = 0; i < j->n; i++)
                 J.group_prefix[i + 1] = J.group_prefix[i] + (J.streams[i].frame_count + J.frames_per_group - 1) / J.frames_per_group;
+            J.group_table.reserve(J.group_prefix[j->n]);
+            for (uint32_t i = 0; i < j->n; i++)
+                for (uint32_t f = 0; f < J.streams[i].frame_count; f += J.frames_per_group) J.group_table.push_back(make_uint2(i, f));
         }
     }
     for (uint32_t i = 0; i < j->n; i++) {
@@ -415,6 +418,7 @@ int upload_hca_tables(cri_ctx* c, cri_job* j) {
     if (r == OK) r = upload(c, s, J.crc_mul, &J.d_crc_mul);
     if (r == OK) r = upload(c, s, J.dec_prefix, &J.d_dec_prefix);
     if (r == OK) r = upload(c, s, J.group_prefix, &J.d_group_prefix);
+    if (r == OK) r = upload(c, s, J.group_table, &J.d_group_table);
     if (r == OK && J.spec_bytes) r = pool_alloc(c, (void**)&J.d_spec, J.spec_bytes);
     if (r == OK && J.q_bytes) r = pool_alloc(c, (void**)&J.d_q, J.q_bytes);
     if (r == OK && J.g_bytes) r = pool_alloc(c, (void**)&J.d_g, J.g_bytes);
@@ -479,6 +483,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_streams = j->n;
         a.n_tables = (uint32_t)(J.cipher_tables.size() / 256);
         a.group_prefix = J.d_group_prefix;
+        a.group_table = J.d_group_table;
         a.n_groups = J.group_prefix.empty() ? 0 : J.group_prefix.back();
         a.frames_per_group = J.frames_per_group;
         a.group_bytes = J.group_bytes;
@@ -517,7 +522,7 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
 void free_hca_tables(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
     for (void* p : {(void*)J.d_streams, (void*)J.d_units, (void*)J.d_s, (void*)J.d_frame_prefix, (void*)J.d_crc_mul,
-                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec, (void*)J.d_group_prefix, (void*)J.d_n})
+                    (void*)J.d_cipher, (void*)J.d_ath, (void*)J.d_q, (void*)J.d_g, (void*)J.d_i, (void*)J.d_dec_prefix, (void*)J.d_spec, (void*)J.d_group_prefix, (void*)J.d_group_table, (void*)J.d_n})
         pool_free(c, p);
 }
 

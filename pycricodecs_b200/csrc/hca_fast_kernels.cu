@@ -62,6 +62,7 @@ __device__ __forceinline__ void hca_sum2(unsigned long long one, float p0, float
 }
 
 #include "hca_dct_thread_gen.inc"
+#include "hca_dct_pair_gen.inc"
 
 constexpr int kFastThreads = 128;             // unpack kernel
 constexpr int kFastWarps = kFastThreads / 32;
@@ -667,6 +668,213 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ transform, warp pairs
+// The same transform with every column split over a PAIR of warps: warp h of the pair keeps coefficients 64 h .. 64 h + 63
+// of the pair's 32 columns (lane = column, as above) in 64 registers. Twelve of the fourteen passes, the window and the
+// overlap state stay inside a half (tools/gen_dct.py: gen_imdct_half); for the two passes in the middle every lane
+// publishes its 64 values in shared memory once, the pair meets at a named barrier and each lane recomputes the sums
+// from its own and its partner's value. Half the registers per thread means twice the warps per SM for the same number
+// of columns in flight -- the thread-resident kernel above sits at two warps per scheduler, which is what left it at
+// about half of the fp32 rate -- and half the straight-line code per warp. The two warps of a pair run different
+// instruction streams (all rotation factors are immediates), so the split is by warp, not by lane.
+//
+// Shared memory per pair: exchange area 2 x 16 x 32 float4 (16 KB), PCM tile (both warps' samples of a subframe meet
+// there; rows leave coalesced, half of them by each warp), overlap state 8 float4 per thread.
+template <int H, class Store, class Barrier, class Load, class Sync>
+__device__ __forceinline__ void dct_half(float (&x)[64], const unsigned long long one, Store store, Barrier barrier, Load load, Sync sync) {
+    if (H == 0) hca_dct4_dec_h0(x, one, store, barrier, load, sync);
+    else hca_dct4_dec_h1(x, one, store, barrier, load, sync);
+}
+
+template <int NCH, int PAIRS, int CONVOY, bool JOINT>
+struct PairXf {
+    static constexpr int THREADS = PAIRS * 64;
+    static constexpr int RW = 32 / NCH;                 // runs (= tile rows) per pair
+    static constexpr int ROW_WORDS = 64 * NCH;          // 128 samples x NCH channels x int16
+    static constexpr int PITCH = ROW_WORDS + 1;         // odd word pitch: the column writes of the window are conflict-free
+    static constexpr int TILE_WORDS = RW * PITCH + RW * 4;
+    static constexpr size_t kCarryBytes = (size_t)8 * THREADS * sizeof(float4);
+    static constexpr size_t kXchgBytes = (size_t)2 * 16 * 32 * sizeof(float4);
+    static constexpr size_t kPairBytes = kXchgBytes + (size_t)TILE_WORDS * sizeof(uint32_t);
+    static constexpr size_t kSmem = kCarryBytes + PAIRS * kPairBytes;
+
+    template <int H>
+    static __device__ __forceinline__ void body(const HcaDecodeArgs& a, uint8_t* s_dyn) {
+        const int lane = threadIdx.x & 31, pair = threadIdx.x >> 6;
+        float4* carry = reinterpret_cast<float4*>(s_dyn) + threadIdx.x;                                  // [8][THREADS]
+        uint8_t* pair_mem = s_dyn + kCarryBytes + (size_t)pair * kPairBytes;
+        float4* xw = reinterpret_cast<float4*>(pair_mem) + H * 512 + lane;                                 // own half: [16][32]
+        const float4* xr = reinterpret_cast<const float4*>(pair_mem) + (1 - H) * 512 + lane;               // the partner's
+        uint32_t* tile = reinterpret_cast<uint32_t*>(pair_mem + kXchgBytes);
+        RowDesc* rows = reinterpret_cast<RowDesc*>(tile + RW * PITCH);
+
+        const int rr = lane % RW, ch = lane / RW;
+        const uint32_t W = blockIdx.x * PAIRS + pair;
+        const uint32_t R = a.run_len;
+        const uint32_t r = W * RW + rr;
+        const bool live = r < a.n_runs;
+        const uint32_t G = (uint32_t)a.total_frames;
+        uint32_t g = live ? r * R : G;
+        uint32_t s = 0, f = 0, cnt = 0;
+        if (live) {
+            s = find_stream(a.dec_prefix, a.n_streams, g);
+            const uint32_t p0 = __ldg(a.dec_prefix + s);
+            f = g - p0;
+            cnt = __ldg(a.dec_prefix + s + 1) - p0;
+        }
+        auto convoy = [&](int k) {
+            if (CONVOY > 0 && k % CONVOY == 0) __syncthreads();
+        };
+        auto meet = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); };
+        auto publish = [&](int q, float v0, float v1, float v2, float v3) { xw[q * 32] = make_float4(v0, v1, v2, v3); };
+        auto partner = [&](int q) -> float4 { return xr[q * 32]; };
+        // intensity stereo (see hca_imdct_fast_kernel): this half's bands only
+        auto intensity = [&](float (&x)[64], bool pair_joint, uint32_t inten, int sub, int base, int total) {
+            if (!JOINT || NCH != 2 || !__any_sync(kFull, pair_joint)) return;
+            const float rl = __uint_as_float(c_intensity[(inten >> (4 * sub)) & 15]);
+            const float mine = ch == 0 ? rl : __fsub_rn(2.0f, rl);
+#pragma unroll
+            for (int i = 0; i < 64; i++) {
+                const float left = __shfl_sync(kFull, x[i], lane & (RW - 1));
+                if (pair_joint && 64 * H + i >= base && 64 * H + i < total) x[i] = __fmul_rn(left, mine);
+            }
+        };
+        auto load_half = [&](float (&x)[64], const float4* __restrict__ src, bool ok) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v = __ldcs(src + (16 * H + i) * 32);
+                x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+            }
+        };
+        float x[64];
+        {   // look-back: the DCT output of the last subframe in front of the run (zero at the start of a stream)
+            const bool lb = live && f > 0;
+            const uint32_t r1 = lb ? r - 1 : 0;
+            const float4* src = a.spec + (((uint64_t)(r1 / RW) * R + (R - 1)) * 8 + 7) * 1024 + ch * RW + (r1 % RW);
+            load_half(x, src, lb);
+            {
+                const HcaStreamDev& S = a.streams[s];
+                const bool pj = JOINT && lb && S.type[ch] != 0;
+                intensity(x, pj, pj ? __ldg(a.inten + g - 1) : 0u, 7, (int)S.base_bands, (int)S.total_bands);
+            }
+            dct_half<H>(x, a.one2, publish, meet, partner, convoy);
+            if (H == 0) hca_carry_h0<THREADS>(x, carry); else hca_carry_h1<THREADS>(x, carry);
+            meet();                                   // the partner has read this half's published values
+        }
+
+        const float4* src = a.spec + (uint64_t)W * R * (8 * 1024) + lane;     // block (j, sub) at + (j * 8 + sub) * 1024
+        uint8_t* trow = reinterpret_cast<uint8_t*>(tile + rr * PITCH) + 2 * ch;
+        load_half(x, src, live && g < G);
+        for (uint32_t j = 0; j < R; j++, g++) {
+            const bool ok = live && g < G;
+            bool fresh = false;
+            if (ok && f >= cnt) {                    // the run crosses into the next stream: the overlap state starts at zero
+                do {
+                    s++;
+                    cnt = __ldg(a.dec_prefix + s + 1) - __ldg(a.dec_prefix + s);
+                } while (cnt == 0);
+                f = 0;
+                fresh = true;
+            }
+            if (__any_sync(kFull, fresh)) {
+                if (fresh) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) carry[q * THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            long long out_off = 0;
+            int out_samples = 0, delay = 0;
+            bool pair_joint = false;
+            uint32_t inten = 0;
+            int jbase = 0, jtotal = 0;
+            if (ok) {
+                const HcaStreamDev& S = a.streams[s];
+                out_off = (long long)S.out_off;
+                out_samples = (int)S.out_samples;
+                delay = (int)S.delay;
+                if (JOINT && NCH == 2 && S.type[ch] != 0) {
+                    pair_joint = true;
+                    inten = __ldg(a.inten + g);
+                    jbase = (int)S.base_bands; jtotal = (int)S.total_bands;
+                }
+            }
+            const bool ok_next_frame = live && j + 1 < R && g + 1 < G;
+#pragma unroll 1
+            for (int sub = 0; sub < 8; sub++) {
+                intensity(x, pair_joint, inten, sub, jbase, jtotal);
+                dct_half<H>(x, a.one2, publish, meet, partner, convoy);
+                if (ch == 0 && H == 0) {
+                    const long long n0 = (long long)f * 1024 + sub * 128 - delay;     // stream sample index of the row's sample 0
+                    RowDesc d;
+                    d.off = out_off + n0 * (2 * NCH);
+                    d.lo = ok ? (int)max(0ll, min(128ll, -n0)) : 0;
+                    d.hi = ok ? (int)max(0ll, min(128ll, (long long)out_samples - n0)) : 0;
+                    rows[rr] = d;
+                }
+                src += 1024;
+                const bool ok_next = sub < 7 ? ok : ok_next_frame;
+                const float4* nsrc = ok_next ? src : a.spec + lane;   // idle lanes read block 0: never stored, no predicate needed
+                auto cvt = [](float v) { return pcm16_sat(v); };
+                auto emit = [&](int i, short v) { *reinterpret_cast<short*>(trow + i * (2 * NCH)) = v; };
+                auto refill = [&](int c) {
+                    const float4 v = __ldcs(nsrc + (16 * H + c) * 32);
+                    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                };
+                if (H == 0) hca_window_h0<THREADS>(x, carry, a.one2, cvt, emit, refill);
+                else hca_window_h1<THREADS>(x, carry, a.one2, cvt, emit, refill);
+                meet();                              // both halves' samples are in the tile
+                // ---- coalesced copy-out, one tile row (= 128 consecutive samples of one stream, all channels) at a time;
+                // the rows are shared out between the two warps
+#pragma unroll 4
+                for (int row = H; row < RW; row += 2) {
+                    const RowDesc d = rows[row];
+                    if (d.lo >= d.hi) continue;
+                    uint8_t* dst = a.out + d.off;
+                    const uint32_t* trw = tile + row * PITCH;
+                    const bool full = d.lo == 0 && d.hi == 128;
+                    if (NCH == 2) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int w = lane + 32 * k;                      // word w = sample w (left | right << 16)
+                            if (full || (w >= d.lo && w < d.hi)) reinterpret_cast<uint32_t*>(dst)[w] = trw[w];
+                        }
+                    } else if (full && (d.off & 3) == 0) {
+#pragma unroll
+                        for (int k = 0; k < 2; k++) reinterpret_cast<uint32_t*>(dst)[lane + 32 * k] = trw[lane + 32 * k];
+                    } else {
+                        const uint16_t* t16 = reinterpret_cast<const uint16_t*>(trw);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int i = lane + 32 * k;
+                            if (i >= d.lo && i < d.hi) reinterpret_cast<uint16_t*>(dst)[i] = t16[i];
+                        }
+                    }
+                }
+            }
+            f++;
+        }
+    }
+};
+
+template <int NCH, int PAIRS, int CONVOY, bool JOINT>
+__global__ void __launch_bounds__(PAIRS * 64, 1)
+hca_imdct_pair_kernel(const __grid_constant__ HcaDecodeArgs a) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    if ((threadIdx.x >> 5) & 1) PairXf<NCH, PAIRS, CONVOY, JOINT>::template body<1>(a, s_dyn);
+    else PairXf<NCH, PAIRS, CONVOY, JOINT>::template body<0>(a, s_dyn);
+}
+
+constexpr int kPairs = 6;                     // warp pairs per CTA (one CTA per SM): 12 warps, 192 columns in flight
+
+template <int NCH, int PAIRS, int CONVOY, bool JOINT>
+void launch_xf_pair(const HcaDecodeArgs& a, cudaStream_t s) {
+    using K = PairXf<NCH, PAIRS, CONVOY, JOINT>;
+    cudaFuncSetAttribute(hca_imdct_pair_kernel<NCH, PAIRS, CONVOY, JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::kSmem);
+    const uint32_t col_warps = (a.n_runs + K::RW - 1) / K::RW;
+    hca_imdct_pair_kernel<NCH, PAIRS, CONVOY, JOINT><<<(col_warps + PAIRS - 1) / PAIRS, PAIRS * 64, K::kSmem, s>>>(a);
+}
+
 constexpr int kXfThreads = 256;
 
 template <int NCH, int THREADS, int CONVOY, bool JOINT>
@@ -686,22 +894,32 @@ void launch_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cud
     hca_unpack_fast_kernel<NCH, JOINT><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
+    static const int xf = [] { const char* e = getenv("CRI_HCA_XF"); return e && *e ? atoi(e) : 1; }();
+    if (xf == 0) launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // thread-resident; CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
+    else if (xf == 2) launch_xf_pair<NCH, kPairs, 2, JOINT>(a, s);
+    else launch_xf_pair<NCH, kPairs, 0, JOINT>(a, s);
     ++*launches;
 }
 
 }  // namespace
 
-uint32_t hca_fast_threads_per_cta() { return kXfThreads; }
+uint32_t hca_fast_threads_per_cta() {
+    const char* e = getenv("CRI_HCA_XF");
+    return e && *e && atoi(e) == 0 ? kXfThreads : kPairs * 32;   // columns per CTA (the host sizes run_len by it)
+}
 uint32_t hca_fast_ctas_per_sm() { return 1; }
 
 void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
     if (!a.n_runs) return;
+#ifdef CRI_DEV_ONE_VARIANT       // development builds: one template variant only (compile time)
+    launch_fast<2, false>(a, s, launches, mid);
+#else
     if (a.uniform == 2) {
         if (a.joint) launch_fast<2, true>(a, s, launches, mid); else launch_fast<2, false>(a, s, launches, mid);
     } else {
         if (a.joint) launch_fast<1, true>(a, s, launches, mid); else launch_fast<1, false>(a, s, launches, mid);
     }
+#endif
 }
 
 }  // namespace cri

@@ -67,6 +67,7 @@ struct HcaCryptArgs {
     uint32_t n_tables;
     // staged kernel: groups of up to frames_per_group consecutive frames of one stream, one warp each
     const uint64_t* group_prefix;  // [n_streams + 1] exclusive prefix of groups per stream
+    const uint2* group_table;      // [n_groups] (stream, first frame of the group): what the LUT kernel reads instead of searching
     uint64_t n_groups;             // 0 = lane-per-frame kernel (frames too large to stage)
     uint32_t frames_per_group;
     uint32_t group_bytes;          // shared-memory bytes per group (multiple of 16, >= frames_per_group * frame_size + 32)

@@ -72,6 +72,8 @@ struct HcaJob {
     uint64_t* d_frame_prefix = nullptr;
     std::vector<uint64_t> group_prefix;    // crypt, staged kernel: exclusive prefix of frame groups per stream
     uint64_t* d_group_prefix = nullptr;
+    std::vector<uint2> group_table;        // crypt, LUT kernel: (stream, first frame) of every group
+    uint2* d_group_table = nullptr;
     uint32_t frames_per_group = 0, group_bytes = 0, lut_table = 0, min_frame = 0;
     uint32_t enc_frame_words = 0;
     std::vector<uint16_t> crc_mul;         // encode: [stream][32] CRC chunk multipliers

@@ -297,6 +297,256 @@ def gen_thread_window(lockstep: int = 0, packed: bool = False) -> list[str]:
     return out
 
 
+def _final_mapping():
+    """phys[m] = register (= input coefficient index) that holds dct[m] after the fourteen passes."""
+    phys = list(range(128))
+    half = 64
+    while half >= 1:
+        nxt = [None] * 128
+        for j in range(64 // half):
+            for k in range(half):
+                a, b = phys[j * 2 * half + 2 * k], phys[j * 2 * half + 2 * k + 1]
+                nxt[j * 2 * half + k], nxt[j * 2 * half + half + k] = a, b
+        phys = nxt
+        half //= 2
+    for stage in range(7):
+        half = 1 << stage
+        nxt = [None] * 128
+        for j in range(64 >> stage):
+            for k in range(half):
+                a, b = phys[j * 2 * half + k], phys[j * 2 * half + half + k]
+                nxt[j * 2 * half + k], nxt[j * 2 * half + 2 * half - 1 - k] = a, b
+        phys = nxt
+    return phys
+
+
+def gen_imdct_half(h: int, lockstep: int = 0) -> list[str]:
+    """One HALF of the decoder's 128-point DCT-IV for the warp-pair transform kernel (hca_imdct_pair_kernel): a lane
+    of warp h of a pair keeps the coefficients with register index 64 h .. 64 h + 63 (= input coefficients, the network
+    never moves a value out of its register). The fourteen passes pair registers that differ in bit 0, 1, .., 6 (sums
+    and differences) and then 6, 5, .., 0 (rotations), so only the two passes in the middle cross the halves -- and
+    they work on the SAME pairs (r, r + 64): sum / difference a' = a + b, b' = a - b, then the rotation a'' = a' sin -
+    b' cos, b'' = a' cos + b' sin. A lane therefore publishes its 64 values once (store), the pair meets (barrier), and
+    each lane recomputes a' and b' from its own and its partner's value and keeps the output it owns. The two halves
+    run different instruction streams (every rotation factor is an immediate), which is why the split is by warp.
+
+    Arithmetic contract as gen_imdct: the reference network (hca.cpp:1898-1972), operand order and rounding points
+    unchanged; two-wide forms (hca_bfly2 / hca_sum2) for sums whose registers are an even/odd pair."""
+    sin, cos = T.imdct_trig()
+    sin = sin.reshape(7, 64)
+    cos = cos.reshape(7, 64)
+    base = 64 * h
+    out = []
+    out.append(f"// Half {h} (registers {base}..{base + 63}) of the 128-point DCT-IV of the HCA decoder, in place on x[0..63] = coefficient {base} + r.")
+    out.append("// store(q, a, b, c, d): publish own values 4q..4q+3 after the first six passes; barrier(): the pair meets;")
+    out.append("// load(q): the partner's values 4q..4q+3. Afterwards dct[m] lives in x[phys(m) - base] (see hca_window_half).")
+    out.append("template <class Store, class Barrier, class Load, class Sync>")
+    out.append(f"__device__ __forceinline__ void hca_dct4_dec_h{h}(float (&x)[64], const unsigned long long one, Store store, Barrier barrier, Load load, Sync sync) {{")
+    out.append("    float t0, t1, t2, t3, u0, u1, u2, u3, r0, r1, r2, r3, w0, w1, w2, w3, y0, y1, y2, y3, z0, z1, z2, z3;")
+    out.append("    float4 p;")
+    since = 0
+    nsync = [0]
+
+    def sync_line():
+        nsync[0] += 1
+        return f"    sync({nsync[0]});"
+    phys = list(range(128))
+    half = 64
+    cross = None
+    while half >= 1:
+        blocks = 64 // half
+        nxt = [None] * 128
+        pairs = set()
+        for j in range(blocks):
+            for k in range(half):
+                pairs.add((phys[j * 2 * half + 2 * k], phys[j * 2 * half + 2 * k + 1]))
+        if half == 1:
+            cross = sorted(pairs)
+            assert all(b == a + 64 and a < 64 for a, b in cross)
+        for j in range(blocks):
+            for k in range(half):
+                a = phys[j * 2 * half + 2 * k]
+                b = phys[j * 2 * half + 2 * k + 1]
+                nxt[j * 2 * half + k] = a
+                nxt[j * 2 * half + half + k] = b
+                if half == 1 or a // 64 != h:
+                    continue
+                assert b // 64 == h
+                la, lb = a - base, b - base
+                if a % 2 == 0 and b % 2 == 0 and (a + 1, b + 1) in pairs:
+                    out.append(f"    hca_bfly2(x[{la}], x[{la + 1}], x[{lb}], x[{lb + 1}]);")
+                elif a % 2 == 1 and b % 2 == 1 and (a - 1, b - 1) in pairs:
+                    continue
+                else:
+                    out.append(f"    t0 = __fadd_rn(x[{la}], x[{lb}]); x[{lb}] = __fsub_rn(x[{la}], x[{lb}]); x[{la}] = t0;")
+                since += 2
+                if lockstep and since >= lockstep:
+                    out.append(sync_line())
+                    since = 0
+        phys = nxt
+        half //= 2
+    # ---- the two passes on bit 6: publish, meet, recompute both sums from own + partner, keep the own output
+    for q in range(16):
+        out.append(f"    store({q}, x[{4 * q}], x[{4 * q + 1}], x[{4 * q + 2}], x[{4 * q + 3}]);")
+    out.append("    barrier();")
+    rot0 = {}
+    for j in range(64):
+        a, b = phys[j * 2], phys[j * 2 + 1]
+        assert b == a + 64 and a < 64
+        rot0[a] = (sin[0, j], cos[0, j])
+    nxt = [None] * 128
+    for j in range(64):
+        a, b = phys[j * 2], phys[j * 2 + 1]
+        nxt[j * 2], nxt[j * 2 + 1] = a, b
+    phys = nxt
+    for q in range(16):
+        out.append(f"    p = load({q});")
+        for e, (c0, c1) in enumerate((("x", "y"), ("z", "w"))):
+            r = 4 * q + 2 * e
+            (s_a, c_a), (s_b, c_b) = rot0[r], rot0[r + 1]
+            if h == 0:
+                # own = a, partner = b:  a' = a + b -> x, b' = a - b -> p;  keep a'' = a' sin - b' cos
+                out.append(f"    hca_bfly2(x[{r}], x[{r + 1}], p.{c0}, p.{c1});")
+                out.append(f"    t0 = __fmul_rn(x[{r}], {f(s_a)}); t1 = __fmul_rn(p.{c0}, {f(neg(c_a))}); "
+                           f"u0 = __fmul_rn(x[{r + 1}], {f(s_b)}); u1 = __fmul_rn(p.{c1}, {f(neg(c_b))});")
+            else:
+                # own = b, partner = a:  a' = a + b -> p, b' = a - b -> x;  keep b'' = a' cos + b' sin
+                out.append(f"    hca_bfly2(p.{c0}, p.{c1}, x[{r}], x[{r + 1}]);")
+                out.append(f"    t0 = __fmul_rn(p.{c0}, {f(c_a)}); t1 = __fmul_rn(x[{r}], {f(s_a)}); "
+                           f"u0 = __fmul_rn(p.{c1}, {f(c_b)}); u1 = __fmul_rn(x[{r + 1}], {f(s_b)});")
+            out.append(f"    hca_sum2(one, t0, u0, t1, u1, x[{r}], x[{r + 1}]);")
+            since += 7
+            if lockstep and since >= lockstep:
+                out.append(sync_line())
+                since = 0
+    # ---- rotation passes on bits 5 .. 0 (stages 1 .. 6), local to the half
+    pending, flip, DEPTH = [], [0], 2
+    for stage in range(1, 7):
+        half = 1 << stage
+        blocks = 64 >> stage
+        nxt = [None] * 128
+        rot = {}
+        for j in range(blocks):
+            for k in range(half):
+                rot[(phys[j * 2 * half + k], phys[j * 2 * half + half + k])] = (sin[stage, j * half + k], cos[stage, j * half + k])
+        for j in range(blocks):
+            for k in range(half):
+                a = phys[j * 2 * half + k]
+                b = phys[j * 2 * half + half + k]
+                nxt[j * 2 * half + k] = a
+                nxt[j * 2 * half + 2 * half - 1 - k] = b
+                if a // 64 != h:
+                    continue
+                assert b // 64 == h
+                la, lb = a - base, b - base
+                sb, cb = rot[(a, b)]
+                if a % 2 == 0 and b % 2 == 0 and (a + 1, b + 1) in rot:
+                    sb2, cb2 = rot[(a + 1, b + 1)]
+                    t, u = (("t", "u"), ("r", "w"), ("y", "z"))[flip[0] % 3]
+                    flip[0] += 1
+                    out.append(f"    {t}0 = __fmul_rn(x[{la}], {f(sb)}); {t}1 = __fmul_rn(x[{lb}], {f(neg(cb))}); "
+                               f"{t}2 = __fmul_rn(x[{la}], {f(cb)}); {t}3 = __fmul_rn(x[{lb}], {f(sb)});")
+                    out.append(f"    {u}0 = __fmul_rn(x[{la + 1}], {f(sb2)}); {u}1 = __fmul_rn(x[{lb + 1}], {f(neg(cb2))}); "
+                               f"{u}2 = __fmul_rn(x[{la + 1}], {f(cb2)}); {u}3 = __fmul_rn(x[{lb + 1}], {f(sb2)});")
+                    if len(pending) >= DEPTH:
+                        out.append(pending.pop(0))
+                    pending.append(f"    hca_sum2(one, {t}0, {u}0, {t}1, {u}1, x[{la}], x[{la + 1}]); "
+                                   f"hca_sum2(one, {t}2, {u}2, {t}3, {u}3, x[{lb}], x[{lb + 1}]);")
+                    since += 10
+                elif a % 2 == 1 and b % 2 == 1 and (a - 1, b - 1) in rot:
+                    continue
+                else:
+                    s_, c_ = f(sb), f(cb)
+                    out.append(f"    t0 = __fmul_rn(x[{la}], {s_}); t1 = __fmul_rn(x[{lb}], {c_}); "
+                               f"t2 = __fmul_rn(x[{la}], {c_}); t3 = __fmul_rn(x[{lb}], {s_}); "
+                               f"x[{la}] = __fsub_rn(t0, t1); x[{lb}] = __fadd_rn(t2, t3);")
+                    since += 6
+                if lockstep and since >= lockstep:
+                    out.append(sync_line())
+                    since = 0
+        out += pending
+        del pending[:]
+        phys = nxt
+    assert phys == _final_mapping()
+    out.append("}")
+    return out
+
+
+def gen_window_half(h: int) -> list[str]:
+    """Window + overlap-add + carry of one half (hca.cpp:1983-1992), straight to PCM-scaled floats. After the DCT an odd
+    register of the half holds dct[64 + i] and its even neighbour dct[63 - i] for the same i, so a lane produces the
+    samples i and 127 - i of its 32 values of i and carries its own 32 values of dct[0..63]: nothing crosses the halves.
+    carry[g] (g = 0..7, stride CARRY_STRIDE float4) holds the previous subframe's even registers 8g, 8g+2, 8g+4, 8g+6;
+    after group g the registers 8g..8g+7 are dead and refill(2g), refill(2g+1) may load the next subframe's chunks."""
+    win = T.window()
+    phys = _final_mapping()
+    final = [0] * 128
+    for m, r in enumerate(phys):
+        final[r] = m
+    base = 64 * h
+
+    def scaled(bits: int) -> str:
+        bits = int(bits)
+        e = (bits >> 23) & 0xFF
+        assert 1 <= e <= 200, "window constant must be a normal float"
+        return f(bits + (15 << 23))
+    out = []
+    out.append(f"// Window + overlap-add of half {h}: emit(i, s) for the lane's 64 samples, carry replaced, refill(c) for dead quads.")
+    out.append("template <int CARRY_STRIDE, class Cvt, class Emit, class Refill>")
+    out.append(f"__device__ __forceinline__ void hca_window_h{h}(float (&x)[64], float4* carry, const unsigned long long one, Cvt cvt, Emit emit, Refill refill) {{")
+    out.append("    float p0, p1, q0, q1;")
+    out.append("    float " + ", ".join(f"va{k}, vb{k}" for k in range(WSLOTS)) + ";")
+    out.append("    decltype(cvt(0.f)) " + ", ".join(f"sa{k}, sb{k}" for k in range(WSLOTS)) + ";")
+    out.append("    float4 c;")
+    wpend, wcount = [], [0]
+    for g in range(8):
+        out.append(f"    c = carry[{g} * CARRY_STRIDE];")
+        for e, comp in enumerate("xyzw"):
+            ev = 8 * g + 2 * e
+            od = ev + 1
+            j = final[base + od]
+            assert j >= 64 and final[base + ev] == 127 - j
+            i = j - 64
+            d = f"x[{od}]"
+            wa, wb, wan = scaled(win[i]), scaled(win[127 - i]), scaled(neg(win[i]))
+            out.append(f"    p0 = __fmul_rn({wa}, {d}); p1 = __fmul_rn({wb}, {d}); q0 = __fmul_rn({wb}, c.{comp}); q1 = __fmul_rn({wan}, c.{comp});")
+            slot = wcount[0] % WSLOTS
+            wcount[0] += 1
+            out.append(f"    hca_sum2(one, p0, p1, q0, q1, va{slot}, vb{slot});")
+            wpend.append((i, slot))
+            if len(wpend) > CVT_LAG:
+                jj, sl = wpend[-1 - CVT_LAG]
+                out.append(f"    sa{sl} = cvt(va{sl}); sb{sl} = cvt(vb{sl});")
+            if len(wpend) > CVT_LAG + STORE_LAG:
+                jj, sl = wpend[-1 - CVT_LAG - STORE_LAG]
+                out.append(f"    emit({jj}, sa{sl}); emit({127 - jj}, sb{sl});")
+        out.append(f"    carry[{g} * CARRY_STRIDE] = make_float4(x[{8 * g}], x[{8 * g + 2}], x[{8 * g + 4}], x[{8 * g + 6}]);")
+        out.append(f"    refill({2 * g}); refill({2 * g + 1});")
+    n = len(wpend)
+    for k in range(n - CVT_LAG, n):
+        jj, sl = wpend[k]
+        out.append(f"    sa{sl} = cvt(va{sl}); sb{sl} = cvt(vb{sl});")
+    for k in range(n - CVT_LAG - STORE_LAG, n):
+        jj, sl = wpend[k]
+        out.append(f"    emit({jj}, sa{sl}); emit({127 - jj}, sb{sl});")
+    out.append("}")
+    out.append("")
+    out.append(f"// Carry only (the look-back subframe in front of a run of frames), half {h}.")
+    out.append("template <int CARRY_STRIDE>")
+    out.append(f"__device__ __forceinline__ void hca_carry_h{h}(const float (&x)[64], float4* carry) {{")
+    for g in range(8):
+        out.append(f"    carry[{g} * CARRY_STRIDE] = make_float4(x[{8 * g}], x[{8 * g + 2}], x[{8 * g + 4}], x[{8 * g + 6}]);")
+    out.append("}")
+    return out
+
+
+def gen_pair_file(lockstep: int = 128) -> list[str]:
+    lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""]
+    for h in (0, 1):
+        lines += gen_imdct_half(h, lockstep) + [""] + gen_window_half(h) + [""]
+    return lines
+
+
 def gen_mdct() -> list[str]:
     sin, cos = T.mdct_trig()
     sin = sin.reshape(8, 128)
@@ -462,6 +712,12 @@ def main():
     end = dct.index("}")                    # first function = hca_dct4_dec
     lines = ["// GENERATED by tools/gen_dct.py -- do not edit.", "#pragma once", ""] + dct[: end + 1] + [""] + gen_thread_window(LOCKSTEP, packed=True)
     path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_thread_gen.inc")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    print("wrote", path, len(lines), "lines")
+    # the same transform split over a pair of warps (hca_imdct_pair_kernel)
+    lines = gen_pair_file(LOCKSTEP)
+    path = os.path.join(ROOT, "pycricodecs_b200", "csrc", "hca_dct_pair_gen.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
     print("wrote", path, len(lines), "lines")
