@@ -18,6 +18,10 @@
 // -Wl,-Bsymbolic-functions) because BitWriter::Write ORs into its first byte
 // (CriCodecs/IO.cpp:139,143,148) while ADX::Encode only clears the header
 // (CriCodecs/adx.cpp:487-488): "bit-exact" is defined on zero-filled memory.
+// For the same reason the reference's three malloc(sizeof(clHCA)) calls (hca.cpp:390,
+// 3302, 3356) see zero-filled memory here: a v1.x header (`dec` chunk, hca.cpp:710-727)
+// never sets ms_stereo, which clHCA_DecodeHeader then tests (hca.cpp:976-977), so on a
+// recycled heap block the reference rejects or accepts such a stream at random.
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <cstdlib>
@@ -27,7 +31,9 @@ void* operator new[](std::size_t n) { void* p = std::calloc(1, n ? n : 1); if (!
 void operator delete[](void* p) noexcept { std::free(p); }
 void operator delete[](void* p, std::size_t) noexcept { std::free(p); }
 
+#define malloc(n) calloc(1, (n))
 #include "CriCodecs.cpp"
+#undef malloc
 
 extern "C" {
 

@@ -11,7 +11,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcricodecs_b200.so")
+LIB_PATH = os.environ.get("CRI_LIB_PATH") or os.path.join(HERE, "libcricodecs_b200.so")   # CRI_LIB_PATH: kernel experiments (tools/build_variant.sh)
 
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_u64p = ctypes.POINTER(ctypes.c_uint64)

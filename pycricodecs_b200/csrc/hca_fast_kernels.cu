@@ -44,7 +44,15 @@ __constant__ uint32_t c_intensity[16] = CRI_TBL_INTENSITY_RATIO;  // intensity s
 // hca_bfly2: (a, b) <- (a + b, a - b) on two register pairs. hca_sum2: d = p + q, written as fma(q, one, p) with `one`
 // = {1.0f, 1.0f} read from the kernel arguments: ptxas contracts a packed add of products into FFMA2 even under
 // -fmad=false, which would drop the rounding of the products; it cannot contract through a multiplier it does not know.
+#ifndef HCA_SCALAR_SUMS
+#define HCA_SCALAR_SUMS 0          // experiments: 1 = every sum a scalar instruction (tools/build_variant.sh)
+#endif
 __device__ __forceinline__ void hca_bfly2(float& a0, float& a1, float& b0, float& b1) {
+    if (HCA_SCALAR_SUMS) {
+        const float s0 = __fadd_rn(a0, b0), s1 = __fadd_rn(a1, b1), d0 = __fsub_rn(a0, b0), d1 = __fsub_rn(a1, b1);
+        a0 = s0; a1 = s1; b0 = d0; b1 = d1;
+        return;
+    }
     unsigned long long a, b, s, d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
     asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
@@ -54,6 +62,7 @@ __device__ __forceinline__ void hca_bfly2(float& a0, float& a1, float& b0, float
     asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(d));
 }
 __device__ __forceinline__ void hca_sum2(unsigned long long one, float p0, float p1, float q0, float q1, float& d0, float& d1) {
+    if (HCA_SCALAR_SUMS) { d0 = __fadd_rn(p0, q0); d1 = __fadd_rn(p1, q1); return; }
     unsigned long long p, q, d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(p0), "f"(p1));
     asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(q0), "f"(q1));
@@ -62,7 +71,9 @@ __device__ __forceinline__ void hca_sum2(unsigned long long one, float p0, float
 }
 
 #include "hca_dct_thread_gen.inc"
+#ifdef CRI_HCA_PAIR_KERNEL        // experiment ("measured and dropped"): tools/build_variant.sh pair -DCRI_HCA_PAIR_KERNEL
 #include "hca_dct_pair_gen.inc"
+#endif
 
 constexpr int kFastThreads = 128;             // unpack kernel
 constexpr int kFastWarps = kFastThreads / 32;
@@ -668,6 +679,7 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
     }
 }
 
+#ifdef CRI_HCA_PAIR_KERNEL
 // ------------------------------------------------------------------------------------------------ transform, warp pairs
 // The same transform with every column split over a PAIR of warps: warp h of the pair keeps coefficients 64 h .. 64 h + 63
 // of the pair's 32 columns (lane = column, as above) in 64 registers. Twelve of the fourteen passes, the window and the
@@ -865,7 +877,10 @@ hca_imdct_pair_kernel(const __grid_constant__ HcaDecodeArgs a) {
     else PairXf<NCH, PAIRS, CONVOY, JOINT>::template body<0>(a, s_dyn);
 }
 
-constexpr int kPairs = 6;                     // warp pairs per CTA (one CTA per SM): 12 warps, 192 columns in flight
+#ifndef HCA_PAIRS
+#define HCA_PAIRS 6
+#endif
+constexpr int kPairs = HCA_PAIRS;             // warp pairs per CTA (one CTA per SM): 12 warps, 192 columns in flight
 
 template <int NCH, int PAIRS, int CONVOY, bool JOINT>
 void launch_xf_pair(const HcaDecodeArgs& a, cudaStream_t s) {
@@ -874,6 +889,8 @@ void launch_xf_pair(const HcaDecodeArgs& a, cudaStream_t s) {
     const uint32_t col_warps = (a.n_runs + K::RW - 1) / K::RW;
     hca_imdct_pair_kernel<NCH, PAIRS, CONVOY, JOINT><<<(col_warps + PAIRS - 1) / PAIRS, PAIRS * 64, K::kSmem, s>>>(a);
 }
+
+#endif  // CRI_HCA_PAIR_KERNEL
 
 constexpr int kXfThreads = 256;
 
@@ -894,18 +911,24 @@ void launch_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cud
     hca_unpack_fast_kernel<NCH, JOINT><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
     ++*launches;
     if (mid) cudaEventRecord(mid, s);
-    static const int xf = [] { const char* e = getenv("CRI_HCA_XF"); return e && *e ? atoi(e) : 1; }();
-    if (xf == 0) launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // thread-resident; CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
-    else if (xf == 2) launch_xf_pair<NCH, kPairs, 2, JOINT>(a, s);
-    else launch_xf_pair<NCH, kPairs, 0, JOINT>(a, s);
+#ifdef CRI_HCA_PAIR_KERNEL
+    static const int xf = [] { const char* e = getenv("CRI_HCA_XF"); return e && *e ? atoi(e) : 0; }();
+    if (xf == 2) launch_xf_pair<NCH, kPairs, 2, JOINT>(a, s);
+    else if (xf == 1) launch_xf_pair<NCH, kPairs, 0, JOINT>(a, s);
+    else
+#endif
+    launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
     ++*launches;
 }
 
 }  // namespace
 
-uint32_t hca_fast_threads_per_cta() {
+uint32_t hca_fast_threads_per_cta() {          // columns per CTA (the host sizes run_len by it)
+#ifdef CRI_HCA_PAIR_KERNEL
     const char* e = getenv("CRI_HCA_XF");
-    return e && *e && atoi(e) == 0 ? kXfThreads : kPairs * 32;   // columns per CTA (the host sizes run_len by it)
+    if (e && *e && atoi(e) != 0) return kPairs * 32;
+#endif
+    return kXfThreads;
 }
 uint32_t hca_fast_ctas_per_sm() { return 1; }
 

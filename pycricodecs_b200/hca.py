@@ -15,17 +15,42 @@ from typing import BinaryIO
 from . import engine
 from .chunk import CriHcaQuality, HCAType, WavDataHeaderStruct, WavHeaderStruct, WavSmplHeaderStruct
 
-HcaHeaderStruct = Struct(">4sHH")
-HcaFmtHeaderStruct = Struct(">4sIIHH")
-HcaCompHeaderStruct = Struct(">4sHBBBBBBBBBB")
-HcaDecHeaderStruct = Struct(">4sHBBBBBB")
-HcaLoopHeaderStruct = Struct(">4sIIHH")
-HcaAthHeaderStruct = Struct(">4sH")
-HcaVbrHeaderStruct = Struct(">4sHH")
-HcaCiphHeaderStruct = Struct(">4sH")
-HcaRvaHeaderStruct = Struct(">4sf")
-
 DEFAULT_KEY = 0xCF222F1FE0748978
+
+# ---- header description tables ---------------------------------------------------------------------------------
+# An HCA header is the base chunk and `fmt` followed by optional chunks in any order the writer chose; every chunk
+# is a tag (its letters carry bit 7 when the file is encrypted, hence the 0x7F mask) and a fixed big-endian layout.
+# `info()` reports each field under the reference's key (PyCriCodecs/hca.py:78-170, including its `BaseBandCoung`
+# spelling); a key of None drops the field, `_split_tracks` post-processes the packed track / config byte of `dec`.
+def _split_tracks(fields):
+    packed = fields.pop("_tracks")
+    fields["TrackCount"], fields["ChannelConfig"] = packed >> 4, packed & 0xF
+    return {k: fields[k] for k in ("DecSig", "FrameSize", "MinResolution", "MaxResolution", "TotalBandCount", "BaseBandCoung",
+                                   "TrackCount", "ChannelConfig", "StereoType")}
+
+
+_HCA_CHUNKS = {
+    b"comp": (Struct(">4sHBBBBBBBBBB"), ("CompSig", "FrameSize", "MinResolution", "MaxResolution", "TrackCount", "ChannelConfig",
+                                         "TotalBandCount", "BaseBandCount", "StereoBandCount", "BandsPerHfrGroup", "ReservedByte1",
+                                         "ReservedByte2"), None),
+    b"dec\x00": (Struct(">4sHBBBBBB"), ("DecSig", "FrameSize", "MaxResolution", "MinResolution", "TotalBandCount", "BaseBandCoung",
+                                        "_tracks", "StereoType"), _split_tracks),
+    b"vbr\x00": (Struct(">4sHH"), ("VbrSig", "MaxFrameSize", "NoiseLevel"), None),
+    b"ath\x00": (Struct(">4sH"), ("AthSig", "TableType"), None),
+    b"loop": (Struct(">4sIIHH"), ("LoopSig", "LoopStart", "LoopEnd", "LoopStartDelay", "LoopEndPadding"), None),
+    b"ciph": (Struct(">4sH"), ("CiphSig", "CipherType"), None),
+    b"rva\x00": (Struct(">4sf"), ("RvaSig", "Volume"), None),
+}
+_HCA_BASE = Struct(">4sHH")
+_HCA_FMT = Struct(">4sIIHH")
+_KEY_LIMITS = (("key", 0xFFFFFFFFFFFFFFFF, "HCA key cannot be a negative.", "HCA key cannot exceed the maximum size of 8 bytes."),
+               ("subkey", 0xFFFF, "HCA subkey cannot be a negative.", "HCA subkey cannot exceed 65535."))
+# optional RIFF chunks between `fmt ` and `data`: tag -> handler name
+_WAV_OPTIONAL = {b"smpl": "_wav_smpl", b"note": "_wav_note"}
+
+
+def _unmask(tag: bytes) -> bytes:
+    return bytes(c & 0x7F for c in tag)
 
 
 class HCA:
@@ -45,99 +70,82 @@ class HCA:
         self.looping = False
         self.Pyparse_header()
 
-    # -- header sniffing, field for field as the reference's Pyparse_header (hca.py:78-236)
+    # -- header sniffing: what `info()` reports (same keys and values as the reference's Pyparse_header) ------------
     def Pyparse_header(self) -> None:
-        self.HcaSig, self.version, self.header_size = HcaHeaderStruct.unpack(self.hcastream.read(HcaHeaderStruct.size))
+        self.HcaSig, self.version, self.header_size = _HCA_BASE.unpack(self.hcastream.read(_HCA_BASE.size))
         if self.HcaSig in (HCAType.HCA.value, HCAType.EHCA.value):
-            if not self.hcabytes:
-                self.filetype = "hca"
-            self.encrypted = self.HcaSig == HCAType.EHCA.value
-            if self.HcaSig == HCAType.EHCA.value and not self.key:
-                self.key = DEFAULT_KEY
-            elif self.key < 0:
-                raise ValueError("HCA key cannot be a negative.")
-            elif self.key > 0xFFFFFFFFFFFFFFFF:
-                raise OverflowError("HCA key cannot exceed the maximum size of 8 bytes.")
-            elif self.subkey < 0:
-                raise ValueError("HCA subkey cannot be a negative.")
-            elif self.subkey > 0xFFFF:
-                raise OverflowError("HCA subkey cannot exceed 65535.")
-            fmtsig, temp, framecount, delay, padding = HcaFmtHeaderStruct.unpack(self.hcastream.read(HcaFmtHeaderStruct.size))
-            self.hca = dict(Encrypted=self.encrypted, Header=self.HcaSig, version=hex(self.version), HeaderSize=self.header_size,
-                            FmtSig=fmtsig, ChannelCount=temp >> 24, SampleRate=temp & 0x00FFFFFF, FrameCount=framecount,
-                            EncoderDelay=delay, EncoderPadding=padding)
-            while True:
-                sig = unpack(">I", self.hcastream.read(4))[0]
-                self.hcastream.seek(-4, 1)
-                sig = int.to_bytes(sig & 0x7F7F7F7F, 4, "big")
-                if sig == b"comp":
-                    v = HcaCompHeaderStruct.unpack(self.hcastream.read(HcaCompHeaderStruct.size))
-                    self.hca.update(dict(zip(("CompSig", "FrameSize", "MinResolution", "MaxResolution", "TrackCount", "ChannelConfig",
-                                              "TotalBandCount", "BaseBandCount", "StereoBandCount", "BandsPerHfrGroup",
-                                              "ReservedByte1", "ReservedByte2"), v)))
-                elif sig == b"ciph":
-                    ciphsig, ciphertype = HcaCiphHeaderStruct.unpack(self.hcastream.read(HcaCiphHeaderStruct.size))
-                    if ciphertype == 1:
-                        self.encrypted = True
-                    self.hca.update(dict(CiphSig=ciphsig, CipherType=ciphertype))
-                elif sig == b"loop":
-                    self.looping = True
-                    v = HcaLoopHeaderStruct.unpack(self.hcastream.read(HcaLoopHeaderStruct.size))
-                    self.hca.update(dict(zip(("LoopSig", "LoopStart", "LoopEnd", "LoopStartDelay", "LoopEndPadding"), v)))
-                elif sig == b"dec\00":
-                    decsig, framesize, maxres, minres, total, base, temp, stereotype = HcaDecHeaderStruct.unpack(
-                        self.hcastream.read(HcaDecHeaderStruct.size))
-                    self.hca.update(dict(DecSig=decsig, FrameSize=framesize, MinResolution=minres, MaxResolution=maxres,
-                                         TotalBandCount=total, BaseBandCoung=base, TrackCount=temp >> 4, ChannelConfig=temp & 0xF,
-                                         StereoType=stereotype))
-                elif sig == b"ath\00":
-                    athsig, tabletype = HcaAthHeaderStruct.unpack(self.hcastream.read(HcaAthHeaderStruct.size))
-                    self.hca.update(dict(AthSig=athsig, TableType=tabletype))
-                elif sig == b"vbr\00":
-                    vbrsig, maxframesize, noiselevel = HcaVbrHeaderStruct.unpack(self.hcastream.read(HcaVbrHeaderStruct.size))
-                    self.hca.update(dict(VbrSig=vbrsig, MaxFrameSize=maxframesize, NoiseLevel=noiselevel))
-                elif sig == b"rva\00":
-                    rvasig, volume = HcaRvaHeaderStruct.unpack(self.hcastream.read(HcaRvaHeaderStruct.size))
-                    self.hca.update(dict(RvaSig=rvasig, Volume=volume))
-                else:
-                    break
-            self.hca.update(dict(Crc16=self.hcastream.read(2)))
+            self._parse_hca()
         elif self.HcaSig == b"RIFF":
-            self.filetype = "wav"
-            (self.riffSignature, self.riffSize, self.wave, self.fmt, self.fmtSize, self.fmtType, self.fmtChannelCount,
-             self.fmtSamplingRate, self.fmtSamplesPerSec, self.fmtSamplingSize, self.fmtBitCount) = WavHeaderStruct.unpack(
-                self.stream.read(WavHeaderStruct.size))
-            if self.riffSignature == b"RIFF" and self.wave == b"WAVE" and self.fmt == b"fmt ":
-                if self.fmtBitCount != 16:
-                    raise ValueError(f"WAV bitdepth of {self.fmtBitCount} is not supported, only 16 bit WAV files are supported.")
-                elif self.fmtSize != 16:
-                    raise ValueError(f"WAV file has an FMT chunk of an unsupported size: {self.fmtSize}, the only supported size is 16.")
-                if self.stream.read(4) == b"smpl":
-                    self.stream.seek(-4, 1)
-                    self.looping = True
-                    v = WavSmplHeaderStruct.unpack(self.stream.read(WavSmplHeaderStruct.size))
-                    smplesize, self.LoopCount, self.LoopStartSample, self.LoopEndSample = v[1], v[9], v[13], v[14]
-                    if self.LoopCount != 1:
-                        self.looping = False
-                        self.stream.seek(-WavSmplHeaderStruct.size, 1)
-                        self.stream.seek(8 + smplesize, 1)
-                else:
-                    self.stream.seek(-4, 1)
-                    self.looping = False
-                if self.stream.read(4) == b"note":
-                    ln = unpack("<I", self.stream.read(4))[0]
-                    self.stream.seek(ln + 4)
-                else:
-                    self.stream.seek(-4, 1)
-                if self.stream.read(4) == b"data":
-                    self.stream.seek(-4, 1)
-                    self.dataSig, self.dataSize = WavDataHeaderStruct.unpack(self.stream.read(WavDataHeaderStruct.size))
-                else:
-                    raise ValueError("Invalid or an unsupported wav file.")
+            self._parse_wav()
         else:
             raise ValueError("Invalid HCA or WAV file.")
         self.stream.seek(0)
         self.hcastream.seek(0)
+
+    def _parse_hca(self) -> None:
+        if not self.hcabytes:
+            self.filetype = "hca"
+        self.encrypted = self.HcaSig == HCAType.EHCA.value
+        if self.encrypted and not self.key:
+            self.key = DEFAULT_KEY
+        for name, top, negative, too_big in _KEY_LIMITS:
+            value = getattr(self, name)
+            if value < 0:
+                raise ValueError(negative)
+            if value > top:
+                raise OverflowError(too_big)
+        fmtsig, packed, frames, delay, padding = _HCA_FMT.unpack(self.hcastream.read(_HCA_FMT.size))
+        self.hca = dict(Encrypted=self.encrypted, Header=self.HcaSig, version=hex(self.version), HeaderSize=self.header_size,
+                        FmtSig=fmtsig, ChannelCount=packed >> 24, SampleRate=packed & 0x00FFFFFF, FrameCount=frames,
+                        EncoderDelay=delay, EncoderPadding=padding)
+        while True:                                            # known chunks, in whatever order they come
+            tag = self.hcastream.read(4)
+            entry = _HCA_CHUNKS.get(_unmask(tag)) if len(tag) == 4 else None
+            if entry is None:
+                self.hcastream.seek(-len(tag), 1)
+                break
+            layout, keys, finish = entry
+            fields = dict(zip(keys, layout.unpack(tag + self.hcastream.read(layout.size - 4))))
+            self.hca.update(finish(fields) if finish else fields)
+            self.looping = self.looping or "LoopSig" in fields
+            if fields.get("CipherType") == 1:
+                self.encrypted = True
+        self.hca["Crc16"] = self.hcastream.read(2)
+
+    def _parse_wav(self) -> None:
+        self.filetype = "wav"
+        (self.riffSignature, self.riffSize, self.wave, self.fmt, self.fmtSize, self.fmtType, self.fmtChannelCount,
+         self.fmtSamplingRate, self.fmtSamplesPerSec, self.fmtSamplingSize, self.fmtBitCount) = WavHeaderStruct.unpack(
+            self.stream.read(WavHeaderStruct.size))
+        if (self.riffSignature, self.wave, self.fmt) != (b"RIFF", b"WAVE", b"fmt "):
+            return                                             # the reference looks no further either
+        if self.fmtBitCount != 16:
+            raise ValueError(f"WAV bitdepth of {self.fmtBitCount} is not supported, only 16 bit WAV files are supported.")
+        if self.fmtSize != 16:
+            raise ValueError(f"WAV file has an FMT chunk of an unsupported size: {self.fmtSize}, the only supported size is 16.")
+        for tag, handler in _WAV_OPTIONAL.items():             # the two chunks the reference knows, in its order
+            if self.stream.read(4) == tag:
+                getattr(self, handler)()
+            else:
+                self.stream.seek(-4, 1)
+        head = self.stream.read(WavDataHeaderStruct.size)
+        if head[:4] != b"data":
+            raise ValueError("Invalid or an unsupported wav file.")
+        self.dataSig, self.dataSize = WavDataHeaderStruct.unpack(head)
+
+    def _wav_smpl(self) -> None:
+        """One sampler loop makes the stream a looping one; any other count is skipped like an unknown chunk."""
+        self.stream.seek(-4, 1)
+        v = WavSmplHeaderStruct.unpack(self.stream.read(WavSmplHeaderStruct.size))
+        size, self.LoopCount, self.LoopStartSample, self.LoopEndSample = v[1], v[9], v[13], v[14]
+        self.looping = self.LoopCount == 1
+        if not self.looping:
+            self.stream.seek(8 + size - WavSmplHeaderStruct.size, 1)
+
+    def _wav_note(self) -> None:
+        """Skip a `note` chunk (the reference seeks to an absolute offset here and then loses the data chunk)."""
+        size = unpack("<I", self.stream.read(4))[0]
+        self.stream.seek(size, 1)
 
     def info(self) -> dict:
         """ Returns info related to the input file. """

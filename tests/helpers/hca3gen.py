@@ -51,10 +51,19 @@ class Bits:
 
 
 def header(version=0x0300, channels=2, rate=44100, frames=8, delay=128, padding=0, frame_size=1024, min_res=0, max_res=15,
-           tracks=1, config=0, total=128, base=40, stereo=30, bands_per_hfr=4, ciph=0):
+           tracks=1, config=0, total=128, base=40, stereo=30, bands_per_hfr=4, ciph=0, dec=False, ath=None):
+    """dec=True writes the v1.x `dec` chunk instead of `comp` (hca.cpp:710-727: band counts minus one, track count and
+    channel config in one byte, a stereo type flag; stereo bands = total - base, no HFR groups); ath = 0 / 1 adds an
+    `ath` chunk (absent: type 1 below v2.0, else 0, hca.cpp:745-756)."""
     h = b"HCA\x00" + version.to_bytes(2, "big") + b"\x00\x00"
     h += b"fmt\x00" + bytes([channels]) + rate.to_bytes(3, "big") + frames.to_bytes(4, "big") + delay.to_bytes(2, "big") + padding.to_bytes(2, "big")
-    h += b"comp" + frame_size.to_bytes(2, "big") + bytes([min_res, max_res, tracks, config, total, base, stereo, bands_per_hfr, 0, 0])
+    if dec:
+        assert bands_per_hfr == 0 and total - base == stereo
+        h += b"dec\x00" + frame_size.to_bytes(2, "big") + bytes([min_res, max_res, total - 1, base - 1, (tracks << 4) | config, 1 if stereo else 0])
+    else:
+        h += b"comp" + frame_size.to_bytes(2, "big") + bytes([min_res, max_res, tracks, config, total, base, stereo, bands_per_hfr, 0, 0])
+    if ath is not None:
+        h += b"ath\x00" + ath.to_bytes(2, "big")
     h += b"ciph" + ciph.to_bytes(2, "big")
     h += b"pad\x00" + bytes(8)
     size = len(h) + 2
@@ -63,10 +72,11 @@ def header(version=0x0300, channels=2, rate=44100, frames=8, delay=128, padding=
 
 
 def stream(seed, frames=8, channels=2, frame_size=1024, total=128, base=40, stereo=30, bands_per_hfr=4, min_res=0, max_res=15,
-           delay=128, version=0x0300, level=(40, 110), rate=44100, sf_max=44):
-    """One v3.0 stream. Channel pairs are primary/secondary when stereo > 0 (hca.cpp:909-960, 2 channels per track)."""
+           delay=128, version=0x0300, level=(40, 110), rate=44100, sf_max=44, dec=False, ath=None):
+    """One v3.0 stream (or, with version <= 0x0200, a stream in the older bitstream layout; dec / ath: see header()).
+    Channel pairs are primary/secondary when stereo > 0 (hca.cpp:909-960, 2 channels per track)."""
     rng = np.random.default_rng(seed)
-    out = header(version, channels, rate, frames, delay, 0, frame_size, min_res, max_res, 1, 0, total, base, stereo, bands_per_hfr)
+    out = header(version, channels, rate, frames, delay, 0, frame_size, min_res, max_res, 1, 0, total, base, stereo, bands_per_hfr, 0, dec, ath)
     # channel roles for one track and channel_config 0 (hca.cpp:909-960): 1 primary, 2 secondary, 0 discrete
     roles = {1: [0], 2: [1, 2], 3: [1, 2, 0], 4: [1, 2, 1, 2]}[channels] if stereo > 0 else [0] * channels
     rest = total - base - stereo
