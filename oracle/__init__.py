@@ -162,11 +162,14 @@ class _Ref:
         hits = glob.glob(os.path.join(HERE, "_ref", "CriCodecs*.so"))
         if not hits:
             raise FileNotFoundError("oracle/_ref is not built (make -C oracle ref, needs /root/reference)")
-        d = os.path.dirname(hits[0])
-        if d not in sys.path:
-            sys.path.insert(0, d)
-        import CriCodecs  # noqa: the reference's module
-        self.mod = CriCodecs
+        # load THIS build under its own module object: another `CriCodecs` (the drop-in, or the stock build under
+        # baseline/_ref) may already sit in sys.modules, and `import CriCodecs` would silently hand that one back
+        import importlib.machinery
+        import importlib.util
+        loader = importlib.machinery.ExtensionFileLoader("CriCodecs", hits[0])
+        spec = importlib.util.spec_from_loader("CriCodecs", loader)
+        self.mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(self.mod)
         self.lib = ctypes.PyDLL(hits[0])
         self.lib.ref_crc16.restype = ctypes.c_uint
         self.lib.ref_hca_decode_range.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p]

@@ -15,11 +15,15 @@ REF_PKG = os.path.join(ROOT, "baseline", "_ref")
 def RefHCA():
     if not os.path.isdir(os.path.join(REF_PKG, "PyCriCodecs")):
         pytest.skip("baseline/_ref (pip install --target of the reference) is not present")
+    before = set(sys.modules)
     sys.path.insert(0, REF_PKG)
     try:
         from PyCriCodecs.hca import HCA
     finally:
         sys.path.remove(REF_PKG)
+        for name in set(sys.modules) - before:              # leave no `CriCodecs` / `PyCriCodecs` behind for other tests
+            if name.split(".")[0] in ("CriCodecs", "PyCriCodecs"):
+                del sys.modules[name]
     return HCA
 
 
