@@ -230,9 +230,15 @@ struct AdxLists {
     }
 };
 
+// Shared by cri_adx_decode_sizes and the planner. A header may promise any sample count; the decoder clips to the blocks
+// that are there and zero-fills the rest, but a stream that promises more than twice what its payload can hold (plus a
+// block) is refused as truncated rather than answered with gigabytes of silence.
 static int adx_decode_size_one(const uint8_t* d, size_t n, AdxInfo* a, uint64_t* size) {
     const int r = parse_adx(d, n, a);
     if (r < 0) return r;
+    const uint64_t data = (uint64_t)a->data_offset + 4, frame_bytes = (uint64_t)a->channels * a->block_size;
+    const uint64_t avail = n > data && frame_bytes ? (n - data) / frame_bytes : 0;
+    if ((uint64_t)a->samples > 2 * (avail + 1) * a->samples_per_block) return ERR_BUFFER;
     *size = wav_header_size(a->looping) + (uint64_t)a->samples * a->channels * 2;
     return OK;
 }
@@ -293,7 +299,9 @@ static void plan_adx_decode(cri_job* j) {
 namespace cri {
 uint64_t pcm16_offset(cri_job* j, uint32_t i, const WavInfo& w) {
     const uint64_t data = j->in_off[i] + w.data_offset;
-    if (w.format == WAV_S16) return data;
+    if (w.format == WAV_S16 && (data & 1) == 0) return data;
+    // other encodings, and PCM16 that lands on an odd byte of the blob (an odd-sized stream in front of it): a converted /
+    // aligned copy behind the blob, so that a stream's result never depends on its neighbours in the batch
     if (!j->conv_base) j->conv_base = (j->in_bytes + 128 + 255) & ~(uint64_t)255;      // behind the blob and its read slack
     PcmConv c{};
     c.src_off = data;
@@ -935,9 +943,8 @@ extern "C" int cri_hca_decode_sizes(const uint8_t* blob, const uint64_t* off, ui
     for (uint32_t i = 0; i < n; i++) {
         HcaInfo h;
         sizes[i] = 0;
-        const int r = parse_hca(blob + off[i], off[i + 1] - off[i], &h);
-        if (r == OK) sizes[i] = wav_header_size(h.loop_flag) + (uint64_t)(h.frame_count * 1024u - h.delay - h.padding) * h.channels * 2;
-        if (status) status[i] = r == OK ? OK : ERR_HCA_HEADER;
+        const int r = hca_decode_size_one(blob + off[i], off[i + 1] - off[i], &h, &sizes[i]);
+        if (status) status[i] = r;
     }
     return OK;
 }

@@ -114,6 +114,8 @@ void add_patch_public(cri_job* j, uint64_t dst, const uint8_t* bytes, uint32_t n
 uint64_t pcm16_offset(cri_job* j, uint32_t i, const cri::WavInfo& w);
 // the same for a looping HCA encode: the virtual input of the reference's frame feeder, assembled on the device
 uint64_t hca_loop_input_offset(cri_job* j, uint32_t i, const cri::WavInfo& w, const cri::HcaEncPlan& p);
+// header checks + exact WAV size of one HCA stream (cri_hca_decode_sizes and the planner agree by construction)
+int hca_decode_size_one(const uint8_t* d, uint64_t len, cri::HcaInfo* h, uint64_t* size);
 int plan_hca_decode(cri_ctx* c, cri_job* j);
 int plan_hca_crypt(cri_ctx* c, cri_job* j);
 int plan_hca_encode(cri_ctx* c, cri_job* j);

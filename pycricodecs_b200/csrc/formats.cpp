@@ -427,6 +427,9 @@ int parse_hca(const uint8_t* d, size_t n, HcaInfo* h) {
     if (h->total_bands > 128 || h->base_bands > 128 || h->stereo_bands > 128 || h->base_bands + h->stereo_bands > 128 ||
         h->bands_per_hfr > 128)
         return -2;
+    // total < base + stereo makes the reference's group count wrap (hca.cpp:872-874) and its decoder write far outside its
+    // scalefactor array: no defined behaviour to reproduce, so such a header is refused
+    if (h->total_bands < h->base_bands + h->stereo_bands) return -2;
     if (h->bands_per_hfr) {
         const unsigned rest = h->total_bands - h->base_bands - h->stereo_bands;
         h->hfr_groups = rest / h->bands_per_hfr + (rest % h->bands_per_hfr ? 1 : 0);

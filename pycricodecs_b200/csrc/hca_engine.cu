@@ -28,6 +28,11 @@ static uint16_t crc16_append(uint16_t crc, uint8_t b) {
     return (uint16_t)(((crc << 8) ^ t) & 0xFFFF);
 }
 
+// The bit readers keep advancing (and prefetching) when a corrupt frame's codes run past its end: the values they return are
+// forced to zero, but the loads go on for at most 16 channels x 1024 codes x 12 bits = 24 KB behind the row. Inside the
+// scratch array that lands in other rows; behind the last row it lands in this tail.
+constexpr uint64_t kScratchTail = 32 * 1024;
+
 static uint32_t env_u32(const char* name, uint32_t fallback) {
     const char* v = getenv(name);
     if (!v || !*v) return fallback;
@@ -97,6 +102,16 @@ static bool v3_supported(const HcaInfo& h) {
     return true;
 }
 
+int hca_decode_size_one(const uint8_t* d, uint64_t len, HcaInfo* h, uint64_t* size) {
+    *size = 0;
+    if (parse_hca(d, len, h) != OK) return ERR_HCA_HEADER;
+    if ((uint64_t)h->header_size + (uint64_t)h->frame_count * h->frame_size > len) return ERR_HCA_HEADER;   // frames missing
+    const uint64_t total = (uint64_t)h->frame_count * 1024;
+    if (total < (uint64_t)h->delay + h->padding) return ERR_HCA_HEADER;
+    *size = wav_header_size(h->loop_flag) + (total - h->delay - h->padding) * h->channels * 2;
+    return OK;
+}
+
 int plan_hca_decode(cri_ctx* c, cri_job* j) {
     (void)c;
     HcaJob& J = j->hca;
@@ -106,11 +121,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         const uint8_t* d = j->blob + j->in_off[i];
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         HcaInfo& h = infos[i];
-        if (parse_hca(d, len, &h) != OK) { j->status[i] = ERR_HCA_HEADER; continue; }
-        if ((uint64_t)h.header_size + (uint64_t)h.frame_count * h.frame_size > len) { j->status[i] = ERR_HCA_HEADER; continue; }
-        const uint64_t total = (uint64_t)h.frame_count * 1024;
-        if (total < (uint64_t)h.delay + h.padding) { j->status[i] = ERR_HCA_HEADER; continue; }
-        sizes[i] = wav_header_size(h.loop_flag) + (total - h.delay - h.padding) * h.channels * 2;   // as cri_hca_decode_sizes
+        if ((j->status[i] = hca_decode_size_one(d, len, &h, &sizes[i])) != OK) continue;
         if (!v3_supported(h)) { j->status[i] = ERR_UNSUPPORTED; j->needs_clear = true; }           // region stays zero
     }
     finish_layout_public(j, sizes);
@@ -160,7 +171,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         const HcaStreamDev& st = J.streams[i];
         const bool types_ok = st.channels == 1 ? st.type[0] == 0
                                                : (st.type[0] == 0 && st.type[1] == 0) || (st.type[0] == 1 && st.type[1] == 2);
-        if (st.channels != J.uniform || !types_ok) J.uniform = 0;
+        if (st.channels != J.uniform || !types_ok || st.hfr_groups > 10) J.uniform = 0;   // the fast unpack kernel keeps <= 10 HFR scales (6 bits each) in one word
         any_joint = any_joint || st.joint;
     }
     J.any_joint = any_joint;
@@ -202,7 +213,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         const uint64_t runs_per_warp = 32 / J.uniform;
         const uint64_t warps = (J.n_runs + runs_per_warp - 1) / runs_per_warp;
         J.spec_bytes = warps * J.run_len * 8 * 1024 * sizeof(float4);
-        J.s_bytes = (G + 1) * J.scratch_words * sizeof(uint32_t);
+        J.s_bytes = (G + 1) * J.scratch_words * sizeof(uint32_t) + kScratchTail;
         J.i_bytes = (G + 1) * sizeof(uint32_t);                      // intensity nibbles of the frame's secondary channel
         J.total_groups = 0;
         J.max_steps = 0;
@@ -227,7 +238,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     J.max_steps = run + 1;
     J.total_groups = (J.units.size() / 32) * J.max_steps;
     const uint64_t slots = (uint64_t)J.units.size() * J.max_steps;
-    J.s_bytes = slots * J.scratch_words * sizeof(uint32_t);
+    J.s_bytes = slots * J.scratch_words * sizeof(uint32_t) + kScratchTail;
     J.q_bytes = slots * J.max_channels * 8 * 16 * sizeof(uint4);
     J.g_bytes = slots * J.max_channels * 128 * sizeof(float);
     J.i_bytes = slots * J.max_channels * sizeof(uint32_t);
@@ -331,7 +342,6 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
         const int r = parse_wav(d, len, &wavs[i]);
         if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
         const bool looping = wavs[i].looping && !j->adx.force_not_looping;
-        if (!looping && wavs[i].format == WAV_S16 && ((j->in_off[i] + wavs[i].data_offset) & 1)) { j->status[i] = ERR_UNSUPPORTED; continue; }   // PCM must be 2-byte aligned in the blob
         int pr;
         if (looping) pr = plan_hca_encode_loop(wavs[i], j->quality, &plans[i]);   // loop chunk + pre / post audio (hca.cpp:2292-2321, 3000-3053)
         else pr = plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels, j->quality, &plans[i]);

@@ -107,3 +107,41 @@ def test_hca_header_sniffing_matches_reference_fields(port):
     with pytest.raises(ValueError, match="Invalid HCA or WAV"):
         HCA(b"nothing useful here....")
     assert [q.value for q in CriHcaQuality] == [0, 1, 2, 3, 5]
+
+
+def test_size_queries_reject_what_the_planner_rejects():
+    """Headers that lie (advisor findings, round 1): band counts that make the reference's HFR group count wrap, delay +
+    padding beyond the stream, frames that are not there, an ADX sample count the payload cannot back."""
+    import ctypes
+    import numpy as np
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from helpers import hca3gen
+    from pycricodecs_b200 import _lib, engine, synth
+    L = _lib.lib()
+
+    def hca_sizes(stream):
+        blob, off = engine.pack([stream])
+        sizes, st = np.zeros(1, np.uint64), np.zeros(1, np.int32)
+        L.cri_hca_decode_sizes(blob.ctypes.data, off.ctypes.data, 1, sizes.ctypes.data, st.ctypes.data)
+        return int(sizes[0]), int(st[0])
+
+    good = hca3gen.stream(seed=1, version=0x0200, min_res=1, frames=3, frame_size=2048)
+    assert hca_sizes(good) == (44 + (3 * 1024 - 128) * 4, 0)
+    wrap = hca3gen.header(version=0x0200, min_res=1, frames=3, total=20, base=30, stereo=10, bands_per_hfr=1) + bytes(3 * 1024)
+    assert hca_sizes(wrap) == (0, -201)
+    lying = hca3gen.header(version=0x0200, min_res=1, frames=1, delay=900, padding=900) + bytes(1024)
+    assert hca_sizes(lying) == (0, -201)
+    assert hca_sizes(good[:-100]) == (0, -201)                       # last frame cut short
+
+    wav = synth.wav(2, 1, 320)
+    # a hand-made ADX header (adx.cpp:145-183): 10 blocks of payload, sample count 2^31
+    hdr = bytearray(b"\x80\x00" + (0x20 - 4).to_bytes(2, "big") + bytes([3, 18, 4, 1]) + (48000).to_bytes(4, "big") + (1 << 31).to_bytes(4, "big")
+                    + (500).to_bytes(2, "big") + bytes([3, 0]))
+    hdr += bytes(0x20 - 6 - len(hdr)) + b"(c)CRI"
+    adx = bytes(hdr) + bytes(18 * 10)
+    blob, off = engine.pack([adx])
+    sizes, st = np.zeros(1, np.uint64), np.zeros(1, np.int32)
+    L.cri_adx_decode_sizes(blob.ctypes.data, off.ctypes.data, 1, sizes.ctypes.data, st.ctypes.data)
+    assert (int(sizes[0]), int(st[0])) == (0, -301)
+    assert wav[:4] == b"RIFF"
