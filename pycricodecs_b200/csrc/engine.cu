@@ -63,6 +63,12 @@ extern "C" void cri_ctx_destroy(cri_ctx* c) {
     for (auto& e : c->idle_events) cudaEventDestroy(e);
     if (c->pin_stage) cudaFreeHost(c->pin_stage);
     for (auto& sh : c->idle_shadows) munmap(sh.first, sh.second);
+    if (c->hca_pipe.side) {
+        cudaStreamDestroy(c->hca_pipe.side);
+        cudaEventDestroy(c->hca_pipe.start);
+        cudaEventDestroy(c->hca_pipe.done);
+        for (auto& e : c->hca_pipe.unpacked) cudaEventDestroy(e);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
 }

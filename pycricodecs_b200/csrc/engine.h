@@ -11,6 +11,7 @@
 #include "../../include/cricodecs_b200.h"
 #include "formats.h"
 #include "hca_tables_dev.h"
+#include "hca_kernels.h"
 #include "kernels.h"
 
 // Size-bucketed cache of HBM blocks owned by a context: a batch call needs a
@@ -32,6 +33,7 @@ struct cri_ctx {
     int32_t* pin_status[kPipeDepth] = {};       // page-locked landing buffers of the chunks' status words (a copy to
     size_t pin_status_cap[kPipeDepth] = {};     //  pageable memory would block the host until the chunk's kernels end)
     DevPool pool;
+    cri::HcaFastPipe hca_pipe;                  // side stream + events of the pipelined HCA decode (created on first use)
     std::vector<cudaEvent_t> idle_events;       // events of finished jobs, reused by the next ones
     std::vector<std::pair<uint8_t*, size_t>> idle_shadows;   // header shadows of finished device-pointer jobs (all zero again)
     uint8_t* pin_stage = nullptr;               // page-locked landing buffer of the header fetches of device-pointer jobs

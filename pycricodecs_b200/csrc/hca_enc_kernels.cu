@@ -40,6 +40,7 @@ __constant__ uint32_t e_inv_step[16] = CRI_TBL_ENC_INV_STEP;
 __constant__ uint32_t e_dead_zone[16] = CRI_TBL_ENC_DEAD_ZONE;
 __constant__ uint32_t e_ratio_bounds[14] = CRI_TBL_ENC_RATIO_BOUNDS;
 __constant__ uint8_t e_max_bits[16] = CRI_TBL_MAX_BITS;
+__constant__ uint32_t e_cost_rows[64] = CRI_TBL_ENC_COST_ROWS;
 
 #include "hca_dct_gen.inc"
 
@@ -48,6 +49,7 @@ constexpr int kSpecRow = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 struct EncTables {              // per-CTA shared copies (per-lane indices diverge)
+    uint4 cost[16];             // per resolution: bits(-N), bits(P), 8 * full, overfull (tools/gen_tables.py: enc_cost_rows)
     float scaling[64];
     float qscaling[64];
     float inv_step[16];
@@ -95,7 +97,7 @@ struct FrameSmem {
     float* spec;        // [nch][8][128] spectra, later scaled spectra
     int16_t* pcm;       // [nch][1152] previous 128 + current 1024 samples
     uint8_t* sf;        // [nch][128]
-    uint8_t* res;       // [nch][128]
+    uint8_t* res;       // [nch][128] during the bit allocation: coefficients of the band that sit on the positive clamp; then the final resolutions
     uint32_t* bits;     // packed frame, MSB-first 32-bit words
     float* hfr_avg;     // [nch][8]
     int* hfr_scale;     // [nch][8]
@@ -122,22 +124,21 @@ __device__ __forceinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_
     }
 }
 
-// Bits of one band's eight coefficients at resolution r (the per-coefficient terms of CalculateUsedBits, hca.cpp:2772-2787).
-__device__ __forceinline__ int band_cost(const EncTables& tb, const float* sp_band, int r) {
-    int len = 0;
-    if (r >= 8) {
-        const int bits = tb.max_bits[r] - 1;
-        const float dz = tb.dead_zone[r];
+// Bits of one band's eight coefficients at resolution r (the per-coefficient terms of CalculateUsedBits, hca.cpp:2772-2787):
+// a coefficient costs full[r] bits, one less inside (-N[r], P[r]) -- the dead zone of the sign-magnitude codes, the short
+// codes of the prefix codebooks -- and nothing at all where the clamp value quantises out of the codebook (`clamped`
+// = how many of the band's coefficients sit on the clamp). tests/test_tables.py checks the rows against the reference's
+// quantise-and-look-up arithmetic.
+__device__ __forceinline__ int band_cost(const EncTables& tb, const float* sp_band, int r, int clamped) {
+    const uint4 row = tb.cost[r];
+    const float neg_n = __uint_as_float(row.x), p = __uint_as_float(row.y);
+    int inside = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) len += bits + (fabsf(sp_band[j * kSpecRow]) >= dz ? 1 : 0);
-    } else {
-        const float inv = tb.inv_step[r];
-        const float up = __fadd_rn(inv, 1.0f);
-        const uint8_t* qb = tb.qbits + r * 16 - (r - 7);                   // - (int)(inv + 0.5 - 8)
-#pragma unroll
-        for (int j = 0; j < 8; j++) len += qb[__float2int_rz(__fadd_rn(__fmul_rn(sp_band[j * kSpecRow], inv), up))];
+    for (int j = 0; j < 8; j++) {
+        const float x = sp_band[j * kSpecRow];
+        inside += (x > neg_n && x < p) ? 1 : 0;
     }
-    return len;
+    return (int)row.z - inside - (int)row.w * clamped;
 }
 
 // Total frame bits for (noise level, evaluation boundary): CalculateUsedBits, hca.cpp:2763-2790.
@@ -150,7 +151,7 @@ __device__ __forceinline__ int used_bits(const EncTables& tb, const FrameSmem& f
         const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
         for (int b = lane; b < coded; b += 32) {
             const int noise = b < boundary ? noise_level - 1 : noise_level;
-            len += band_cost(tb, sp + b, enc_resolution(tb, fs.sf[c * 128 + b], noise));
+            len += band_cost(tb, sp + b, enc_resolution(tb, fs.sf[c * 128 + b], noise), fs.res[c * 128 + b]);
         }
     }
     len = warp_sum(len);
@@ -178,8 +179,9 @@ __device__ __forceinline__ void boundary_table(const EncTables& tb, const FrameS
             if (b < coded) {
                 const int sfv = fs.sf[c * 128 + b];
                 const int r_hi = enc_resolution(tb, sfv, noise_level), r_lo = enc_resolution(tb, sfv, noise_level - 1);
-                const int c_hi = band_cost(tb, sp + b, r_hi);
-                const int c_lo = r_lo == r_hi ? c_hi : band_cost(tb, sp + b, r_lo);
+                const int clamped = fs.res[c * 128 + b];
+                const int c_hi = band_cost(tb, sp + b, r_hi, clamped);
+                const int c_lo = r_lo == r_hi ? c_hi : band_cost(tb, sp + b, r_lo, clamped);
                 tot += c_hi;
                 diff[k] += c_lo - c_hi;
             }
@@ -228,7 +230,7 @@ __device__ __forceinline__ void header_lengths(const FrameSmem& fs, const HcaStr
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kEncWarps * 32)
+__global__ void __launch_bounds__(kEncWarps * 32, 5)   // shared memory admits five CTAs per SM: up to 102 registers
 hca_encode_kernel(HcaEncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ EncTables tb;
@@ -237,6 +239,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         tb.qscaling[i] = __uint_as_float(e_qscaling[i]);
     }
     for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        tb.cost[i] = make_uint4(e_cost_rows[4 * i], e_cost_rows[4 * i + 1], e_cost_rows[4 * i + 2], e_cost_rows[4 * i + 3]);
         tb.inv_step[i] = __uint_as_float(e_inv_step[i]);
         tb.dead_zone[i] = __uint_as_float(e_dead_zone[i]);
         tb.max_bits[i] = e_max_bits[i];
@@ -287,30 +290,33 @@ hca_encode_kernel(HcaEncodeArgs a) {
     const int16_t* pcm_base = reinterpret_cast<const int16_t*>(a.in + S.in_off);
     const long long pcm_n0 = (long long)frame * 1024 - 128;             // stream index of the frame's first wanted sample frame
     const long long pcm_end = (long long)S.out_samples;
+    // a frame whose whole window lies inside the stream (all but the first and the last one) loads without bounds checks
+    const bool interior = pcm_n0 >= 0 && pcm_n0 + 1152 <= pcm_end;
     auto sample = [&](int idx /* sample frame inside the 1152-frame window */, int c) -> float {
         const long long n = pcm_n0 + idx;
-        const int v = (n >= 0 && n < pcm_end) ? (int)__ldg(pcm_base + n * nch + c) : 0;
+        const int v = (interior || (n >= 0 && n < pcm_end)) ? (int)__ldg(pcm_base + n * nch + c) : 0;
         return (float)v;
     };
     // ---- MDCT: 8 subframes x channels (hca.cpp:2470-2559)
     {
-        const float w0 = __uint_as_float(kMdctWin[4 * lane]), w1 = __uint_as_float(kMdctWin[4 * lane + 1]);
-        const float w2 = __uint_as_float(kMdctWin[4 * lane + 2]), w3 = __uint_as_float(kMdctWin[4 * lane + 3]);
+        // PcmToFloat's factor 1/32768 (hca.cpp:2470-2479) is folded into the window: w * (s * 2^-15) and (w * 2^-15) * s
+        // are the same real number rounded once (both scalings are exact), so the products are bit-identical
+        const float k = 1.0f / 32768.0f;
+        const float w0 = __fmul_rn(__uint_as_float(kMdctWin[4 * lane]), k), w1 = __fmul_rn(__uint_as_float(kMdctWin[4 * lane + 1]), k);
+        const float w2 = __fmul_rn(__uint_as_float(kMdctWin[4 * lane + 2]), k), w3 = __fmul_rn(__uint_as_float(kMdctWin[4 * lane + 3]), k);
         const float pc0 = __uint_as_float(kMdctPreCos[lane]), ps0 = __uint_as_float(kMdctPreSin[lane]);
         const float pc1 = __uint_as_float(kMdctPreCos[lane + 32]), ps1 = __uint_as_float(kMdctPreSin[lane + 32]);
         float tc[6], ts[6];
 #pragma unroll
         for (int s = 0; s < 6; s++) { tc[s] = __uint_as_float(kMdctCos[s * 32 + lane]); ts[s] = __uint_as_float(kMdctSin[s * 32 + lane]); }
         const int d0 = kMdctDest[4 * lane], d1 = kMdctDest[4 * lane + 1], d2 = kMdctDest[4 * lane + 2], d3 = kMdctDest[4 * lane + 3];
-        const float k = 1.0f / 32768.0f;
+        const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
         for (int c = 0; c < nch; c++) {
+            // the block in front of a subframe is the previous subframe's own block: four loads per subframe, not eight
+            float p0 = sample(i0, c), p1 = sample(i1, c), p2 = sample(i2, c), p3 = sample(i3, c);
             for (int sub = 0; sub < 8; sub++) {
-                const int cur = 128 + sub * 128, prv = sub * 128;          // window positions of the subframe / the one before it
-                const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
-                const float c0 = __fmul_rn(sample(cur + i0, c), k), c1 = __fmul_rn(sample(cur + i1, c), k);
-                const float c2 = __fmul_rn(sample(cur + i2, c), k), c3 = __fmul_rn(sample(cur + i3, c), k);
-                const float p0 = __fmul_rn(sample(prv + i0, c), k), p1 = __fmul_rn(sample(prv + i1, c), k);
-                const float p2 = __fmul_rn(sample(prv + i2, c), k), p3 = __fmul_rn(sample(prv + i3, c), k);
+                const int cur = 128 + sub * 128;                           // window position of the subframe
+                const float c0 = sample(cur + i0, c), c1 = sample(cur + i1, c), c2 = sample(cur + i2, c), c3 = sample(cur + i3, c);
                 // windowing (hca.cpp:2537-2546): in[i] = W[63-i]*(-cur[64+i]) - (-W[64+i])*cur[63-i],
                 //                               in[64+i] = W[i]*prv[i] - (-W[127-i])*prv[127-i]
                 const float in_a = __fsub_rn(__fmul_rn(w1, -c2), __fmul_rn(-w2, c1));   // in[2l]
@@ -351,6 +357,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
                 float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
                 sp[d0] = __fmul_rn(re0, 0.125f); sp[d1] = __fmul_rn(im0, 0.125f);
                 sp[d2] = __fmul_rn(re1, 0.125f); sp[d3] = __fmul_rn(im1, 0.125f);
+                p0 = c0; p1 = c1; p2 = c2; p3 = c3;
             }
         }
     }
@@ -444,13 +451,18 @@ hca_encode_kernel(HcaEncodeArgs a) {
         for (int b = lane; b < coded; b += 32) {
             const int sfv = fs.sf[c * 128 + b];
             const float ks = tb.qscaling[sfv];
+            int clamped = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 float v = __fmul_rn(sp[j * kSpecRow + b], ks);
                 v = v > 0.9999999f ? 0.9999999f : v < -0.9999999f ? -0.9999999f : v;
-                sp[j * kSpecRow + b] = sfv == 0 ? 0.f : v;
+                v = sfv == 0 ? 0.f : v;
+                clamped += v == 0.9999999f ? 1 : 0;
+                sp[j * kSpecRow + b] = v;
             }
+            fs.res[c * 128 + b] = (uint8_t)clamped;
         }
+        for (int b = coded + lane; b < 128; b += 32) fs.res[c * 128 + b] = 0;
     }
     __syncwarp();
 
@@ -569,40 +581,71 @@ hca_encode_kernel(HcaEncodeArgs a) {
         else if (S.hfr_groups > 0)
             emit_bits(fs, lane, lane < S.hfr_groups ? (uint32_t)fs.hfr_scale[c * 8 + lane] : 0u, lane < S.hfr_groups ? 6 : 0, &cursor, limit_bits);
     }
+    // Spectra in two phases. (1) Every lane quantises its bands (4 l .. 4 l + 3 of every channel) for all eight subframes --
+    // the band's constants are fetched once, not once per subframe -- and leaves (length << 16 | code) in place of the
+    // scaled value (QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936). (2) In bitstream order (subframe-major, channel-
+    // minor) a lane picks its four words up with one 16-byte load, joins them into two codes of at most 24 bits, and one
+    // warp prefix sum of the lengths places them: 16 prefix sums per stereo frame.
+    for (int c = 0; c < nch; c++) {
+        const int coded = S.coded[c];
+        int r[4], mb[4], down[4];
+        float inv[4], up[4];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const int b = 4 * lane + h;
+            r[h] = b < coded ? (int)fs.res[c * 128 + b] : 0;
+            inv[h] = tb.inv_step[r[h]];
+            up[h] = __fadd_rn(inv[h], 1.0f);
+            mb[h] = (int)tb.max_bits[r[h]] - 1;
+            down[h] = r[h] < 8 ? r[h] + 1 : (1 << mb[h]);                  // (int)(inv + 0.5)
+        }
+        for (int sub = 0; sub < 8; sub++) {
+            uint4* row = reinterpret_cast<uint4*>(fs.spec + ((size_t)c * 8 + sub) * kSpecRow + 4 * lane);
+            const uint4 v = *row;
+            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                const int q = __float2int_rz(__fadd_rn(__fmul_rn(__uint_as_float(x[h]), inv[h]), up[h])) - down[h];
+                uint32_t cd;
+                int ln;
+                if (r[h] < 8) {                                            // r = 0: row 0 of both tables is all zero
+                    ln = tb.qbits[r[h] * 16 + q + 8];
+                    cd = tb.qcode[r[h] * 16 + q + 8];
+                } else {
+                    const uint32_t mag = (uint32_t)abs(q) & ((1u << mb[h]) - 1u);
+                    if (q != 0) { cd = (mag << 1) | (q > 0 ? 0u : 1u); ln = mb[h] + 1; }
+                    else { cd = mag; ln = mb[h]; }
+                }
+                o[h] = r[h] == 0 ? 0u : ((uint32_t)ln << 16) | (cd & ((1u << ln) - 1u));
+            }
+            *row = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncwarp();
+    auto put_bits = [&](uint32_t code, int len, int at) {                 // the reference's writer drops what does not fit (IO.cpp:131-134)
+        if (len > 0 && at + len <= limit_bits) {
+            const int w = at >> 5, bo = at & 31;
+            if (bo + len <= 32) {
+                atomicOr(&fs.bits[w], code << (32 - bo - len));
+            } else {
+                const int spill = bo + len - 32;
+                atomicOr(&fs.bits[w], code >> spill);
+                atomicOr(&fs.bits[w + 1], code << (32 - spill));
+            }
+        }
+    };
     for (int sub = 0; sub < 8; sub++) {
         for (int c = 0; c < nch; c++) {
-            const int coded = S.coded[c];
-            const float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
-            // two consecutive bands per lane and step: 64 bands per warp prefix sum (a code is at most 12 bits)
-            for (int b0 = 0; b0 < coded; b0 += 64) {
-                uint32_t code = 0;
-                int len = 0;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int b = b0 + 2 * lane + h;
-                    if (b >= coded) continue;
-                    const int r = fs.res[c * 128 + b];
-                    if (r == 0) continue;
-                    // QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936
-                    const float inv = tb.inv_step[r];
-                    const int down = r < 8 ? r + 1 : (1 << (tb.max_bits[r] - 1));   // (int)(inv + 0.5)
-                    const int q = __float2int_rz(__fadd_rn(__fmul_rn(sp[b], inv), __fadd_rn(inv, 1.0f))) - down;
-                    uint32_t cd;
-                    int ln;
-                    if (r < 8) {
-                        ln = tb.qbits[r * 16 + q + 8];
-                        cd = tb.qcode[r * 16 + q + 8];
-                    } else {
-                        const int mb = tb.max_bits[r] - 1;
-                        const uint32_t mag = (uint32_t)abs(q) & ((1u << mb) - 1u);
-                        if (q != 0) { cd = (mag << 1) | (q > 0 ? 0u : 1u); ln = mb + 1; }
-                        else { cd = mag; ln = mb; }
-                    }
-                    code = (code << ln) | (cd & ((1u << ln) - 1u));
-                    len += ln;
-                }
-                emit_bits(fs, lane, code, len, &cursor, limit_bits);
-            }
+            const uint4 e = *reinterpret_cast<const uint4*>(fs.spec + ((size_t)c * 8 + sub) * kSpecRow + 4 * lane);
+            const int l0 = (int)(e.x >> 16), l1 = (int)(e.y >> 16), l2 = (int)(e.z >> 16), l3 = (int)(e.w >> 16);
+            const uint32_t code_a = ((e.x & 0xFFFFu) << l1) | (e.y & 0xFFFFu), code_b = ((e.z & 0xFFFFu) << l3) | (e.w & 0xFFFFu);
+            const int len_a = l0 + l1, len_b = l2 + l3;
+            int total;
+            const int at = cursor + warp_excl_scan(len_a + len_b, lane, &total);
+            cursor += total;
+            put_bits(code_a, len_a, at);
+            put_bits(code_b, len_b, at + len_a);
         }
     }
     __syncwarp();

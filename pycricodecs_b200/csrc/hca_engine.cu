@@ -186,7 +186,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         // run_len is chosen so that the transform kernel's CTAs fill the resident slots of the GPU in whole waves.
         const uint64_t G = j->units;
         const uint64_t cols_per_cta = hca_fast_threads_per_cta() / J.uniform;        // runs per CTA
-        const uint64_t slots = (uint64_t)std::max(1, c->sm_count) * hca_fast_ctas_per_sm();
+        const uint64_t slots = (uint64_t)std::max(1, c->sm_count) * hca_fast_ctas_per_sm() * hca_fast_chunks();   // pipelined: one wave per chunk
         uint32_t best = 1;
         const uint32_t forced = env_u32("CRI_HCA_FAST_RUN", 0);
         if (forced) {
@@ -476,7 +476,19 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
             a.frame_state = a.frame_draws + J.noise_frames;
         }
         // dominant kernel = the transform (second) kernel: ev[2] sits between the two launches
-        if (J.n_runs) launch_hca_decode_fast(a, j->stream, &c->launches, j->ev[2]);
+        if (J.n_runs) {
+            HcaFastPipe& P = c->hca_pipe;
+            P.chunks = hca_fast_chunks();
+            if (P.chunks > 1 && !P.side) {                  // first pipelined job of this context
+                int lo = 0, hi = 0;
+                cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                CU_TRY(c, cudaStreamCreateWithPriority(&P.side, cudaStreamNonBlocking, hi));
+                CU_TRY(c, cudaEventCreateWithFlags(&P.start, cudaEventDisableTiming));
+                CU_TRY(c, cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+                for (auto& e : P.unpacked) CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            launch_hca_decode_fast(a, j->stream, &c->launches, j->ev[2], &P);
+        }
         else launch_hca_decode(a, j->stream, &c->launches, j->ev[2]);
         CU_TRY(c, cudaEventRecord(j->ev[3], j->stream));
         *have_dominant = J.total_groups != 0 || J.n_runs != 0;

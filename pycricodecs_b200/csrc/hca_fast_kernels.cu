@@ -22,6 +22,7 @@
 // Intermediate array (HBM): spec[imdct warp W][frame in run j][subframe][chunk 0..31][lane 0..31] float4, where lane =
 // channel * (32 / NCH) + run % (32 / NCH) and chunk i holds coefficients 4i .. 4i+3. Both kernels touch it with
 // fully coalesced 512-byte rows. Algorithmic bytes per stereo frame: 8192 written + 8192 read, 4096 PCM written.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -212,9 +213,9 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     const uint32_t R = a.run_len;
     const uint32_t wid = blockIdx.x * kFastWarps + warp;     // (block of 32 runs, frame in run)
     const uint32_t rb = wid / R, j = wid - rb * R;
-    const uint32_t r = rb * 32 + lane;
+    const uint32_t r = a.run_base + rb * 32 + lane;
     const uint64_t g64 = (uint64_t)r * R + j;
-    const bool active = r < a.n_runs && g64 < a.total_frames;
+    const bool active = r < a.n_runs && r - a.run_base < a.run_count && g64 < a.total_frames;
     const uint32_t g = active ? (uint32_t)g64 : (uint32_t)a.total_frames;   // scratch row G is a dummy for idle lanes
     uint32_t stream = 0, frame = 0;
     if (active) {
@@ -239,7 +240,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
     }
     __syncthreads();
 
-    if ((uint64_t)rb * 32 >= a.n_runs) return;               // whole warp
+    if ((uint64_t)rb * 32 >= a.run_count || (uint64_t)a.run_base + rb * 32 >= a.n_runs) return;   // whole warp
     const HcaStreamDev& S = a.streams[stream];
 
     uint16_t* tab = reinterpret_cast<uint16_t*>(s_dyn) + (size_t)warp * (NCH * 128 * 32) + lane;   // + (c * 128 + band) * 32
@@ -537,10 +538,10 @@ hca_imdct_fast_kernel(HcaDecodeArgs a) {
     RowDesc* rows = reinterpret_cast<RowDesc*>(tile + RW * PITCH);
 
     const int rr = lane % RW, ch = lane / RW;
-    const uint32_t W = blockIdx.x * (THREADS / 32) + warp;
+    const uint32_t W = a.run_base / RW + blockIdx.x * (THREADS / 32) + warp;
     const uint32_t R = a.run_len;
     const uint32_t r = W * RW + rr;
-    const bool live = r < a.n_runs;
+    const bool live = r < a.n_runs && r - a.run_base < a.run_count;
     const uint32_t G = (uint32_t)a.total_frames;
     uint32_t g = live ? r * R : G;
     uint32_t s = 0, f = 0, cnt = 0;
@@ -892,55 +893,106 @@ void launch_xf_pair(const HcaDecodeArgs& a, cudaStream_t s) {
 
 #endif  // CRI_HCA_PAIR_KERNEL
 
-constexpr int kXfThreads = 256;
+constexpr int kXfThreads = 256;          // one launch per kernel: one transform CTA owns an SM
+constexpr int kXfThreadsPiped = 128;     // pipelined launches: half an SM's registers, the rest hosts unpack CTAs
 
 template <int NCH, int THREADS, int CONVOY, bool JOINT>
 void launch_xf(const HcaDecodeArgs& a, cudaStream_t s) {
     constexpr int RW = 32 / NCH;
     const size_t smem_t = 16 * THREADS * sizeof(float4) + (size_t)(THREADS / 32) * (RW * (64 * NCH + 1) + RW * 4) * sizeof(uint32_t);
     cudaFuncSetAttribute(hca_imdct_fast_kernel<NCH, THREADS, CONVOY, JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
-    const uint32_t warps = (a.n_runs + RW - 1) / RW, per_cta = THREADS / 32;
+    const uint32_t runs = std::min(a.run_count, a.n_runs - std::min(a.n_runs, a.run_base));
+    const uint32_t warps = (runs + RW - 1) / RW, per_cta = THREADS / 32;
+    if (!warps) return;
     hca_imdct_fast_kernel<NCH, THREADS, CONVOY, JOINT><<<(warps + per_cta - 1) / per_cta, THREADS, smem_t, s>>>(a);
 }
 
 template <int NCH, bool JOINT>
-void launch_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
+void launch_unpack(const HcaDecodeArgs& a, cudaStream_t s) {
     const size_t smem_u = (size_t)kFastWarps * (NCH * 128 * 32 * sizeof(uint16_t) + 1024);   // band tables + the bit readers' rings
     cudaFuncSetAttribute(hca_unpack_fast_kernel<NCH, JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u);
-    const uint64_t unpack_warps = (uint64_t)((a.n_runs + 31) / 32) * a.run_len;
+    const uint32_t runs = std::min(a.run_count, a.n_runs - std::min(a.n_runs, a.run_base));
+    const uint64_t unpack_warps = (uint64_t)((runs + 31) / 32) * a.run_len;
+    if (!unpack_warps) return;
     hca_unpack_fast_kernel<NCH, JOINT><<<(unsigned)((unpack_warps + kFastWarps - 1) / kFastWarps), kFastThreads, smem_u, s>>>(a);
-    ++*launches;
-    if (mid) cudaEventRecord(mid, s);
-#ifdef CRI_HCA_PAIR_KERNEL
-    static const int xf = [] { const char* e = getenv("CRI_HCA_XF"); return e && *e ? atoi(e) : 0; }();
-    if (xf == 2) launch_xf_pair<NCH, kPairs, 2, JOINT>(a, s);
-    else if (xf == 1) launch_xf_pair<NCH, kPairs, 0, JOINT>(a, s);
-    else
+}
+
+template <int NCH, bool JOINT>
+void launch_fast(HcaDecodeArgs a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid, const HcaFastPipe* pipe) {
+#ifdef CRI_HCA_PIPELINED
+    const uint32_t chunks = pipe && pipe->side ? std::min<uint32_t>(pipe->chunks, 16) : 1;
+#else
+    const uint32_t chunks = 1;
+    (void)pipe;
 #endif
-    launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
-    ++*launches;
+    if (chunks <= 1) {
+        a.run_base = 0;
+        a.run_count = a.n_runs;
+        launch_unpack<NCH, JOINT>(a, s);
+        ++*launches;
+        if (mid) cudaEventRecord(mid, s);
+#ifdef CRI_HCA_PAIR_KERNEL
+        static const int xf = [] { const char* e = getenv("CRI_HCA_XF"); return e && *e ? atoi(e) : 0; }();
+        if (xf) launch_xf_pair<NCH, kPairs, 0, JOINT>(a, s);
+        else
+#endif
+        launch_xf<NCH, kXfThreads, 2, JOINT>(a, s);   // CONVOY = 2: the CTA meets every 256 fp32 instructions (measured: -5 % vs none)
+        ++*launches;
+        return;
+    }
+#ifdef CRI_HCA_PIPELINED
+    // pipelined: chunk k's transform (side stream, high priority, 128-thread CTAs) runs beside chunk k + 1's unpack
+    const uint32_t gran = 128;                                            // runs: whole unpack warps and whole transform CTAs
+    const uint32_t per = ((a.n_runs + chunks - 1) / chunks + gran - 1) / gran * gran;
+    cudaEventRecord(pipe->start, s);
+    cudaStreamWaitEvent(pipe->side, pipe->start, 0);
+    uint32_t k = 0;
+    for (uint32_t base = 0; base < a.n_runs; base += per, k++) {
+        a.run_base = base;
+        a.run_count = std::min(per, a.n_runs - base);
+        launch_unpack<NCH, JOINT>(a, s);
+        ++*launches;
+        cudaEventRecord(pipe->unpacked[k], s);
+        cudaStreamWaitEvent(pipe->side, pipe->unpacked[k], 0);
+        launch_xf<NCH, kXfThreadsPiped, 2, JOINT>(a, pipe->side);
+        ++*launches;
+    }
+    if (mid) cudaEventRecord(mid, s);                                      // all unpack kernels are done here
+    cudaEventRecord(pipe->done, pipe->side);
+    cudaStreamWaitEvent(s, pipe->done, 0);
+#endif
 }
 
 }  // namespace
 
-uint32_t hca_fast_threads_per_cta() {          // columns per CTA (the host sizes run_len by it)
+uint32_t hca_fast_threads_per_cta() {          // columns per transform CTA (the host sizes run_len by it)
 #ifdef CRI_HCA_PAIR_KERNEL
     const char* e = getenv("CRI_HCA_XF");
     if (e && *e && atoi(e) != 0) return kPairs * 32;
 #endif
-    return kXfThreads;
+    return hca_fast_chunks() > 1 ? kXfThreadsPiped : kXfThreads;
 }
 uint32_t hca_fast_ctas_per_sm() { return 1; }
 
-void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid) {
+uint32_t hca_fast_chunks() {
+#ifdef CRI_HCA_PIPELINED          // experiment ("measured and dropped"): build with -DCRI_HCA_PIPELINED, run with CRI_HCA_CHUNKS=k
+    const char* e = getenv("CRI_HCA_CHUNKS");
+    const int v = e && *e ? atoi(e) : 1;
+    return (uint32_t)std::min(std::max(v, 1), 16);
+#else
+    return 1;
+#endif
+}
+
+void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid, const HcaFastPipe* pipe) {
     if (!a.n_runs) return;
 #ifdef CRI_DEV_ONE_VARIANT       // development builds: one template variant only (compile time)
-    launch_fast<2, false>(a, s, launches, mid);
+    launch_fast<2, false>(a, s, launches, mid, pipe);
 #else
     if (a.uniform == 2) {
-        if (a.joint) launch_fast<2, true>(a, s, launches, mid); else launch_fast<2, false>(a, s, launches, mid);
+        if (a.joint) launch_fast<2, true>(a, s, launches, mid, pipe); else launch_fast<2, false>(a, s, launches, mid, pipe);
     } else {
-        if (a.joint) launch_fast<1, true>(a, s, launches, mid); else launch_fast<1, false>(a, s, launches, mid);
+        if (a.joint) launch_fast<1, true>(a, s, launches, mid, pipe); else launch_fast<1, false>(a, s, launches, mid, pipe);
     }
 #endif
 }

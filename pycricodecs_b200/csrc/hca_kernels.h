@@ -37,6 +37,8 @@ struct HcaDecodeArgs {
     uint32_t run_len;
     uint32_t n_runs;            // 0 = not on the fast path
     uint32_t joint;             // fast path: some stream has an intensity-stereo pair or HFR bands
+    uint32_t run_base;          // fast path, pipelined launches: this launch covers runs [run_base, run_base + run_count)
+    uint32_t run_count;
     // v3.0 noise generator (null when no stream needs it): the unpack kernel leaves, per frame slot and channel, the
     // band classes and the number of generator draws per subframe; a scan turns the per-frame totals into the
     // generator state at the start of every frame (the state runs through the whole stream, hca.cpp:1602-1635)
@@ -52,8 +54,18 @@ struct HcaDecodeArgs {
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
 void launch_hca_noise_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // between the two, when a.sfres
 void launch_hca_imdct(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // second half of launch_hca_decode
-void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
-uint32_t hca_fast_threads_per_cta();
+// Streams and events of the pipelined form of the fast path (owned by the context): the job's runs are cut into `chunks`
+// pieces, the unpack kernels run back to back on the job's stream and every transform kernel follows its own unpack kernel
+// on the high-priority `side` stream, so the transform of chunk k shares the SMs with the unpack of chunk k + 1.
+struct HcaFastPipe {
+    cudaStream_t side = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr;
+    cudaEvent_t unpacked[16] = {};
+    uint32_t chunks = 1;
+};
+void launch_hca_decode_fast(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid, const HcaFastPipe* pipe);
+uint32_t hca_fast_chunks();              // CRI_HCA_CHUNKS (default 1 = two launches, no overlap)
+uint32_t hca_fast_threads_per_cta();     // columns per transform CTA
 uint32_t hca_fast_ctas_per_sm();
 
 struct HcaCryptArgs {

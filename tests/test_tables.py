@@ -14,6 +14,7 @@ PINNED = {
     "INVERT": "596fe25e69de6eab", "MAX_BITS": "bccecd5122d1510e", "READ_BITS": "2e1cc91f0d50f0d4", "READ_VALS": "2cc4f662b2917a8c",
     "ENC_RES_CURVE": "ae26f4723b8c0df3", "ENC_Q_BITS": "4dea801cd96da815", "ENC_Q_CODE": "7c9c807b445fc2a3", "ENC_INV_STEP": "cd2e4715a8858fa3",
     "ENC_DEAD_ZONE": "46be60ec7b43774b", "ENC_RATIO_BOUNDS": "7b0403a9464abe57", "ENC_Q_SCALING": "40bb54ebaca01923",
+    "ENC_COST_ROWS": "ad41c2373ac9383d",
     "MDCT_SIN": "f6e0ce2a262954bb", "MDCT_COS": "5cd990a6f62da25a", "ENC_SHUFFLE": "143d219b1e658c0b", "ADX_STATIC_COEF": "f0a57863809129eb",
     "ATH_BASE": "103a013614c0f314",
 }
@@ -84,3 +85,33 @@ def test_code_length_threshold_restatement():
             want = step(want, b)
         x = (bs[0] | bs[1] << 8 | bs[2] << 16 | bs[3] << 24) ^ (((c >> 8) & 0xFF) | ((c & 0xFF) << 8))
         assert tk[3][x & 0xFF] ^ tk[2][(x >> 8) & 0xFF] ^ tk[1][(x >> 16) & 0xFF] ^ tk[0][x >> 24] == want
+
+
+def test_encoder_cost_rows_reproduce_the_table_driven_bit_count():
+    """ENC_COST_ROWS (two comparisons per coefficient) against the reference's own arithmetic (quantise, look the code
+    length up; hca.cpp:2772-2787) on random values, on every threshold +- a few ulps, on zero and on the clamp value."""
+    import importlib.util
+    import os
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(root, "tools", "gen_tables.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    rows = g.enc_cost_rows()
+    rng = np.random.default_rng(3)
+    clamp = np.float32(0.9999999)
+    xs = [rng.uniform(-1, 1, 200000).astype(np.float32), (rng.standard_normal(100000) * 0.05).astype(np.float32),
+          np.array([0.0, -0.0, clamp, -clamp], np.float32)]
+    for r in range(1, 16):
+        for w in rows[r][:2]:
+            u = int(w) & 0x7FFFFFFF
+            near = np.arange(u - 40, u + 41, dtype=np.uint32).view(np.float32)
+            xs.append(near)
+            xs.append(-near)
+    x = np.clip(np.concatenate(xs), -clamp, clamp).astype(np.float32)
+    for r in range(0, 16):
+        neg_n, p = rows[r][:2].view(np.float32)
+        full8, overfull = int(rows[r][2]), int(rows[r][3])
+        model = full8 // 8 - ((x > neg_n) & (x < p)).astype(np.int64) - overfull * (x == clamp)
+        want = g._enc_table_bits(x, r) if r else np.zeros(len(x), np.int64)
+        assert np.array_equal(model, want), r

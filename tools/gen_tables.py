@@ -185,6 +185,59 @@ def enc_dead_zone():
     return f32bits([0.0] + [1.0 / (2 * m + 1) for m in MAXQ[1:]])
 
 
+def _enc_table_bits(x: np.ndarray, r: int) -> np.ndarray:
+    """Bits of coefficient x at resolution r exactly as CalculateUsedBits counts them (hca.cpp:2772-2787), fp32 step by step."""
+    x = np.asarray(x, np.float32)
+    qbits, _ = enc_codebooks()
+    inv = enc_inv_step().view(np.float32)
+    dz = enc_dead_zone().view(np.float32)
+    if r >= 8:
+        return (MAX_BITS[r] - 1 + (np.abs(x) >= dz[r])).astype(np.int64)
+    up = np.float32(inv[r] + np.float32(1.0))
+    v = ((x * inv[r]).astype(np.float32) + up).astype(np.float32)
+    idx = np.trunc(v).astype(np.int64) + (r * 16 - (r - 7))          # = r * 16 + q + 8
+    return qbits.ravel()[idx].astype(np.int64)
+
+
+ENC_CLAMP = np.float32(0.9999999)          # ScaleSpectra's clamp (hca.cpp:2648-2650)
+
+
+def enc_cost_rows():
+    """The per-coefficient terms of CalculateUsedBits as two comparisons: at resolution r a coefficient x costs
+    full[r] bits, one less when -N[r] < x < P[r] -- for r >= 8 that is the dead zone (|x| < dz), for the prefix codebooks
+    (r <= 7) the quantised values whose codes are one bit short; the quantiser (int)(x * inv + inv + 1) is monotone in x,
+    so the set is an interval and its ends are found by bisection over the float bit patterns with the reference's own
+    fp32 steps. One oddity is kept: at r = 2, 4, 5 the clamp value 0.9999999 rounds up to the quantised value r + 1,
+    which is outside the codebook and counts (and is written as) 0 bits (`overfull` = full[r] there).
+    Rows of four words: bits(-N), bits(P), 8 * full, overfull; row 0 (resolution 0: no bits) never matches."""
+    rows = np.zeros((16, 4), np.uint32)
+    rows[0] = (0xFF800000, 0xFF800000, 0, 0)                         # x > -inf ... x < -inf: never inside, 0 bits
+    dz = enc_dead_zone()
+    clamp_u = int(ENC_CLAMP.view(np.uint32))
+    for r in range(1, 16):
+        if r >= 8:
+            rows[r] = (int(dz[r]) | 0x80000000, int(dz[r]), 8 * MAX_BITS[r], 0)
+            continue
+        at = lambda u, sign: int(_enc_table_bits(np.array([u], np.uint32).view(np.float32) * np.float32(sign), r)[0])
+        full = at(clamp_u - 64, 1)
+        assert at(0, 1) == full - 1 and at(clamp_u - 64, -1) == full and at(clamp_u, -1) == full
+
+        def first_long(sign):
+            lo, hi = 0, clamp_u - 64
+            while hi - lo > 1:
+                mid = (lo + hi) // 2
+                if at(mid, sign) == full - 1:
+                    lo = mid
+                else:
+                    hi = mid
+            return hi
+        p, n = first_long(1), first_long(-1)
+        top = [at(u, 1) for u in range(clamp_u - 64, clamp_u + 1)]
+        assert all(b == full for b in top[:-1]) and top[-1] in (full, 0)
+        rows[r] = (n | 0x80000000, p, 8 * full, full if top[-1] == 0 else 0)
+    return rows
+
+
 def enc_ratio_bounds():
     return f32bits([(27 - 2 * i) / 14.0 for i in range(14)])
 
@@ -266,6 +319,7 @@ def all_tables():
         ("ENC_DEAD_ZONE", "uint32_t", enc_dead_zone()),
         ("ENC_RATIO_BOUNDS", "uint32_t", enc_ratio_bounds()),
         ("ENC_Q_SCALING", "uint32_t", enc_q_scaling()),
+        ("ENC_COST_ROWS", "uint32_t", enc_cost_rows()),
         ("MDCT_SIN", "uint32_t", msin),
         ("MDCT_COS", "uint32_t", mcos),
         ("ENC_SHUFFLE", "uint8_t", enc_shuffle()),
