@@ -44,7 +44,16 @@ __constant__ uint32_t e_cost_rows[64] = CRI_TBL_ENC_COST_ROWS;
 
 #include "hca_dct_gen.inc"
 
-constexpr int kEncWarps = 4;
+#ifndef HCA_ENC_WARPS
+#define HCA_ENC_WARPS 20          // 20 x 9.6 KB of shared memory per stereo frame: one CTA per SM (measured: 4 / 8 / 16 / 20 warps -> 20.6 / 20.5 / 21.4 / 19.2 ms)
+#endif
+constexpr int kEncWarps = HCA_ENC_WARPS;
+// The kernel is ~120 KB of SASS that every frame walks once, far more than the 32 KB instruction cache next to the SM:
+// with independent warps every warp streams its own copy of the code from L2 ("no instruction" was the top stall). The
+// warps of a CTA therefore meet at every phase boundary (CONVOY) and fetch the same lines at about the same time; a CTA is
+// as many warps as shared memory allows. No warp may leave early for this to be legal: surplus warps redo the last
+// frame and frames that fail the bit allocation run to the end, both without storing anything.
+#define CONVOY() __syncthreads()
 constexpr int kSpecRow = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -76,7 +85,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
     return x - v;
 }
 
-__device__ __forceinline__ int find_scalefactor(const float* table, float v) {   // hca.cpp:2611-2623
+__device__ __noinline__ int find_scalefactor(const float* table, float v) {   // hca.cpp:2611-2623
     unsigned lo = 0, hi = 63;
     while (lo < hi) {
         const unsigned mid = (lo + hi) >> 1;
@@ -107,7 +116,7 @@ struct FrameSmem {
 };
 
 // Append `len` (<= 32) bits per lane, lanes in order, at bit cursor *cursor of the frame buffer.
-__device__ __forceinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_t code, int len, int* cursor, int limit_bits) {
+__device__ __noinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_t code, int len, int* cursor, int limit_bits) {
     int total;
     const int at = *cursor + warp_excl_scan(len, lane, &total);
     *cursor += total;
@@ -201,7 +210,7 @@ __device__ __forceinline__ void boundary_table(const EncTables& tb, const FrameS
 }
 
 // CalculateOptimalDeltaLength + CalculateFrameHeaderLength, hca.cpp:2708-2750 (warp-collective).
-__device__ __forceinline__ void header_lengths(const FrameSmem& fs, const HcaStreamDev& S, int lane) {
+__device__ __noinline__ void header_lengths(const FrameSmem& fs, const HcaStreamDev& S, int lane) {
     const int nch = S.channels;
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
@@ -230,7 +239,7 @@ __device__ __forceinline__ void header_lengths(const FrameSmem& fs, const HcaStr
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kEncWarps * 32, 5)   // shared memory admits five CTAs per SM: up to 102 registers
+__global__ void __launch_bounds__(kEncWarps * 32, 1)
 hca_encode_kernel(HcaEncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ EncTables tb;
@@ -249,8 +258,9 @@ hca_encode_kernel(HcaEncodeArgs a) {
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t f = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (f >= a.n_frames) return;
+    const uint64_t f_own = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool surplus = f_own >= a.n_frames;                  // a warp behind the last frame redoes it (and stores nothing)
+    const uint64_t f = surplus ? a.n_frames - 1 : f_own;
     uint32_t lo = 0, hi = a.n_streams;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -361,7 +371,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
             }
         }
     }
-    __syncwarp();
+    CONVOY();
 
     // ---- intensity stereo (hca.cpp:2561-2609): one lane per subframe accumulates the energies in band order
     if (S.stereo_bands > 0) {
@@ -406,6 +416,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         __syncwarp();
     }
 
+    CONVOY();
     // ---- scalefactors (hca.cpp:2625-2637)
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
@@ -444,6 +455,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         __syncwarp();
     }
 
+    CONVOY();
     // ---- scaled spectra, in place (hca.cpp:2639-2654)
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
@@ -495,6 +507,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         __syncwarp();
     }
 
+    CONVOY();
     // ---- bit allocation (hca.cpp:2809-2866)
     header_lengths(fs, S, lane);
     const int avail = frame_size * 8;
@@ -519,6 +532,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
             header_lengths(fs, S, lane);
         }
     }
+    CONVOY();
     if (!failed && noise_level != 0) {                        // BinarySearchBoundary
         int* pre = reinterpret_cast<int*>(fs.pcm);            // scratch shared with the frame buffer, which is filled later
         boundary_table(tb, fs, S, lane, noise_level, pre);
@@ -532,10 +546,8 @@ hca_encode_kernel(HcaEncodeArgs a) {
         else boundary = pre[hi_b] > avail ? lo_b : hi_b;
         if (boundary < 0) failed = true;
     }
-    if (failed) {                                             // EncodeFrame gives up: HcaErrorCode, hca.cpp:2976-2984
-        if (lane == 0) a.status[stream] = ERR_HCA_ENCODE;
-        return;
-    }
+    if (failed && lane == 0 && !surplus) a.status[stream] = ERR_HCA_ENCODE;   // EncodeFrame gives up (HcaErrorCode, hca.cpp:2976-2984);
+    CONVOY();                                                                 //  the warp stays with its CTA, nothing of the frame is stored
 
     // ---- final resolutions (hca.cpp:2868-2876)
     for (int c = 0; c < nch; c++) {
@@ -581,6 +593,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         else if (S.hfr_groups > 0)
             emit_bits(fs, lane, lane < S.hfr_groups ? (uint32_t)fs.hfr_scale[c * 8 + lane] : 0u, lane < S.hfr_groups ? 6 : 0, &cursor, limit_bits);
     }
+    CONVOY();
     // Spectra in two phases. (1) Every lane quantises its bands (4 l .. 4 l + 3 of every channel) for all eight subframes --
     // the band's constants are fetched once, not once per subframe -- and leaves (length << 16 | code) in place of the
     // scaled value (QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936). (2) In bitstream order (subframe-major, channel-
@@ -622,7 +635,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
             *row = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
-    __syncwarp();
+    CONVOY();
     auto put_bits = [&](uint32_t code, int len, int at) {                 // the reference's writer drops what does not fit (IO.cpp:131-134)
         if (len > 0 && at + len <= limit_bits) {
             const int w = at >> 5, bo = at & 31;
@@ -648,7 +661,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
             put_bits(code_b, len_b, at + len_a);
         }
     }
-    __syncwarp();
+    CONVOY();
 
     // ---- CRC16 over the first frame_size - 2 bytes. The CRC (init 0, no final xor) is linear: every lane takes a
     // contiguous chunk, multiplies its partial CRC by x^(8 * bytes behind the chunk) mod P (host-made per-stream
@@ -675,7 +688,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(kFull, crc, o);
     }
-    for (int i = lane; i < frame_size; i += 32) {
+    for (int i = lane; i < frame_size && !failed && !surplus; i += 32) {
         uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
         if (i == frame_size - 2) byte = crc >> 8;
         if (i == frame_size - 1) byte = crc & 0xFF;
@@ -697,7 +710,7 @@ int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
     a.smem_per_warp = (uint32_t)hca_encode_smem_per_warp(a.max_channels, a.frame_words);
     // wide streams (up to 8 channels x 6.6 KB) get fewer warps per CTA so the CTA still fits in shared memory
     int warps = kEncWarps;
-    while (warps > 1 && (size_t)a.smem_per_warp * warps > 96 * 1024) warps >>= 1;
+    while (warps > 1 && (size_t)a.smem_per_warp * warps > 200 * 1024) warps >>= 1;
     const size_t smem = (size_t)a.smem_per_warp * warps;
     if (smem > 200 * 1024) return -1;
     cudaFuncSetAttribute(hca_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
