@@ -321,9 +321,16 @@ __device__ __forceinline__ int div_trunc(int v, uint32_t magic, int d) {
 }
 
 // ------------------------------------------------------------ encode, fast
+// Per (chain, block) result of the movers' share of ChannelFrame::Encode's first pass (adx.cpp:221-230). The residuals of a
+// block's samples 2 .. 31 are taken against RAW samples of the same block; only the first two see the history the previous
+// block left behind (its SIMULATED samples), so those two stay with the worker.
+struct BlockHead {
+    int32_t mn, mx;     // range of the residuals of samples 2 .. 31 of the block
+};
 struct alignas(16) EncodeStage {
     uint32_t pcm[2][kPcmWords];
     uint8_t code[2][32 * kTile * kBlk + 128];   // per stream: blocks in file order
+    BlockHead head[2][32 * kTile];              // [tile parity][block in tile][chain]
     StreamInfo info[32];
 };
 
@@ -333,6 +340,10 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const int group = (threadIdx.x >> 5) % kGroups, role = (threadIdx.x >> 5) / kGroups, lane = threadIdx.x & 31;
     EncodeStage& stage = reinterpret_cast<EncodeStage*>(s_dyn)[group];
+    // reciprocals of every scale the quantiser can meet on this path: a table look-up instead of a division per block
+    uint32_t* s_magic = reinterpret_cast<uint32_t*>(s_dyn + kGroups * sizeof(EncodeStage));
+    for (int i = threadIdx.x; i <= 0x1000; i += blockDim.x) s_magic[i] = i ? 0x7FFFFFFFu / (uint32_t)i + 1u : 0u;
+    __syncthreads();
     auto& s_pcm = stage.pcm;
     auto& s_code = stage.code;
     StreamInfo* s_info = stage.info;
@@ -370,16 +381,46 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
         }
     };
 
+    const int c0 = ch.coef0, c1 = ch.coef1;
+    const int limit = 7;
+    // movers, first pass of tile t (lane = chain, the tile's blocks shared out over the three movers): range of the residuals
+    // that depend on raw samples only. Samples past the end of the stream are silence (adx.cpp:450-460): zeroed in the
+    // tile, so the worker reads them without a bounds check.
+    auto first_pass = [&](uint32_t t) {
+        const int buf = t & 1;
+        const uint32_t b0 = t * kTile;
+        const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+        int16_t* row = reinterpret_cast<int16_t*>(reinterpret_cast<uint8_t*>(&s_pcm[buf][slot * row_words]) +
+                                                  (int)((stream_base + (uint64_t)b0 * frame_bytes) & 15)) + ch.channel;
+        for (uint32_t tb = role - 1; tb < nb; tb += kMovers) {
+            const uint32_t sbase = (b0 + tb) * kSpb;
+            int h1 = 0, h2 = 0;
+            int mn = 0, mx = 0;
+#pragma unroll 8
+            for (int i = 0; i < kSpb; i++) {
+                int16_t* q = row + (size_t)(tb * kSpb + i) * nch;
+                int sm = *q;
+                if (sbase + i >= ch.samples) { sm = 0; *q = 0; }
+                if (i >= 2) {
+                    const int r = (sm * 4096 - c0 * h1 - c1 * h2) >> 12;
+                    mn = min(mn, r); mx = max(mx, r);
+                }
+                h2 = h1; h1 = sm;
+            }
+            stage.head[buf][tb * 32 + lane] = BlockHead{mn, mx};
+        }
+    };
+
     if (role >= 1) {
         mover_request(&s_pcm[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, true, nch, lane, role - 1);
         cp_commit();
         cp_wait_all();
     }
     group_sync(group);
+    if (role >= 1 && ntiles) first_pass(0);
+    group_sync(group);
 
     int h1 = ch.hist1, h2 = ch.hist2;
-    const int c0 = ch.coef0, c1 = ch.coef1;
-    const int limit = 7;
     for (uint32_t t = 0; t < ntiles; t++) {
         const int buf = t & 1;
         const uint32_t b0 = t * kTile;
@@ -388,32 +429,29 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
             cp_commit();
             if (t >= 1) store_tile(t - 1);
             cp_wait_all();
+            asm volatile("bar.sync %0, %1;" ::"r"(5 + group), "n"(32 * kMovers) : "memory");   // every mover's part of tile t + 1 has landed
+            if (t + 1 < ntiles) first_pass(t + 1);
         } else {
             const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
             const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_pcm[buf][slot * row_words]) +
                                  (int)((stream_base + (uint64_t)b0 * frame_bytes) & 15);
             for (uint32_t tb = 0; tb < nb; tb++) {
                 uint8_t* dst = &s_code[buf][slot * code_row + (tb * nch + ch.channel) * kBlk];
-                // this block's samples; past the end of the stream the reference pads with silence (adx.cpp:450-460)
+                const BlockHead hd = stage.head[buf][tb * 32 + lane];
+                // this block's samples (the movers have zeroed what lies past the end of the stream)
                 int smp[kSpb];
-                const uint32_t sbase = (b0 + tb) * kSpb;
 #pragma unroll
-                for (int i = 0; i < kSpb; i++) {
-                    const int16_t* q = reinterpret_cast<const int16_t*>(row) + (size_t)(tb * kSpb + i) * nch + ch.channel;
-                    smp[i] = sbase + i < ch.samples ? (int)*q : 0;
-                }
-                // pass 1: residual range against RAW history (adx.cpp:221-230)
-                const int o1 = h1, o2 = h2;
-                int mn = 0, mx = 0;
-#pragma unroll
-                for (int i = 0; i < kSpb; i++) {
-                    const int r = (smp[i] * 4096 - c0 * h1 - c1 * h2) >> 12;
-                    mn = min(mn, r); mx = max(mx, r);
-                    h2 = h1; h1 = smp[i];
-                }
+                for (int i = 0; i < kSpb; i++)
+                    smp[i] = *(reinterpret_cast<const int16_t*>(row) + (size_t)(tb * kSpb + i) * nch + ch.channel);
+                // pass 1 (adx.cpp:221-230): the first two residuals see the history the previous block left, the others came
+                // from the movers
+                const int r0 = (smp[0] * 4096 - c0 * h1 - c1 * h2) >> 12;
+                const int r1 = (smp[1] * 4096 - c0 * smp[0] - c1 * h1) >> 12;
+                const int mn = min(min(hd.mn, r0), r1), mx = max(max(hd.mx, r0), r1);
                 if (mn == 0 && mx == 0) {  // silent residual: all-zero block, history stays raw (adx.cpp:231-234)
 #pragma unroll
                     for (int k = 0; k < kBlk; k++) dst[k] = 0;
+                    h1 = smp[kSpb - 1]; h2 = smp[kSpb - 2];
                     continue;
                 }
                 const ScaleChoice sc = choose_scale(mn, mx, limit, ch.mode, ch.filter);
@@ -430,9 +468,8 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 // delta clamp stays: the scale comes from residuals against RAW history, so it fires in ~1 block of 8.)
                 // Division: q = ((2*|r| + 2*half) * ceil(2^31 / scale)) >> 32 is exact while (|r| + half) * scale < 2^31.
                 bool exact = abs(c0) > 0x2000 || abs(c1) > 0x2000 || scale > 0x1000;
-                h1 = o1; h2 = o2;
                 if (!exact) {
-                    const uint32_t magic31 = 0x7FFFFFFFu / (uint32_t)scale + 1u;      // ceil(2^31 / scale), scale >= 1
+                    const uint32_t magic31 = s_magic[scale];                          // ceil(2^31 / scale), 1 <= scale <= 0x1000
                     const int half2 = 2 * half;
                     // Serial path per sample: t -> r -> |r| -> 2|r| + half2 -> q -> min(q, limit) -> t'. The next t is
                     //   s'*4096 - c1*sim_{n-1} - c0*sim_n  with  sim_n = delta*scale + P  =  B - (c0*scale) * delta,
@@ -638,8 +675,9 @@ void launch_adx_encode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_ch
                        cudaStream_t s, uint64_t* launches) {
     if (n_fast) {
         const unsigned groups = (n_fast + 31) / 32;
-        cudaFuncSetAttribute(adx_encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroups * sizeof(EncodeStage)));
-        adx_encode_fast_kernel<<<(groups + kGroups - 1) / kGroups, kGroups * kGroupThreads, kGroups * sizeof(EncodeStage), s>>>(d_in, d_out, d_chains, n_fast);
+        const size_t smem_e = kGroups * sizeof(EncodeStage) + (0x1000 + 4) * sizeof(uint32_t);   // stages + the reciprocal table
+        cudaFuncSetAttribute(adx_encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+        adx_encode_fast_kernel<<<(groups + kGroups - 1) / kGroups, kGroups * kGroupThreads, smem_e, s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {

@@ -27,6 +27,13 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def checker():
+    """The compiled reference when oracle/_ref is there (it travels to the GPU box), else the C restatement."""
+    import oracle
+    return oracle.checker()
+
+
+@pytest.fixture(scope="session")
 def ctx():
     from pycricodecs_b200 import engine
     return engine.Context(0)

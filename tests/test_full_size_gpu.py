@@ -1,4 +1,4 @@
-"""GPU, BASELINE.json sizes (8192 x 2 s 48 kHz stereo streams per GPU): sampled bit-exactness against the oracle plus
+"""GPU, BASELINE.json sizes (8192 x 2 s 48 kHz stereo streams per GPU): sampled bit-exactness against the compiled reference (oracle/_ref, where present; else its C restatement) plus
 size-independent properties over the WHOLE batch -- results must not depend on how the batch is tiled, an
 encrypt -> decrypt round trip must return every byte, decrypt+decode must equal plain decode, and a batch must equal
 the concatenation of its halves."""
@@ -48,17 +48,17 @@ def _stream(blob, off, i):
     return bytes(blob[int(off[i]):int(off[i + 1])])
 
 
-def test_hca_full_batch(port, ctx, corpus, monkeypatch):
+def test_hca_full_batch(checker, ctx, corpus, monkeypatch):
     from pycricodecs_b200 import _lib, engine
     wav, woff = corpus
     hca, hoff = _run(ctx, _lib.JOB_HCA_ENCODE, wav, woff, quality=1, adx=engine.adx_params())
     assert len(hoff) == STREAMS + 1 and int(hoff[-1]) == STREAMS * 64204
     for i in SAMPLE:
-        assert _stream(hca, hoff, i) == port.hca_encode(_stream(wav, woff, i), 1)[1], f"encode, stream {i}"
+        assert _stream(hca, hoff, i) == checker.hca_encode(_stream(wav, woff, i), 1), f"encode, stream {i} ({checker.kind})"
     pcm, poff = _run(ctx, _lib.JOB_HCA_DECODE, hca, hoff, keys=None)
     assert int(poff[-1]) == STREAMS * 384044
     for i in SAMPLE:
-        assert _stream(pcm, poff, i) == port.hca_decode(_stream(hca, hoff, i))[1], f"decode, stream {i}"
+        assert _stream(pcm, poff, i) == checker.hca_decode(_stream(hca, hoff, i)), f"decode, stream {i} ({checker.kind})"
     whole = _digest(pcm, poff)
     # tiling independence: another run length (runs cross stream boundaries elsewhere), and the general kernels
     monkeypatch.setenv("CRI_HCA_FAST_RUN", "7")
@@ -75,24 +75,24 @@ def test_hca_full_batch(port, ctx, corpus, monkeypatch):
     enc, eoff = _run(ctx, _lib.JOB_HCA_CRYPT, hca, hoff, keys=keys, encrypt=1, ciph_type=56)
     assert np.array_equal(eoff, hoff) and not np.array_equal(enc, hca)
     for i in SAMPLE[:6]:
-        assert _stream(enc, eoff, i) == port.hca_crypt(_stream(hca, hoff, i), 1, 56, KEY)[1]
+        assert _stream(enc, eoff, i) == checker.hca_crypt(_stream(hca, hoff, i), 1, 56, KEY)
     dec, doff = _run(ctx, _lib.JOB_HCA_CRYPT, enc, eoff, keys=keys, encrypt=0, ciph_type=0)
     assert np.array_equal(dec, hca)
     pcm4, poff4 = _run(ctx, _lib.JOB_HCA_DECODE, enc, eoff, keys=keys)
     assert _digest(pcm4, poff4) == whole
 
 
-def test_adx_full_batch(port, ctx, corpus):
+def test_adx_full_batch(checker, ctx, corpus):
     from pycricodecs_b200 import _lib, engine
     wav, woff = corpus
     adx, aoff = _run(ctx, _lib.JOB_ADX_ENCODE, wav, woff, adx=engine.adx_params())
     assert int(aoff[-1]) == STREAMS * 108066
     for i in SAMPLE:
-        assert _stream(adx, aoff, i) == port.adx_encode(_stream(wav, woff, i))[1], f"encode, stream {i}"
+        assert _stream(adx, aoff, i) == checker.adx_encode(_stream(wav, woff, i)), f"encode, stream {i} ({checker.kind})"
     pcm, poff = _run(ctx, _lib.JOB_ADX_DECODE, adx, aoff)
     assert int(poff[-1]) == STREAMS * 384044
     for i in SAMPLE:
-        assert _stream(pcm, poff, i) == port.adx_decode(_stream(adx, aoff, i))[1], f"decode, stream {i}"
+        assert _stream(pcm, poff, i) == checker.adx_decode(_stream(adx, aoff, i)), f"decode, stream {i} ({checker.kind})"
     # a batch equals the concatenation of its halves (chains are independent; tiles / groups / CTAs differ)
     half = STREAMS // 2
     a2, o2 = _run(ctx, _lib.JOB_ADX_ENCODE, wav[int(woff[half]):], woff[half:] - woff[half], adx=engine.adx_params())
