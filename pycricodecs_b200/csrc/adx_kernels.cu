@@ -394,17 +394,19 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                                                   (int)((stream_base + (uint64_t)b0 * frame_bytes) & 15)) + ch.channel;
         for (uint32_t tb = role - 1; tb < nb; tb += kMovers) {
             const uint32_t sbase = (b0 + tb) * kSpb;
-            int h1 = 0, h2 = 0;
+            int16_t* q = row + (size_t)tb * kSpb * nch;
+            if (sbase + kSpb > ch.samples) {                               // the stream ends inside this block: silence behind it
+                for (int i = 0; i < kSpb; i++)
+                    if (sbase + i >= ch.samples) q[i * nch] = 0;
+            }
+            int h2 = q[0], h1 = q[nch];
             int mn = 0, mx = 0;
-#pragma unroll 8
-            for (int i = 0; i < kSpb; i++) {
-                int16_t* q = row + (size_t)(tb * kSpb + i) * nch;
-                int sm = *q;
-                if (sbase + i >= ch.samples) { sm = 0; *q = 0; }
-                if (i >= 2) {
-                    const int r = (sm * 4096 - c0 * h1 - c1 * h2) >> 12;
-                    mn = min(mn, r); mx = max(mx, r);
-                }
+            q += 2 * nch;
+#pragma unroll 6
+            for (int i = 2; i < kSpb; i++, q += nch) {
+                const int sm = *q;
+                const int r = (sm * 4096 - c0 * h1 - c1 * h2) >> 12;
+                mn = min(mn, r); mx = max(mx, r);
                 h2 = h1; h1 = sm;
             }
             stage.head[buf][tb * 32 + lane] = BlockHead{mn, mx};

@@ -252,8 +252,9 @@ static int adx_decode_size_one(const uint8_t* d, size_t n, AdxInfo* a, uint64_t*
 static void plan_adx_decode(cri_job* j) {
     std::vector<uint64_t> sizes(j->n, 0);
     std::vector<AdxInfo> infos(j->n);
-    for (uint32_t i = 0; i < j->n; i++)
+    parallel_for(j->n, [&](uint32_t i) {
         j->status[i] = adx_decode_size_one(j->blob + j->in_off[i], j->in_off[i + 1] - j->in_off[i], &infos[i], &sizes[i]);
+    });
     finish_layout(j, sizes);
     AdxLists lists;
     std::vector<AdxChain> one;
@@ -946,12 +947,12 @@ extern "C" int cri_adx_encode_batch(cri_ctx* c, const uint8_t* blob, const uint6
 }
 
 extern "C" int cri_hca_decode_sizes(const uint8_t* blob, const uint64_t* off, uint32_t n, uint64_t* sizes, int32_t* status) {
-    for (uint32_t i = 0; i < n; i++) {
+    parallel_for(n, [&](uint32_t i) {
         HcaInfo h;
         sizes[i] = 0;
         const int r = hca_decode_size_one(blob + off[i], off[i + 1] - off[i], &h, &sizes[i]);
         if (status) status[i] = r;
-    }
+    });
     return OK;
 }
 

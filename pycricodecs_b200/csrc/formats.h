@@ -12,8 +12,11 @@
 //   HCA encode planning  hca.cpp:2206-2462 ; header writer hca.cpp:3109-3164
 //   CryptHeader          hca.cpp:3166-3250
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <thread>
+#include <vector>
 
 namespace cri {
 
@@ -42,6 +45,25 @@ inline void put_le16(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_
 inline void put_le32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 
 uint16_t crc16(const uint8_t* p, size_t n);
+
+// Header parsing is independent per stream and, for a batch of thousands of streams scattered over a blob, mostly cache
+// misses: large batches are parsed by a handful of host threads (fn(i) must only touch stream i's slots).
+template <class F>
+inline void parallel_for(uint32_t n, F fn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint32_t workers = n < 2048 ? 1u : std::min<uint32_t>(std::min<uint32_t>(hw ? hw : 1u, 8u), n / 1024);
+    if (workers <= 1) {
+        for (uint32_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (uint32_t w = 0; w < workers; w++)
+        pool.emplace_back([=] {
+            const uint32_t lo = (uint32_t)((uint64_t)n * w / workers), hi = (uint32_t)((uint64_t)n * (w + 1) / workers);
+            for (uint32_t i = lo; i < hi; i++) fn(i);
+        });
+    for (auto& t : pool) t.join();
+}
 
 // ---------------------------------------------------------------- WAV
 // Sample encodings the reference converts to PCM16 before encoding (PCM::load_WAVE / Get_PCM16, pcm.cpp:291-327, 455-545)

@@ -117,13 +117,16 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     HcaJob& J = j->hca;
     std::vector<uint64_t> sizes(j->n, 0);
     std::vector<HcaInfo> infos(j->n);
-    for (uint32_t i = 0; i < j->n; i++) {
+    std::vector<uint8_t> unsupported(j->n, 0);
+    parallel_for(j->n, [&](uint32_t i) {
         const uint8_t* d = j->blob + j->in_off[i];
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         HcaInfo& h = infos[i];
-        if ((j->status[i] = hca_decode_size_one(d, len, &h, &sizes[i])) != OK) continue;
-        if (!v3_supported(h)) { j->status[i] = ERR_UNSUPPORTED; j->needs_clear = true; }           // region stays zero
-    }
+        if ((j->status[i] = hca_decode_size_one(d, len, &h, &sizes[i])) != OK) return;
+        if (!v3_supported(h)) { j->status[i] = ERR_UNSUPPORTED; unsupported[i] = 1; }              // region stays zero
+    });
+    for (uint32_t i = 0; i < j->n; i++)
+        if (unsupported[i]) j->needs_clear = true;
     finish_layout_public(j, sizes);
 
     CipherPool pool(&J.cipher_tables);
@@ -336,19 +339,19 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
     std::vector<uint64_t> sizes(j->n, 0);
     std::vector<WavInfo> wavs(j->n);
     std::vector<HcaEncPlan> plans(j->n);
-    for (uint32_t i = 0; i < j->n; i++) {
+    parallel_for(j->n, [&](uint32_t i) {
         const uint8_t* d = j->blob + j->in_off[i];
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         const int r = parse_wav(d, len, &wavs[i]);
-        if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
+        if (r < 0) { j->status[i] = ERR_WAV_BASE + r; return; }
         const bool looping = wavs[i].looping && !j->adx.force_not_looping;
         int pr;
         if (looping) pr = plan_hca_encode_loop(wavs[i], j->quality, &plans[i]);   // loop chunk + pre / post audio (hca.cpp:2292-2321, 3000-3053)
         else pr = plan_hca_encode((unsigned)wavs[i].channels, (unsigned)wavs[i].rate, wavs[i].total_samples / (unsigned)wavs[i].channels, j->quality, &plans[i]);
-        if (pr == ERR_UNSUPPORTED) { j->status[i] = ERR_UNSUPPORTED; continue; }
-        if (pr < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; continue; }
+        if (pr == ERR_UNSUPPORTED) { j->status[i] = ERR_UNSUPPORTED; return; }
+        if (pr < 0 || plans[i].frame_size < 8) { j->status[i] = ERR_HCA_CHANNELS; return; }
         sizes[i] = (uint64_t)plans[i].header_size + (uint64_t)plans[i].frame_count * plans[i].frame_size;
-    }
+    });
     finish_layout_public(j, sizes);
     J.streams.assign(j->n, HcaStreamDev{});
     J.frame_prefix.assign(j->n + 1, 0);

@@ -242,13 +242,15 @@ def sizes_device(kind: int, blob, offsets: np.ndarray, ctx: Optional[Context] = 
 
 
 def batch_device(kind: int, blob, offsets: np.ndarray, ctx: Optional[Context] = None, out=None, stream=None, *, keys=None,
-                 subkeys=None, adx: Optional[AdxParams] = None, quality: int = 1, encrypt: int = 0, ciph_type: int = 0):
+                 subkeys=None, adx: Optional[AdxParams] = None, quality: int = 1, encrypt: int = 0, ciph_type: int = 0,
+                 out_offsets: Optional[np.ndarray] = None):
     """Device-resident batch: `blob` is a CUDA uint8 tensor on the context's GPU (anything with `data_ptr()`), the result
     is a CUDA uint8 tensor too -- the payload never crosses PCIe (the `cri_*_batch_dev` calls of the C-ABI).
 
     Returns (out, out_offsets, status). `out` may be passed in (a CUDA uint8 tensor of at least the packed output
     size); `stream` is a torch.cuda.Stream (default: the current stream of the blob's device). Headers are fetched from
-    the device blob for planning (a few hundred bytes per stream).
+    the device blob for planning (a few hundred bytes per stream). `out_offsets` (the packed layout, e.g. from
+    `sizes_device`) saves the size query.
     """
     import torch
     ctx = ctx or default_context()
@@ -266,11 +268,14 @@ def batch_device(kind: int, blob, offsets: np.ndarray, ctx: Optional[Context] = 
     sp = None if subkeys is None else subkeys.ctypes.data
     adx = adx if adx is not None else adx_params()
     bp, op = blob.data_ptr(), offsets.ctypes.data
-    ctx.check(L.cri_sizes_dev(ctx.handle, kind, bp, op, n, ctypes.byref(adx), int(quality), sizes.ctypes.data, status.ctypes.data, sp_))
-    out_offsets = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(sizes[:n], out=out_offsets[1:])
     if kind == _lib.JOB_HCA_CRYPT:
         out_offsets = offsets
+    elif out_offsets is None:
+        ctx.check(L.cri_sizes_dev(ctx.handle, kind, bp, op, n, ctypes.byref(adx), int(quality), sizes.ctypes.data, status.ctypes.data, sp_))
+        out_offsets = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(sizes[:n], out=out_offsets[1:])
+    else:
+        out_offsets = np.ascontiguousarray(out_offsets, dtype=np.uint64)
     total = int(out_offsets[-1])
     if out is None:
         out = torch.empty(max(total, 1), dtype=torch.uint8, device=blob.device)

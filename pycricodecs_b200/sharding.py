@@ -111,8 +111,8 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
         ctx = ctx or engine.default_context()
         device = torch.device("cuda", ctx.device)
 
-        def compute(piece_blob, piece_offsets, out, **pkw):
-            return engine.batch_device(kind, piece_blob, piece_offsets, ctx, out=out, **pkw)[2]
+        def compute(piece_blob, piece_offsets, out, out_offsets=None, **pkw):
+            return engine.batch_device(kind, piece_blob, piece_offsets, ctx, out=out, out_offsets=out_offsets, **pkw)[2]
 
         def sizes_of(piece_blob, piece_offsets, **pkw):
             return engine.sizes_device(kind, piece_blob, piece_offsets, ctx, **pkw)[0]
@@ -168,7 +168,8 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
     for k, (lo, hi) in enumerate(mine):
         o0, o1 = int(out_offsets[lo]), int(out_offsets[hi])
         if hi > lo:
-            status[lo:hi] = compute(piece_input(lo, hi), offsets[lo:hi + 1] - offsets[lo], final[o0:max(o1, o0 + 1)], **piece_kw(lo, hi))
+            status[lo:hi] = compute(piece_input(lo, hi), offsets[lo:hi + 1] - offsets[lo], final[o0:max(o1, o0 + 1)],
+                                    out_offsets=out_offsets[lo:hi + 1] - out_offsets[lo], **piece_kw(lo, hi))
         inputs.pop((lo, hi), None)
         if world == 1 or not gather:
             continue

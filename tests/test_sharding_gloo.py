@@ -59,7 +59,7 @@ GATHER_WORKER = textwrap.dedent("""
     # stand-in for the engine: stream i becomes its bytes + key, twice (sizes known up front, like header-derived sizes)
     def sizes_of(piece, poff, keys=None, **kw):
         return np.diff(poff.astype(np.int64)) * 2
-    def compute(piece, poff, out, keys=None, **kw):
+    def compute(piece, poff, out, keys=None, out_offsets=None, **kw):
         p = piece.numpy(); at = 0
         for i in range(len(poff) - 1):
             x = (p[int(poff[i]):int(poff[i + 1])].astype(np.int64) + int(keys[i])) %% 256
