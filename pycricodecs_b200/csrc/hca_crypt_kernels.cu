@@ -262,7 +262,10 @@ __device__ __forceinline__ void crypt_frame(uint8_t* dat, uint32_t q0, uint32_t 
     for (int i = 0; i < 2; i++) {
         const uint32_t addr = (wE - N + i) * 4;                 // wraps below zero for a word in front of the slot: then drop = 4
         const uint32_t drop = (int32_t)(q0 - addr) <= 0 ? 0u : min(q0 - addr, 4u);
-        uint32_t o = map4(wp[i]);
+        uint32_t w = 0;                                         // only this frame's bytes are read: the others are the
+        if (drop == 0) w = wp[i];                               // neighbour lane's tail, which that lane is rewriting
+        else for (uint32_t b = drop; b < 4; b++) w |= (uint32_t)reinterpret_cast<const uint8_t*>(wp + i)[b] << (8 * b);
+        uint32_t o = map4(w);
         o = drop >= 4 ? 0u : o & (0xFFFFFFFFu << (8 * drop));
         if (drop == 0) wp[i] = o;
         else for (uint32_t b = drop; b < 4; b++) reinterpret_cast<uint8_t*>(wp + i)[b] = (uint8_t)(o >> (8 * b));
@@ -300,8 +303,11 @@ __device__ __forceinline__ void crypt_frame(uint8_t* dat, uint32_t q0, uint32_t 
         r = modq_word(r, __byte_perm(o, 0, 0x0123));
     }
     {   // the word with the last CRC-covered byte: byte stores (what follows is the CRC field and the next frame)
-        const uint32_t o = map4(p[rest]);
         uint8_t* pb = reinterpret_cast<uint8_t*>(p + rest);
+        uint32_t w = 0;
+        if (k_tail == 4) w = p[rest];
+        else for (uint32_t b = 0; b < k_tail; b++) w |= (uint32_t)pb[b] << (8 * b);
+        const uint32_t o = map4(w);
         for (uint32_t b = 0; b < k_tail; b++) {
             const uint32_t m = (o >> (8 * b)) & 0xFF;
             pb[b] = (uint8_t)m;
