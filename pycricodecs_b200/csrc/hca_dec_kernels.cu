@@ -232,11 +232,14 @@ hca_unpack_kernel(HcaDecodeArgs a) {
         if (type == 2) {
             const uint32_t v0 = br.position() + 4 <= nbits ? br.peek(4) : 0u;
             uint32_t inten = v0;
+            uint32_t keep = 0;                               // first nibble that keeps the previous frame's value (0: none)
             if (!S.v3) {
                 if (v0 < 15) {
                     br.skip(4);
                     br.top_up();
                     for (int i = 1; i < 8; i++) inten |= br.read(4, nbits) << (4 * i);
+                } else {
+                    keep = 1;                                // 15 is stored, not consumed, and nothing else is read (:1368-1372)
                 }
             } else {                                         // hca.cpp:1382-1424
                 br.skip(4);
@@ -254,9 +257,9 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                                 v = br.read(4, nbits);
                             } else {
                                 v = (v - (escape >> 1) + d) & 0xFF;
-                                // the reference stops here and keeps the PREVIOUS frame's remaining intensities
-                                // (its caller ignores the error); only corrupt data gets here: the stream fails
-                                if (v > 15) { bad = true; break; }
+                                // out of range: unpack_intensity returns here (:1410-1412), its caller ignores that
+                                // (:1185) and goes on with the bits that follow and the older intensities
+                                if (v > 15) { keep = (uint32_t)i; break; }
                             }
                             inten |= v << (4 * i);
                         }
@@ -265,6 +268,7 @@ hca_unpack_kernel(HcaDecodeArgs a) {
                     inten = 0x77777777u;
                 }
             }
+            a.carry[slot * a.max_channels + c] = (uint8_t)keep;
             a.inten[slot * a.max_channels + c] = inten;
         } else if (!S.v3) {
             for (int g = 0; g < S.hfr_groups; g++) s_sf[(128 - S.hfr_groups + g) * 32] = (uint8_t)br.read(6, nbits);
@@ -417,6 +421,7 @@ void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launche
     hca_unpack_kernel<<<(unsigned)((a.total_groups + groups_per_cta - 1) / groups_per_cta), kUnpackThreads, smem, s>>>(a);
     ++*launches;
     if (a.sfres) launch_hca_noise_scan(a, s, launches);
+    if (a.carry_scan) launch_hca_intensity_scan(a, s, launches);
     if (mid) cudaEventRecord(mid, s);
     launch_hca_imdct(a, s, launches);
 }

@@ -163,6 +163,7 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         needed_frames[i] = (uint32_t)std::min<uint64_t>(h.frame_count, ((uint64_t)samples + h.delay + 1023) / 1024);
         J.streams[i].frame_base = (uint32_t)j->units;
         any_v3 = any_v3 || s.v3;
+        for (unsigned ch = 1; ch < h.channels; ch++) J.any_pair = J.any_pair || s.type[ch] == 2;
         any_noise = any_noise || s.noise;
         j->units += needed_frames[i];
     }
@@ -217,13 +218,15 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
         const uint64_t warps = (J.n_runs + runs_per_warp - 1) / runs_per_warp;
         J.spec_bytes = warps * J.run_len * 8 * 1024 * sizeof(float4);
         J.s_bytes = (G + 1) * J.scratch_words * sizeof(uint32_t) + kScratchTail;
-        J.i_bytes = (G + 1) * sizeof(uint32_t);                      // intensity nibbles of the frame's secondary channel
+        J.i_count = G + 1;                                           // intensity nibbles of the frame's secondary channel,
+        J.i_bytes = J.i_count * (sizeof(uint32_t) + 1);              // then one "kept from the previous frame" byte each
         J.total_groups = 0;
         J.max_steps = 0;
         return OK;
     }
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
+        J.streams[i].unit_base = (uint32_t)J.units.size();
         for (uint32_t f = 0; f < needed_frames[i]; f += run) {
             HcaUnit u{i, f, std::min(run, needed_frames[i] - f)};
             J.units.push_back(u);
@@ -244,7 +247,8 @@ int plan_hca_decode(cri_ctx* c, cri_job* j) {
     J.s_bytes = slots * J.scratch_words * sizeof(uint32_t) + kScratchTail;
     J.q_bytes = slots * J.max_channels * 8 * 16 * sizeof(uint4);
     J.g_bytes = slots * J.max_channels * 128 * sizeof(float);
-    J.i_bytes = slots * J.max_channels * sizeof(uint32_t);
+    J.i_count = slots * J.max_channels;
+    J.i_bytes = J.i_count * (sizeof(uint32_t) + 1);
     if (any_noise && j->units < 0xFFFF0000ull) {
         J.noise_frames = j->units;
         J.n_bytes = slots * J.max_channels * (128 + sizeof(uint32_t)) + 2 * J.noise_frames * sizeof(uint32_t);
@@ -458,6 +462,8 @@ int run_hca(cri_ctx* c, cri_job* j, bool* have_dominant) {
         a.n_units = (uint32_t)J.units.size();
         a.uniform = J.uniform;
         a.inten = reinterpret_cast<uint32_t*>(J.d_i);
+        a.carry = J.d_i + J.i_count * sizeof(uint32_t);
+        a.carry_scan = J.any_pair ? 1u : 0u;
         a.status = j->d_status;
         a.total_groups = J.total_groups;
         a.steps = J.max_steps;

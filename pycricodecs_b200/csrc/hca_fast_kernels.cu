@@ -386,6 +386,7 @@ hca_unpack_fast_kernel(HcaDecodeArgs a) {
                     br.top_up();
                 }
                 a.inten[g] = inten;
+                a.carry[g] = v0 < 15 ? 0 : 1;           // 15: the other seven keep the previous frame's values (:1368-1372)
             } else {
                 uint64_t packed_sf = 0;
                 for (int grp = 0; grp < hfr_groups; grp++) {
@@ -930,6 +931,7 @@ void launch_fast(HcaDecodeArgs a, cudaStream_t s, uint64_t* launches, cudaEvent_
         a.run_count = a.n_runs;
         launch_unpack<NCH, JOINT>(a, s);
         ++*launches;
+        if (JOINT && a.carry_scan) launch_hca_intensity_scan(a, s, launches);
         if (mid) cudaEventRecord(mid, s);
 #ifdef CRI_HCA_PAIR_KERNEL
         static const int xf = [] { const char* e = getenv("CRI_HCA_XF"); return e && *e ? atoi(e) : 0; }();

@@ -357,6 +357,44 @@ __global__ void hca_noise_scan_kernel(HcaDecodeArgs a) {
     }
 }
 
+// Intensities a frame did not code keep the previous frame's values (unpack_intensity leaves its channel state alone:
+// v <= 2.0 with a first index of 15, hca.cpp:1368-1372; v3.0 with a delta that leaves 0..15, :1410-1412 + :1185). The
+// unpack kernels mark such frames (carry = first kept nibble); here one warp looks at one stream and, only if it has a
+// marked frame, lane 0 walks its frames in order. General kernels: a frame's slot is unit * steps + step, and the last
+// frame of a unit is also the look-back frame (step 0) of the next one.
+__global__ void hca_intensity_scan_kernel(HcaDecodeArgs a) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= a.n_streams) return;
+    const HcaStreamDev& S = a.streams[i];
+    const bool fast = a.n_runs != 0;
+    const uint32_t frames = fast ? a.dec_prefix[i + 1] - a.dec_prefix[i]
+                                 : (uint32_t)min((uint64_t)S.frame_count, ((uint64_t)S.out_samples + S.delay + 1023) / 1024);
+    const uint32_t run = a.steps - 1, MC = a.max_channels;
+    for (uint32_t c = 1; c < S.channels; c++) {
+        if (S.type[c] != 2) continue;
+        auto slot_of = [&](uint32_t f) -> uint64_t {
+            if (fast) return (uint64_t)a.dec_prefix[i] + f;
+            return ((uint64_t)(S.unit_base + f / run) * a.steps + f % run + 1) * MC + c;
+        };
+        bool any = false;
+        for (uint32_t f = lane; f < frames; f += 32) any = any || a.carry[slot_of(f)] != 0;
+        if (!__any_sync(0xFFFFFFFFu, any) || lane != 0) continue;
+        uint32_t prev = 0;                                                   // channel state starts zeroed (hca.cpp:962)
+        for (uint32_t f = 0; f < frames; f++) {
+            const uint64_t at = slot_of(f);
+            const uint32_t k = a.carry[at];
+            uint32_t v = a.inten[at];
+            if (k) {
+                const uint32_t kept = 0xFFFFFFFFu << (4 * k);
+                v = (v & ~kept) | (prev & kept);
+                a.inten[at] = v;
+            }
+            if (!fast && f % run == run - 1 && f + 1 < frames) a.inten[((uint64_t)(S.unit_base + f / run + 1) * a.steps) * MC + c] = v;
+            prev = v;
+        }
+    }
+}
+
 template <int NCH>
 void launch_one(const HcaDecodeArgs& a, cudaStream_t s) {
     const size_t per_warp = 2 * 768 + (size_t)a.max_channels * 256 + (NCH ? 0 : (size_t)a.max_channels * 256 + 512 + 256);
@@ -370,6 +408,12 @@ void launch_one(const HcaDecodeArgs& a, cudaStream_t s) {
 void launch_hca_noise_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches) {
     if (!a.sfres || !a.n_streams) return;
     hca_noise_scan_kernel<<<(a.n_streams + 127) / 128, 128, 0, s>>>(a);
+    ++*launches;
+}
+
+void launch_hca_intensity_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches) {
+    if (!a.carry_scan || !a.n_streams) return;
+    hca_intensity_scan_kernel<<<(a.n_streams + 3) / 4, 128, 0, s>>>(a);
     ++*launches;
 }
 

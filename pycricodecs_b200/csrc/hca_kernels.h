@@ -21,6 +21,9 @@ struct HcaDecodeArgs {
     uint4* quant;               // [slot][channel][8 subframes][16] x 8 int16 quantised spectra
     float* gain;                // [slot][channel][128] gain per coded band, HFR multiplier per reconstructed band
     uint32_t* inten;            // [slot][channel] 8 intensity nibbles
+    uint8_t* carry;             // [slot][channel] k > 0: nibbles k..7 were not coded and keep the previous frame's values
+                                // (hca.cpp:1368-1372, 1410-1412 + its caller :1185); resolved by the intensity scan
+    uint32_t carry_scan;        // some stream has an intensity pair: run the scan between unpack and transform
     int32_t* status;
     uint64_t total_groups;      // unit blocks (32 units) x steps: one unpack warp each
     uint32_t n_units;
@@ -53,6 +56,7 @@ struct HcaDecodeArgs {
 // `mid` (optional) is recorded between the unpack and the transform kernel.
 void launch_hca_decode(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches, cudaEvent_t mid);
 void launch_hca_noise_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // between the two, when a.sfres
+void launch_hca_intensity_scan(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // between the two, when a.carry_scan
 void launch_hca_imdct(const HcaDecodeArgs& a, cudaStream_t s, uint64_t* launches);   // second half of launch_hca_decode
 // Streams and events of the pipelined form of the fast path (owned by the context): the job's runs are cut into `chunks`
 // pieces, the unpack kernels run back to back on the job's stream and every transform kernel follows its own unpack kernel

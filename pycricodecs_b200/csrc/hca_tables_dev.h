@@ -26,6 +26,7 @@ struct HcaStreamDev {
     uint32_t cipher;        // index into the cipher-table array (0 = identity)
     uint32_t ath;           // index into the ATH-curve array (0 = all zero)
     uint32_t frame_base;    // decode: index of the stream's frame 0 in the job-wide per-frame arrays (noise generator)
+    uint32_t unit_base;     // decode, general kernels: index of the stream's first unit (runs of frames, in order)
     uint8_t channels, total_bands, base_bands, stereo_bands;
     uint8_t bands_per_hfr, hfr_groups, min_res, max_res;
     uint8_t type[kHcaMaxChannels];    // 0 discrete, 1 stereo primary, 2 stereo secondary
@@ -64,6 +65,7 @@ struct HcaJob {
     std::vector<uint8_t> cipher_tables;    // 256 bytes each, [0] identity
     std::vector<uint8_t> ath_tables;       // 128 bytes each, [0] zero
     uint64_t q_bytes = 0, g_bytes = 0, i_bytes = 0, s_bytes = 0;
+    uint64_t i_count = 0;                  // entries of the intensity array (the "kept" bytes follow them)
     uint64_t n_bytes = 0;                  // noise generator side arrays (v3.0 streams with min_res == 0), see run_hca
     uint64_t noise_frames = 0;             // frames of the job-wide per-frame arrays
     uint8_t* d_n = nullptr;
@@ -84,6 +86,7 @@ struct HcaJob {
     uint32_t* d_dec_prefix = nullptr;
     uint32_t run_len = 0, n_runs = 0;      // n_runs == 0: general path
     bool any_joint = false;                // some stream has an intensity-stereo pair or HFR bands
+    bool any_pair = false;                 // some stream has an intensity-stereo pair
     uint64_t total_frames = 0, spec_bytes = 0;
     uint8_t* d_spec = nullptr;
     uint8_t* d_s = nullptr;

@@ -72,9 +72,12 @@ def header(version=0x0300, channels=2, rate=44100, frames=8, delay=128, padding=
 
 
 def stream(seed, frames=8, channels=2, frame_size=1024, total=128, base=40, stereo=30, bands_per_hfr=4, min_res=0, max_res=15,
-           delay=128, version=0x0300, level=(40, 110), rate=44100, sf_max=44, dec=False, ath=None):
+           delay=128, version=0x0300, level=(40, 110), rate=44100, sf_max=44, dec=False, ath=None, kept=0.0):
     """One v3.0 stream (or, with version <= 0x0200, a stream in the older bitstream layout; dec / ath: see header()).
-    Channel pairs are primary/secondary when stereo > 0 (hca.cpp:909-960, 2 channels per track)."""
+    Channel pairs are primary/secondary when stereo > 0 (hca.cpp:909-960, 2 channels per track).
+    kept > 0: that share of the secondary-channel frames stop coding their intensities early, so the decoder keeps the
+    previous frame's values for the rest -- v <= 2.0: a first index of 15 (hca.cpp:1368-1372); v3.0: a delta that
+    leaves 0..15 (hca.cpp:1410-1412, the caller at :1185 carries on). Streams with kept == 0 are unchanged."""
     rng = np.random.default_rng(seed)
     out = header(version, channels, rate, frames, delay, 0, frame_size, min_res, max_res, 1, 0, total, base, stereo, bands_per_hfr, 0, dec, ath)
     # channel roles for one track and channel_config 0 (hca.cpp:909-960): 1 primary, 2 secondary, 0 discrete
@@ -115,9 +118,24 @@ def stream(seed, frames=8, channels=2, frame_size=1024, total=128, base=40, ster
                         v = nv
                         b.put(d, db)
             if secondary:
+                stop = kept > 0 and rng.random() < kept
                 if version <= 0x0200:
-                    for _i in range(8):
-                        b.put(int(rng.integers(0, 15)), 4)
+                    if stop:
+                        b.put(15, 4)                        # peeked, not consumed: the spectra start at these bits
+                    else:
+                        for _i in range(8):
+                            b.put(int(rng.integers(0, 15)), 4)
+                elif stop:
+                    up = bool(rng.integers(0, 2))
+                    db = 2 if up else int(rng.integers(1, 3))   # 1-bit deltas cannot leave the range, 2-bit ones only downwards
+                    bmax, bits = (2 << db) - 1, db + 1
+                    at = int(rng.integers(1, 8))            # the delta that leaves the range
+                    v = 14 if up else 0
+                    b.put(v, 4)
+                    b.put(db, 2)
+                    for _i in range(1, at):
+                        b.put(bmax >> 1, bits)              # delta 0
+                    b.put(bmax - 1 if up else 0, bits)      # 14 + (bmax >> 1) > 15, or 0 - (bmax >> 1) wraps past 15
                 else:
                     kind = int(rng.integers(0, 6))
                     if kind == 0:                           # "15": all intensities 7

@@ -30,6 +30,11 @@ CASES = [   # wider than the committed fixtures; expected = oracle port (pinned 
     dict(seed=11, frame_size=4096, version=0x0200, min_res=1),
     dict(seed=12, frame_size=8192, channels=4, frames=6),                  # two primary / secondary pairs
     dict(seed=13, frame_size=6144, channels=3, frames=6, base=50, stereo=20, bands_per_hfr=5, total=110),
+    # intensities cut short (the decoder keeps the previous frame's): across units of the general kernels, two pairs
+    dict(seed=14, frame_size=4096, frames=40, kept=0.4),
+    dict(seed=15, frame_size=4096, frames=40, kept=0.9, min_res=1),
+    dict(seed=16, frame_size=8192, channels=4, frames=20, kept=0.5),
+    dict(seed=17, frame_size=4096, frames=40, version=0x0200, min_res=1, kept=0.4),
 ]
 
 
@@ -97,6 +102,23 @@ def test_mixed_v2_and_v3_batch(ctx, port):
     got = HCA.decode_batch(streams, ctx=ctx)
     for s, g in zip(streams, got):
         assert g == port.hca_decode(s)[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("run", [None, "1", "7"])
+def test_kept_intensities_on_the_fast_path(ctx, port, monkeypatch, run):
+    """v2.0 pairs whose first intensity index is 15 keep the previous frame's other seven (hca.cpp:1368-1372): a batch of
+    such streams alone takes the fast kernels, where the chain of kept values crosses run boundaries."""
+    from pycricodecs_b200 import HCA
+    if run:
+        monkeypatch.setenv("CRI_HCA_FAST_RUN", run)
+    streams = [hca3gen.stream(seed=40 + i, frame_size=3072, frames=50 + i, version=0x0200, min_res=1, kept=k)
+               for i, k in enumerate((0.3, 0.95, 0.0, 0.6, 1.0))]
+    streams.insert(2, _fixture("v2_joint_kept_intensities"))
+    got = HCA.decode_batch(streams, ctx=ctx)
+    for s, g in zip(streams, got):
+        assert g == port.hca_decode(s)[1]
+    assert h(got[2]) == D["v2_joint_kept_intensities"]["wav_sha"]
 
 
 @pytest.mark.gpu

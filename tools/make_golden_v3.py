@@ -16,6 +16,9 @@ CASES = {   # name -> generator arguments
     "v3_joint_hfr_noise": dict(seed=101, frames=6, frame_size=3072),
     "v3_mono_hfr_noise": dict(seed=102, frames=6, frame_size=1536, channels=1, stereo=0, base=60, bands_per_hfr=8),
     "v3_joint_minres1": dict(seed=103, frames=5, frame_size=3072, min_res=1, base=30, stereo=20, bands_per_hfr=6, total=120),
+    # intensities cut short: the decoder keeps the previous frame's values (hca.cpp:1410-1412 + :1185; v2.0: :1368-1372)
+    "v3_joint_kept_intensities": dict(seed=104, frames=24, frame_size=3072, kept=0.5),
+    "v2_joint_kept_intensities": dict(seed=105, frames=24, frame_size=3072, version=0x0200, min_res=1, kept=0.5),
 }
 
 
