@@ -19,6 +19,10 @@
 // same arithmetic, one thread per chain straight on global memory.
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
+#ifdef CRI_ADX_TIMING
+#include <cstdio>
+#endif
 
 #include "kernels.h"
 
@@ -51,7 +55,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ int decode_scale(int raw, int mode, int& c0, int& c1) {
     if (mode == 3) return raw + 1;
@@ -92,20 +95,41 @@ __device__ __forceinline__ void mover_request(uint32_t* stage, int row_words, co
 }
 
 // ------------------------------------------------------------ decode, fast
+// Decode groups are one worker and ONE mover warp: the mover does not copy, it issues bulk copies (cp.async.bulk: the
+// copy engine moves a stream's tile between HBM and shared memory by itself and reports on an mbarrier / bulk group),
+// one lane per stream. With cp.async requests and load / store loops the movers issued 40 % of the kernel's
+// instructions on the worker's own scheduler, and the lone recurrence warp ran a third slower for it.
+constexpr int kDecGroupThreads = 64;
+__device__ __forceinline__ void dec_group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kDecGroupThreads) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+// PCM tile: per stream one row of kTile x 32 x channels samples, as in the WAV, placed p = (address of the row's first
+// byte in the output blob) mod 16 bytes into a 16-byte aligned row of 16 more bytes: shared and global addresses of
+// every sample then agree modulo 16, so all whole 16-byte units of the row leave in one bulk store (both ends of a bulk
+// copy must be 16-byte aligned) and only the < 16 bytes at either end are stored by the lane itself.
+constexpr int kPcmTileBytes = 32 * kTile * kSpb * 2 + 32 * 16;
 struct alignas(16) DecodeStage {
     uint32_t code[3][kCodeWords];             // tile t in stage t % 3: two tiles are in flight
-    int16_t pcm[2][32 * kTile * kSpb + 64];   // per stream: interleaved samples, as in the WAV
+    alignas(16) uint8_t pcm[2][kPcmTileBytes];
     StreamInfo info[32];
+    alignas(8) uint64_t full[3];              // mbarriers: the bulk loads of a stage have landed
 };
 
-__global__ void __launch_bounds__(kGroups * kGroupThreads, 1)
+__global__ void __launch_bounds__(kGroups * kDecGroupThreads, 1)
 adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const AdxChain* __restrict__ chains,
                        uint32_t n_chains) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const int group = (threadIdx.x >> 5) % kGroups, role = (threadIdx.x >> 5) / kGroups, lane = threadIdx.x & 31;
     DecodeStage& stage = reinterpret_cast<DecodeStage*>(s_dyn)[group];
     auto& s_code = stage.code;
-    auto& s_pcm = stage.pcm;
     StreamInfo* s_info = stage.info;
     const uint32_t first = (blockIdx.x * kGroups + group) * 32u;
     if (first >= n_chains) return;
@@ -114,134 +138,214 @@ adx_decode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     const int nstreams = 32 / nch;
     const int frame_bytes = nch * kBlk;
     const int row_words = ((kTile * frame_bytes + 15) / 16 + 1) * 4;   // whole 16-byte chunks
-    const int out_row = kTile * kSpb * nch + 2;             // int16 per stream in the PCM tile (odd word stride)
+    const uint32_t tile_bytes = (uint32_t)(kTile * kSpb * 2 * nch);   // PCM of one stream's tile
+    const uint32_t out_row = tile_bytes + 16;               // bytes per stream in the PCM tile
     uint32_t warp_blocks = ch.blocks;
 #pragma unroll
     for (int o = 16; o; o >>= 1) warp_blocks = max(warp_blocks, __shfl_xor_sync(kFull, warp_blocks, o));
     const int slot = lane / nch;                            // this lane's stream within the CTA
     if (role == 0 && ch.channel == 0) s_info[slot] = StreamInfo{ch.eof_off, ch.out_off, ch.blocks, ch.samples};
-    group_sync(group);
+    if (role == 1 && lane == 0) {
+        for (int k = 0; k < 3; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&stage.full[k])), "r"(nstreams));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    dec_group_sync(group);
     const uint32_t ntiles = (warp_blocks + kTile - 1) / kTile;
 
-    auto store_tile = [&](uint32_t t) {                     // mover: tile t of every stream is one contiguous run in the WAV
-        const uint32_t b0 = t * kTile, s0 = b0 * kSpb;
-        for (int s = role - 1; s < nstreams; s += kMovers) {
-            const StreamInfo si = s_info[s];
+    // mover, lane s = stream s: one bulk load brings the aligned 16-byte units that cover the stream's tile into its
+    // stage row (the blob starts 256-byte aligned and has slack behind it); every stream lane arrives once per tile
+    auto request = [&](uint32_t t) {
+        if (lane >= nstreams) return;
+        const StreamInfo si = s_info[lane];
+        const uint32_t b0 = t * kTile;
+        const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
+        const uint32_t bar = smem_u32(&stage.full[t % 3]);
+        if (nb) {
+            const uint64_t lo = si.in_base + (uint64_t)b0 * frame_bytes, hi = lo + (uint64_t)nb * frame_bytes;
+            const uint64_t from = lo & ~(uint64_t)15;
+            const uint32_t bytes = (uint32_t)(((hi + 15) & ~(uint64_t)15) - from);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(&s_code[t % 3][lane * row_words])), "l"(in + from), "r"(bytes), "r"(bar) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+    };
+    // mover, lane s = stream s: tile t of the stream is one contiguous run of the WAV. Whole 16-byte units go out in one
+    // bulk store, the < 16 bytes in front of and behind them sample by sample; returns once the copy engine has read the
+    // tile (the worker overwrites it two tiles later).
+    auto store_tile = [&](uint32_t t) {
+#ifdef CRI_ADX_NOSTORE                                      // development: the worker's pace without the stores
+        if (t != 0xFFFFFFFFu) return;
+#endif
+        if (lane < nstreams) {
+            const StreamInfo si = s_info[lane];
+            const uint32_t b0 = t * kTile, s0 = b0 * kSpb;
             const uint32_t nb = si.blocks > b0 ? min((uint32_t)kTile, si.blocks - b0) : 0u;
             const uint32_t count = s0 < si.samples ? min(nb * kSpb, si.samples - s0) : 0u;
-            uint8_t* dst = out + si.out_base + (size_t)s0 * nch * 2;
-            const int16_t* srow = &s_pcm[t & 1][s * out_row];
-            const uint32_t halfs = count * nch;
-            if (((reinterpret_cast<uintptr_t>(dst) | (halfs * 2)) & 3) == 0) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(srow);
-                const uint32_t words = halfs / 2;
-                uint32_t e = lane;
-                for (; e + 96 < words; e += 128) {          // four independent shared loads, then four stores
-                    const uint32_t v0 = w[e], v1 = w[e + 32], v2 = w[e + 64], v3 = w[e + 96];
-                    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-                    d32[e] = v0; d32[e + 32] = v1; d32[e + 64] = v2; d32[e + 96] = v3;
-                }
-                for (; e < words; e += 32) reinterpret_cast<uint32_t*>(dst)[e] = w[e];
-            } else {
-                for (uint32_t e = lane; e < halfs; e += 32) reinterpret_cast<int16_t*>(dst)[e] = srow[e];
+            const uint32_t bytes = count * nch * 2;
+            uint8_t* dst = out + si.out_base + (size_t)t * tile_bytes;
+            const uint32_t ph = (uint32_t)(si.out_base & 15);             // tile_bytes is a multiple of 16
+            const uint8_t* src = &stage.pcm[t & 1][lane * out_row + ph];
+            const uint32_t head = min((16u - ph) & 15u, bytes), mid = (bytes - head) & ~15u, tail = bytes - head - mid;
+            if (mid)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(dst + head), "r"(smem_u32(src + head)), "r"(mid) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#pragma unroll
+            for (uint32_t k = 0; k < 14; k += 2) {          // ph is even: at most 7 samples on either side
+                if (k < head) *reinterpret_cast<int16_t*>(dst + k) = *reinterpret_cast<const int16_t*>(src + k);
+                if (k < tail) *reinterpret_cast<int16_t*>(dst + head + mid + k) = *reinterpret_cast<const int16_t*>(src + head + mid + k);
             }
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     };
 
-    if (role >= 1) {
-        mover_request(&s_code[0][0], row_words, in, s_info, nstreams, 0, frame_bytes, false, nch, lane, role - 1);
-        cp_commit();
-        if (ntiles > 1) mover_request(&s_code[1][0], row_words, in, s_info, nstreams, kTile, frame_bytes, false, nch, lane, role - 1);
-        cp_commit();
-        cp_wait_all_but_one();                              // tile 0 has landed, tile 1 is in flight
+    if (role == 1) {
+        request(0);
+        if (ntiles > 1) request(1);
+        if (ntiles) mbar_wait(smem_u32(&stage.full[0]), 0);  // tile 0 has landed, tile 1 is in flight
     }
-    group_sync(group);
+    dec_group_sync(group);
 
     int h1 = ch.hist1, h2 = ch.hist2, c0 = ch.coef0, c1 = ch.coef1;
+    const int zero = ch.pad[0];
     bool ended = false;   // EOF block seen (adx.cpp:405-406): the rest of the stream stays silent
+#ifdef CRI_ADX_TIMING     // development: where a tile's time goes (tools/build_variant.sh, UNIT=adx_kernels.cu)
+    long long t_work = 0, t_wait = 0;
+#endif
     for (uint32_t t = 0; t < ntiles; t++) {
         const int buf = t & 1;
         const uint32_t b0 = t * kTile;
-        if (role >= 1) {
-            if (t + 2 < ntiles) mover_request(&s_code[(t + 2) % 3][0], row_words, in, s_info, nstreams, b0 + 2 * kTile, frame_bytes, false, nch, lane, role - 1);
-            cp_commit();
+#ifdef CRI_ADX_TIMING
+        const long long t_begin = clock64();
+#endif
+        if (role == 1) {
+#ifndef CRI_ADX_NOMOVE                                      // development: the worker's pace with an idle mover (stale data)
+            if (t + 2 < ntiles) request(t + 2);
             if (t >= 1) store_tile(t - 1);
-            cp_wait_all_but_one();                          // tile t + 1 has landed (tile t + 2 may still be in flight)
+            if (t + 1 < ntiles) mbar_wait(smem_u32(&stage.full[(t + 1) % 3]), ((t + 1) / 3) & 1);   // tile t + 1 has landed
+#endif
         } else {
             const uint32_t nb = ch.blocks > b0 ? min((uint32_t)kTile, ch.blocks - b0) : 0u;
+            const int nch_rt = nch;
+#ifndef CRI_ADX_NOMOVE
+            mbar_wait(smem_u32(&stage.full[t % 3]), (t / 3) & 1);   // (the mover saw it before the barrier: passes at once)
+#endif
             // byte 0 of this lane's first frame inside its stream's row
             const uint8_t* row = reinterpret_cast<const uint8_t*>(&s_code[t % 3][slot * row_words]) +
                                  (int)((ch.eof_off + (uint64_t)b0 * frame_bytes) & 15);
-            int16_t* my_pcm = &s_pcm[buf][slot * out_row + ch.channel];
-            for (uint32_t tb = 0; tb < nb; tb++) {
+            int16_t* my_pcm = reinterpret_cast<int16_t*>(&stage.pcm[buf][slot * out_row + ((ch.out_off - 2u * ch.channel) & 15)]) + ch.channel;
+            // A block reaches the registers as five words (six aligned shared-memory loads and a funnel shift: blocks start
+            // on any byte), one block AHEAD of the one being decoded, so that its latency -- and that of the EOF probe,
+            // which needs channel 0's scale word -- hides under 32 samples of recurrence instead of standing in front of
+            // them. The loop runs to the warp's block count so that the shuffle below is warp-wide.
+            const uint32_t nb_warp = warp_blocks > b0 ? min((uint32_t)kTile, warp_blocks - b0) : 0u;
+            auto fetch = [&](uint32_t tb, uint32_t (&w)[5]) {
+                const uint32_t at = (uint32_t)__cvta_generic_to_shared(row + tb * frame_bytes + ch.channel * kBlk);
+                uint32_t r[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[i]) : "r"((at & ~3u) + 4u * i));
+#pragma unroll
+                for (int i = 0; i < 5; i++) w[i] = __funnelshift_r(r[i], r[i + 1], (at & 3u) * 8u);
+            };
+            // the sample stride in the PCM tile as a compile-time constant for mono and stereo (store offsets become
+            // immediates; with a run-time stride every store waits for its own uniform-register add)
+            auto decode_tile = [&](auto stride_tag) {
+            constexpr int kStride = decltype(stride_tag)::value;
+            const int nch = kStride ? kStride : nch_rt;
+            uint32_t cur[5], nxt[5];
+            fetch(0, cur);
+            // A lone warp pays for every branch in full (nothing else issues while it resolves), so the block loop has
+            // one: blocks past a lane's count decode stale bytes into samples the movers never copy; an EOF block
+            // (adx.cpp:405-406) zeroes scale and coefficients, which makes the recurrence emit the silence the reference
+            // writes; the scale modes are selects; the exact, clamped recurrence is one rarely taken branch at the end.
+            for (uint32_t tb = 0; tb < nb_warp; tb++) {
+                fetch(tb + 1, nxt);                           // past the tile: stale bytes of the stage, never used
                 int16_t* dst = my_pcm + tb * kSpb * nch;      // sample i of this block -> dst[i * nch]
-                const uint8_t* frame = row + tb * frame_bytes;
-                if (!ended) ended = frame[0] == 0x80 && frame[1] == 0x01;       // channel 0's scale word of this frame
-                if (ended) {
+                const int head = (int)__byte_perm(cur[0], 0, 0x4401);            // the block's scale word (big-endian)
+                const int head0 = __shfl_sync(kFull, head, lane - ch.channel);   // channel 0's scale word of this frame
+                uint32_t blkw[5];
 #pragma unroll
-                    for (int i = 0; i < kSpb; i++) dst[i * nch] = 0;
-                    continue;
+                for (int i = 0; i < 5; i++) { blkw[i] = cur[i]; cur[i] = nxt[i]; }
+                ended = ended || head0 == 0x8001;
+                // decode_scale, as selects
+                const int pred = (head >> 13) & 3;
+                const bool m3 = ch.mode == 3, m4 = ch.mode == 4;
+                if (!m3 && !m4) {
+                    c0 = pred == 0 ? 0 : pred == 1 ? 0x0F00 : pred == 2 ? 0x1CC0 : 0x1880;
+                    c1 = pred == 0 ? 0 : pred == 1 ? 0 : pred == 2 ? -0x0D00 : -0x0DC0;
                 }
-                const uint8_t* src = frame + ch.channel * kBlk;
-                // the whole block goes to registers first: one shared-memory latency per block instead of one per byte
-                // (the compiler cannot hoist these loads over the PCM stores below by itself)
-                int blk[kBlk];
-#pragma unroll
-                for (int k = 0; k < kBlk; k++) blk[k] = src[k];
-                const int scale = decode_scale((blk[0] << 8) | blk[1], ch.mode, c0, c1);
+                const int scale_raw = m3 ? head + 1 : m4 ? (int)(1u << ((12 - head) & 31)) : (head & 0x1FFF) + 1;
+                const bool silent = ended || tb >= nb;        // (past the lane's blocks: keeps stale bytes from forcing the redo)
+                const int scale = silent ? 0 : scale_raw, k0 = silent ? 0 : c0, k1 = silent ? 0 : c1;
+                auto mul = [](int a, int b2) -> int { return (int)((uint32_t)a * (uint32_t)b2); };   // wraps (a discarded pass may overflow)
                 // Speculative pass without the int16 clamp (adx.cpp:209): as long as no sample leaves the int16 range
-                // the clamp is the identity, and without it the recurrence can be regrouped so that only a multiply-add
-                // and a shift per sample sit on the serial path:
-                //   s_n = a_n + x_n,  x_n = q_n*scale + (c1*s_{n-2} >> 12),  a_{n+1} = (c0*a_n + c0*x_n) >> 12 = c0*s_n >> 12
-                // (the two floor shifts stay separate, exactly as in the reference). Every product stays below 2^31 for
-                // scales up to 0x2000 and |c| <= 0x2000; `range` ORs the biased samples, so any excursion shows in its
-                // high bits and the block is then redone with the reference's clamped recurrence from the saved history.
-                bool exact = scale > 0x2000 || abs(c0) > 0x2000 || abs(c1) > 0x2000;
-                if (!exact) {
-                    const int o1 = h1, o2 = h2;
-                    int a1 = (c0 * h1) >> 12;                 // a_n
-                    int range = 0;
-                    int sm1 = h1, sm2 = h2;                   // s_{n-1}, s_{n-2}
+                // the clamp is the identity. Every product stays below 2^31 for scales up to 0x2000 and |c| <= 0x2000;
+                // otherwise, or when a sample leaves the range, the block is redone with the reference's clamped
+                // recurrence from the saved history.
+                int prod[kSpb];                               // the products do not depend on the history: all 32 first
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        const int byte = blk[2 + k];
-                        const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
-                        int x = q_hi * scale + ((c1 * sm2) >> 12);
-                        int sn = a1 + x;
-                        a1 = (c0 * a1 + c0 * x) >> 12;
-                        dst[(2 * k) * nch] = (int16_t)sn;
-                        sm2 = sm1; sm1 = sn;
-                        const int r0 = sn + 32768;
-                        x = q_lo * scale + ((c1 * sm2) >> 12);
-                        sn = a1 + x;
-                        a1 = (c0 * a1 + c0 * x) >> 12;
-                        dst[(2 * k + 1) * nch] = (int16_t)sn;
-                        sm2 = sm1; sm1 = sn;
-                        range |= r0 | (sn + 32768);
-                    }
-                    h1 = sm1; h2 = sm2;
-                    if ((unsigned)range > 0xFFFFu) { exact = true; h1 = o1; h2 = o2; }
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t wd = blkw[(2 + k) >> 2];
+                    const int pos = 8 * ((2 + k) & 3);        // the byte's high nibble is the first sample
+                    // `zero` (a padding byte of the chain record) occupies the multiply-add's addend: the assembler
+                    // would otherwise fold the product into the addition below, where it would wait for the shift
+                    prod[2 * k] = mul(((int)(wd << (24 - pos))) >> 28, scale) + zero;
+                    prod[2 * k + 1] = mul(((int)(wd << (28 - pos))) >> 28, scale) + zero;
                 }
-                if (exact) {
+                // s_n = (c0*s_{n-1} >> 12) + x_n with x_n = prod_n + (c1*s_{n-2} >> 12) formed one sample ahead: two
+                // dependent instructions per sample (multiply, shift-add) sit on the serial path, the rest fills the
+                // gaps between them
+                int s1 = h1, s2 = h2;
+                int x = prod[0] + (mul(k1, s2) >> 12);
+                int lo = 0, hi = 0;
+#pragma unroll
+                for (int n = 0; n < kSpb; n++) {
+                    const int sn = (mul(k0, s1) >> 12) + x;
+                    if (n + 1 < kSpb) x = prod[n + 1] + (mul(k1, s1) >> 12);
+                    dst[n * nch] = (int16_t)sn;
+                    lo = min(lo, sn); hi = max(hi, sn);
+                    s2 = s1; s1 = sn;
+                }
+                const bool redo = lo < -32768 || hi > 32767 || scale > 0x2000 || abs(k0) > 0x2000 || abs(k1) > 0x2000;
+                if (!redo) { h1 = s1; h2 = s2; }
+                if (redo) {
 #pragma unroll
                     for (int k = 0; k < 16; k++) {
-                        const int byte = blk[2 + k];
+                        const int byte = (int)((blkw[(2 + k) >> 2] >> (8 * ((2 + k) & 3))) & 0xFFu);
                         const int q_hi = ((int)(byte << 24)) >> 28, q_lo = ((int)(byte << 28)) >> 28;
-                        int s = (q_hi * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);
+                        int s = (q_hi * scale + ((k1 * h2) >> 12)) + ((k0 * h1) >> 12);
                         s = clamp16(s);
                         h2 = h1; h1 = s;
                         dst[(2 * k) * nch] = (int16_t)s;
-                        s = (q_lo * scale + ((c1 * h2) >> 12)) + ((c0 * h1) >> 12);
+                        s = (q_lo * scale + ((k1 * h2) >> 12)) + ((k0 * h1) >> 12);
                         s = clamp16(s);
                         h2 = h1; h1 = s;
                         dst[(2 * k + 1) * nch] = (int16_t)s;
                     }
                 }
             }
+            };
+            if (nch_rt == 2) decode_tile(std::integral_constant<int, 2>{});
+            else if (nch_rt == 1) decode_tile(std::integral_constant<int, 1>{});
+            else decode_tile(std::integral_constant<int, 0>{});
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile's samples, before the bulk store reads them
         }
-        group_sync(group);
+#ifdef CRI_ADX_TIMING
+        const long long t_mid = clock64();
+        dec_group_sync(group);
+        t_work += t_mid - t_begin;
+        t_wait += clock64() - t_mid;
+#else
+        dec_group_sync(group);
+#endif
     }
-    if (role >= 1 && ntiles) store_tile(ntiles - 1);
+    if (role == 1 && ntiles) store_tile(ntiles - 1);
+#ifdef CRI_ADX_TIMING
+    if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && group < 2)
+        printf("adx decode cta %d group %d role %d: tiles %u work %lld wait %lld cycles\n", blockIdx.x, group, role, ntiles, t_work, t_wait);
+#endif
 }
 
 // --------------------------------------------------------- decode, generic
@@ -664,7 +768,7 @@ void launch_adx_decode(const uint8_t* d_in, uint8_t* d_out, const AdxChain* d_ch
     if (n_fast) {
         const unsigned groups = (n_fast + 31) / 32;
         cudaFuncSetAttribute(adx_decode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGroups * sizeof(DecodeStage)));
-        adx_decode_fast_kernel<<<(groups + kGroups - 1) / kGroups, kGroups * kGroupThreads, kGroups * sizeof(DecodeStage), s>>>(d_in, d_out, d_chains, n_fast);
+        adx_decode_fast_kernel<<<(groups + kGroups - 1) / kGroups, kGroups * kDecGroupThreads, kGroups * sizeof(DecodeStage), s>>>(d_in, d_out, d_chains, n_fast);
         ++*launches;
     }
     if (n_generic) {
