@@ -527,9 +527,15 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     group_sync(group);
 
     int h1 = ch.hist1, h2 = ch.hist2;
+#ifdef CRI_ADX_TIMING
+    long long t_work = 0, t_wait = 0;
+#endif
     for (uint32_t t = 0; t < ntiles; t++) {
         const int buf = t & 1;
         const uint32_t b0 = t * kTile;
+#ifdef CRI_ADX_TIMING
+        const long long t_begin = clock64();
+#endif
         if (role >= 1) {
             if (t + 1 < ntiles) mover_request(&s_pcm[buf ^ 1][0], row_words, in, s_info, nstreams, b0 + kTile, frame_bytes, true, nch, lane, role - 1);
             cp_commit();
@@ -630,9 +636,20 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 }
             }
         }
+#ifdef CRI_ADX_TIMING
+        const long long t_mid = clock64();
         group_sync(group);
+        t_work += t_mid - t_begin;
+        t_wait += clock64() - t_mid;
+#else
+        group_sync(group);
+#endif
     }
     if (role >= 1 && ntiles) store_tile(ntiles - 1);
+#ifdef CRI_ADX_TIMING
+    if (blockIdx.x == 0 && lane == 0 && group == 0)
+        printf("adx encode cta %d group %d role %d: tiles %u work %lld wait %lld cycles\n", blockIdx.x, group, role, ntiles, t_work, t_wait);
+#endif
 }
 
 // --------------------------------------------------------- encode, generic
