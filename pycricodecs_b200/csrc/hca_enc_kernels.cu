@@ -24,6 +24,7 @@
 //     shared-memory atomicOr, 32 bands per step in band order.
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
 
 #include "cri_tables.h"
 #include "hca_kernels.h"
@@ -41,6 +42,9 @@ __constant__ uint32_t e_dead_zone[16] = CRI_TBL_ENC_DEAD_ZONE;
 __constant__ uint32_t e_ratio_bounds[14] = CRI_TBL_ENC_RATIO_BOUNDS;
 __constant__ uint8_t e_max_bits[16] = CRI_TBL_MAX_BITS;
 __constant__ uint32_t e_cost_rows[64] = CRI_TBL_ENC_COST_ROWS;
+__constant__ uint32_t e_rank_keys[2 * 49 * 2] = CRI_TBL_ENC_RANK_KEYS;
+__constant__ uint32_t e_rank_rows[16] = CRI_TBL_ENC_RANK_ROWS;
+constexpr uint32_t kRankShift = 21, kRankBase = 459, kRankBuckets = 49;   // tools/gen_tables.py: enc_cost_ranks()
 
 #include "hca_dct_gen.inc"
 
@@ -59,6 +63,9 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 struct EncTables {              // per-CTA shared copies (per-lane indices diverge)
     uint4 cost[16];             // per resolution: bits(-N), bits(P), 8 * full, overfull (tools/gen_tables.py: enc_cost_rows)
+    uint2 rank_key[2 * 49];     // counted bit costs: [x < 0][bucket] = (interval end inside the bucket or 0, ends in higher buckets)
+    uint2 rank_mask[16];        // [rank] = one in every nibble whose resolution holds a coefficient of that rank inside its interval
+    uint32_t rank_row[16];      // per resolution: nibble shift | word B << 7 | 8 * full << 8 | overfull << 16
     float scaling[64];
     float qscaling[64];
     float inv_step[16];
@@ -239,10 +246,27 @@ __device__ __noinline__ void header_lengths(const FrameSmem& fs, const HcaStream
     __syncwarp();
 }
 
+// COUNTED (mono / stereo batches): the bit-allocation search does not go back to the 2048 scaled coefficients for every
+// probe. Each coefficient is classified ONCE, when it is scaled: its rank r* (tools/gen_tables.py: enc_cost_ranks) says
+// in which resolutions' short-code intervals it lies, and a band keeps, per resolution, how many of its eight
+// coefficients do -- fifteen 4-bit counts in two registers per band (word A: resolutions 1..7 in sorted order + the
+// number of coefficients on the positive clamp in nibble 7; word B: resolutions 8..15). A probe of CalculateUsedBits
+// (hca.cpp:2763-2790) is then, per band, one table row and one nibble: the same integers as the per-coefficient count.
+template <bool COUNTED>
 __global__ void __launch_bounds__(kEncWarps * 32, 1)
 hca_encode_kernel(HcaEncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ EncTables tb;
+    if (COUNTED) {
+        for (int i = threadIdx.x; i < 2 * (int)kRankBuckets; i += blockDim.x) tb.rank_key[i] = make_uint2(e_rank_keys[2 * i], e_rank_keys[2 * i + 1]);
+        for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+            const int na = min(i, 7), nb = max(i - 7, 0);
+            tb.rank_mask[i] = make_uint2(na ? 0x01111111u >> (28 - 4 * na) : 0u, nb ? 0x11111111u >> (32 - 4 * nb) : 0u);
+            const uint32_t row = e_rank_rows[i], pos = (row & 63u) >> 2;       // position in the sorted order; 15 = resolution 0
+            const uint32_t where = pos < 7 ? 4 * pos : pos < 15 ? (4 * (pos - 7)) | 0x80u : 28u;
+            tb.rank_row[i] = (row & ~63u) | where;
+        }
+    }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) {
         tb.scaling[i] = __uint_as_float(e_scaling[i]);
         tb.qscaling[i] = __uint_as_float(e_qscaling[i]);
@@ -316,9 +340,19 @@ hca_encode_kernel(HcaEncodeArgs a) {
         const float w2 = __fmul_rn(__uint_as_float(kMdctWin[4 * lane + 2]), k), w3 = __fmul_rn(__uint_as_float(kMdctWin[4 * lane + 3]), k);
         const float pc0 = __uint_as_float(kMdctPreCos[lane]), ps0 = __uint_as_float(kMdctPreSin[lane]);
         const float pc1 = __uint_as_float(kMdctPreCos[lane + 32]), ps1 = __uint_as_float(kMdctPreSin[lane + 32]);
-        float tc[6], ts[6];
+        // Passes 1..5 exchange with lane ^ (32 >> s). The lane with that bit set ("back") takes other - mine and rotates
+        // it; the front lane takes mine + other as it is. Both are ONE instruction stream: the sum is fma(mine, +-1, other)
+        // (the product is exact, so this is the add or the subtract, rounded once), and a front lane rotates by
+        // (cos, sin, "-cos") = (1, 0, 1): x * 1 + y * 0 and x * 0 + y * 1 return x and y unchanged up to the sign of a
+        // zero, which nothing downstream can tell apart (magnitudes, comparisons against non-zero bounds, products).
+        float tc[6], ts[6], tn[6];
 #pragma unroll
-        for (int s = 0; s < 6; s++) { tc[s] = __uint_as_float(kMdctCos[s * 32 + lane]); ts[s] = __uint_as_float(kMdctSin[s * 32 + lane]); }
+        for (int s = 0; s < 6; s++) {
+            const bool front = s > 0 && !(lane & (32 >> s));
+            tc[s] = front ? 1.0f : __uint_as_float(kMdctCos[s * 32 + lane]);
+            ts[s] = front ? 0.0f : __uint_as_float(kMdctSin[s * 32 + lane]);
+            tn[s] = front ? 1.0f : -tc[s];
+        }
         const int d0 = kMdctDest[4 * lane], d1 = kMdctDest[4 * lane + 1], d2 = kMdctDest[4 * lane + 2], d3 = kMdctDest[4 * lane + 3];
         const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
         for (int c = 0; c < nch; c++) {
@@ -349,20 +383,16 @@ hca_encode_kernel(HcaEncodeArgs a) {
 #pragma unroll
                 for (int s = 1; s < 6; s++) {
                     const int d = 32 >> s;
-                    const bool back = lane & d;
+                    const float sgn = (lane & d) ? -1.0f : 1.0f;
                     const float o_re0 = __shfl_xor_sync(kFull, re0, d), o_im0 = __shfl_xor_sync(kFull, im0, d);
                     const float o_re1 = __shfl_xor_sync(kFull, re1, d), o_im1 = __shfl_xor_sync(kFull, im1, d);
                     // front: mine + other; back: other - mine
-                    const float a_re0 = back ? __fsub_rn(o_re0, re0) : __fadd_rn(re0, o_re0);
-                    const float a_im0 = back ? __fsub_rn(o_im0, im0) : __fadd_rn(im0, o_im0);
-                    const float a_re1 = back ? __fsub_rn(o_re1, re1) : __fadd_rn(re1, o_re1);
-                    const float a_im1 = back ? __fsub_rn(o_im1, im1) : __fadd_rn(im1, o_im1);
-                    const float r_re0 = __fadd_rn(__fmul_rn(a_re0, tc[s]), __fmul_rn(a_im0, ts[s]));
-                    const float r_im0 = __fsub_rn(__fmul_rn(a_re0, ts[s]), __fmul_rn(a_im0, tc[s]));
-                    const float r_re1 = __fadd_rn(__fmul_rn(a_re1, tc[s]), __fmul_rn(a_im1, ts[s]));
-                    const float r_im1 = __fsub_rn(__fmul_rn(a_re1, ts[s]), __fmul_rn(a_im1, tc[s]));
-                    re0 = back ? r_re0 : a_re0; im0 = back ? r_im0 : a_im0;
-                    re1 = back ? r_re1 : a_re1; im1 = back ? r_im1 : a_im1;
+                    const float a_re0 = __fmaf_rn(re0, sgn, o_re0), a_im0 = __fmaf_rn(im0, sgn, o_im0);
+                    const float a_re1 = __fmaf_rn(re1, sgn, o_re1), a_im1 = __fmaf_rn(im1, sgn, o_im1);
+                    re0 = __fadd_rn(__fmul_rn(a_re0, tc[s]), __fmul_rn(a_im0, ts[s]));
+                    im0 = __fadd_rn(__fmul_rn(a_re0, ts[s]), __fmul_rn(a_im0, tn[s]));
+                    re1 = __fadd_rn(__fmul_rn(a_re1, tc[s]), __fmul_rn(a_im1, ts[s]));
+                    im1 = __fadd_rn(__fmul_rn(a_re1, ts[s]), __fmul_rn(a_im1, tn[s]));
                 }
                 float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
                 sp[d0] = __fmul_rn(re0, 0.125f); sp[d1] = __fmul_rn(im0, 0.125f);
@@ -457,7 +487,37 @@ hca_encode_kernel(HcaEncodeArgs a) {
 
     CONVOY();
     // ---- scaled spectra, in place (hca.cpp:2639-2654)
-    for (int c = 0; c < nch; c++) {
+    uint32_t cnt_a[2][4] = {}, cnt_b[2][4] = {};    // COUNTED: per band (channel c, band lane + 32 k) the interval counts
+    if constexpr (COUNTED) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int coded = c < nch ? (int)S.coded[c] : 0;
+            float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int b = lane + 32 * k;
+                uint32_t wa = 0, wb = 0;
+                if (b < coded) {
+                    const int sfv = fs.sf[c * 128 + b];
+                    const float ks = tb.qscaling[sfv];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float v = __fmul_rn(sp[j * kSpecRow + b], ks);
+                        v = v > 0.9999999f ? 0.9999999f : v < -0.9999999f ? -0.9999999f : v;
+                        v = sfv == 0 ? 0.f : v;
+                        sp[j * kSpecRow + b] = v;
+                        const uint32_t u = __float_as_uint(v), au = u & 0x7FFFFFFFu;
+                        const uint2 key = tb.rank_key[max(au >> kRankShift, kRankBase) - kRankBase + (u >> 31) * kRankBuckets];
+                        const uint2 m = tb.rank_mask[key.y + (au < key.x ? 1u : 0u)];
+                        wa += m.x + (v == 0.9999999f ? 1u << 28 : 0u);
+                        wb += m.y;
+                    }
+                }
+                cnt_a[c][k] = wa; cnt_b[c][k] = wb;
+            }
+        }
+    }
+    for (int c = 0; c < nch && !COUNTED; c++) {
         const int coded = S.coded[c];
         float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
         for (int b = lane; b < coded; b += 32) {
@@ -513,13 +573,63 @@ hca_encode_kernel(HcaEncodeArgs a) {
     const int avail = frame_size * 8;
     int noise_level, boundary = 0;
     bool failed = false;
+    // COUNTED: what a probe needs of a band besides its counts -- the scalefactor's share of the resolution index
+    // (hca.cpp:2752-2761) and the row stride (0 for bands without a scalefactor: row 0 costs nothing)
+    int band_off[2][4] = {}, band_nz4[2][4] = {}, hdr_total = 48;
+    bool any_clamped = false;
+    auto load_bands = [&]() {
+        if constexpr (COUNTED) {
+            bool cl = false;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int coded = c < nch ? (int)S.coded[c] : 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int b = lane + 32 * k;
+                    const int sfv = b < coded ? (int)fs.sf[c * 128 + b] : 0;
+                    band_off[c][k] = 2 - 5 * sfv / 2;
+                    band_nz4[c][k] = sfv ? 4 : 0;
+                    if (!sfv) { cnt_a[c][k] = 0; cnt_b[c][k] = 0; }     // also after the search below gave a band up
+                    cl |= (cnt_a[c][k] >> 28) != 0;
+                }
+            }
+            any_clamped = __any_sync(kFull, cl);
+            hdr_total = 48;
+            for (int c = 0; c < nch; c++) hdr_total += fs.header_bits[c];
+        }
+    };
+    auto band_bits = [&](int c, int k, int noise, auto with_clamped) -> int {
+        const int pos = min(max(noise + band_off[c][k], 0), 58);
+        const uint32_t row = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(tb.rank_row) + (uint32_t)tb.curve[pos] * (uint32_t)band_nz4[c][k]);
+        const uint32_t w = (row & 0x80u) ? cnt_b[c][k] : cnt_a[c][k];
+        int bits = (int)((row >> 8) & 0xFFu) - (int)(__funnelshift_r(w, 0u, row) & 15u);       // shift = row & 31
+        if (decltype(with_clamped)::value) bits -= (int)(row >> 16) * (int)(cnt_a[c][k] >> 28);
+        return bits;
+    };
+    auto used_bits_counted = [&](int noise) -> int {
+        int len = 0;
+        if (any_clamped) {
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) len += band_bits(c, k, noise, std::true_type{});
+        } else {
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) len += band_bits(c, k, noise, std::false_type{});
+        }
+        return warp_sum(len) + hdr_total;
+    };
+    load_bands();
     {
         int highest = (int)S.base_bands + (int)S.stereo_bands - 1;
         for (;;) {
             int lo_l = 0, hi_l = 255, mid_value = 0;          // BinarySearchLevel
             while (lo_l != hi_l) {
                 const int mid = (lo_l + hi_l) / 2;
-                mid_value = used_bits(tb, fs, S, lane, mid, 0);
+                if constexpr (COUNTED) mid_value = used_bits_counted(mid);
+                else mid_value = used_bits(tb, fs, S, lane, mid, 0);
                 if (mid_value > avail) lo_l = mid + 1; else hi_l = mid;
             }
             noise_level = (lo_l == 255 && mid_value > avail) ? -1 : lo_l;
@@ -530,11 +640,33 @@ hca_encode_kernel(HcaEncodeArgs a) {
                 for (int c = 0; c < nch; c++) { fs.sf[c * 128 + highest + 1] = 0; fs.sf[c * 128 + highest + 2] = 0; }
             __syncwarp();
             header_lengths(fs, S, lane);
+            load_bands();
         }
     }
     CONVOY();
     if (!failed && noise_level != 0) {                        // BinarySearchBoundary
         int* pre = reinterpret_cast<int*>(fs.pcm);            // scratch shared with the frame buffer, which is filled later
+        if constexpr (COUNTED) {                              // boundary_table() from the counts
+            int diff[4] = {0, 0, 0, 0}, tot = 0;
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c_hi = band_bits(c, k, noise_level, std::true_type{}), c_lo = band_bits(c, k, noise_level - 1, std::true_type{});
+                    tot += c_hi;
+                    diff[k] += c_lo - c_hi;
+                }
+            int base = warp_sum(tot) + hdr_total;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int total;
+                const int excl = warp_excl_scan(diff[k], lane, &total);
+                pre[lane + 32 * k] = base + excl;
+                base += total;
+            }
+            if (lane == 0) pre[128] = base;
+            __syncwarp();
+        } else
         boundary_table(tb, fs, S, lane, noise_level, pre);
         int lo_b = 0, hi_b = 127;
         while (abs(hi_b - lo_b) > 1) {
@@ -713,8 +845,9 @@ int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
     while (warps > 1 && (size_t)a.smem_per_warp * warps > 200 * 1024) warps >>= 1;
     const size_t smem = (size_t)a.smem_per_warp * warps;
     if (smem > 200 * 1024) return -1;
-    cudaFuncSetAttribute(hca_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    hca_encode_kernel<<<(unsigned)((a.n_frames + warps - 1) / warps), warps * 32, smem, s>>>(a);
+    auto kernel = a.max_channels <= 2 ? hca_encode_kernel<true> : hca_encode_kernel<false>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<(unsigned)((a.n_frames + warps - 1) / warps), warps * 32, smem, s>>>(a);
     ++*launches;
     return 0;
 }

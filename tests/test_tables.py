@@ -14,7 +14,7 @@ PINNED = {
     "INVERT": "596fe25e69de6eab", "MAX_BITS": "bccecd5122d1510e", "READ_BITS": "2e1cc91f0d50f0d4", "READ_VALS": "2cc4f662b2917a8c",
     "ENC_RES_CURVE": "ae26f4723b8c0df3", "ENC_Q_BITS": "4dea801cd96da815", "ENC_Q_CODE": "7c9c807b445fc2a3", "ENC_INV_STEP": "cd2e4715a8858fa3",
     "ENC_DEAD_ZONE": "46be60ec7b43774b", "ENC_RATIO_BOUNDS": "7b0403a9464abe57", "ENC_Q_SCALING": "40bb54ebaca01923",
-    "ENC_COST_ROWS": "ad41c2373ac9383d",
+    "ENC_COST_ROWS": "ad41c2373ac9383d", "ENC_RANK_KEYS": "93e36edbab3de372", "ENC_RANK_ROWS": "65aff724ccb0bb05",
     "MDCT_SIN": "f6e0ce2a262954bb", "MDCT_COS": "5cd990a6f62da25a", "ENC_SHUFFLE": "143d219b1e658c0b", "ADX_STATIC_COEF": "f0a57863809129eb",
     "ATH_BASE": "103a013614c0f314",
 }
@@ -115,3 +115,34 @@ def test_encoder_cost_rows_reproduce_the_table_driven_bit_count():
         model = full8 // 8 - ((x > neg_n) & (x < p)).astype(np.int64) - overfull * (x == clamp)
         want = g._enc_table_bits(x, r) if r else np.zeros(len(x), np.int64)
         assert np.array_equal(model, want), r
+
+
+def test_encoder_rank_tables_reproduce_the_cost_rows():
+    """ENC_RANK_KEYS / ENC_RANK_ROWS (one bucket look-up and one comparison per coefficient, hca_encode_kernel's counted
+    bit costs) against ENC_COST_ROWS (two comparisons per coefficient and probe): for every resolution, `inside` of the
+    row model == the coefficient's rank reaches past the resolution's position in the sorted order."""
+    rows = G.enc_cost_rows()
+    pos, keys, packed, base = G.enc_cost_ranks()
+    rng = np.random.default_rng(5)
+    clamp = np.float32(0.9999999)
+    xs = [rng.uniform(-1, 1, 200000).astype(np.float32), (rng.standard_normal(200000) * 0.01).astype(np.float32),
+          (rng.standard_normal(100000) * 1e-4).astype(np.float32), np.array([0.0, -0.0, clamp, -clamp, 1e-30, -1e-30], np.float32)]
+    for r in range(1, 16):
+        for w in rows[r][:2]:
+            u = int(w) & 0x7FFFFFFF
+            near = np.arange(u - 40, u + 41, dtype=np.uint32).view(np.float32)
+            xs += [near, -near]
+    x = np.clip(np.concatenate(xs), -clamp, clamp).astype(np.float32)
+    bits = x.view(np.uint32)
+    a = bits & 0x7FFFFFFF
+    sign = (bits >> 31).astype(np.int64)
+    q = np.maximum(a >> G.ENC_RANK_SHIFT, base).astype(np.int64) - base
+    assert q.max() == G.ENC_RANK_BUCKETS - 1
+    entry = keys[sign, q]
+    rank = entry[:, 1].astype(np.int64) + (a < entry[:, 0])
+    for r in range(0, 16):
+        neg_n, p = rows[r][:2].view(np.float32)
+        inside = (x > neg_n) & (x < p)
+        assert np.array_equal(inside, rank > int(pos[r])), r
+        assert int(packed[r]) == 4 * int(pos[r]) | int(rows[r][2]) << 8 | int(rows[r][3]) << 16
+

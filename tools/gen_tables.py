@@ -238,6 +238,40 @@ def enc_cost_rows():
     return rows
 
 
+ENC_RANK_SHIFT = 21                         # float bits >> 21: eight exponent and two mantissa bits select a bucket
+ENC_RANK_BUCKETS = 49
+
+
+def enc_cost_ranks():
+    """The same per-coefficient term, counted once per coefficient instead of once per probe of the bit-allocation search.
+    Sorted by size the fifteen interval ends are nested the same way on both sides of zero (order: resolutions 4, 2, 5, 1,
+    6, 3, 7, 8 .. 15), so a coefficient x is inside the intervals of exactly the first `rank` resolutions of that order,
+    rank = number of ends above |x|. No two ends share a quarter octave, so the rank is a table entry selected by the top
+    bits of |x| plus ONE comparison: entry = (end inside this bucket or 0, number of ends in higher buckets).
+    Returns (order position of each resolution (0 -> 15, an always-empty slot), keys[2][49][2] for x >= 0 / x < 0,
+    packed rows shift | full8 << 8 | overfull << 16 with shift = 4 * position)."""
+    rows = enc_cost_rows()
+    ends = {0: [int(rows[r][1]) for r in range(1, 16)], 1: [int(rows[r][0]) & 0x7FFFFFFF for r in range(1, 16)]}
+    order = sorted(range(1, 16), key=lambda r: -ends[0][r - 1])
+    assert order == sorted(range(1, 16), key=lambda r: -ends[1][r - 1]) and order == [4, 2, 5, 1, 6, 3, 7] + list(range(8, 16))
+    pos = np.full(16, 15, np.uint8)
+    for i, r in enumerate(order):
+        pos[r] = i
+    lowest = min(min(v) for v in ends.values()) >> ENC_RANK_SHIFT
+    top = int(ENC_CLAMP.view(np.uint32)) >> ENC_RANK_SHIFT
+    assert top - (lowest - 1) + 1 == ENC_RANK_BUCKETS
+    keys = np.zeros((2, ENC_RANK_BUCKETS, 2), np.uint32)
+    for s in (0, 1):
+        buckets = [e >> ENC_RANK_SHIFT for e in ends[s]]
+        assert len(set(buckets)) == 15
+        for q in range(ENC_RANK_BUCKETS):
+            key = lowest - 1 + q                      # bucket 0 = everything below the smallest end
+            here = [e for e, b in zip(ends[s], buckets) if b == key]
+            keys[s, q] = (here[0] if here else 0, sum(1 for b in buckets if b > key))
+    packed = np.array([4 * int(pos[r]) | int(rows[r][2]) << 8 | int(rows[r][3]) << 16 for r in range(16)], np.uint32)
+    return pos, keys, packed, lowest - 1
+
+
 def enc_ratio_bounds():
     return f32bits([(27 - 2 * i) / 14.0 for i in range(14)])
 
@@ -320,6 +354,8 @@ def all_tables():
         ("ENC_RATIO_BOUNDS", "uint32_t", enc_ratio_bounds()),
         ("ENC_Q_SCALING", "uint32_t", enc_q_scaling()),
         ("ENC_COST_ROWS", "uint32_t", enc_cost_rows()),
+        ("ENC_RANK_KEYS", "uint32_t", enc_cost_ranks()[1]),
+        ("ENC_RANK_ROWS", "uint32_t", enc_cost_ranks()[2]),
         ("MDCT_SIN", "uint32_t", msin),
         ("MDCT_COS", "uint32_t", mcos),
         ("ENC_SHUFFLE", "uint8_t", enc_shuffle()),
