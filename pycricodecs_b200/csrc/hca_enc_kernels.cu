@@ -71,8 +71,7 @@ struct EncTables {              // per-CTA shared copies (per-lane indices diver
     float inv_step[16];
     float dead_zone[16];
     uint8_t curve[60];
-    uint8_t qbits[128];
-    uint8_t qcode[128];
+    uint32_t qpack[128];        // [resolution * 16 + value + 8] = code length << 16 | code (prefix codebooks)
     uint8_t max_bits[16];
 };
 
@@ -278,7 +277,9 @@ hca_encode_kernel(HcaEncodeArgs a) {
         tb.max_bits[i] = e_max_bits[i];
     }
     for (int i = threadIdx.x; i < 59; i += blockDim.x) tb.curve[i] = e_curve[i];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) { tb.qbits[i] = e_qbits[i]; tb.qcode[i] = e_qcode[i]; }
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        tb.qpack[i] = ((uint32_t)e_qbits[i] << 16) | ((uint32_t)e_qcode[i] & ((1u << e_qbits[i]) - 1u));
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -355,51 +356,73 @@ hca_encode_kernel(HcaEncodeArgs a) {
         }
         const int d0 = kMdctDest[4 * lane], d1 = kMdctDest[4 * lane + 1], d2 = kMdctDest[4 * lane + 2], d3 = kMdctDest[4 * lane + 3];
         const int i0 = 2 * lane, i1 = 63 - 2 * lane, i2 = 64 + 2 * lane, i3 = 127 - 2 * lane;
-        for (int c = 0; c < nch; c++) {
-            // the block in front of a subframe is the previous subframe's own block: four loads per subframe, not eight
-            float p0 = sample(i0, c), p1 = sample(i1, c), p2 = sample(i2, c), p3 = sample(i3, c);
-            for (int sub = 0; sub < 8; sub++) {
-                const int cur = 128 + sub * 128;                           // window position of the subframe
-                const float c0 = sample(cur + i0, c), c1 = sample(cur + i1, c), c2 = sample(cur + i2, c), c3 = sample(cur + i3, c);
-                // windowing (hca.cpp:2537-2546): in[i] = W[63-i]*(-cur[64+i]) - (-W[64+i])*cur[63-i],
-                //                               in[64+i] = W[i]*prv[i] - (-W[127-i])*prv[127-i]
-                const float in_a = __fsub_rn(__fmul_rn(w1, -c2), __fmul_rn(-w2, c1));   // in[2l]
-                const float in_b = __fsub_rn(__fmul_rn(w1, p1), __fmul_rn(-w2, p2));    // in[127-2l]
-                const float in_c = __fsub_rn(__fmul_rn(w0, p0), __fmul_rn(-w3, p3));    // in[64+2l]
-                const float in_d = __fsub_rn(__fmul_rn(w0, -c3), __fmul_rn(-w3, c0));   // in[63-2l]
-                // pre-rotation (hca.cpp:2490-2498): z[k] from in[2k], in[127-2k]
-                float re0 = __fadd_rn(__fmul_rn(in_a, pc0), __fmul_rn(in_b, ps0));
-                float im0 = __fsub_rn(__fmul_rn(in_a, ps0), __fmul_rn(in_b, pc0));
-                float re1 = __fadd_rn(__fmul_rn(in_c, pc1), __fmul_rn(in_d, ps1));
-                float im1 = __fsub_rn(__fmul_rn(in_c, ps1), __fmul_rn(in_d, pc1));
-                // pass 0: z[l] with z[l+32], in lane
-                {
-                    const float ar = __fsub_rn(re0, re1), ai = __fsub_rn(im0, im1);
-                    re0 = __fadd_rn(re0, re1); im0 = __fadd_rn(im0, im1);
-                    re1 = __fadd_rn(__fmul_rn(ar, tc[0]), __fmul_rn(ai, ts[0]));
-                    im1 = __fsub_rn(__fmul_rn(ar, ts[0]), __fmul_rn(ai, tc[0]));
-                }
-                // passes 1..5: partner lane = lane ^ (32 >> s); the lane with that bit set holds the "back" element
+        float sg[6];
 #pragma unroll
-                for (int s = 1; s < 6; s++) {
-                    const int d = 32 >> s;
-                    const float sgn = (lane & d) ? -1.0f : 1.0f;
-                    const float o_re0 = __shfl_xor_sync(kFull, re0, d), o_im0 = __shfl_xor_sync(kFull, im0, d);
-                    const float o_re1 = __shfl_xor_sync(kFull, re1, d), o_im1 = __shfl_xor_sync(kFull, im1, d);
-                    // front: mine + other; back: other - mine
-                    const float a_re0 = __fmaf_rn(re0, sgn, o_re0), a_im0 = __fmaf_rn(im0, sgn, o_im0);
-                    const float a_re1 = __fmaf_rn(re1, sgn, o_re1), a_im1 = __fmaf_rn(im1, sgn, o_im1);
-                    re0 = __fadd_rn(__fmul_rn(a_re0, tc[s]), __fmul_rn(a_im0, ts[s]));
-                    im0 = __fadd_rn(__fmul_rn(a_re0, ts[s]), __fmul_rn(a_im0, tn[s]));
-                    re1 = __fadd_rn(__fmul_rn(a_re1, tc[s]), __fmul_rn(a_im1, ts[s]));
-                    im1 = __fadd_rn(__fmul_rn(a_re1, ts[s]), __fmul_rn(a_im1, tn[s]));
+        for (int s = 1; s < 6; s++) sg[s] = (lane & (32 >> s)) ? -1.0f : 1.0f;
+        // INTERIOR (all but the first and the last frame of a stream: the whole window lies inside the stream): a sample
+        // is one address and one 2-byte load; the other frames check every index against the stream's ends
+        auto mdct_channels = [&](auto interior_tag) {
+            constexpr bool INTERIOR = decltype(interior_tag)::value;
+            const int e0 = i0 * nch, e1 = i1 * nch, e2 = i2 * nch, e3 = i3 * nch;
+            for (int c = 0; c < nch; c++) {
+                const int16_t* qc = pcm_base + pcm_n0 * nch + c;          // window index 0 (in front of the blob for frame 0: INTERIOR only)
+                auto block = [&](int at, float& v0, float& v1, float& v2, float& v3) {     // the four samples of this lane, window position `at`
+                    if (INTERIOR) {
+                        const int16_t* q = qc + at * nch;
+                        v0 = (float)(int)__ldg(q + e0); v1 = (float)(int)__ldg(q + e1);
+                        v2 = (float)(int)__ldg(q + e2); v3 = (float)(int)__ldg(q + e3);
+                    } else {
+                        v0 = sample(at + i0, c); v1 = sample(at + i1, c); v2 = sample(at + i2, c); v3 = sample(at + i3, c);
+                    }
+                };
+                // the block in front of a subframe is the previous subframe's own block: four loads per subframe, not
+                // eight; the next subframe's block is requested before this one's butterflies
+                float p0, p1, p2, p3, n0, n1, n2, n3;
+                block(0, p0, p1, p2, p3);
+                block(128, n0, n1, n2, n3);
+                for (int sub = 0; sub < 8; sub++) {
+                    const float c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+                    if (sub < 7) block(256 + sub * 128, n0, n1, n2, n3);
+                    // windowing (hca.cpp:2537-2546): in[i] = W[63-i]*(-cur[64+i]) - (-W[64+i])*cur[63-i],
+                    //                               in[64+i] = W[i]*prv[i] - (-W[127-i])*prv[127-i]
+                    const float in_a = __fsub_rn(__fmul_rn(w1, -c2), __fmul_rn(-w2, c1));   // in[2l]
+                    const float in_b = __fsub_rn(__fmul_rn(w1, p1), __fmul_rn(-w2, p2));    // in[127-2l]
+                    const float in_c = __fsub_rn(__fmul_rn(w0, p0), __fmul_rn(-w3, p3));    // in[64+2l]
+                    const float in_d = __fsub_rn(__fmul_rn(w0, -c3), __fmul_rn(-w3, c0));   // in[63-2l]
+                    // pre-rotation (hca.cpp:2490-2498): z[k] from in[2k], in[127-2k]
+                    float re0 = __fadd_rn(__fmul_rn(in_a, pc0), __fmul_rn(in_b, ps0));
+                    float im0 = __fsub_rn(__fmul_rn(in_a, ps0), __fmul_rn(in_b, pc0));
+                    float re1 = __fadd_rn(__fmul_rn(in_c, pc1), __fmul_rn(in_d, ps1));
+                    float im1 = __fsub_rn(__fmul_rn(in_c, ps1), __fmul_rn(in_d, pc1));
+                    // pass 0: z[l] with z[l+32], in lane
+                    {
+                        const float ar = __fsub_rn(re0, re1), ai = __fsub_rn(im0, im1);
+                        re0 = __fadd_rn(re0, re1); im0 = __fadd_rn(im0, im1);
+                        re1 = __fadd_rn(__fmul_rn(ar, tc[0]), __fmul_rn(ai, ts[0]));
+                        im1 = __fsub_rn(__fmul_rn(ar, ts[0]), __fmul_rn(ai, tc[0]));
+                    }
+                    // passes 1..5: partner lane = lane ^ (32 >> s); the lane with that bit set holds the "back" element
+#pragma unroll
+                    for (int s = 1; s < 6; s++) {
+                        const int d = 32 >> s;
+                        const float o_re0 = __shfl_xor_sync(kFull, re0, d), o_im0 = __shfl_xor_sync(kFull, im0, d);
+                        const float o_re1 = __shfl_xor_sync(kFull, re1, d), o_im1 = __shfl_xor_sync(kFull, im1, d);
+                        // front: mine + other; back: other - mine
+                        const float a_re0 = __fmaf_rn(re0, sg[s], o_re0), a_im0 = __fmaf_rn(im0, sg[s], o_im0);
+                        const float a_re1 = __fmaf_rn(re1, sg[s], o_re1), a_im1 = __fmaf_rn(im1, sg[s], o_im1);
+                        re0 = __fadd_rn(__fmul_rn(a_re0, tc[s]), __fmul_rn(a_im0, ts[s]));
+                        im0 = __fadd_rn(__fmul_rn(a_re0, ts[s]), __fmul_rn(a_im0, tn[s]));
+                        re1 = __fadd_rn(__fmul_rn(a_re1, tc[s]), __fmul_rn(a_im1, ts[s]));
+                        im1 = __fadd_rn(__fmul_rn(a_re1, ts[s]), __fmul_rn(a_im1, tn[s]));
+                    }
+                    float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
+                    sp[d0] = __fmul_rn(re0, 0.125f); sp[d1] = __fmul_rn(im0, 0.125f);
+                    sp[d2] = __fmul_rn(re1, 0.125f); sp[d3] = __fmul_rn(im1, 0.125f);
+                    p0 = c0; p1 = c1; p2 = c2; p3 = c3;
                 }
-                float* sp = fs.spec + ((size_t)c * 8 + sub) * kSpecRow;
-                sp[d0] = __fmul_rn(re0, 0.125f); sp[d1] = __fmul_rn(im0, 0.125f);
-                sp[d2] = __fmul_rn(re1, 0.125f); sp[d3] = __fmul_rn(im1, 0.125f);
-                p0 = c0; p1 = c1; p2 = c2; p3 = c3;
             }
-        }
+        };
+        if (interior) mdct_channels(std::true_type{}); else mdct_channels(std::false_type{});
     }
     CONVOY();
 
@@ -499,12 +522,10 @@ hca_encode_kernel(HcaEncodeArgs a) {
                 uint32_t wa = 0, wb = 0;
                 if (b < coded) {
                     const int sfv = fs.sf[c * 128 + b];
-                    const float ks = tb.qscaling[sfv];
+                    const float ks = sfv ? tb.qscaling[sfv] : 0.f;       // no scalefactor: every coefficient becomes (+-) 0
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        float v = __fmul_rn(sp[j * kSpecRow + b], ks);
-                        v = v > 0.9999999f ? 0.9999999f : v < -0.9999999f ? -0.9999999f : v;
-                        v = sfv == 0 ? 0.f : v;
+                        const float v = fminf(fmaxf(__fmul_rn(sp[j * kSpecRow + b], ks), -0.9999999f), 0.9999999f);
                         sp[j * kSpecRow + b] = v;
                         const uint32_t u = __float_as_uint(v), au = u & 0x7FFFFFFFu;
                         const uint2 key = tb.rank_key[max(au >> kRankShift, kRankBase) - kRankBase + (u >> 31) * kRankBuckets];
@@ -733,16 +754,22 @@ hca_encode_kernel(HcaEncodeArgs a) {
     // warp prefix sum of the lengths places them: 16 prefix sums per stereo frame.
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
-        int r[4], mb[4], down[4];
+        int mb[4], down[4], tbase[4];
+        uint32_t mmask[4];
+        bool prefix[4], looked_up[4];
         float inv[4], up[4];
 #pragma unroll
         for (int h = 0; h < 4; h++) {
             const int b = 4 * lane + h;
-            r[h] = b < coded ? (int)fs.res[c * 128 + b] : 0;
-            inv[h] = tb.inv_step[r[h]];
+            const int r = b < coded ? (int)fs.res[c * 128 + b] : 0;
+            inv[h] = tb.inv_step[r];
             up[h] = __fadd_rn(inv[h], 1.0f);
-            mb[h] = (int)tb.max_bits[r[h]] - 1;
-            down[h] = r[h] < 8 ? r[h] + 1 : (1 << mb[h]);                  // (int)(inv + 0.5)
+            mb[h] = (int)tb.max_bits[r] - 1;
+            down[h] = r < 8 ? r + 1 : (1 << mb[h]);                        // (int)(inv + 0.5)
+            prefix[h] = r < 8;
+            looked_up[h] = r >= 1 && r < 8;                                // resolution 0: entry 8 of row 0 (all zero), whatever the band holds
+            tbase[h] = looked_up[h] ? r * 16 + 8 : 8;
+            mmask[h] = (1u << (mb[h] & 31)) - 1u;
         }
         for (int sub = 0; sub < 8; sub++) {
             uint4* row = reinterpret_cast<uint4*>(fs.spec + ((size_t)c * 8 + sub) * kSpecRow + 4 * lane);
@@ -752,17 +779,12 @@ hca_encode_kernel(HcaEncodeArgs a) {
 #pragma unroll
             for (int h = 0; h < 4; h++) {
                 const int q = __float2int_rz(__fadd_rn(__fmul_rn(__uint_as_float(x[h]), inv[h]), up[h])) - down[h];
-                uint32_t cd;
-                int ln;
-                if (r[h] < 8) {                                            // r = 0: row 0 of both tables is all zero
-                    ln = tb.qbits[r[h] * 16 + q + 8];
-                    cd = tb.qcode[r[h] * 16 + q + 8];
-                } else {
-                    const uint32_t mag = (uint32_t)abs(q) & ((1u << mb[h]) - 1u);
-                    if (q != 0) { cd = (mag << 1) | (q > 0 ? 0u : 1u); ln = mb[h] + 1; }
-                    else { cd = mag; ln = mb[h]; }
-                }
-                o[h] = r[h] == 0 ? 0u : ((uint32_t)ln << 16) | (cd & ((1u << ln) - 1u));
+                // prefix codebooks (r <= 7): length << 16 | code from the table; sign-magnitude (r >= 8): |q| then the sign
+                // bit, and a zero gives the sign bit back (|q| <= 2^mb - 1, so neither form needs a mask)
+                const uint32_t from_table = tb.qpack[tbase[h] + (looked_up[h] ? q : 0)];
+                const uint32_t mag = (uint32_t)abs(q) & mmask[h];
+                const uint32_t computed = ((uint32_t)(mb[h] + (q != 0 ? 1 : 0)) << 16) | (mag << 1) | ((uint32_t)q >> 31);
+                o[h] = prefix[h] ? from_table : computed;
             }
             *row = make_uint4(o[0], o[1], o[2], o[3]);
         }
