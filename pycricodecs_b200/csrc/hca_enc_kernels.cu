@@ -49,15 +49,22 @@ constexpr uint32_t kRankShift = 21, kRankBase = 459, kRankBuckets = 49;   // too
 #include "hca_dct_gen.inc"
 
 #ifndef HCA_ENC_WARPS
-#define HCA_ENC_WARPS 20          // 20 x 9.6 KB of shared memory per stereo frame: one CTA per SM (measured: 4 / 8 / 16 / 20 warps -> 20.6 / 20.5 / 21.4 / 19.2 ms)
+#define HCA_ENC_WARPS 10          // x 9.6 KB of shared memory per stereo frame: two CTAs per SM
 #endif
 constexpr int kEncWarps = HCA_ENC_WARPS;
-// The kernel is ~120 KB of SASS that every frame walks once, far more than the 32 KB instruction cache next to the SM:
-// with independent warps every warp streams its own copy of the code from L2 ("no instruction" was the top stall). The
-// warps of a CTA therefore meet at every phase boundary (CONVOY) and fetch the same lines at about the same time; a CTA is
-// as many warps as shared memory allows. No warp may leave early for this to be legal: surplus warps redo the last
-// frame and frames that fail the bit allocation run to the end, both without storing anything.
-#define CONVOY() __syncthreads()
+#ifndef HCA_ENC_MIN_CTAS
+#define HCA_ENC_MIN_CTAS (HCA_ENC_WARPS >= 20 ? 1 : 20 / HCA_ENC_WARPS)
+#endif
+// CONVOY: the warps of a CTA meet at every phase boundary, so that they fetch the same instruction-cache lines at about
+// the same time. It paid while the kernel was ~120 KB of SASS with a per-coefficient bit-cost loop (one CTA of 20 warps:
+// 23.5 -> 19.2 ms per 8192 streams); with the counted bit costs the barrier stalls cost more than the shared fetches
+// save. Measured per 8192 streams: 20 warps with convoy 15.9 ms, without 14.7; 2 x 10 warps without 14.4; 3 x 7 warps
+// (80 registers) 15.9; 4 x 5 warps 16.4. A warp behind the last frame redoes it and stores nothing, so the barrier stays
+// legal if it is switched back on (-DHCA_ENC_CONVOY=1).
+#ifndef HCA_ENC_CONVOY
+#define HCA_ENC_CONVOY 0
+#endif
+#define CONVOY() do { if (HCA_ENC_CONVOY) __syncthreads(); } while (0)
 constexpr int kSpecRow = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -252,7 +259,7 @@ __device__ __noinline__ void header_lengths(const FrameSmem& fs, const HcaStream
 // number of coefficients on the positive clamp in nibble 7; word B: resolutions 8..15). A probe of CalculateUsedBits
 // (hca.cpp:2763-2790) is then, per band, one table row and one nibble: the same integers as the per-coefficient count.
 template <bool COUNTED>
-__global__ void __launch_bounds__(kEncWarps * 32, 1)
+__global__ void __launch_bounds__(kEncWarps * 32, HCA_ENC_MIN_CTAS)
 hca_encode_kernel(HcaEncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ EncTables tb;
