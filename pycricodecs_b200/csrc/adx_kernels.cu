@@ -503,17 +503,21 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 for (int i = 0; i < kSpb; i++)
                     if (sbase + i >= ch.samples) q[i * nch] = 0;
             }
+            // the arithmetic shift is monotone, so the range is taken over the unshifted values (two samples per
+            // three-input min / max) and shifted once
             int h2 = q[0], h1 = q[nch];
             int mn = 0, mx = 0;
             q += 2 * nch;
-#pragma unroll 6
-            for (int i = 2; i < kSpb; i++, q += nch) {
-                const int sm = *q;
-                const int r = (sm * 4096 - c0 * h1 - c1 * h2) >> 12;
-                mn = min(mn, r); mx = max(mx, r);
-                h2 = h1; h1 = sm;
+            const int nc0 = -c0, nc1 = -c1;
+#pragma unroll 5
+            for (int i = 2; i < kSpb; i += 2, q += 2 * nch) {
+                const int sa = q[0], sb = q[nch];
+                const int va = sa * 4096 + (nc0 * h1 + nc1 * h2);
+                const int vb = sb * 4096 + (nc0 * sa + nc1 * h1);
+                mn = __vimin3_s32(mn, va, vb); mx = __vimax3_s32(mx, va, vb);
+                h2 = sa; h1 = sb;
             }
-            stage.head[buf][tb * 32 + lane] = BlockHead{mn, mx};
+            stage.head[buf][tb * 32 + lane] = BlockHead{mn >> 12, mx >> 12};
         }
     };
 

@@ -91,6 +91,7 @@ class UTF:
     def _read(self) -> None:
         at = UTFChunkHeader.size
         per_row, shared = [], {}
+        null_cols, const_cols = [], []                                  # (name, the entry the reference's `table` holds)
         for _ in range(self.num_columns):
             flag = self.data[at]
             storage, kind = flag >> 4, flag & 0xF
@@ -101,8 +102,11 @@ class UTF:
             if storage == 0x1:
                 shared[name] = ((UTFTypeValues.string, "<NULL>") if kind == 0xA else
                                 (UTFTypeValues.bytes, b"") if kind == 0xB else (_TYPES[kind], None))
+                null_cols.append((name, "<NULL>" if kind == 0xA else b"" if kind == 0xB else 0))
             elif storage == 0x3:
                 shared[name], used = self._value(kind, at)
+                # numeric constants sit in the reference's table as the raw unpack() tuple (utf.py:124)
+                const_cols.append((name, shared[name][1] if kind in (0xA, 0xB) else (shared[name][1],)))
                 at += used
             elif storage == 0x5:
                 per_row.append((name, kind))
@@ -111,7 +115,6 @@ class UTF:
             else:
                 raise Exception("Unknown storage flag.")
         self._payload: List[dict] = []
-        self.table = {}
         if not per_row or self.num_rows == 0:
             self._payload.append(dict(shared))
         else:
@@ -123,9 +126,15 @@ class UTF:
                     at += used
                 row.update(shared)
                 self._payload.append(row)
-        for row in self._payload:                                         # the column-major view (utf.py `table`)
-            for k, v in row.items():
-                self.table.setdefault(k, []).append(v[1])
+        # The column-major view, as read_rows_and_columns builds it (utf.py:113-152): columns without storage first
+        # (one entry: 0 / "<NULL>" / b""), then constants (one entry), then the per-row columns (one entry per row).
+        self.table = {}
+        for name, entry in null_cols + const_cols:
+            self.table.setdefault(name, []).append(entry)
+        if per_row and self.num_rows:
+            for row in self._payload:
+                for name, _ in per_row:
+                    self.table.setdefault(name, []).append(row[name][1])
 
     def get_payload(self) -> list:
         return self._payload

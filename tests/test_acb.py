@@ -43,6 +43,24 @@ def test_utf_payload_matches_the_reference_reader():
     assert t.table["Name"] == ["sheet"] and t.num_rows == 1
 
 
+def plain_table(table):
+    conv = lambda v: {"len": len(v), "sha": h(v)} if isinstance(v, (bytes, bytearray)) else list(v) if isinstance(v, tuple) else v
+    return {k: [conv(v) for v in col] for k, col in table.items()}
+
+
+def test_utf_table_view_follows_the_reference_rules():
+    """`UTF.table` (column-major): columns without storage hold one 0 / "<NULL>" / b"", constants one entry (numbers as
+    the raw 1-tuple), per-row columns one entry per row, in that key order (PyCriCodecs/utf.py:113-152)."""
+    from pycricodecs_b200.utf import UTF
+    sheet = open(os.path.join(GOLD, "sheet.acb"), "rb").read()
+    t = UTF(sheet)
+    assert plain_table(t.table) == D["table"] and list(t.table) == list(D["table"])
+    m = UTF(open(os.path.join(GOLD, "sheet_masked.utf"), "rb").read())
+    assert plain_table(m.table) == D["masked_table"] and list(m.table) == list(D["masked_table"])
+    cue = UTF(t.get_payload()[0]["CueNameTable"][1])
+    assert plain_table(cue.table) == D["cue_table"] and list(cue.table) == list(D["cue_table"])
+
+
 def test_masked_utf_is_unmasked():
     from pycricodecs_b200.utf import UTF
     t = UTF(open(os.path.join(GOLD, "sheet_masked.utf"), "rb").read())

@@ -33,6 +33,12 @@ def plain(payload):
     return out
 
 
+def plain_table(table):
+    """JSON-able view of the reader's column-major `table` (bytes as digest, tuples as lists)."""
+    conv = lambda v: {"len": len(v), "sha": h(v)} if isinstance(v, (bytes, bytearray)) else list(v) if isinstance(v, tuple) else v
+    return {k: [conv(v) for v in col] for k, col in table.items()}
+
+
 def main():
     oracle.ref()
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
@@ -62,6 +68,7 @@ def main():
 
     a = ACB(sheet)
     d = {"payload": plain(a.payload), "masked_payload": plain(UTF(masked).get_payload()),
+         "table": plain_table(UTF(sheet).table), "masked_table": plain_table(UTF(masked).table), "cue_table": plain_table(UTF(cue_table).table),
          "table_name": UTF(sheet).table_name, "awb_numfiles": a.awb.numfiles, "awb_subkey": a.awb.subkey}
     with tempfile.TemporaryDirectory() as tmp:
         for mode in (True, False):
