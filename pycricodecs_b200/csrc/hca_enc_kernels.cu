@@ -78,6 +78,7 @@ struct EncTables {              // per-CTA shared copies (per-lane indices diver
     float inv_step[16];
     float dead_zone[16];
     uint8_t curve[60];
+    uint16_t crc[4][256];       // CRC-16 (poly 0x8005, MSB first) of byte v followed by k zero bytes
     uint32_t qpack[128];        // [resolution * 16 + value + 8] = code length << 16 | code (prefix codebooks)
     uint8_t max_bits[16];
 };
@@ -284,6 +285,15 @@ hca_encode_kernel(HcaEncodeArgs a) {
         tb.max_bits[i] = e_max_bits[i];
     }
     for (int i = threadIdx.x; i < 59; i += blockDim.x) tb.curve[i] = e_curve[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        auto step = [](uint32_t c, uint32_t byte) {             // table-free byte step
+            const uint32_t v = ((c >> 8) ^ byte) & 0xFF;
+            return ((c << 8) ^ (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u)) & 0xFFFFu;
+        };
+        uint32_t c = step(0, (uint32_t)i);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { tb.crc[k][i] = (uint16_t)c; c = step(c, 0); }
+    }
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
         tb.qpack[i] = ((uint32_t)e_qbits[i] << 16) | ((uint32_t)e_qcode[i] & ((1u << e_qbits[i]) - 1u));
     }
@@ -293,10 +303,15 @@ hca_encode_kernel(HcaEncodeArgs a) {
     const uint64_t f_own = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const bool surplus = f_own >= a.n_frames;                  // a warp behind the last frame redoes it (and stores nothing)
     const uint64_t f = surplus ? a.n_frames - 1 : f_own;
+    // the frame's stream = the last s with frame_prefix[s] <= f. The warp searches together: 32 probes spread over the
+    // open interval per step (three dependent loads for 8192 streams where a bisection takes thirteen)
     uint32_t lo = 0, hi = a.n_streams;
     while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (a.frame_prefix[mid] <= f) lo = mid; else hi = mid;
+        const uint32_t probe = lo + (uint32_t)(((uint64_t)(hi - lo) * (uint32_t)(lane + 1)) / 33u);      // lo <= probe < hi, non-decreasing in lane
+        const int k = __popc(__ballot_sync(kFull, a.frame_prefix[probe] <= f));                         // probes 0 .. k - 1 hold
+        const uint32_t below = __shfl_sync(kFull, probe, max(k - 1, 0)), above = __shfl_sync(kFull, probe, min(k, 31));
+        lo = k ? below : lo;
+        hi = k < 32 ? above : hi;
     }
     const uint32_t stream = lo;
     const HcaStreamDev& S = a.streams[stream];
@@ -334,6 +349,10 @@ hca_encode_kernel(HcaEncodeArgs a) {
     const long long pcm_end = (long long)S.out_samples;
     // a frame whose whole window lies inside the stream (all but the first and the last one) loads without bounds checks
     const bool interior = pcm_n0 >= 0 && pcm_n0 + 1152 <= pcm_end;
+    if (interior) {                                           // pull the window towards L2 while the first block is on its way
+        const uint8_t* w0p = reinterpret_cast<const uint8_t*>(pcm_base + pcm_n0 * nch);
+        for (int k = lane * 128; k < 1152 * 2 * nch; k += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0p + k));
+    }
     auto sample = [&](int idx /* sample frame inside the 1152-frame window */, int c) -> float {
         const long long n = pcm_n0 + idx;
         const int v = (interior || (n >= 0 && n < pcm_end)) ? (int)__ldg(pcm_base + n * nch + c) : 0;
@@ -825,18 +844,22 @@ hca_encode_kernel(HcaEncodeArgs a) {
     CONVOY();
 
     // ---- CRC16 over the first frame_size - 2 bytes. The CRC (init 0, no final xor) is linear: every lane takes a
-    // contiguous chunk, multiplies its partial CRC by x^(8 * bytes behind the chunk) mod P (host-made per-stream
-    // constants) and the 32 products are XORed together.
+    // contiguous chunk of whole words (four bytes per step: slice-by-4 tables), multiplies its partial CRC by
+    // x^(8 * bytes behind the chunk) mod P (host-made per-stream constants) and the 32 products are XORed together.
     uint8_t* dst = a.out + S.out_off + (uint64_t)frame * frame_size;
     uint32_t crc = 0;
     {
-        const int body = frame_size - 2, chunk = (body + 31) >> 5;
+        const int body = frame_size - 2, chunk = ((((body + 3) >> 2) + 31) >> 5) << 2;     // bytes per lane, a multiple of 4
         const int b0 = min(lane * chunk, body), b1 = min(b0 + chunk, body);
         uint32_t part = 0;
-        for (int i = b0; i < b1; i++) {
+        int i = b0;
+        for (; i + 4 <= b1; i += 4) {                        // fs.bits words hold the frame's bytes first-byte-on-top
+            const uint32_t x = fs.bits[i >> 2] ^ (part << 16);
+            part = (uint32_t)tb.crc[3][x >> 24] ^ (uint32_t)tb.crc[2][(x >> 16) & 0xFF] ^ (uint32_t)tb.crc[1][(x >> 8) & 0xFF] ^ (uint32_t)tb.crc[0][x & 0xFF];
+        }
+        for (; i < b1; i++) {
             const uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
-            const uint32_t v = ((part >> 8) ^ byte) & 0xFF;
-            part = ((part << 8) ^ (v << 1) ^ (v << 2) ^ ((__popc(v) & 1) ? 0x8003u : 0u)) & 0xFFFF;
+            part = ((part << 8) & 0xFFFF) ^ (uint32_t)tb.crc[0][((part >> 8) ^ byte) & 0xFF];
         }
         const uint32_t mul = a.crc_mul[(size_t)stream * 32 + lane];
         uint32_t prod = 0;                                   // carry-less part * mul mod x^16 + x^15 + x^2 + 1
@@ -849,11 +872,28 @@ hca_encode_kernel(HcaEncodeArgs a) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(kFull, crc, o);
     }
-    for (int i = lane; i < frame_size && !failed && !surplus; i += 32) {
-        uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
-        if (i == frame_size - 2) byte = crc >> 8;
-        if (i == frame_size - 1) byte = crc & 0xFF;
-        dst[i] = (uint8_t)byte;
+    // ---- the frame leaves as 32-bit words wherever it lands in the blob: bytes up to the first aligned address and
+    // behind the last whole word go one by one, word k in between is the frame's bytes nh + 4k .. nh + 4k + 3, i.e.
+    // the packed words k and k + 1 funnel-shifted by nh bytes and turned into memory order. The CRC takes the place of
+    // the last two bytes first.
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = frame_size - 2 + k, sh = 24 - 8 * (i & 3);
+            fs.bits[i >> 2] = (fs.bits[i >> 2] & ~(0xFFu << sh)) | (((k == 0 ? crc >> 8 : crc) & 0xFFu) << sh);
+        }
+    }
+    __syncwarp();
+    if (!failed && !surplus) {
+        auto byte_at = [&](int i) -> uint8_t { return (uint8_t)(fs.bits[i >> 2] >> (24 - 8 * (i & 3))); };
+        const int nh = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), frame_size);
+        const int nw = (frame_size - nh) >> 2, nt = frame_size - nh - 4 * nw;
+        if (lane < nh) dst[lane] = byte_at(lane);
+        if (lane >= 8 && lane < 8 + nt) dst[nh + 4 * nw + lane - 8] = byte_at(nh + 4 * nw + lane - 8);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + nh);
+        for (int k = lane; k < nw; k += 32)
+            dw[k] = __byte_perm(__funnelshift_l(fs.bits[k + 1], fs.bits[k], 8 * nh), 0, 0x0123);
     }
 }
 

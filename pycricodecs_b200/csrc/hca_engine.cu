@@ -391,12 +391,12 @@ int plan_hca_encode(cri_ctx* c, cri_job* j) {
             add_patch_public(j, j->out_off[i], hdr.data(), p.header_size);
             frames = p.frame_count;
             j->units += frames;
-            // CRC chunk multipliers: lane l covers bytes [l*chunk, (l+1)*chunk) of the frame body; appending k bytes
+            // CRC chunk multipliers: lane l covers bytes [l*chunk, (l+1)*chunk) of the frame body (whole words); appending k bytes
             // multiplies a CRC by x^(8k), i.e. k table steps on the value 1 (the CRC register is x^16-scaled already)
             auto& mul = crc_mul_by_size[p.frame_size];
             if (mul.empty()) {
                 mul.resize(32);
-                const int body = (int)p.frame_size - 2, chunk = (body + 31) / 32;
+                const int body = (int)p.frame_size - 2, chunk = (((body + 3) / 4 + 31) / 32) * 4;
                 uint16_t v = 1;
                 int done = 0;
                 const uint8_t zero = 0;
