@@ -299,9 +299,16 @@ hca_encode_kernel(HcaEncodeArgs a) {
     }
     __syncthreads();
 
+    // Every warp walks the frame list with the stride of the whole grid (one round with the default launch: a CTA per
+    // kEncWarps frames; see launch_hca_encode). With the convoy barrier all warps make the same number of rounds: a
+    // warp behind the last frame redoes it and stores nothing.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t f_own = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    const bool surplus = f_own >= a.n_frames;                  // a warp behind the last frame redoes it (and stores nothing)
+    const uint64_t grid_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint32_t rounds = (uint32_t)((a.n_frames + grid_warps - 1) / grid_warps);
+    for (uint32_t round = 0; round < rounds; round++) {
+    const uint64_t f_own = round * grid_warps + (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool surplus = f_own >= a.n_frames;
+    if (surplus && !HCA_ENC_CONVOY) break;
     const uint64_t f = surplus ? a.n_frames - 1 : f_own;
     // the frame's stream = the last s with frame_prefix[s] <= f. The warp searches together: 32 probes spread over the
     // open interval per step (three dependent loads for 8192 streams where a bisection takes thirteen)
@@ -314,6 +321,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         hi = k < 32 ? above : hi;
     }
     const uint32_t stream = lo;
+    const uint32_t mul = a.crc_mul[(size_t)stream * 32 + lane];      // this lane's CRC chunk multiplier (needed last, requested first)
     const HcaStreamDev& S = a.streams[stream];
     const uint32_t frame = (uint32_t)(f - a.frame_prefix[stream]);
     const int nch = S.channels;
@@ -500,16 +508,32 @@ hca_encode_kernel(HcaEncodeArgs a) {
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
         const float* sp = fs.spec + (size_t)c * 8 * kSpecRow;
-        for (int b = lane; b < 128; b += 32) {
-            int sfv = 0;
-            if (b < coded) {
-                float mx = 0.f;
+        // the lane's four bands are searched side by side: 63 table entries = always six halvings, so the four
+        // bisections (find_scalefactor) run in lock step as independent chains of shared-memory loads
+        float mx[4];
+        unsigned lo4[4], hi4[4];
 #pragma unroll
-                for (int j = 0; j < 8; j++) { const float v = fabsf(sp[j * kSpecRow + b]); mx = mx < v ? v : mx; }
-                sfv = find_scalefactor(tb.scaling, mx);
+        for (int k = 0; k < 4; k++) {
+            const int b = lane + 32 * k;
+            mx[k] = 0.f;
+            if (b < coded) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const float v = fabsf(sp[j * kSpecRow + b]); mx[k] = mx[k] < v ? v : mx[k]; }
             }
-            fs.sf[c * 128 + b] = (uint8_t)sfv;
+            lo4[k] = 0; hi4[k] = 63;
         }
+#pragma unroll
+        for (int step = 0; step < 6; step++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned mid = (lo4[k] + hi4[k]) >> 1;
+                const bool le = tb.scaling[mid] <= mx[k];
+                lo4[k] = le ? mid + 1 : lo4[k];
+                hi4[k] = le ? hi4[k] : mid;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) fs.sf[c * 128 + lane + 32 * k] = lane + 32 * k < coded ? (uint8_t)lo4[k] : (uint8_t)0;
     }
     __syncwarp();
 
@@ -828,18 +852,27 @@ hca_encode_kernel(HcaEncodeArgs a) {
             }
         }
     };
-    for (int sub = 0; sub < 8; sub++) {
-        for (int c = 0; c < nch; c++) {
+    // rows in bitstream order (subframe-major, channel-minor), two per prefix sum: the lengths of a lane's codes in rows
+    // i and i + 1 travel through the scan as two 16-bit fields (a row holds at most 128 x 12 bits)
+    for (int i = 0; i < 8 * nch; i += 2) {
+        uint32_t code[2][2];
+        int len[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int sub = (i + h) / nch, c = (i + h) - sub * nch;
             const uint4 e = *reinterpret_cast<const uint4*>(fs.spec + ((size_t)c * 8 + sub) * kSpecRow + 4 * lane);
-            const int l0 = (int)(e.x >> 16), l1 = (int)(e.y >> 16), l2 = (int)(e.z >> 16), l3 = (int)(e.w >> 16);
-            const uint32_t code_a = ((e.x & 0xFFFFu) << l1) | (e.y & 0xFFFFu), code_b = ((e.z & 0xFFFFu) << l3) | (e.w & 0xFFFFu);
-            const int len_a = l0 + l1, len_b = l2 + l3;
-            int total;
-            const int at = cursor + warp_excl_scan(len_a + len_b, lane, &total);
-            cursor += total;
-            put_bits(code_a, len_a, at);
-            put_bits(code_b, len_b, at + len_a);
+            const int l1 = (int)(e.y >> 16), l3 = (int)(e.w >> 16);
+            code[h][0] = ((e.x & 0xFFFFu) << l1) | (e.y & 0xFFFFu); code[h][1] = ((e.z & 0xFFFFu) << l3) | (e.w & 0xFFFFu);
+            len[h][0] = (int)(e.x >> 16) + l1; len[h][1] = (int)(e.z >> 16) + l3;
         }
+        int total;
+        const int excl = warp_excl_scan((len[0][0] + len[0][1]) | ((len[1][0] + len[1][1]) << 16), lane, &total);
+        const int at0 = cursor + (excl & 0xFFFF), at1 = cursor + (total & 0xFFFF) + (excl >> 16);
+        cursor += (total & 0xFFFF) + (total >> 16);
+        put_bits(code[0][0], len[0][0], at0);
+        put_bits(code[0][1], len[0][1], at0 + len[0][0]);
+        put_bits(code[1][0], len[1][0], at1);
+        put_bits(code[1][1], len[1][1], at1 + len[1][0]);
     }
     CONVOY();
 
@@ -861,7 +894,6 @@ hca_encode_kernel(HcaEncodeArgs a) {
             const uint32_t byte = (fs.bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
             part = ((part << 8) & 0xFFFF) ^ (uint32_t)tb.crc[0][((part >> 8) ^ byte) & 0xFF];
         }
-        const uint32_t mul = a.crc_mul[(size_t)stream * 32 + lane];
         uint32_t prod = 0;                                   // carry-less part * mul mod x^16 + x^15 + x^2 + 1
 #pragma unroll
         for (int bit = 15; bit >= 0; bit--) {
@@ -895,6 +927,8 @@ hca_encode_kernel(HcaEncodeArgs a) {
         for (int k = lane; k < nw; k += 32)
             dw[k] = __byte_perm(__funnelshift_l(fs.bits[k + 1], fs.bits[k], 8 * nh), 0, 0x0123);
     }
+    __syncwarp();                                             // the next round reuses the warp's shared memory
+    }
 }
 
 }  // namespace
@@ -916,7 +950,20 @@ int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
     if (smem > 200 * 1024) return -1;
     auto kernel = a.max_channels <= 2 ? hca_encode_kernel<true> : hca_encode_kernel<false>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)((a.n_frames + warps - 1) / warps), warps * 32, smem, s>>>(a);
+    // One CTA per `warps` frames. The kernel can walk the frame list with resident CTAs only (HCA_ENC_GRID = 2: 2 x SMs
+    // CTAs, tables built once per CTA), but measured 16.1 ms against 12.7 ms per 8192 streams: warps that start together
+    // stay in the same phase, so the fp32-heavy MDCT and the integer-heavy search and packing stop overlapping on the SM.
+    const uint64_t want = (a.n_frames + warps - 1) / warps;
+    uint64_t grid = want;
+#ifdef HCA_ENC_GRID
+    if (HCA_ENC_GRID == 2) {
+        int dev = 0, sm_count = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        grid = std::min<uint64_t>(want, 2ull * (uint64_t)std::max(sm_count, 1));
+    }
+#endif
+    kernel<<<(unsigned)grid, warps * 32, smem, s>>>(a);
     ++*launches;
     return 0;
 }
