@@ -64,7 +64,7 @@ constexpr int kEncWarps = HCA_ENC_WARPS;
 #ifndef HCA_ENC_CONVOY
 #define HCA_ENC_CONVOY 0
 #endif
-#define CONVOY() do { if (HCA_ENC_CONVOY) __syncthreads(); } while (0)
+#define CONVOY() do { if (HCA_ENC_CONVOY) __syncthreads(); else __syncwarp(); } while (0)   // a phase boundary always orders the warp's shared memory
 constexpr int kSpecRow = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
