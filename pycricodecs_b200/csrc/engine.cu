@@ -357,19 +357,19 @@ static void plan_adx_encode(cri_job* j) {
     std::vector<WavInfo> wavs(j->n);
     std::vector<AdxEncPlan> plans(j->n);
     const cri_adx_params& q = j->adx;
-    for (uint32_t i = 0; i < j->n; i++) {
+    parallel_for(j->n, [&](uint32_t i) {
         const uint8_t* d = j->blob + j->in_off[i];
         const size_t len = j->in_off[i + 1] - j->in_off[i];
         int r = parse_wav(d, len, &wavs[i]);
-        if (r < 0) { j->status[i] = ERR_WAV_BASE + r; continue; }
+        if (r < 0) { j->status[i] = ERR_WAV_BASE + r; return; }
         // A looping WAV (smpl chunk) encodes a loop table unless version 5 + force flag (adx.cpp:421). One loop is what every
         // tool writes; the reference's multi-loop / zero-loop paths read past its own arrays and stay unsupported.
         const bool looping = wavs[i].looping && !(q.force_not_looping && q.version == 5);
-        if (looping && wavs[i].loop_count != 1) { j->status[i] = ERR_UNSUPPORTED; continue; }
+        if (looping && wavs[i].loop_count != 1) { j->status[i] = ERR_UNSUPPORTED; return; }
         r = plan_adx_encode(wavs[i], q.bit_depth, q.block_size, q.encoding, q.highpass, q.filter, q.version, &plans[i], looping);
-        if (r < 0) { j->status[i] = r; continue; }
+        if (r < 0) { j->status[i] = r; return; }
         sizes[i] = plans[i].out_size;
-    }
+    });
     finish_layout(j, sizes);
     AdxLists lists;
     std::vector<AdxChain> one;
@@ -382,10 +382,13 @@ static void plan_adx_encode(cri_job* j) {
         int16_t firsts[256];
         for (int c = 0; c < p.channels; c++) firsts[c] = wav_sample_s16(wavs[i], d + wavs[i].data_offset, (size_t)c);
         // header + EOF block are host-built patches; block payload comes from the kernel
-        tmp.assign(p.out_size, 0);
-        write_adx_frame(tmp.data(), p, firsts);
+        // (written into a header + one block image: zero-filling a whole output per stream cost 16 ms per 8192 streams)
+        AdxEncPlan ends = p;
+        ends.out_size = (uint32_t)p.header_size + (uint32_t)p.block_size;
+        tmp.assign(ends.out_size, 0);
+        write_adx_frame(tmp.data(), ends, firsts);
         add_patch(j, j->out_off[i], tmp.data(), (uint32_t)p.header_size);
-        add_patch(j, j->out_off[i] + p.out_size - p.block_size, tmp.data() + p.out_size - p.block_size, (uint32_t)p.block_size);
+        add_patch(j, j->out_off[i] + p.out_size - p.block_size, tmp.data() + p.header_size, (uint32_t)p.block_size);
         const uint64_t pcm0 = pcm16_offset(j, i, wavs[i]);
         const bool is_fast = (pcm0 & 1) == 0 && p.bit_depth == 4 && p.block_size == 18;
         for (int c = 0; c < p.channels; c++) {
@@ -428,6 +431,27 @@ static int upload_vec(cri_ctx* c, cudaStream_t s, const std::vector<T>& v, T** d
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// CRI_TRACE=1: one line per device-pointer batch call on stderr with the host-side phases (ms)
+static bool trace_on() {
+    static const bool on = [] { const char* e = getenv("CRI_TRACE"); return e && *e && *e != '0'; }();
+    return on;
+}
+struct Trace {
+    double t0 = 0, last = 0;
+    char line[512];
+    int at = 0;
+    Trace() { if (trace_on()) { t0 = last = now_ms(); line[0] = 0; } }
+    void mark(const char* what) {
+        if (!trace_on()) return;
+        const double t = now_ms();
+        at += snprintf(line + at, sizeof(line) - (size_t)at, " %s %.3f", what, t - last);
+        if (at > (int)sizeof(line) - 40) at = (int)sizeof(line) - 40;
+        last = t;
+    }
+    void done(const char* call, uint32_t n) { if (trace_on()) fprintf(stderr, "[cri trace] %s n=%u:%s | total %.3f ms\n", call, n, line, now_ms() - t0); }
+};
+static thread_local Trace* g_trace = nullptr;
+static void trace_mark(const char* what) { if (g_trace) g_trace->mark(what); }
 
 // ---------------------------------------------------------- device-resident input
 // A device-pointer job plans from headers like every other job; the headers are fetched from the caller's HBM into a
@@ -615,6 +639,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         j->d_src = d->d_blob;
         rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, stream, &j->shadow, &j->shadow_bytes, &j->shadow_dirty);
         j->blob = j->shadow;
+        trace_mark("headers");
     }
     if (d->d_out) {      // kernels take a 256-byte aligned blob start: align the pointer down and shift every offset instead
         const uintptr_t addr = reinterpret_cast<uintptr_t>(d->d_out);
@@ -630,6 +655,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         case CRI_JOB_HCA_ENCODE: rc = plan_hca_encode(c, j); break;
         default: rc = ERR_UNSUPPORTED;
     }
+    trace_mark("plan");
     if (rc == OK && expect_out)      // the caller's buffer is laid out by *_sizes(): it must be the packed layout planned here
         for (uint32_t i = 0; i <= j->n && rc == OK; i++)
             if (expect_out[i] - expect_out[0] != j->out_off_pub[i]) rc = ERR_BUFFER;
@@ -657,6 +683,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         }
         return OK;
     }();
+    trace_mark("alloc+uploads");
     if (rc != OK) {
         cudaStreamSynchronize(stream);
         cri_job_destroy(c, j);
@@ -1021,12 +1048,18 @@ static int run_batch_dev(cri_ctx* c, cri_job_desc d, const uint64_t* out_offsets
     if (out_offsets) d.d_out += out_offsets[0];
     c->last_ms = c->last_dominant_ms = 0.f;
     cri_job* j = nullptr;
+    Trace tr;
+    g_trace = trace_on() ? &tr : nullptr;
+    struct Untrace { ~Untrace() { g_trace = nullptr; } } untrace;
     int rc = job_create_on(c, &d, st, &j, out_offsets);
     if (rc != OK) return rc;
     rc = job_enqueue_run(c, j);
+    trace_mark("enqueue");
     if (rc == OK) rc = job_wait_run(c, j, false);
+    trace_mark("wait");
     if (rc == OK) rc = job_enqueue_download(c, j, nullptr, status, nullptr);
     if (rc == OK) rc = job_wait_download(c, j);
+    trace_mark("status");
     if (rc == OK) {
         bool any = false;
         for (uint32_t i = 0; i < j->n; i++)       // a stream that failed on the device leaves silence, not garbage
@@ -1037,6 +1070,8 @@ static int run_batch_dev(cri_ctx* c, cri_job_desc d, const uint64_t* out_offsets
         if (any) CU_TRY(c, cudaStreamSynchronize(st));
     }
     cri_job_destroy(c, j);
+    trace_mark("destroy");
+    tr.done("batch_dev", d.n);
     return rc;
 }
 

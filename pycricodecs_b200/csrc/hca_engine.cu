@@ -266,13 +266,19 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
     J.streams.assign(j->n, HcaStreamDev{});
     J.frame_prefix.assign(j->n + 1, 0);
     std::vector<uint8_t> hdr;
+    std::vector<HcaInfo> infos(j->n);
+    std::vector<uint8_t> parsed(j->n, 0);
+    parallel_for(j->n, [&](uint32_t i) {
+        const uint64_t len = j->in_off[i + 1] - j->in_off[i];
+        HcaInfo& h = infos[i];
+        parsed[i] = parse_hca(j->blob + j->in_off[i], len, &h) == OK && (uint64_t)h.header_size + (uint64_t)h.frame_count * h.frame_size <= len;
+    });
     for (uint32_t i = 0; i < j->n; i++) {
-        const uint8_t* d = j->blob + j->in_off[i];
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         sizes[i] = len;
-        HcaInfo h;
+        const HcaInfo& h = infos[i];
         uint64_t frames = 0;
-        if (parse_hca(d, len, &h) != OK || (uint64_t)h.header_size + (uint64_t)h.frame_count * h.frame_size > len) {
+        if (!parsed[i]) {
             j->status[i] = ERR_HCA_HEADER;
         } else {
             const unsigned type = j->encrypt ? j->ciph_type : h.ciph_type;   // hca.cpp:3307
@@ -320,14 +326,22 @@ int plan_hca_crypt(cri_ctx* c, cri_job* j) {
                 for (uint32_t f = 0; f < J.streams[i].frame_count; f += J.frames_per_group) J.group_table.push_back(make_uint2(i, f));
         }
     }
+    // the rewritten headers (CryptHeader, hca.cpp:3166-3250: cipher type, CRC) side by side in one buffer, then the patches
+    std::vector<uint64_t> hdr_at(j->n + 1, 0);
+    for (uint32_t i = 0; i < j->n; i++) hdr_at[i + 1] = hdr_at[i] + (j->status[i] == OK ? (unsigned)be16(j->blob + j->in_off[i] + 6) : 0u);
+    hdr.resize(hdr_at[j->n]);
+    parallel_for(j->n, [&](uint32_t i) {
+        const unsigned hs = (unsigned)(hdr_at[i + 1] - hdr_at[i]);
+        if (!hs) return;
+        memcpy(hdr.data() + hdr_at[i], j->blob + j->in_off[i], hs);
+        crypt_header(hdr.data() + hdr_at[i], hs, j->encrypt ? j->ciph_type : 0);
+    });
     for (uint32_t i = 0; i < j->n; i++) {
         if (j->status[i] != OK) continue;
         const uint8_t* d = j->blob + j->in_off[i];
         const uint64_t len = j->in_off[i + 1] - j->in_off[i];
         const unsigned hs = (unsigned)be16(d + 6);
-        hdr.assign(d, d + hs);
-        crypt_header(hdr.data(), hs, j->encrypt ? j->ciph_type : 0);
-        add_patch_public(j, j->out_off[i], hdr.data(), hs);
+        add_patch_public(j, j->out_off[i], hdr.data() + hdr_at[i], hs);
         const uint64_t body_end = (uint64_t)hs + (uint64_t)J.streams[i].frame_count * J.streams[i].frame_size;
         if (body_end < len) {        // bytes behind the last frame pass through unchanged
             if (j->d_src) j->dev_copies.push_back({j->in_off[i] + body_end, j->out_off[i] + body_end, len - body_end});
