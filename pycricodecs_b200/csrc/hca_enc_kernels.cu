@@ -304,7 +304,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
     // warp behind the last frame redoes it and stores nothing.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t grid_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint32_t rounds = (uint32_t)((a.n_frames + grid_warps - 1) / grid_warps);
+    const uint32_t rounds = grid_warps >= a.n_frames ? 1u : (uint32_t)((a.n_frames + grid_warps - 1) / grid_warps);   // (64-bit division: rare path)
     for (uint32_t round = 0; round < rounds; round++) {
     const uint64_t f_own = round * grid_warps + (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const bool surplus = f_own >= a.n_frames;
