@@ -615,7 +615,10 @@ static int take_events(cri_ctx* c, cri_job* j) {
 
 // Plan on the host, take HBM from the context's cache, and enqueue every upload on `stream`. Nothing here waits for the GPU
 // (a device-pointer job waits for its header fetches).
-static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream, cri_job** out, const uint64_t* expect_out = nullptr) {
+// `aux` (device-pointer jobs of a pipelined batch call): header fetches, table uploads and the payload copy go there, so
+// that they neither wait for nor hold up the kernels of the previous piece on `stream`; `stream` waits for them (`staged`).
+static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream, cri_job** out, const uint64_t* expect_out = nullptr,
+                         cudaStream_t aux = nullptr, cudaEvent_t staged = nullptr) {
     *out = nullptr;
     if (!c || !d || (!d->blob && !d->d_blob && d->n) || !d->offsets) return ERR_BUFFER;
     CU_TRY(c, cudaSetDevice(c->device));
@@ -637,7 +640,7 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     int rc = OK;
     if (d->d_blob) {
         j->d_src = d->d_blob;
-        rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, stream, &j->shadow, &j->shadow_bytes, &j->shadow_dirty);
+        rc = build_shadow(c, d->kind, d->d_blob, d->offsets, d->n, aux ? aux : stream, &j->shadow, &j->shadow_bytes, &j->shadow_dirty);
         j->blob = j->shadow;
         trace_mark("headers");
     }
@@ -662,6 +665,9 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
     if (rc == OK) rc = [&]() -> int {
         int r = take_events(c, j);
         if (r != OK) return r;
+        cudaStream_t run_stream = stream;
+        if (aux) { stream = aux; j->stream = aux; }             // uploads below (upload_hca_tables reads j->stream)
+        struct Back { cri_job* j; cudaStream_t s; ~Back() { j->stream = s; } } back{j, run_stream};
         // slack: kernels read whole 16-byte rows, up to four rows ahead; then the WAV ingest's conversion region
         const uint64_t in_alloc = j->conv_bytes ? j->conv_base + j->conv_bytes + 128 : std::max<uint64_t>(j->in_bytes, 16) + 128;
         r = pool_alloc(c, (void**)&j->d_in, in_alloc);
@@ -680,6 +686,10 @@ static int job_create_on(cri_ctx* c, const cri_job_desc* d, cudaStream_t stream,
         if (j->in_bytes) {
             if (j->d_src) CU_TRY(c, cudaMemcpyAsync(j->d_in, j->d_src, j->in_bytes, cudaMemcpyDeviceToDevice, stream));
             else CU_TRY(c, cudaMemcpyAsync(j->d_in, j->blob, j->in_bytes, cudaMemcpyHostToDevice, stream));
+        }
+        if (aux && staged) {
+            CU_TRY(c, cudaEventRecord(staged, aux));
+            CU_TRY(c, cudaStreamWaitEvent(run_stream, staged, 0));
         }
         return OK;
     }();
@@ -1040,37 +1050,136 @@ extern "C" int cri_hca_encode_batch(cri_ctx* c, const uint8_t* blob, const uint6
 // One job for the whole batch (there is no PCIe transfer to hide, so no chunking): headers are fetched for planning,
 // the payload is copied once inside HBM into the engine's padded input buffer (kernels read whole 16-byte rows past
 // the last stream), kernels write straight into the caller's output buffer.
+// One call = up to four pieces of whole streams, each a job of its own: while piece k's kernels run on the caller's stream,
+// the host fetches and parses piece k + 1's headers and plans it (stream c->pipe[0], which also carries the uploads and the
+// payload copy), and piece k - 1 is torn down. Per 8192 HCA streams the host side is ~4 ms (header fetch 1.5, planning 1.5,
+// teardown 1.0) against ~6 ms of kernels: unpipelined the GPU idles for 40 % of the call.
+struct DevPiece {
+    cri_job* job = nullptr;
+    cudaEvent_t staged = nullptr, done = nullptr;
+    uint32_t s0 = 0;
+    int slot = 0;
+};
+
+static int dev_piece_finish(cri_ctx* c, DevPiece& p, cudaStream_t st, int32_t* status, bool* zeroed) {
+    if (!p.job) return OK;
+    cri_job* j = p.job;
+    p.job = nullptr;
+    int rc = OK;
+    if (cudaEventSynchronize(p.done) != cudaSuccess) { c->error = "cudaEventSynchronize"; rc = ERR_CUDA; }
+    if (rc == OK) {
+        float ms = 0.f, dom = 0.f;
+        cudaEventElapsedTime(&ms, j->ev[0], j->ev[1]);
+        if (j->have_dominant) cudaEventElapsedTime(&dom, j->ev[2], j->ev[3]);
+        c->last_ms += ms;
+        c->last_dominant_ms += dom;
+        for (uint32_t i = 0; i < j->n; i++) {
+            const int32_t v = j->status[i] != OK ? j->status[i] : j->h_status[i];
+            if (status) status[p.s0 + i] = v;
+            if (j->status[i] == OK && j->h_status[i] != OK && j->out_off[i + 1] > j->out_off[i]) {   // failed on the device: silence, not garbage
+                cudaMemsetAsync(j->d_out + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i], st);
+                *zeroed = true;
+            }
+        }
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    cri_job_destroy(c, j);
+    return rc;
+}
+
 static int run_batch_dev(cri_ctx* c, cri_job_desc d, const uint64_t* out_offsets, int32_t* status) {
     if (!c) return ERR_CUDA;
     if (!d.offsets || (d.n && (!d.d_blob || !d.d_out))) return ERR_BUFFER;
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = d.stream ? (cudaStream_t)d.stream : c->stream;
-    if (out_offsets) d.d_out += out_offsets[0];
+    cudaStream_t aux = c->pipe[0];
     c->last_ms = c->last_dominant_ms = 0.f;
-    cri_job* j = nullptr;
     Trace tr;
     g_trace = trace_on() ? &tr : nullptr;
     struct Untrace { ~Untrace() { g_trace = nullptr; } } untrace;
-    int rc = job_create_on(c, &d, st, &j, out_offsets);
-    if (rc != OK) return rc;
-    rc = job_enqueue_run(c, j);
-    trace_mark("enqueue");
-    if (rc == OK) rc = job_wait_run(c, j, false);
-    trace_mark("wait");
-    if (rc == OK) rc = job_enqueue_download(c, j, nullptr, status, nullptr);
-    if (rc == OK) rc = job_wait_download(c, j);
-    trace_mark("status");
-    if (rc == OK) {
-        bool any = false;
-        for (uint32_t i = 0; i < j->n; i++)       // a stream that failed on the device leaves silence, not garbage
-            if (j->status[i] == OK && j->h_status[i] != OK && j->out_off[i + 1] > j->out_off[i]) {
-                cudaMemsetAsync(j->d_out + j->out_off[i], 0, j->out_off[i + 1] - j->out_off[i], st);
-                any = true;
-            }
-        if (any) CU_TRY(c, cudaStreamSynchronize(st));
+
+    // Only where a piece's kernels shrink with the piece: the HCA frame kernels. An ADX chain is serial over its whole
+    // stream, so a quarter of the chains takes as long as all of them (measured: 11.3 -> 16.7 ms per 8192 streams when cut
+    // in four), and the crypt kernel is 0.25 ms against ~5 ms of host work that only grows with the number of pieces.
+    uint32_t n_pieces = 1;
+    if (d.kind == CRI_JOB_HCA_DECODE || d.kind == CRI_JOB_HCA_ENCODE) n_pieces = d.n >= 4096 ? 4 : d.n >= 1024 ? 2 : 1;   // 8192 HCA streams: 1 / 2 / 4 / 8 pieces -> 10.3 / 8.9 / 7.9 / 8.1 ms
+    if (const char* e = getenv("CRI_DEV_PIECES")) n_pieces = (uint32_t)std::max(1, atoi(e));
+    n_pieces = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(n_pieces, 16), std::max<uint32_t>(d.n, 1)));
+    if (!out_offsets) n_pieces = 1;                                  // no caller layout to place later pieces by
+
+    std::vector<cudaEvent_t> events;
+    auto event = [&]() -> cudaEvent_t {
+        cudaEvent_t e = nullptr;
+        if (!c->idle_events.empty()) { e = c->idle_events.back(); c->idle_events.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+        if (e) events.push_back(e);
+        return e;
+    };
+    int rc = OK;
+    // the caller's input is ready when the work already on its stream is: the fetch stream starts behind that point
+    if (cudaEvent_t in_ready = event()) {
+        cudaEventRecord(in_ready, st);
+        cudaStreamWaitEvent(aux, in_ready, 0);
+    } else rc = ERR_CUDA;
+
+    DevPiece pieces[2];
+    std::vector<uint64_t> local, local_out;
+    bool zeroed = false;
+    for (uint32_t k = 0; k < n_pieces && rc == OK; k++) {
+        DevPiece& p = pieces[k & 1];
+        const uint32_t s0 = (uint32_t)((uint64_t)d.n * k / n_pieces), s1 = (uint32_t)((uint64_t)d.n * (k + 1) / n_pieces), m = s1 - s0;
+        local.resize(m + 1);
+        for (uint32_t i = 0; i <= m; i++) local[i] = d.offsets[s0 + i] - d.offsets[s0];
+        cri_job_desc sub = d;
+        sub.d_blob = d.d_blob + d.offsets[s0];
+        sub.offsets = local.data();
+        sub.n = m;
+        if (d.keys) sub.keys = d.keys + s0;
+        if (d.subkeys) sub.subkeys = d.subkeys + s0;
+        const uint64_t* expect = nullptr;
+        if (out_offsets) {
+            sub.d_out = d.d_out + out_offsets[s0];
+            expect = out_offsets + s0;
+        }
+        p.s0 = s0;
+        p.slot = (int)(k & 1);
+        p.staged = event();
+        p.done = event();
+        if (!p.staged || !p.done) { rc = ERR_CUDA; break; }
+        rc = job_create_on(c, &sub, st, &p.job, expect, aux, p.staged);
+        if (rc != OK) { p.job = nullptr; break; }
+        cri_job* j = p.job;
+        rc = job_enqueue_run(c, j);
+        if (rc != OK) break;
+        const int slot = p.slot;
+        if (c->pin_status_cap[slot] < m) {
+            cudaFreeHost(c->pin_status[slot]);
+            c->pin_status[slot] = nullptr;
+            c->pin_status_cap[slot] = 0;
+            if (cudaHostAlloc((void**)&c->pin_status[slot], sizeof(int32_t) * m * 2, cudaHostAllocDefault) == cudaSuccess)
+                c->pin_status_cap[slot] = (size_t)m * 2;
+            else
+                cudaGetLastError();
+        }
+        rc = job_enqueue_download(c, j, nullptr, nullptr, c->pin_status_cap[slot] >= m ? c->pin_status[slot] : nullptr);
+        if (rc == OK && cudaEventRecord(p.done, st) != cudaSuccess) rc = ERR_CUDA;
+        trace_mark("enqueue");
+        if (rc == OK) rc = dev_piece_finish(c, pieces[(k & 1) ^ 1], st, status, &zeroed);      // the piece in front of this one
+        trace_mark("finish-prev");
     }
-    cri_job_destroy(c, j);
-    trace_mark("destroy");
+    for (auto& p : pieces) {
+        if (rc == OK) rc = dev_piece_finish(c, p, st, status, &zeroed);
+        else if (p.job) {
+            cudaStreamSynchronize(st);
+            cudaStreamSynchronize(aux);
+            cri_job_destroy(c, p.job);
+            p.job = nullptr;
+        }
+    }
+    trace_mark("finish-last");
+    if (rc == OK && zeroed) CU_TRY(c, cudaStreamSynchronize(st));
+    for (cudaEvent_t e : events) c->idle_events.push_back(e);
     tr.done("batch_dev", d.n);
     return rc;
 }

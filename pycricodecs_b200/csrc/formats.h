@@ -51,7 +51,7 @@ uint16_t crc16(const uint8_t* p, size_t n);
 template <class F>
 inline void parallel_for(uint32_t n, F fn) {
     const unsigned hw = std::thread::hardware_concurrency();
-    const uint32_t workers = n < 2048 ? 1u : std::min<uint32_t>(std::min<uint32_t>(hw ? hw : 1u, 8u), n / 1024);
+    const uint32_t workers = n < 512 ? 1u : std::min<uint32_t>(std::min<uint32_t>(hw ? hw : 1u, 8u), n / 256);
     if (workers <= 1) {
         for (uint32_t i = 0; i < n; i++) fn(i);
         return;
