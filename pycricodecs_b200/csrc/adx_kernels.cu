@@ -446,7 +446,7 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
     EncodeStage& stage = reinterpret_cast<EncodeStage*>(s_dyn)[group];
     // reciprocals of every scale the quantiser can meet on this path: a table look-up instead of a division per block
     uint32_t* s_magic = reinterpret_cast<uint32_t*>(s_dyn + kGroups * sizeof(EncodeStage));
-    for (int i = threadIdx.x; i <= 0x1000; i += blockDim.x) s_magic[i] = i ? 0x7FFFFFFFu / (uint32_t)i + 1u : 0u;
+    for (int i = threadIdx.x; i <= 0x1000; i += blockDim.x) s_magic[i] = i >= 2 ? 0xFFFFFFFFu / (uint32_t)i + 1u : 0xFFFFFFFFu;   // ceil(2^32 / i); i = 1: see below
     __syncthreads();
     auto& s_pcm = stage.pcm;
     auto& s_code = stage.code;
@@ -582,12 +582,15 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                 // without it (9 dependent operations per sample instead of 14; `range_s` collects the biased values), and
                 // redone with the reference's own sequence from the saved history if a value left the int16 range. (The
                 // delta clamp stays: the scale comes from residuals against RAW history, so it fires in ~1 block of 8.)
-                // Division: q = ((2*|r| + 2*half) * ceil(2^31 / scale)) >> 32 is exact while (|r| + half) * scale < 2^31.
                 bool exact = abs(c0) > 0x2000 || abs(c1) > 0x2000 || scale > 0x1000;
                 if (!exact) {
-                    const uint32_t magic31 = s_magic[scale];                          // ceil(2^31 / scale), 1 <= scale <= 0x1000
-                    const int half2 = 2 * half;
-                    // Serial path per sample: t -> r -> |r| -> 2|r| + half2 -> q -> min(q, limit) -> t'. The next t is
+                    // q = floor((|r| + half) / scale) as the upper word of (|r| + half) * M, M = ceil(2^32 / scale): exact
+                    // while (|r| + half) * scale < 2^32. The addend half * M is a block constant, so the division is ONE
+                    // wide multiply-add on the path (|r| * M + c64). scale = 1 (M would be 2^32): M = c64 = 2^32 - 1 gives
+                    // upper(|r| * 2^32 + (2^32 - 1 - |r|)) = |r|.
+                    const uint32_t magic = s_magic[scale];                            // 1 <= scale <= 0x1000
+                    const unsigned long long c64 = (unsigned long long)(uint32_t)half * magic + (scale == 1 ? 0xFFFFFFFFull : 0ull);
+                    // Serial path per sample: t -> r -> |r| -> q -> min(q, limit) -> t' (five operations). The next t is
                     //   s'*4096 - c1*sim_{n-1} - c0*sim_n  with  sim_n = delta*scale + P  =  B - (c0*scale) * delta,
                     // where B = s'*4096 - c1*sim_{n-1} - c0*P and the sign of delta (known from r, early) is folded into
                     // the multiplier, so neither the sign nor the simulated sample itself sits on the path.
@@ -604,13 +607,16 @@ adx_encode_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out
                             const int sm = smp[i];
                             const int r = t >> 12;
                             const bool neg = r < 0;
-                            const int q = (int)__umulhi((uint32_t)(2 * abs(r) + half2), magic31);
+                            const int q = (int)(((unsigned long long)(uint32_t)abs(r) * magic + c64) >> 32);
                             const int qc = min(q, neg ? 8 : 7);                       // clamp of delta to [-8, 7], on the magnitude
                             const int pshift = sm - ((t + 4095) >> 12);               // pred >> 12
                             const int d = neg ? -qc : qc;
                             const int sim = d * scale + pshift;
                             range_s |= sim + 32768;
-                            if (i < kSpb - 1) t = (smp[i + 1] * 4096 - c1 * g1 - c0 * pshift) - (neg ? -a_pos : a_pos) * qc;
+                            if (i < kSpb - 1) {         // one multiply-add behind qc: everything else of the next t is ready by then
+                                const int ready = smp[i + 1] * 4096 - c1 * g1 - c0 * pshift, step = neg ? a_pos : -a_pos;
+                                asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(qc), "r"(step), "r"(ready));
+                            }
                             g2 = g1; g1 = sim;
                             byte = (byte << 4) | (d & 0xF);
                         }
