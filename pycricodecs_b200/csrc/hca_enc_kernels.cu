@@ -253,6 +253,20 @@ __device__ __noinline__ void header_lengths(const FrameSmem& fs, const HcaStream
     __syncwarp();
 }
 
+// The last s with prefix[s] <= f, searched by the whole warp: 32 probes spread over the open interval per step (three
+// dependent loads for 8192 streams where a bisection takes thirteen).
+__device__ __forceinline__ uint32_t find_stream_warp(const uint64_t* __restrict__ prefix, uint32_t n, uint64_t f, int lane) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t probe = lo + (uint32_t)(((uint64_t)(hi - lo) * (uint32_t)(lane + 1)) / 33u);      // lo <= probe < hi, non-decreasing in lane
+        const int k = __popc(__ballot_sync(kFull, prefix[probe] <= f));                                  // probes 0 .. k - 1 hold
+        const uint32_t below = __shfl_sync(kFull, probe, max(k - 1, 0)), above = __shfl_sync(kFull, probe, min(k, 31));
+        lo = k ? below : lo;
+        hi = k < 32 ? above : hi;
+    }
+    return lo;
+}
+
 // COUNTED (mono / stereo batches): the bit-allocation search does not go back to the 2048 scaled coefficients for every
 // probe. Each coefficient is classified ONCE, when it is scaled: its rank r* (tools/gen_tables.py: enc_cost_ranks) says
 // in which resolutions' short-code intervals it lies, and a band keeps, per resolution, how many of its eight
@@ -264,6 +278,12 @@ __global__ void __launch_bounds__(kEncWarps * 32, HCA_ENC_MIN_CTAS)
 hca_encode_kernel(HcaEncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ EncTables tb;
+    __shared__ uint32_t s_first_stream;
+    if (threadIdx.x < 32) {                                   // stream of the CTA's first frame (round 0)
+        const uint64_t f0 = min((uint64_t)blockIdx.x * (blockDim.x >> 5), a.n_frames - 1);
+        const uint32_t s0 = find_stream_warp(a.frame_prefix, a.n_streams, f0, (int)threadIdx.x);
+        if (threadIdx.x == 0) s_first_stream = s0;
+    }
     if (COUNTED) {
         for (int i = threadIdx.x; i < 2 * (int)kRankBuckets; i += blockDim.x) tb.rank_key[i] = make_uint2(e_rank_keys[2 * i], e_rank_keys[2 * i + 1]);
         for (int i = threadIdx.x; i < 16; i += blockDim.x) {
@@ -310,16 +330,10 @@ hca_encode_kernel(HcaEncodeArgs a) {
     const bool surplus = f_own >= a.n_frames;
     if (surplus && !HCA_ENC_CONVOY) break;
     const uint64_t f = surplus ? a.n_frames - 1 : f_own;
-    // the frame's stream = the last s with frame_prefix[s] <= f. The warp searches together: 32 probes spread over the
-    // open interval per step (three dependent loads for 8192 streams where a bisection takes thirteen)
-    uint32_t lo = 0, hi = a.n_streams;
-    while (hi - lo > 1) {
-        const uint32_t probe = lo + (uint32_t)(((uint64_t)(hi - lo) * (uint32_t)(lane + 1)) / 33u);      // lo <= probe < hi, non-decreasing in lane
-        const int k = __popc(__ballot_sync(kFull, a.frame_prefix[probe] <= f));                         // probes 0 .. k - 1 hold
-        const uint32_t below = __shfl_sync(kFull, probe, max(k - 1, 0)), above = __shfl_sync(kFull, probe, min(k, 31));
-        lo = k ? below : lo;
-        hi = k < 32 ? above : hi;
-    }
+    // the frame's stream = the last s with frame_prefix[s] <= f. In the first round the CTA's frames are neighbours: warp 0
+    // has looked the first one up while the tables were built, the others walk on from there (usually zero or one step).
+    uint32_t lo = round == 0 ? s_first_stream : find_stream_warp(a.frame_prefix, a.n_streams, f, lane);
+    while (lo + 1 < a.n_streams && a.frame_prefix[lo + 1] <= f) lo++;
     const uint32_t stream = lo;
     const uint32_t mul = a.crc_mul[(size_t)stream * 32 + lane];      // this lane's CRC chunk multiplier (needed last, requested first)
     const HcaStreamDev& S = a.streams[stream];
@@ -955,6 +969,9 @@ int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
     // stay in the same phase, so the fp32-heavy MDCT and the integer-heavy search and packing stop overlapping on the SM.
     const uint64_t want = (a.n_frames + warps - 1) / warps;
     uint64_t grid = want;
+#ifdef HCA_ENC_ROUNDS               // experiments: every CTA makes this many rounds over the frame list
+    grid = (want + HCA_ENC_ROUNDS - 1) / HCA_ENC_ROUNDS;
+#endif
 #ifdef HCA_ENC_GRID
     if (HCA_ENC_GRID == 2) {
         int dev = 0, sm_count = 148;
