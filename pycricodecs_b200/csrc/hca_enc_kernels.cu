@@ -60,9 +60,13 @@ constexpr int kEncWarps = HCA_ENC_WARPS;
 // 23.5 -> 19.2 ms per 8192 streams); with the counted bit costs the barrier stalls cost more than the shared fetches
 // save. Measured per 8192 streams: 20 warps with convoy 15.9 ms, without 14.7; 2 x 10 warps without 14.4; 3 x 7 warps
 // (80 registers) 15.9; 4 x 5 warps 16.4. A warp behind the last frame redoes it and stores nothing, so the barrier stays
-// legal if it is switched back on (-DHCA_ENC_CONVOY=1).
+// legal if it is switched back on (-DHCA_ENC_CONVOY=1). What still matters is that the warps of a CTA run the same phase
+// at about the same time: see the round experiments in launch_hca_encode.
 #ifndef HCA_ENC_CONVOY
 #define HCA_ENC_CONVOY 0
+#endif
+#ifndef HCA_ENC_ROUND_SYNC
+#define HCA_ENC_ROUND_SYNC 0
 #endif
 #define CONVOY() do { if (HCA_ENC_CONVOY) __syncthreads(); else __syncwarp(); } while (0)   // a phase boundary always orders the warp's shared memory
 constexpr int kSpecRow = 128;
@@ -323,12 +327,19 @@ hca_encode_kernel(HcaEncodeArgs a) {
     // kEncWarps frames; see launch_hca_encode). With the convoy barrier all warps make the same number of rounds: a
     // warp behind the last frame redoes it and stores nothing.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef HCA_ENC_STAGGER_NS           // experiment: resident CTAs whose warps start one after the other, spread over one frame time
+    __nanosleep((unsigned)(((blockIdx.x / 148u) * (blockDim.x >> 5) + warp) % 20u) * HCA_ENC_STAGGER_NS);
+#endif
     const uint64_t grid_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     const uint32_t rounds = grid_warps >= a.n_frames ? 1u : (uint32_t)((a.n_frames + grid_warps - 1) / grid_warps);   // (64-bit division: rare path)
     for (uint32_t round = 0; round < rounds; round++) {
     const uint64_t f_own = round * grid_warps + (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const bool surplus = f_own >= a.n_frames;
+#if HCA_ENC_ROUND_SYNC
+    __syncthreads();                                          // the CTA's warps start every round together (shared instruction fetch)
+#else
     if (surplus && !HCA_ENC_CONVOY) break;
+#endif
     const uint64_t f = surplus ? a.n_frames - 1 : f_own;
     // the frame's stream = the last s with frame_prefix[s] <= f. In the first round the CTA's frames are neighbours: warp 0
     // has looked the first one up while the tables were built, the others walk on from there (usually zero or one step).
@@ -964,14 +975,17 @@ int launch_hca_encode(HcaEncodeArgs a, cudaStream_t s, uint64_t* launches) {
     if (smem > 200 * 1024) return -1;
     auto kernel = a.max_channels <= 2 ? hca_encode_kernel<true> : hca_encode_kernel<false>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // One CTA per `warps` frames. The kernel can walk the frame list with resident CTAs only (HCA_ENC_GRID = 2: 2 x SMs
-    // CTAs, tables built once per CTA), but measured 16.1 ms against 12.7 ms per 8192 streams: warps that start together
-    // stay in the same phase, so the fp32-heavy MDCT and the integer-heavy search and packing stop overlapping on the SM.
+    // One CTA per 2 x `warps` frames: every warp makes two rounds over the frame list. More rounds per CTA amortise the
+    // table set-up further, but the warps of a CTA drift apart from round to round and stop sharing instruction fetches (the
+    // kernel is ~100 KB of SASS). Measured per 8192 streams: 1 / 2 / 3 / 4 / 8 rounds -> 12.83 / 12.42 / 14.55 / 15.23 /
+    // 16.30 ms, resident CTAs only (HCA_ENC_GRID = 2) 16.1 ms; with a CTA barrier at the top of every round
+    // (HCA_ENC_ROUND_SYNC) 2 / 4 / 8 rounds / resident -> 12.78 / 12.87 / 13.10 / 13.72 ms; resident CTAs whose warps are
+    // deliberately spread over a frame time (HCA_ENC_STAGGER_NS) 17.1 ms -- twenty phases per SM are the worst case.
     const uint64_t want = (a.n_frames + warps - 1) / warps;
-    uint64_t grid = want;
-#ifdef HCA_ENC_ROUNDS               // experiments: every CTA makes this many rounds over the frame list
-    grid = (want + HCA_ENC_ROUNDS - 1) / HCA_ENC_ROUNDS;
+#ifndef HCA_ENC_ROUNDS
+#define HCA_ENC_ROUNDS 2
 #endif
+    uint64_t grid = (want + HCA_ENC_ROUNDS - 1) / HCA_ENC_ROUNDS;
 #ifdef HCA_ENC_GRID
     if (HCA_ENC_GRID == 2) {
         int dev = 0, sm_count = 148;
