@@ -68,7 +68,10 @@ constexpr int kEncWarps = HCA_ENC_WARPS;
 #ifndef HCA_ENC_ROUND_SYNC
 #define HCA_ENC_ROUND_SYNC 0
 #endif
-#define CONVOY() do { if (HCA_ENC_CONVOY) __syncthreads(); else __syncwarp(); } while (0)   // a phase boundary always orders the warp's shared memory
+// HCA_ENC_CONVOY is a bit mask over the nine phase boundaries (0: after the MDCT, 1: intensity, 2: scalefactors, 3: scaled
+// spectra, 4: noise level, 5: boundary, 6: header, 7: quantised, 8: packed); a boundary without the CTA barrier still orders
+// the warp's own shared memory.
+#define CONVOY(k) do { if ((HCA_ENC_CONVOY >> (k)) & 1) __syncthreads(); else __syncwarp(); } while (0)
 constexpr int kSpecRow = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -483,7 +486,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         };
         if (interior) mdct_channels(std::true_type{}); else mdct_channels(std::false_type{});
     }
-    CONVOY();
+    CONVOY(0);
 
     // ---- intensity stereo (hca.cpp:2561-2609): one lane per subframe accumulates the energies in band order
     if (S.stereo_bands > 0) {
@@ -528,7 +531,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         __syncwarp();
     }
 
-    CONVOY();
+    CONVOY(1);
     // ---- scalefactors (hca.cpp:2625-2637)
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
@@ -583,7 +586,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         __syncwarp();
     }
 
-    CONVOY();
+    CONVOY(2);
     // ---- scaled spectra, in place (hca.cpp:2639-2654)
     uint32_t cnt_a[2][4] = {}, cnt_b[2][4] = {};    // COUNTED: per band (channel c, band lane + 32 k) the interval counts
     if constexpr (COUNTED) {
@@ -663,7 +666,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         __syncwarp();
     }
 
-    CONVOY();
+    CONVOY(3);
     // ---- bit allocation (hca.cpp:2809-2866)
     header_lengths(fs, S, lane);
     const int avail = frame_size * 8;
@@ -739,7 +742,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
             load_bands();
         }
     }
-    CONVOY();
+    CONVOY(4);
     if (!failed && noise_level != 0) {                        // BinarySearchBoundary
         int* pre = reinterpret_cast<int*>(fs.pcm);            // scratch shared with the frame buffer, which is filled later
         if constexpr (COUNTED) {                              // boundary_table() from the counts
@@ -775,7 +778,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         if (boundary < 0) failed = true;
     }
     if (failed && lane == 0 && !surplus) a.status[stream] = ERR_HCA_ENCODE;   // EncodeFrame gives up (HcaErrorCode, hca.cpp:2976-2984);
-    CONVOY();                                                                 //  the warp stays with its CTA, nothing of the frame is stored
+    CONVOY(5);                                                                 //  the warp stays with its CTA, nothing of the frame is stored
 
     // ---- final resolutions (hca.cpp:2868-2876)
     for (int c = 0; c < nch; c++) {
@@ -821,7 +824,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         else if (S.hfr_groups > 0)
             emit_bits(fs, lane, lane < S.hfr_groups ? (uint32_t)fs.hfr_scale[c * 8 + lane] : 0u, lane < S.hfr_groups ? 6 : 0, &cursor, limit_bits);
     }
-    CONVOY();
+    CONVOY(6);
     // Spectra in two phases. (1) Every lane quantises its bands (4 l .. 4 l + 3 of every channel) for all eight subframes --
     // the band's constants are fetched once, not once per subframe -- and leaves (length << 16 | code) in place of the
     // scaled value (QuantizeSpectra + WriteSpectra, hca.cpp:2878-2936). (2) In bitstream order (subframe-major, channel-
@@ -864,7 +867,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
             *row = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
-    CONVOY();
+    CONVOY(7);
     auto put_bits = [&](uint32_t code, int len, int at) {                 // the reference's writer drops what does not fit (IO.cpp:131-134)
         if (len > 0 && at + len <= limit_bits) {
             const int w = at >> 5, bo = at & 31;
@@ -899,7 +902,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
         put_bits(code[1][0], len[1][0], at1);
         put_bits(code[1][1], len[1][1], at1 + len[1][0]);
     }
-    CONVOY();
+    CONVOY(8);
 
     // ---- CRC16 over the first frame_size - 2 bytes. The CRC (init 0, no final xor) is linear: every lane takes a
     // contiguous chunk of whole words (four bytes per step: slice-by-4 tables), multiplies its partial CRC by
