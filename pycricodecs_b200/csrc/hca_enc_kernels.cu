@@ -72,6 +72,10 @@ constexpr int kEncWarps = HCA_ENC_WARPS;
 // spectra, 4: noise level, 5: boundary, 6: header, 7: quantised, 8: packed); a boundary without the CTA barrier still orders
 // the warp's own shared memory.
 #define CONVOY(k) do { if ((HCA_ENC_CONVOY >> (k)) & 1) __syncthreads(); else __syncwarp(); } while (0)
+#ifndef HCA_ENC_RANK_UNROLL
+#define HCA_ENC_RANK_UNROLL 8        // coefficients per unrolled body of the rank loop (code size against loop overhead)
+#endif
+constexpr int kRankUnroll = HCA_ENC_RANK_UNROLL;
 constexpr int kSpecRow = 128;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -601,7 +605,7 @@ hca_encode_kernel(HcaEncodeArgs a) {
                 if (b < coded) {
                     const int sfv = fs.sf[c * 128 + b];
                     const float ks = sfv ? tb.qscaling[sfv] : 0.f;       // no scalefactor: every coefficient becomes (+-) 0
-#pragma unroll
+#pragma unroll kRankUnroll
                     for (int j = 0; j < 8; j++) {
                         const float v = fminf(fmaxf(__fmul_rn(sp[j * kSpecRow + b], ks), -0.9999999f), 0.9999999f);
                         sp[j * kSpecRow + b] = v;
