@@ -432,6 +432,8 @@ def run_ours(a):
                 del out_t
                 if it >= 2:
                     tot += dist.reduce([t["total_ms"]], "MAX")[0] / 3
+                if it == 4 and rank == 0 and os.environ.get("CRI_GATHER_TRACE"):
+                    print(f"[gather trace] {label}: compute_ms {t.get('compute_ms'):.3f} total_ms {t.get('total_ms'):.3f} chunks (compute end, gather start, gather end) {t.get('chunks')}", file=sys.stderr)
             res[label] = {"ms_per_step": tot, "value": units * world / (tot * 1e-3)}
         gathered_bytes = int(out_bytes) * world
         extra_ms = max(res["with_gather"]["ms_per_step"] - res["compute_only"]["ms_per_step"], 0.0)

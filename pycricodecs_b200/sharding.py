@@ -176,12 +176,17 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
         ps = range(k * world, (k + 1) * world)
         pbytes = [int(out_offsets[pieces[p][1]] - out_offsets[pieces[p][0]]) for p in ps]
         first = int(out_offsets[pieces[k * world][0]])
+        marks = timings.setdefault("chunks", []) if timings is not None and ev0 is not None else None
         if comm_stream is not None:
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=marks is not None)
             done.record()
         with (torch.cuda.stream(comm_stream) if comm_stream is not None else _Null()):
             if comm_stream is not None:
                 comm_stream.wait_event(done)
+            if marks is not None and comm_stream is not None:    # (compute end, gather start, gather end) of this chunk
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                marks.append((done, g0, g1))
             if len(set(pbytes)) == 1:
                 if pbytes[0]:
                     dist.all_gather_into_tensor(final[first:first + world * pbytes[0]], final[o0:o1], group=group)
@@ -196,6 +201,8 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
                     if r != rank:
                         final[at:at + nb] = staging[r * width:r * width + nb]
                     at += nb
+            if marks is not None and comm_stream is not None:
+                marks[-1][2].record()
     if ev1 is not None:
         ev1.record()
     if comm_stream is not None:
@@ -208,6 +215,8 @@ def sharded_batch(kind: int, blob, offsets: np.ndarray, ctx=None, *, gather: boo
         ev2.record()
         torch.cuda.synchronize(device)
         timings.update(compute_ms=ev0.elapsed_time(ev1), total_ms=ev0.elapsed_time(ev2))
+        if "chunks" in timings:          # ms from the start of the call: when each chunk's compute ended, its gather ran
+            timings["chunks"] = [tuple(round(ev0.elapsed_time(e), 3) for e in m) for m in timings["chunks"]]
     return final[:total], out_offsets, status.astype(np.int32)
 
 
