@@ -32,7 +32,6 @@ namespace {
 constexpr int kTile = 8;                 // blocks per chain per tile
 constexpr int kSpb = 32;                 // samples per block on the fast path
 constexpr int kBlk = 18;                 // bytes per block on the fast path
-constexpr int kPcmRow = kTile * kSpb + 2;            // int16 per chain in the PCM tile: odd word stride
 // input stages: per stream one row of whole 16-byte chunks covering its tile (+ one chunk for the misalignment)
 constexpr int kCodeWords = 32 * ((kTile * kBlk + 15) / 16 + 1) * 4;        // 32 chains x kTile blocks
 constexpr int kPcmWords = 32 * ((kTile * kSpb * 2 + 15) / 16 + 1) * 4;     // 32 chains x kTile x 32 samples
