@@ -126,3 +126,36 @@ def test_wrong_layout_is_refused(ctx):
     rc = ctx._lib.cri_adx_encode_batch_dev(ctx.handle, d_wav.data_ptr(), woff.ctypes.data, 3, ctypes.byref(p), out.data_ptr(),
                                            bad.ctypes.data, st.ctypes.data, None)
     assert rc == -301
+
+
+@pytest.mark.parametrize("pieces", [1, 3, 5])
+def test_device_call_in_pieces_equals_the_host_call(ctx, monkeypatch, pieces):
+    """Large HCA batches run as several pieces inside one `_dev` call (header fetch / planning of a piece beside the
+    kernels of the piece in front). CRI_DEV_PIECES forces that on a small batch: bytes and per-stream status must not
+    depend on the cut, ragged stream sizes and a corrupt stream in a later piece included (it is silenced, its status
+    lands on its own index)."""
+    torch = _torch()
+    wavs = [synth.wav(900 + s, 2, 3000 + 1234 * (s % 7)) for s in range(23)]           # all stereo: the fast decode kernels
+    hcas = engine.hca_encode_batch(wavs, quality=1, ctx=ctx)
+    bad = bytearray(hcas[17])
+    bad[len(bad) // 2] ^= 0x5A                                   # breaks one frame's CRC
+    hcas[17] = bytes(bad)
+    d_hca, hoff = _to_dev(hcas)
+    monkeypatch.setenv("CRI_DEV_PIECES", str(pieces))
+    pcm_t, poff, st = engine.batch_device(_lib.JOB_HCA_DECODE, d_hca, hoff, ctx)
+    got = _split(pcm_t, poff)
+    monkeypatch.setenv("CRI_DEV_PIECES", "1")
+    ref_t, roff, rst = engine.batch_device(_lib.JOB_HCA_DECODE, d_hca, hoff, ctx)
+    assert np.array_equal(poff, roff) and np.array_equal(st, rst)
+    assert got == _split(ref_t, roff)
+    assert st[17] != 0 and not np.delete(st, 17).any()
+    assert set(got[17][44:]) <= {0}                               # a failed stream leaves silence behind its header
+    good = [h for i, h in enumerate(hcas) if i != 17]
+    assert [g for i, g in enumerate(got) if i != 17] == engine.hca_decode_batch(good, ctx=ctx)
+    # the encoder takes the same route
+    d_wav, woff = _to_dev(wavs)
+    monkeypatch.setenv("CRI_DEV_PIECES", str(pieces))
+    hca_t, eoff, est = engine.batch_device(_lib.JOB_HCA_ENCODE, d_wav, woff, ctx, quality=1)
+    assert not est.any()
+    clean = engine.hca_encode_batch(wavs, quality=1, ctx=ctx)
+    assert _split(hca_t, eoff) == clean
