@@ -886,12 +886,14 @@ hca_encode_kernel(HcaEncodeArgs a) {
     };
     // rows in bitstream order (subframe-major, channel-minor), two per prefix sum: the lengths of a lane's codes in rows
     // i and i + 1 travel through the scan as two 16-bit fields (a row holds at most 128 x 12 bits)
+    int row_sub = 0, row_c = 0;                               // (subframe, channel) of the next row: no division in the loop
     for (int i = 0; i < 8 * nch; i += 2) {
         uint32_t code[2][2];
         int len[2][2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int sub = (i + h) / nch, c = (i + h) - sub * nch;
+            const int sub = row_sub, c = row_c;
+            if (++row_c == nch) { row_c = 0; row_sub++; }
             const uint4 e = *reinterpret_cast<const uint4*>(fs.spec + ((size_t)c * 8 + sub) * kSpecRow + 4 * lane);
             const int l1 = (int)(e.y >> 16), l3 = (int)(e.w >> 16);
             code[h][0] = ((e.x & 0xFFFFu) << l1) | (e.y & 0xFFFFu); code[h][1] = ((e.z & 0xFFFFu) << l3) | (e.w & 0xFFFFu);
