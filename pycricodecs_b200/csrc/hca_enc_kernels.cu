@@ -148,13 +148,10 @@ __device__ __noinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_t c
     if (len > 0 && at + len <= limit_bits) {     // the reference's writer silently drops what does not fit (IO.cpp:131-134)
         const int w = at >> 5, bo = at & 31;
         code &= len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
-        if (bo + len <= 32) {
-            atomicOr(&fs.bits[w], code << (32 - bo - len));
-        } else {
-            const int spill = bo + len - 32;
-            atomicOr(&fs.bits[w], code >> spill);
-            atomicOr(&fs.bits[w + 1], code << (32 - spill));
-        }
+        const unsigned long long window = (unsigned long long)code << (64 - bo - len);         // bo + len <= 63
+        const uint32_t second = (uint32_t)window;
+        atomicOr(&fs.bits[w], (uint32_t)(window >> 32));
+        if (second) atomicOr(&fs.bits[w + 1], second);
     }
 }
 
@@ -872,16 +869,15 @@ hca_encode_kernel(HcaEncodeArgs a) {
         }
     }
     CONVOY(7);
+    // One piece (at most 24 bits) into the frame buffer, without a branch on whether it straddles a word: the code is
+    // placed in a 64-bit window that starts at its first word, the second word is ORed only if something landed in it.
     auto put_bits = [&](uint32_t code, int len, int at) {                 // the reference's writer drops what does not fit (IO.cpp:131-134)
         if (len > 0 && at + len <= limit_bits) {
             const int w = at >> 5, bo = at & 31;
-            if (bo + len <= 32) {
-                atomicOr(&fs.bits[w], code << (32 - bo - len));
-            } else {
-                const int spill = bo + len - 32;
-                atomicOr(&fs.bits[w], code >> spill);
-                atomicOr(&fs.bits[w + 1], code << (32 - spill));
-            }
+            const unsigned long long window = (unsigned long long)code << (64 - bo - len);     // bo + len <= 55
+            const uint32_t second = (uint32_t)window;
+            atomicOr(&fs.bits[w], (uint32_t)(window >> 32));
+            if (second) atomicOr(&fs.bits[w + 1], second);
         }
     };
     // rows in bitstream order (subframe-major, channel-minor), two per prefix sum: the lengths of a lane's codes in rows
