@@ -21,7 +21,7 @@
 //     HFR group averages) are accumulated by one lane per subframe / group in the
 //     reference's order; the fp64 corners (sqrt(2), 1.0/avg) are evaluated in fp64;
 //   * the bitstream is assembled with warp prefix sums of code lengths and
-//     shared-memory atomicOr, 32 bands per step in band order.
+//     shared-memory atomicOr (fields of known length at computed offsets).
 #include <algorithm>
 #include <cstdint>
 #include <type_traits>
@@ -139,21 +139,6 @@ struct FrameSmem {
     int* header_bits;   // [nch]
     int* delta_bits;    // [nch]
 };
-
-// Append `len` (<= 32) bits per lane, lanes in order, at bit cursor *cursor of the frame buffer.
-__device__ __noinline__ void emit_bits(const FrameSmem& fs, int lane, uint32_t code, int len, int* cursor, int limit_bits) {
-    int total;
-    const int at = *cursor + warp_excl_scan(len, lane, &total);
-    *cursor += total;
-    if (len > 0 && at + len <= limit_bits) {     // the reference's writer silently drops what does not fit (IO.cpp:131-134)
-        const int w = at >> 5, bo = at & 31;
-        code &= len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
-        const unsigned long long window = (unsigned long long)code << (64 - bo - len);         // bo + len <= 63
-        const uint32_t second = (uint32_t)window;
-        atomicOr(&fs.bits[w], (uint32_t)(window >> 32));
-        if (second) atomicOr(&fs.bits[w + 1], second);
-    }
-}
 
 // Bits of one band's eight coefficients at resolution r (the per-coefficient terms of CalculateUsedBits, hca.cpp:2772-2787):
 // a coefficient costs full[r] bits, one less inside (-N[r], P[r]) -- the dead zone of the sign-magnitude codes, the short
@@ -793,37 +778,67 @@ hca_encode_kernel(HcaEncodeArgs a) {
     __syncwarp();
     // ---- pack (hca.cpp:2894-2963): sync word, noise level, boundary, per-channel headers, spectra, CRC
     const int limit_bits = (frame_size - 2) * 8 + 16;         // writer buffer = frame_size - 2 bytes after the sync word
-    int cursor = 0;
-    emit_bits(fs, lane, lane == 0 ? 0xFFFFu : lane == 1 ? (uint32_t)noise_level : (uint32_t)boundary,
-              lane == 0 ? 16 : lane == 1 ? 9 : lane == 2 ? 7 : 0, &cursor, limit_bits);
+    // One piece (at most 24 bits) into the frame buffer, without a branch on whether it straddles a word: the code is
+    // placed in a 64-bit window that starts at its first word, the second word is ORed only if something landed in it.
+    auto put_bits = [&](uint32_t code, int len, int at) {                 // the reference's writer drops what does not fit (IO.cpp:131-134)
+        if (len > 0 && at + len <= limit_bits) {
+            const int w = at >> 5, bo = at & 31;
+            const unsigned long long window = (unsigned long long)code << (64 - bo - len);     // bo + len <= 55
+            const uint32_t second = (uint32_t)window;
+            atomicOr(&fs.bits[w], (uint32_t)(window >> 32));
+            if (second) atomicOr(&fs.bits[w + 1], second);
+        }
+    };
+    // Header fields of known length need no prefix sum: sync word + noise level + boundary are word 0, the 3-bit delta
+    // width, raw 6-bit scalefactors, intensities and HFR scales sit at computed offsets. Only delta-coded scalefactors have
+    // data-dependent lengths: a lane takes bands 4 l .. 4 l + 3 (two pieces of at most 22 bits) and ONE warp prefix sum
+    // per channel places them.
+    if (lane == 0) fs.bits[0] = 0xFFFF0000u | ((uint32_t)noise_level << 7) | (uint32_t)boundary;
+    __syncwarp();
+    int cursor = 32;
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
         const int db = fs.delta_bits[c];
         const uint8_t* sf = fs.sf + c * 128;
-        emit_bits(fs, lane, (uint32_t)db, lane == 0 ? 3 : 0, &cursor, limit_bits);
+        if (lane == 0) put_bits((uint32_t)db, 3, cursor);
+        cursor += 3;
+        const int b4 = 4 * lane, nb = min(max(coded - b4, 0), 4);         // this lane's bands
         if (db == 6) {
-            for (int b0 = 0; b0 < coded; b0 += 32) {
-                const int b = b0 + lane;
-                emit_bits(fs, lane, b < coded ? sf[b] : 0u, b < coded ? 6 : 0, &cursor, limit_bits);
-            }
+            uint32_t code = 0;
+            for (int h = 0; h < nb; h++) code = (code << 6) | sf[b4 + h];
+            put_bits(code, 6 * nb, cursor + 24 * lane);
+            cursor += 6 * coded;
         } else if (db != 0) {
             const int maxd = (1 << (db - 1)) - 1, esc = (1 << db) - 1;
-            for (int b0 = 0; b0 < coded; b0 += 32) {
-                const int b = b0 + lane;
+            uint32_t piece[2] = {0, 0};
+            int plen[2] = {0, 0};
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                const int b = b4 + h;
                 uint32_t code = 0;
                 int len = 0;
-                if (b == 0) { code = sf[0]; len = 6; }
+                if (b == 0 && coded > 0) { code = sf[0]; len = 6; }
                 else if (b < coded) {
                     const int delta = (int)sf[b] - (int)sf[b - 1];
                     if (abs(delta) > maxd) { code = ((uint32_t)esc << 6) | sf[b]; len = db + 6; }
                     else { code = (uint32_t)(maxd + delta); len = db; }
                 }
-                emit_bits(fs, lane, code, len, &cursor, limit_bits);
+                piece[h >> 1] = (piece[h >> 1] << len) | code;
+                plen[h >> 1] += len;
             }
+            int total;
+            const int at = cursor + warp_excl_scan(plen[0] + plen[1], lane, &total);
+            put_bits(piece[0], plen[0], at);
+            put_bits(piece[1], plen[1], at + plen[0]);
+            cursor += total;
         }
-        if (S.type[c] == 2) emit_bits(fs, lane, lane < 8 ? fs.inten[c * 8 + lane] : 0u, lane < 8 ? 4 : 0, &cursor, limit_bits);
-        else if (S.hfr_groups > 0)
-            emit_bits(fs, lane, lane < S.hfr_groups ? (uint32_t)fs.hfr_scale[c * 8 + lane] : 0u, lane < S.hfr_groups ? 6 : 0, &cursor, limit_bits);
+        if (S.type[c] == 2) {
+            if (lane < 8) put_bits(fs.inten[c * 8 + lane], 4, cursor + 4 * lane);
+            cursor += 32;
+        } else if (S.hfr_groups > 0) {
+            if (lane < S.hfr_groups) put_bits((uint32_t)fs.hfr_scale[c * 8 + lane], 6, cursor + 6 * lane);
+            cursor += 6 * (int)S.hfr_groups;
+        }
     }
     CONVOY(6);
     // Spectra in two phases. (1) Every lane quantises its bands (4 l .. 4 l + 3 of every channel) for all eight subframes --
@@ -869,17 +884,6 @@ hca_encode_kernel(HcaEncodeArgs a) {
         }
     }
     CONVOY(7);
-    // One piece (at most 24 bits) into the frame buffer, without a branch on whether it straddles a word: the code is
-    // placed in a 64-bit window that starts at its first word, the second word is ORed only if something landed in it.
-    auto put_bits = [&](uint32_t code, int len, int at) {                 // the reference's writer drops what does not fit (IO.cpp:131-134)
-        if (len > 0 && at + len <= limit_bits) {
-            const int w = at >> 5, bo = at & 31;
-            const unsigned long long window = (unsigned long long)code << (64 - bo - len);     // bo + len <= 55
-            const uint32_t second = (uint32_t)window;
-            atomicOr(&fs.bits[w], (uint32_t)(window >> 32));
-            if (second) atomicOr(&fs.bits[w + 1], second);
-        }
-    };
     // rows in bitstream order (subframe-major, channel-minor), two per prefix sum: the lengths of a lane's codes in rows
     // i and i + 1 travel through the scan as two 16-bit fields (a row holds at most 128 x 12 bits)
     int row_sub = 0, row_c = 0;                               // (subframe, channel) of the next row: no division in the loop
