@@ -222,20 +222,27 @@ __device__ __noinline__ void header_lengths(const FrameSmem& fs, const HcaStream
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
         const uint8_t* sf = fs.sf + c * 128;
-        int any = 0, cost[5] = {0, 0, 0, 0, 0};
+        // a delta width db costs db bits per band behind the first, 6 more where |delta| > 2^(db-1) - 1, i.e. where delta
+        // has more than db - 1 significant bits: the five escape counts (at most 127 each) travel through the warp sums as
+        // 8-bit fields, four in one word
+        int any = 0;
+        uint32_t esc_lo = 0, esc_5 = 0;
         for (int b = lane; b < coded; b += 32) {
             any |= sf[b] != 0;
             if (b >= 1) {
-                const int delta = abs((int)sf[b] - (int)sf[b - 1]);
-#pragma unroll
-                for (int db = 1; db < 6; db++) cost[db - 1] += delta > ((1 << (db - 1)) - 1) ? db + 6 : db;
+                const uint32_t delta = (uint32_t)abs((int)sf[b] - (int)sf[b - 1]);
+                esc_lo += (delta > 0u ? 1u : 0u) + (delta > 1u ? 1u << 8 : 0u) + (delta > 3u ? 1u << 16 : 0u) + (delta > 7u ? 1u << 24 : 0u);
+                esc_5 += delta > 15u ? 1u : 0u;
             }
         }
         any = __any_sync(kFull, any);
+        esc_lo = (uint32_t)warp_sum((int)esc_lo);
+        esc_5 = (uint32_t)warp_sum((int)esc_5);
         int best_bits = 6, best_len = 3 + 6 * coded;
 #pragma unroll
         for (int db = 1; db < 6; db++) {
-            const int len = 3 + 6 + warp_sum(cost[db - 1]);
+            const int escapes = db < 5 ? (int)((esc_lo >> (8 * (db - 1))) & 0xFFu) : (int)esc_5;
+            const int len = 3 + 6 + db * max(coded - 1, 0) + 6 * escapes;
             if (len < best_len) { best_len = len; best_bits = db; }
         }
         if (!any) { best_len = 3; best_bits = 0; }
