@@ -774,10 +774,21 @@ hca_encode_kernel(HcaEncodeArgs a) {
     CONVOY(5);                                                                 //  the warp stays with its CTA, nothing of the frame is stored
 
     // ---- final resolutions (hca.cpp:2868-2876)
-    for (int c = 0; c < nch; c++) {
-        const int coded = S.coded[c];
-        for (int b = lane; b < 128; b += 32)
-            fs.res[c * 128 + b] = b < coded ? (uint8_t)enc_resolution(tb, fs.sf[c * 128 + b], b < boundary ? noise_level - 1 : noise_level) : 0;
+    if constexpr (COUNTED) {                                  // from the band state the search kept in registers
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int b = lane + 32 * k;
+                const int pos = min(max((b < boundary ? noise_level - 1 : noise_level) + band_off[c][k], 0), 58);
+                if (c < nch) fs.res[c * 128 + b] = band_nz4[c][k] ? tb.curve[pos] : (uint8_t)0;
+            }
+    } else {
+        for (int c = 0; c < nch; c++) {
+            const int coded = S.coded[c];
+            for (int b = lane; b < 128; b += 32)
+                fs.res[c * 128 + b] = b < coded ? (uint8_t)enc_resolution(tb, fs.sf[c * 128 + b], b < boundary ? noise_level - 1 : noise_level) : 0;
+        }
     }
     __syncwarp();
 
