@@ -14,11 +14,11 @@ ie = hdr.index("Instructions Executed"); isamp = hdr.index("# Samples")
 tot = sum(int(r[ie]) for rs in files.values() for r in rs); tots = sum(int(r[isamp]) for rs in files.values() for r in rs)
 print("warp instructions", tot, "per frame", round(tot / frames))
 src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pycricodecs_b200/csrc/hca_enc_kernels.cu")).read().split("\n")
-marks = [("helpers", "namespace {"), ("emit_bits", "void emit_bits"), ("band_cost (uncounted)", "int band_cost"), ("header_lengths", "void header_lengths"),
+marks = [("helpers", "namespace {"), ("band_cost (uncounted)", "int band_cost"), ("header_lengths", "void header_lengths"),
          ("prologue", "hca_encode_kernel(HcaEncodeArgs a)"), ("MDCT", "---- MDCT"), ("intensity", "---- intensity stereo"), ("scalefactors", "---- scalefactors"),
          ("hfr averages", "---- HFR group averages"), ("scaled spectra + ranks", "---- scaled spectra"), ("hfr scales", "---- HFR scales"),
          ("bit allocation", "---- bit allocation"), ("final resolutions", "---- final resolutions"), ("header pack", "---- pack (hca.cpp"),
-         ("quantise", "Spectra in two phases"), ("pack", "auto put_bits"), ("crc + store", "---- CRC16 over")]
+         ("quantise", "Spectra in two phases"), ("pack", "rows in bitstream order"), ("crc + store", "---- CRC16 over")]
 anchors = []
 for name, text in marks:
     hit = [i + 1 for i, l in enumerate(src) if text in l]
