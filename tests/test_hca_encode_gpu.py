@@ -81,3 +81,19 @@ def test_class_surface_and_errors(port):
     assert enc == port.hca_crypt(port.hca_encode(w, 1)[1], 1, 56, 0xCF222F1FE0748978)[1]
     with pytest.raises(ValueError, match="must be a WAV"):
         HCA(port.hca_encode(w, 1)[1]).encode()
+
+
+@pytest.mark.parametrize("quality", [0, 1, 2, 3])
+def test_hard_material_matches_oracle(port, ctx, quality):
+    """tests/helpers/hard_material.py (noise, full-scale squares, impulses, a step) at every quality, mono and stereo:
+    byte-exact with the oracle, which tests/test_oracle_golden.py ties to the compiled reference on the same material."""
+    from helpers import hard_material
+    cases = hard_material.wavs(11 + quality)
+    got = HCA.encode_batch(cases, Q[quality], ctx=ctx, raise_errors=False)
+    for k, (w, g) in enumerate(zip(cases, got)):
+        r, want = port.hca_encode(w, quality)
+        if r == 0:
+            assert not isinstance(g, Exception), (k, g)
+            assert _frame_diff(g, want) is None, (k, quality)
+        else:
+            assert isinstance(g, Exception), (k, quality)

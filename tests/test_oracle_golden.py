@@ -137,3 +137,13 @@ def test_oracle_stage_probes_vs_reference(port, ref):
         for k in ("sf", "res", "intensity"):
             assert np.array_equal(uo[k][:, :uo[k].shape[1]], ur[k]), k
         assert np.array_equal(uo["spectra"].view(np.uint32), ur["spectra"].view(np.uint32))
+
+
+@pytest.mark.parametrize("quality", [0, 1, 2, 3])
+def test_oracle_vs_compiled_reference_hard_material(port, ref, quality):
+    """The encoder's corner material (tests/helpers/hard_material.py): the restatement and the compiled reference agree
+    byte for byte, so the GPU test against the restatement on the same material is a test against the reference."""
+    from helpers import hard_material
+    for k, w in enumerate(hard_material.wavs(11 + quality)):
+        assert port.hca_encode(w, quality) == ref.hca_encode(w, quality), (k, quality)
+
