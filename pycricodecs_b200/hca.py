@@ -8,7 +8,7 @@ in the harmless case it can be observed (keyless=False -> subkey 0).
 """
 from __future__ import annotations
 
-from io import BytesIO, FileIO
+from io import BytesIO
 from struct import Struct, unpack
 from typing import BinaryIO
 
@@ -53,37 +53,59 @@ def _unmask(tag: bytes) -> bytes:
     return bytes(c & 0x7F for c in tag)
 
 
+class _Cursor:
+    """Forward reader over an immutable byte string (the header walkers below never need more)."""
+    __slots__ = ("data", "at")
+
+    def __init__(self, data: bytes, at: int = 0):
+        self.data, self.at = data, at
+
+    def take(self, n: int) -> bytes:
+        piece = self.data[self.at:self.at + n]
+        self.at += len(piece)
+        return piece
+
+    def unpack(self, layout: Struct):
+        return layout.unpack(self.take(layout.size))
+
+    def peek(self, n: int) -> bytes:
+        return self.data[self.at:self.at + n]
+
+    def skip(self, n: int) -> None:
+        self.at += n
+
+
 class HCA:
+    """One HCA or WAV image held in memory. `_source` is what the caller gave (path contents or a private copy of the
+    buffer), `_hca` the current HCA image (after encode / encrypt / decrypt), `_wav` the last decode."""
+
     def __init__(self, stream: BinaryIO, key: int = 0, subkey: int = 0) -> None:
-        if type(stream) == str:
-            self.stream = FileIO(stream)
-            self.hcastream = FileIO(stream)
+        if isinstance(stream, str):
+            with open(stream, "rb") as fh:
+                self._source = fh.read()
         else:
-            stream = bytearray(stream).copy()
-            self.stream = BytesIO(stream)
-            self.hcastream = BytesIO(stream)
-        self.key = int(key, 16) if type(key) == str else key
-        self.subkey = int(subkey, 16) if type(subkey) == str else subkey
-        self.hcabytes = b""
-        self.wavbytes = b""
-        self.encrypted = False
-        self.looping = False
+            self._source = bytes(stream)                       # a private copy: the caller's buffer is never touched
+        self.key = key if not isinstance(key, str) else int(key, 16)
+        self.subkey = subkey if not isinstance(subkey, str) else int(subkey, 16)
+        self._hca = self._source
+        self._wav = b""
+        self._encoded = False
+        self.encrypted = self.looping = False
         self.Pyparse_header()
 
     # -- header sniffing: what `info()` reports (same keys and values as the reference's Pyparse_header) ------------
     def Pyparse_header(self) -> None:
-        self.HcaSig, self.version, self.header_size = _HCA_BASE.unpack(self.hcastream.read(_HCA_BASE.size))
+        cur = _Cursor(self._hca)
+        self.HcaSig, self.version, self.header_size = cur.unpack(_HCA_BASE)
         if self.HcaSig in (HCAType.HCA.value, HCAType.EHCA.value):
-            self._parse_hca()
+            self._parse_hca(cur)
         elif self.HcaSig == b"RIFF":
-            self._parse_wav()
+            self._parse_wav(_Cursor(self._source))
         else:
             raise ValueError("Invalid HCA or WAV file.")
-        self.stream.seek(0)
-        self.hcastream.seek(0)
 
-    def _parse_hca(self) -> None:
-        if not self.hcabytes:
+    def _parse_hca(self, cur: _Cursor) -> None:
+        if not self._encoded:                                  # an encoded WAV stays a "wav" object, as in the reference
             self.filetype = "hca"
         self.encrypted = self.HcaSig == HCAType.EHCA.value
         if self.encrypted and not self.key:
@@ -94,29 +116,27 @@ class HCA:
                 raise ValueError(negative)
             if value > top:
                 raise OverflowError(too_big)
-        fmtsig, packed, frames, delay, padding = _HCA_FMT.unpack(self.hcastream.read(_HCA_FMT.size))
+        fmtsig, packed, frames, delay, padding = cur.unpack(_HCA_FMT)
         self.hca = dict(Encrypted=self.encrypted, Header=self.HcaSig, version=hex(self.version), HeaderSize=self.header_size,
                         FmtSig=fmtsig, ChannelCount=packed >> 24, SampleRate=packed & 0x00FFFFFF, FrameCount=frames,
                         EncoderDelay=delay, EncoderPadding=padding)
         while True:                                            # known chunks, in whatever order they come
-            tag = self.hcastream.read(4)
+            tag = cur.peek(4)
             entry = _HCA_CHUNKS.get(_unmask(tag)) if len(tag) == 4 else None
             if entry is None:
-                self.hcastream.seek(-len(tag), 1)
                 break
             layout, keys, finish = entry
-            fields = dict(zip(keys, layout.unpack(tag + self.hcastream.read(layout.size - 4))))
+            fields = dict(zip(keys, cur.unpack(layout)))
             self.hca.update(finish(fields) if finish else fields)
             self.looping = self.looping or "LoopSig" in fields
             if fields.get("CipherType") == 1:
                 self.encrypted = True
-        self.hca["Crc16"] = self.hcastream.read(2)
+        self.hca["Crc16"] = cur.take(2)
 
-    def _parse_wav(self) -> None:
+    def _parse_wav(self, cur: _Cursor) -> None:
         self.filetype = "wav"
         (self.riffSignature, self.riffSize, self.wave, self.fmt, self.fmtSize, self.fmtType, self.fmtChannelCount,
-         self.fmtSamplingRate, self.fmtSamplesPerSec, self.fmtSamplingSize, self.fmtBitCount) = WavHeaderStruct.unpack(
-            self.stream.read(WavHeaderStruct.size))
+         self.fmtSamplingRate, self.fmtSamplesPerSec, self.fmtSamplingSize, self.fmtBitCount) = cur.unpack(WavHeaderStruct)
         if (self.riffSignature, self.wave, self.fmt) != (b"RIFF", b"WAVE", b"fmt "):
             return                                             # the reference looks no further either
         if self.fmtBitCount != 16:
@@ -124,28 +144,26 @@ class HCA:
         if self.fmtSize != 16:
             raise ValueError(f"WAV file has an FMT chunk of an unsupported size: {self.fmtSize}, the only supported size is 16.")
         for tag, handler in _WAV_OPTIONAL.items():             # the two chunks the reference knows, in its order
-            if self.stream.read(4) == tag:
-                getattr(self, handler)()
-            else:
-                self.stream.seek(-4, 1)
-        head = self.stream.read(WavDataHeaderStruct.size)
+            if cur.peek(4) == tag:
+                getattr(self, handler)(cur)
+        head = cur.take(WavDataHeaderStruct.size)
         if head[:4] != b"data":
             raise ValueError("Invalid or an unsupported wav file.")
         self.dataSig, self.dataSize = WavDataHeaderStruct.unpack(head)
 
-    def _wav_smpl(self) -> None:
+    def _wav_smpl(self, cur: _Cursor) -> None:
         """One sampler loop makes the stream a looping one; any other count is skipped like an unknown chunk."""
-        self.stream.seek(-4, 1)
-        v = WavSmplHeaderStruct.unpack(self.stream.read(WavSmplHeaderStruct.size))
+        start = cur.at
+        v = cur.unpack(WavSmplHeaderStruct)
         size, self.LoopCount, self.LoopStartSample, self.LoopEndSample = v[1], v[9], v[13], v[14]
         self.looping = self.LoopCount == 1
         if not self.looping:
-            self.stream.seek(8 + size - WavSmplHeaderStruct.size, 1)
+            cur.at = start + 8 + size
 
-    def _wav_note(self) -> None:
+    def _wav_note(self, cur: _Cursor) -> None:
         """Skip a `note` chunk (the reference seeks to an absolute offset here and then loses the data chunk)."""
-        size = unpack("<I", self.stream.read(4))[0]
-        self.stream.seek(size, 1)
+        cur.skip(4)
+        cur.skip(unpack("<I", cur.take(4))[0])
 
     def info(self) -> dict:
         """ Returns info related to the input file. """
@@ -160,11 +178,8 @@ class HCA:
     def decode(self) -> bytes:
         if self.filetype == "wav":
             raise ValueError("Input type for decoding must be an HCA file.")
-        self.hcastream.seek(0)
-        self.wavbytes = engine.hca_decode_batch([self.hcastream.read()], keys=self.key, subkeys=self.subkey)[0]
-        self.stream = BytesIO(self.wavbytes)
-        self.hcastream.seek(0)
-        return bytes(self.wavbytes)
+        self._wav = engine.hca_decode_batch([self._hca], keys=self.key, subkeys=self.subkey)[0]
+        return bytes(self._wav)
 
     def encode(self, force_not_looping: bool = False, encrypt: bool = False, keyless: bool = False,
                quality_level: CriHcaQuality = CriHcaQuality.High) -> bytes:
@@ -174,50 +189,59 @@ class HCA:
             raise ValueError("Forcing the encoder to not loop is by either False or True.")
         if quality_level not in list(CriHcaQuality):
             raise ValueError("Chosen quality level is not valid or is not the appropiate enumeration value.")
-        self.stream.seek(0)
-        self.hcabytes = engine.hca_encode_batch([self.stream.read()], quality=quality_level.value,
-                                                force_not_looping=bool(force_not_looping))[0]
-        self.hcastream = BytesIO(self.hcabytes)
+        self._hca = engine.hca_encode_batch([self._source], quality=quality_level.value,
+                                            force_not_looping=bool(force_not_looping))[0]
+        self._encoded = True
         self.Pyparse_header()
         if encrypt:
-            if self.key == 0 and not keyless:
+            if not keyless and self.key == 0:
                 self.key = DEFAULT_KEY
             self.encrypt(self.key, keyless)  # as in the reference: `keyless` is taken as the subkey (hca.py:273)
         return self.get_hca()
 
+    def _recipher(self, to_encrypted: bool, keycode: int, subkey: int, ciph_type: int) -> None:
+        if self.encrypted == to_encrypted:
+            raise ValueError("HCA is already encrypted." if to_encrypted else "HCA is already decrypted.")
+        self._hca = engine.hca_crypt_batch([self._hca], to_encrypted, keys=keycode, subkeys=int(subkey), ciph_type=ciph_type)[0]
+        self.encrypted = to_encrypted
+
     def encrypt(self, keycode: int, subkey: int = 0, keyless: bool = False) -> None:
-        if self.encrypted:
-            raise ValueError("HCA is already encrypted.")
-        self.encrypted = True
-        enc = engine.hca_crypt_batch([self.get_hca()], True, keys=keycode, subkeys=int(subkey), ciph_type=1 if keyless else 56)[0]
-        self.hcastream = BytesIO(enc)
+        self._recipher(True, keycode, subkey, 1 if keyless else 56)
 
     def decrypt(self, keycode: int, subkey: int = 0) -> None:
-        if not self.encrypted:
-            raise ValueError("HCA is already decrypted.")
-        self.encrypted = False
-        dec = engine.hca_crypt_batch([self.get_hca()], False, keys=keycode, subkeys=int(subkey), ciph_type=0)[0]
-        self.hcastream = BytesIO(dec)
+        self._recipher(False, keycode, subkey, 0)
 
     def get_hca(self) -> bytes:
         """ Use this function to get the HCA file bytes after encrypting or decrypting. """
-        self.hcastream.seek(0)
-        fl = self.hcastream.read()
-        self.hcastream.seek(0)
-        return fl
+        return bytes(self._hca)
 
     def get_frames(self):
         """ Generator function to yield Frame number, and Frame data. """
-        self.hcastream.seek(self.header_size, 0)
+        size = self.hca["FrameSize"]
         for i in range(self.hca["FrameCount"]):
-            yield (i, self.hcastream.read(self.hca["FrameSize"]))
+            first = self.header_size + i * size
+            yield (i, self._hca[first:first + size])
 
     def get_header(self) -> bytes:
         """ Use this function to retrieve the HCA Header. """
-        self.hcastream.seek(0)
-        header = self.hcastream.read(self.header_size)
-        self.hcastream.seek(0)
-        return header
+        return self._hca[:self.header_size]
+
+    # the reference keeps its images in file-like members; read-only views for code that looks at them
+    @property
+    def hcastream(self) -> BytesIO:
+        return BytesIO(self._hca)
+
+    @property
+    def stream(self) -> BytesIO:
+        return BytesIO(self._wav if self._wav else self._source)
+
+    @property
+    def hcabytes(self) -> bytes:
+        return self._hca if self._encoded else b""
+
+    @property
+    def wavbytes(self) -> bytes:
+        return self._wav
 
     # -- batch entry points (the performance path) -------------------------
     @staticmethod
