@@ -217,7 +217,7 @@ __device__ __forceinline__ void boundary_table(const EncTables& tb, const FrameS
 }
 
 // CalculateOptimalDeltaLength + CalculateFrameHeaderLength, hca.cpp:2708-2750 (warp-collective).
-__device__ __noinline__ void header_lengths(const FrameSmem& fs, const HcaStreamDev& S, int lane) {
+__device__ __forceinline__ void header_lengths(const FrameSmem& fs, const HcaStreamDev& S, int lane) {
     const int nch = S.channels;
     for (int c = 0; c < nch; c++) {
         const int coded = S.coded[c];
