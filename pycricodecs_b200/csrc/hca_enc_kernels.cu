@@ -110,7 +110,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
     return x - v;
 }
 
-__device__ __noinline__ int find_scalefactor(const float* table, float v) {   // hca.cpp:2611-2623
+__device__ __forceinline__ int find_scalefactor(const float* table, float v) {   // hca.cpp:2611-2623
     unsigned lo = 0, hi = 63;
     while (lo < hi) {
         const unsigned mid = (lo + hi) >> 1;
