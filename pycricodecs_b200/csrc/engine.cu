@@ -495,6 +495,7 @@ void missing_ranges(int kind, const uint8_t* d, uint64_t len, const Valid& v, st
     if (v.prefix < 12 || le32(d) != fourcc_le('R', 'I', 'F', 'F')) return;
     const uint64_t riff_size = le32(d + 4);
     uint64_t at = 12, walked = 4;
+    uint64_t first_frame = 2048;                                           // one sample frame: <= 255 channels x 8 bytes until fmt says
     while (walked < riff_size && at + 8 <= len) {
         if (!v.has(at, 8)) { want(at, at + 512); return; }               // next chunk header (and, likely, its small body)
         const uint32_t tag = le32(d + at), body = le32(d + at + 4);
@@ -502,9 +503,13 @@ void missing_ranges(int kind, const uint8_t* d, uint64_t len, const Valid& v, st
         if ((span & 1) && span + walked + 1 <= riff_size) span += 1;
         uint64_t n = 8;
         if (tag == fourcc_le('f', 'm', 't', ' ') || tag == fourcc_le('s', 'm', 'p', 'l')) n = std::min<uint64_t>(span, 128);
-        else if (tag == fourcc_le('d', 'a', 't', 'a')) n = 8 + 2048;       // first sample frame (<= 255 channels x 8 bytes)
+        else if (tag == fourcc_le('d', 'a', 't', 'a')) n = 8 + first_frame;
         n = std::min(n, len - at);
         if (!v.has(at, n)) { want(at, at + n); return; }
+        if (tag == fourcc_le('f', 'm', 't', ' ') && body >= 16) {          // channels x bytes per sample (the planners read the first frame)
+            const uint64_t channels = (uint64_t)d[at + 10] | ((uint64_t)d[at + 11] << 8), bits = (uint64_t)d[at + 22] | ((uint64_t)d[at + 23] << 8);
+            first_frame = std::min<uint64_t>(std::max<uint64_t>(channels, 1) * std::max<uint64_t>((bits + 7) / 8, 1), 2048);
+        }
         at += span;
         walked += span;
     }
