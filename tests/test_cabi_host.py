@@ -145,3 +145,41 @@ def test_size_queries_reject_what_the_planner_rejects():
     L.cri_adx_decode_sizes(blob.ctypes.data, off.ctypes.data, 1, sizes.ctypes.data, st.ctypes.data)
     assert (int(sizes[0]), int(st[0])) == (0, -301)
     assert wav[:4] == b"RIFF"
+
+
+def test_size_queries_on_host_threads_equal_the_serial_answers(port):
+    """Batches of 512 streams and more are parsed by several host threads (formats.h: parallel_for). The size queries run
+    without a GPU: a mixed batch of 700 streams (good ones of different lengths, truncated ones, garbage) must give, per
+    stream, what a one-stream query gives."""
+    import numpy as np
+    from pycricodecs_b200 import _lib, engine, synth
+    L = _lib.lib()
+    wavs = [synth.wav(40 + k, 1 + k % 2, 1500 + 333 * k) for k in range(5)]
+    hcas = [port.hca_encode(w, 1 + k % 3)[1] for k, w in enumerate(wavs)]
+    pool = hcas + [hcas[0][:-50], b"not an hca stream at all", hcas[3][:40]]
+    streams = [pool[(7 * i + i // 5) % len(pool)] for i in range(700)]
+    blob, off = engine.pack(streams)
+    sizes, st = np.zeros(len(streams), np.uint64), np.zeros(len(streams), np.int32)
+    assert L.cri_hca_decode_sizes(blob.ctypes.data, off.ctypes.data, len(streams), sizes.ctypes.data, st.ctypes.data) == 0
+    single = {}
+    for k, s in enumerate(pool):
+        b1, o1 = engine.pack([s])
+        z, t = np.zeros(1, np.uint64), np.zeros(1, np.int32)
+        L.cri_hca_decode_sizes(b1.ctypes.data, o1.ctypes.data, 1, z.ctypes.data, t.ctypes.data)
+        single[k] = (int(z[0]), int(t[0]))
+    assert len({v for v in single.values()}) >= 5
+    for i in range(len(streams)):
+        assert (int(sizes[i]), int(st[i])) == single[(7 * i + i // 5) % len(pool)], i
+    # WAV -> HCA sizes take the same threaded route
+    wpool = wavs + [wavs[1][:30], b"RIFFxxxxWAVEjunk"]
+    wstreams = [wpool[(3 * i) % len(wpool)] for i in range(600)]
+    blob, off = engine.pack(wstreams)
+    sizes, st = np.zeros(len(wstreams), np.uint64), np.zeros(len(wstreams), np.int32)
+    assert L.cri_hca_encode_sizes(blob.ctypes.data, off.ctypes.data, len(wstreams), 1, sizes.ctypes.data, st.ctypes.data) == 0
+    for k, w in enumerate(wpool):
+        b1, o1 = engine.pack([w])
+        z, t = np.zeros(1, np.uint64), np.zeros(1, np.int32)
+        L.cri_hca_encode_sizes(b1.ctypes.data, o1.ctypes.data, 1, 1, z.ctypes.data, t.ctypes.data)
+        for i in range(k, len(wstreams), len(wpool)):
+            if (3 * i) % len(wpool) == k:
+                assert (int(sizes[i]), int(st[i])) == (int(z[0]), int(t[0])), (i, k)
